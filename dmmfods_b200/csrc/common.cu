@@ -1,0 +1,100 @@
+// Host-side plumbing shared by all kernels: thread-local error string, CUDA error mapping and
+// TMA tensor-map encoding (cuTensorMapEncodeTiled resolved at run time through
+// cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda and can be
+// dlopen'ed on a CPU-only box for symbol checks).
+#include "common.cuh"
+#include "../../include/dmmfods_b200.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace dmm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return -2;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode();
+    DMM_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    DMM_CHECK(rank >= 2 && rank <= 5, "tensor map rank %d", rank);
+    DMM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p is not 16-byte aligned", base);
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        DMM_CHECK(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, "tensor map dim %d: size %llu box %u", i,
+                  (unsigned long long)dims[i], box[i]);
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_elems[i] * 2ull;
+        DMM_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "tensor map stride %d = %llu bytes is not a positive multiple of 16", i,
+                  (unsigned long long)gstr[i]);
+    }
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    else if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+    DMM_CHECK((int)(box[0] * 2) <= (swizzle_bytes ? swizzle_bytes : 512), "tensor map inner box %u elements exceeds the swizzle span",
+              box[0]);
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DMM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu.. box %u,%u..)", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return 0;
+}
+
+}  // namespace dmm
+
+extern "C" const char* dmm_last_error(void) { return dmm::g_err; }
+
+extern "C" int dmm_version(void) { return 100; }
+
+extern "C" int dmm_device_ok(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    return prop.major == 10 ? 1 : 0;
+}

@@ -1,0 +1,1092 @@
+// HBM-bound kernels of the Dense-U-Net hot path: BN-ReLU (+pool) prologue materialisation with the
+// batch-statistics finalize fused in, BN-ReLU backward (two passes), stem im2col, head input
+// (nearest x2 upsample + concat + BN-ReLU), sigmoid-BCE loss + gradient, weight packing, Adam.
+//
+// Layout: activations are pixel-major bf16 matrices [P rows = B*H*W, ld elements per row]; one thread
+// moves 8 channels (16 bytes) of one pixel; a block is (cx channel-chunks) x (ry pixels) = 256
+// threads so that a warp touches contiguous 16*cx-byte row segments.
+#include "common.cuh"
+#include "../../include/dmmfods_b200.h"
+
+namespace dmm {
+
+constexpr int kEwThreads = 256;
+constexpr int kMaxBlocksPerSm = 8;
+constexpr int kNumSm = 148;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+    f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+    f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]);
+    v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]);
+    v.w = pack_bf16x2(f[6], f[7]);
+    return v;
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// Batch-norm coefficients for channel c of a dmm_bn_t (training: from accumulated sum / sumsq).
+// ---------------------------------------------------------------------------------------------
+struct BnCoef {
+    float mean, invstd, scale, shift;
+};
+
+__device__ __forceinline__ BnCoef bn_coef_fwd(const dmm_bn_t& bn, int c, bool writer) {
+    BnCoef k;
+    const float g = bn.gamma ? bn.gamma[c] : 1.f;
+    const float b = bn.beta ? bn.beta[c] : 0.f;
+    if (bn.training) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+            const double* row = bn.stats + (size_t)s * 2 * bn.stats_ld + bn.stats_off + c;
+            s1 += row[0];
+            s2 += row[bn.stats_ld];
+        }
+        const double mean = s1 / bn.count;
+        double var = s2 / bn.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        k.mean = (float)mean;
+        k.invstd = (float)(1.0 / sqrt(var + (double)bn.eps));
+        if (writer) {
+            if (bn.save_mean) bn.save_mean[c] = k.mean;
+            if (bn.save_invstd) bn.save_invstd[c] = k.invstd;
+            if (bn.running_mean) {
+                const double n = bn.count * bn.rep;   // nn.Upsample replicates every element `rep` times
+                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * (float)mean;
+                bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * (float)unbiased;
+            }
+        }
+    } else {
+        k.mean = bn.running_mean[c];
+        k.invstd = 1.f / sqrtf(bn.running_var[c] + bn.eps);
+    }
+    k.scale = g * k.invstd;
+    k.shift = b - k.mean * k.scale;
+    return k;
+}
+
+__device__ __forceinline__ BnCoef bn_coef_bwd(const dmm_bn_bwd_t& bn, int c) {
+    BnCoef k;
+    k.mean = bn.save_mean[c];
+    k.invstd = bn.save_invstd[c];
+    const float g = bn.gamma ? bn.gamma[c] : 1.f;
+    const float b = bn.beta ? bn.beta[c] : 0.f;
+    k.scale = g * k.invstd;
+    k.shift = b - k.mean * k.scale;
+    return k;
+}
+
+struct ColCfg {
+    int cx, ry, chunks;
+    dim3 grid, block;
+};
+static ColCfg col_cfg(int C, long long rows) {
+    ColCfg k;
+    k.chunks = (C + 7) / 8;
+    k.cx = 1;
+    while (k.cx < k.chunks && k.cx < 32) k.cx <<= 1;
+    k.ry = kEwThreads / k.cx;
+    const int gy = (k.chunks + k.cx - 1) / k.cx;
+    long long gx = (rows + k.ry - 1) / k.ry;
+    long long cap = (long long)kNumSm * kMaxBlocksPerSm / gy;
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    k.grid = dim3((unsigned)gx, (unsigned)gy, 1);
+    k.block = dim3((unsigned)k.cx, (unsigned)k.ry, 1);
+    return k;
+}
+
+// Block-wide column reduction of per-thread 8-channel partials, then double atomics into
+// stats[slot][2][ld] at off + channel.   sm: float[2][ry][cx*8].
+__device__ __forceinline__ void block_col_reduce_atomic(float (&a)[8], float (&b)[8], float* sm, int cx, int ry,
+                                                        int chunk, int nchunks, double* stats, int ld, int off) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int wcols = cx * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sm[(0 * ry + ty) * wcols + tx * 8 + j] = a[j];
+        sm[(1 * ry + ty) * wcols + tx * 8 + j] = b[j];
+    }
+    __syncthreads();
+    const int tid = ty * cx + tx;
+    const int slot = blockIdx.x % DMM_STATS_SLOTS;
+    for (int i = tid; i < 2 * wcols; i += kEwThreads) {
+        const int which = i / wcols, col = i - which * wcols;
+        const int ch = (chunk - tx) * 8 + col;   // (chunk - tx) = first chunk of this block
+        if (ch < nchunks * 8) {
+            float s = 0.f;
+            for (int r = 0; r < ry; ++r) s += sm[(which * ry + r) * wcols + col];
+            atomicAdd(stats + ((size_t)slot * 2 + which) * ld + off + ch, (double)s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = relu(bn(x)) with optional pooling of the activated tensor.
+// ---------------------------------------------------------------------------------------------
+template <int POOL>
+__global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_apply_t p, int OH, int OW) {
+    __shared__ float sm[2 * kEwThreads * 8];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    __shared__ float cf[2][kEwThreads];
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_fwd(p.bn, c, blockIdx.x == 0);
+            cf[0][tid] = k.scale;
+            cf[1][tid] = k.shift;
+        }
+    }
+    __syncthreads();
+    float sc[8], sh[8];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = cf[0][threadIdx.x * 8 + j];
+            sh[j] = cf[1][threadIdx.x * 8 + j];
+        }
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y);
+    const long long rows = (long long)p.B * OH * OW;
+    if (active) {
+        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += (long long)gridDim.x * ry) {
+            float o[8];
+            if (POOL == 0) {
+                float f[8];
+                unpack8(ldg16(x + row * p.ldx + chunk * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+            } else {
+                const int ox = (int)(row % OW);
+                const long long t = row / OW;
+                const int oy = (int)(t % OH);
+                const int b = (int)(t / OH);
+                if (POOL == 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const long long r = ((long long)b * p.H + (2 * oy + dy)) * p.W + (2 * ox + dx);
+                            float f[8];
+                            unpack8(ldg16(x + r * p.ldx + chunk * 8), f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] += fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                        }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = -INFINITY;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int iy = 2 * oy + dy;
+                        if (iy < 0 || iy >= p.H) continue;
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int ix = 2 * ox + dx;
+                            if (ix < 0 || ix >= p.W) continue;
+                            const long long r = ((long long)b * p.H + iy) * p.W + ix;
+                            float f[8];
+                            unpack8(ldg16(x + r * p.ldx + chunk * 8), f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f));
+                        }
+                    }
+                }
+            }
+            const uint4 packed = pack8(o);
+            *reinterpret_cast<uint4*>(y + row * p.ldy + chunk * 8) = packed;
+            if (p.ystats) {
+                float r[8];
+                unpack8(packed, r);   // statistics of the stored (bf16-rounded) values
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1[j] += r[j];
+                    s2[j] += r[j] * r[j];
+                }
+            }
+        }
+    }
+    if (p.ystats) block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.ystats, p.ystats_ld, p.ystats_off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN-ReLU backward.  dz = g' * [bn(x) > 0] where g' is the gradient of the activated tensor,
+// addressed through gmode (0 same pixel, 1 avg-pool parent / 4, 2 max-pool 3x3 s2 p1 argmax).
+// ---------------------------------------------------------------------------------------------
+template <typename GT>
+__device__ __forceinline__ void load_g8(const GT* g, long long idx, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_g8<__nv_bfloat16>(const __nv_bfloat16* g, long long idx, float (&f)[8]) {
+    unpack8(ldg16(g + idx), f);
+}
+template <>
+__device__ __forceinline__ void load_g8<float>(const float* g, long long idx, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(g + idx));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(g + idx + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <int GMODE, typename GT>
+__device__ __forceinline__ void bn_relu_dz(const dmm_bn_bwd_args_t& p, const __nv_bfloat16* x, const GT* g,
+                                           long long row, int chunk, const float (&sc)[8], const float (&sh)[8],
+                                           int OH, int OW, float (&xr)[8], float (&dz)[8]) {
+    unpack8(ldg16(x + row * p.ldx + chunk * 8), xr);
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = fmaf(xr[j], sc[j], sh[j]);
+    if (GMODE == 0) {
+        load_g8<GT>(g, row * p.ldg + chunk * 8, dz);
+    } else {
+        const int xx = (int)(row % p.W);
+        const long long t = row / p.W;
+        const int yy = (int)(t % p.H);
+        const int b = (int)(t / p.H);
+        if (GMODE == 1) {
+            const int oy = yy >> 1, ox = xx >> 1;
+            if (oy < OH && ox < OW) {
+                load_g8<GT>(g, (((long long)b * OH + oy) * OW + ox) * p.ldg + chunk * 8, dz);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] *= 0.25f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+            }
+        } else {
+            float a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[j] = fmaxf(z[j], 0.f);
+                dz[j] = 0.f;
+            }
+            const int oy0 = yy >> 1, oy1 = (yy + 1) >> 1;   // windows whose rows 2o-1..2o+1 contain yy
+            const int ox0 = xx >> 1, ox1 = (xx + 1) >> 1;
+            for (int oy = oy0; oy <= oy1; ++oy) {
+                if (oy >= OH) continue;
+                for (int ox = ox0; ox <= ox1; ++ox) {
+                    if (ox >= OW) continue;
+                    bool arg[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) arg[j] = true;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int iy = 2 * oy + dy;
+                        if (iy < 0 || iy >= p.H) continue;
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int ix = 2 * ox + dx;
+                            if (ix < 0 || ix >= p.W) continue;
+                            if (iy == yy && ix == xx) continue;
+                            const bool before = (iy < yy) || (iy == yy && ix < xx);
+                            float f[8];
+                            unpack8(ldg16(x + (((long long)b * p.H + iy) * p.W + ix) * p.ldx + chunk * 8), f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float an = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                                if (before ? (an >= a[j]) : (an > a[j])) arg[j] = false;   // first maximum wins
+                            }
+                        }
+                    }
+                    float gg[8];
+                    load_g8<GT>(g, (((long long)b * OH + oy) * OW + ox) * p.ldg + chunk * 8, gg);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (arg[j]) dz[j] += gg[j];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dz[j] = z[j] > 0.f ? dz[j] : 0.f;
+}
+
+template <int GMODE, typename GT>
+__global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_reduce_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    __shared__ float sm[2 * kEwThreads * 8];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    __shared__ float cf[4][kEwThreads];
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+        }
+    }
+    __syncthreads();
+    float sc[8], sh[8], mu[8], is[8];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = threadIdx.x * 8 + j;
+            sc[j] = cf[0][t]; sh[j] = cf[1][t]; mu[j] = cf[2][t]; is[j] = cf[3][t];
+        }
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
+    const GT* g = reinterpret_cast<const GT*>(p.g);
+    const long long rows = (long long)p.B * p.H * p.W;
+    if (active) {
+        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += (long long)gridDim.x * ry) {
+            float xr[8], dz[8];
+            bn_relu_dz<GMODE, GT>(p, x, g, row, chunk, sc, sh, OH, OW, xr, dz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += dz[j];
+                s2[j] += dz[j] * ((xr[j] - mu[j]) * is[j]);
+            }
+        }
+    }
+    block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+}
+
+template <int GMODE, typename GT>
+__global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_apply_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    __shared__ float cf[7][kEwThreads];
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+                const double* r = p.bn.sums + (size_t)s * 2 * p.bn.sums_ld + p.bn.sums_off + c;
+                a += r[0];
+                b += r[p.bn.sums_ld];
+            }
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+            cf[4][tid] = (float)(a / p.bn.count);
+            cf[5][tid] = (float)(b / p.bn.count);
+            cf[6][tid] = (p.bn.gamma ? p.bn.gamma[c] : 1.f) * k.invstd;
+            if (blockIdx.x == 0) {
+                if (p.bn.dgamma) p.bn.dgamma[c] = (float)b;
+                if (p.bn.dbeta) p.bn.dbeta[c] = (float)a;
+            }
+        }
+    }
+    __syncthreads();
+    if (chunk >= nchunks) return;
+    float sc[8], sh[8], mu[8], is[8], c1[8], c2[8], gi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = threadIdx.x * 8 + j;
+        sc[j] = cf[0][t]; sh[j] = cf[1][t]; mu[j] = cf[2][t]; is[j] = cf[3][t];
+        c1[j] = cf[4][t]; c2[j] = cf[5][t]; gi[j] = cf[6][t];
+    }
+    if (p.out == nullptr) return;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x);
+    const GT* g = reinterpret_cast<const GT*>(p.g);
+    const long long rows = (long long)p.B * p.H * p.W;
+    for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += (long long)gridDim.x * ry) {
+        float xr[8], dz[8], dx[8];
+        bn_relu_dz<GMODE, GT>(p, x, g, row, chunk, sc, sh, OH, OW, xr, dz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] = gi[j] * (dz[j] - c1[j] - (xr[j] - mu[j]) * is[j] * c2[j]);
+        const long long o = row * p.ldo + chunk * 8;
+        if (p.out_mode == 0) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8(dx);
+        } else {
+            float* of = reinterpret_cast<float*>(p.out) + o;
+            float4 a = make_float4(dx[0], dx[1], dx[2], dx[3]);
+            float4 b = make_float4(dx[4], dx[5], dx[6], dx[7]);
+            if (p.out_mode == 2) {
+                const float4 pa = *reinterpret_cast<const float4*>(of);
+                const float4 pb = *reinterpret_cast<const float4*>(of + 4);
+                a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+                b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+            }
+            *reinterpret_cast<float4*>(of) = a;
+            *reinterpret_cast<float4*>(of + 4) = b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stem im2col: fp32 NCHW (B,C1[+C2],H,W) -> bf16 [B*OH*OW, kpad], k = ci*49 + kh*7 + kw
+// (same k order as the flattened Conv2d weight (Cout, Cin*7*7)), zero padded.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ x1, int C1,
+                                                           const float* __restrict__ x2, int C2, int B, int H, int W,
+                                                           int OH, int OW, __nv_bfloat16* __restrict__ out, int kpad) {
+    const int chunks = kpad >> 3;
+    const long long total = (long long)B * OH * OW * chunks;
+    const int K = (C1 + C2) * 49;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long pix = i / chunks;
+        const int ox = (int)(pix % OW);
+        const long long t = pix / OW;
+        const int oy = (int)(t % OH);
+        const int b = (int)(t / OH);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = ch * 8 + j;
+            float v = 0.f;
+            if (k < K) {
+                const int ci = k / 49, tp = k - ci * 49;
+                const int kh = tp / 7, kw = tp - kh * 7;
+                const int iy = 2 * oy - 3 + kh, ix = 2 * ox - 3 + kw;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                    v = ci < C1 ? __ldg(x1 + (((long long)b * C1 + ci) * H + iy) * W + ix)
+                                : __ldg(x2 + (((long long)b * C2 + (ci - C1)) * H + iy) * W + ix);
+                }
+            }
+            f[j] = v;
+        }
+        *reinterpret_cast<uint4*>(out + pix * kpad + ch * 8) = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-plane statistics of fp32 NCHW tensors (raw network inputs feeding the head BN).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict__ x, int C, long long HW,
+                                                         double* stats, int ld, int off, int splits) {
+    __shared__ double sm[2][8];
+    const int plane = blockIdx.x / splits;   // b*C + c
+    const int sp = blockIdx.x - plane * splits;
+    const int c = plane % C;
+    const float* p = x + (long long)plane * HW;
+    const long long lo = HW * sp / splits, hi = HW * (sp + 1) / splits;
+    float s1 = 0.f, s2 = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float v = __ldg(p + i);
+        s1 += v;
+        s2 += v * v;
+    }
+    double d1 = s1, d2 = s2;
+    for (int o = 16; o > 0; o >>= 1) {
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sm[0][threadIdx.x >> 5] = d1;
+        sm[1][threadIdx.x >> 5] = d2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) {
+            a += sm[0][w];
+            b += sm[1][w];
+        }
+        const int slot = blockIdx.x % DMM_STATS_SLOTS;
+        atomicAdd(stats + ((size_t)slot * 2 + 0) * ld + off + c, a);
+        atomicAdd(stats + ((size_t)slot * 2 + 1) * ld + off + c, b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// head input: out[p, :] = relu(bn0(cat(upsample2(u)[p], x1[p], x2[p]))), bf16 rows of pitch ldo
+// (columns >= Cu+C1+C2 are zero).  One thread per (pixel, 8-channel chunk).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
+    extern __shared__ float coef[];   // [2][Cpad]
+    const int Ct = p.Cu + p.C1 + p.C2;
+    const int chunks = (int)(p.ldo >> 3);
+    const int Cpad = chunks * 8;
+    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+        float sc = 0.f, sh = 0.f;
+        if (c < Ct) {
+            const bool writer = blockIdx.x == 0;
+            BnCoef k = c < p.Cu ? bn_coef_fwd(p.bn_u, c, writer) : bn_coef_fwd(p.bn_x, c - p.Cu, writer);
+            sc = k.scale;
+            sh = k.shift;
+        }
+        coef[c] = sc;
+        coef[Cpad + c] = sh;
+    }
+    __syncthreads();
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.u);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    const long long total = (long long)p.B * p.H * p.W * chunks;
+    const long long HW = (long long)p.H * p.W;
+    const int UH = p.H >> 1, UW = p.W >> 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long pix = i / chunks;
+        const int xx = (int)(pix % p.W);
+        const long long t = pix / p.W;
+        const int yy = (int)(t % p.H);
+        const int b = (int)(t / p.H);
+        float f[8];
+        if (ch * 8 + 8 <= p.Cu) {
+            const long long up = ((long long)b * UH + (yy >> 1)) * UW + (xx >> 1);
+            unpack8(ldg16(u + up * p.ldu + ch * 8), f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch * 8 + j;
+                float v = 0.f;
+                if (c < p.Cu) {
+                    const long long up = ((long long)b * UH + (yy >> 1)) * UW + (xx >> 1);
+                    v = __bfloat162float(u[up * p.ldu + c]);
+                } else if (c < p.Cu + p.C1) {
+                    v = __ldg(p.x1 + ((long long)b * p.C1 + (c - p.Cu)) * HW + (long long)yy * p.W + xx);
+                } else if (c < Ct) {
+                    v = __ldg(p.x2 + ((long long)b * p.C2 + (c - p.Cu - p.C1)) * HW + (long long)yy * p.W + xx);
+                }
+                f[j] = v;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], coef[ch * 8 + j], coef[Cpad + ch * 8 + j]), 0.f);
+        *reinterpret_cast<uint4*>(out + pix * p.ldo + ch * 8) = pack8(f);
+    }
+}
+
+// Backward of the head input.  PASS 0: sums += (sum dz, sum dz*xhat) over all Cu+C1+C2 channels.
+// PASS 1: du[parent, c] = sum over the 2x2 children of dx (c < Cu), dgamma/dbeta written.
+// One thread per (UP-SAMPLED-SOURCE pixel, chunk) so that the 4 children are reduced in registers.
+template <int PASS>
+__global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_t p) {
+    extern __shared__ float sm[];   // PASS 0: [2][Cpad] block partial sums ; coefficient tables
+    const int Ct = p.Cu + p.C1 + p.C2;
+    const int chunks = (Ct + 7) >> 3;
+    const int Cpad = chunks * 8;
+    float* mean = sm;
+    float* istd = sm + Cpad;
+    float* scl = sm + 2 * Cpad;
+    float* sft = sm + 3 * Cpad;
+    float* k1 = sm + 4 * Cpad;   // PASS 0: block sums of dz        PASS 1: c1
+    float* k2 = sm + 5 * Cpad;   // PASS 0: block sums of dz*xhat   PASS 1: c2
+    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+        float m = 0.f, is = 0.f, sc = 0.f, sh = 0.f, a1 = 0.f, a2 = 0.f;
+        if (c < Ct) {
+            const dmm_bn_bwd_t& bn = c < p.Cu ? p.bn_u : p.bn_x;
+            const int cc = c < p.Cu ? c : c - p.Cu;
+            BnCoef k = bn_coef_bwd(bn, cc);
+            m = k.mean; is = k.invstd; sc = k.scale; sh = k.shift;
+            if (PASS == 1) {
+                double a = 0.0, b = 0.0;
+                for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+                    const double* r = bn.sums + (size_t)s * 2 * bn.sums_ld + bn.sums_off + cc;
+                    a += r[0];
+                    b += r[bn.sums_ld];
+                }
+                a1 = (float)(a / bn.count);
+                a2 = (float)(b / bn.count);
+                if (blockIdx.x == 0) {
+                    if (bn.dgamma) bn.dgamma[cc] = (float)b;
+                    if (bn.dbeta) bn.dbeta[cc] = (float)a;
+                }
+            }
+        }
+        mean[c] = m; istd[c] = is; scl[c] = sc; sft[c] = sh; k1[c] = a1; k2[c] = a2;
+    }
+    __syncthreads();
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.u);
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g);
+    const int UH = p.H >> 1, UW = p.W >> 1;
+    const long long HW = (long long)p.H * p.W;
+    const int nch = PASS == 0 ? chunks : (p.Cu >> 3);
+    const long long total = (long long)p.B * UH * UW * nch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % nch);
+        const long long up = i / nch;
+        const int ux = (int)(up % UW);
+        const long long t = up / UW;
+        const int uy = (int)(t % UH);
+        const int b = (int)(t / UH);
+        float xu[8];
+        const bool all_u = ch * 8 + 8 <= p.Cu;
+        if (all_u) unpack8(ldg16(u + up * p.ldu + ch * 8), xu);
+        float acc1[8], acc2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int yy = 2 * uy + dy, xx = 2 * ux + dx;
+                const long long pix = ((long long)b * p.H + yy) * p.W + xx;
+                float gg[8];
+                unpack8(ldg16(g + pix * p.ldg + ch * 8), gg);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = ch * 8 + j;
+                    float xv;
+                    if (all_u) {
+                        xv = xu[j];
+                    } else if (c < p.Cu) {
+                        xv = __bfloat162float(u[up * p.ldu + c]);
+                    } else if (c < p.Cu + p.C1) {
+                        xv = __ldg(p.x1 + ((long long)b * p.C1 + (c - p.Cu)) * HW + (long long)yy * p.W + xx);
+                    } else if (c < Ct) {
+                        xv = __ldg(p.x2 + ((long long)b * p.C2 + (c - p.Cu - p.C1)) * HW + (long long)yy * p.W + xx);
+                    } else {
+                        xv = 0.f;
+                    }
+                    const float z = fmaf(xv, scl[c], sft[c]);
+                    const float dz = (z > 0.f && c < Ct) ? gg[j] : 0.f;
+                    const float xh = (xv - mean[c]) * istd[c];
+                    if (PASS == 0) {
+                        acc1[j] += dz;
+                        acc2[j] += dz * xh;
+                    } else {
+                        acc1[j] += dz - k1[c] - xh * k2[c];
+                    }
+                }
+            }
+        if (PASS == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&k1[ch * 8 + j], acc1[j]);
+                atomicAdd(&k2[ch * 8 + j], acc2[j]);
+            }
+        } else {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = ch * 8 + j;
+                const float gam = p.bn_u.gamma ? p.bn_u.gamma[c] : 1.f;
+                o[j] = gam * istd[c] * acc1[j];
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.du) + up * p.lddu + ch * 8) = pack8(o);
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        const int slot = blockIdx.x % DMM_STATS_SLOTS;
+        for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+            const dmm_bn_bwd_t& bn = c < p.Cu ? p.bn_u : p.bn_x;
+            const int cc = c < p.Cu ? c : c - p.Cu;
+            atomicAdd(bn.sums + ((size_t)slot * 2 + 0) * bn.sums_ld + bn.sums_off + cc, (double)k1[c]);
+            atomicAdd(bn.sums + ((size_t)slot * 2 + 1) * bn.sums_ld + bn.sums_off + cc, (double)k2[c]);
+        }
+    }
+}
+
+// fp32 NCHW -> bf16 pixel-major rows (channels >= C zero-filled up to ldo)
+__global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ x, int B, int C, long long HW,
+                                                           __nv_bfloat16* __restrict__ out, int ldo) {
+    const int chunks = ldo >> 3;
+    const long long total = (long long)B * HW * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        // pixel-fastest decomposition keeps the fp32 plane reads coalesced
+        const long long pin = i % HW;
+        const long long t = i / HW;
+        const int ch = (int)(t % chunks);
+        const int b = (int)(t / chunks);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = ch * 8 + j;
+            f[j] = c < C ? __ldg(x + ((long long)b * C + c) * HW + pin) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(out + ((long long)b * HW + pin) * ldo + ch * 8) = pack8(f);
+    }
+}
+
+// fp32 rows -> bf16 rows (gradient slices of the fp32 dense-block gradient buffer)
+__global__ void __launch_bounds__(256) rows_f32_to_bf16_kernel(const float* __restrict__ src, long long lds,
+                                                               __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                               long long P, int C) {
+    const int chunks = C >> 3;
+    const long long total = P * chunks;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long r = i / chunks;
+        float f[8];
+        load_g8<float>(src, r * lds + ch * 8, f);
+        *reinterpret_cast<uint4*>(dst + r * ldd + ch * 8) = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                         long long n4, int C, long long HW4, float* __restrict__ loss,
+                                                         float* __restrict__ grad, double* class_sums) {
+    // vectors of 4 never straddle a (b, c) plane because HW % 4 == 0 (checked on the host)
+    __shared__ double sm[8][8];
+    float cs[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cs[c] = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(t) + i);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float ts[4] = {tv.x, tv.y, tv.z, tv.w};
+        float l[4], g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float e = expf(-fabsf(xs[j]));
+            l[j] = fmaxf(xs[j], 0.f) - xs[j] * ts[j] + log1pf(e);
+            const float r = 1.f / (1.f + e);
+            g[j] = (xs[j] >= 0.f ? r : e * r) - ts[j];
+        }
+        if (loss) reinterpret_cast<float4*>(loss)[i] = make_float4(l[0], l[1], l[2], l[3]);
+        if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(g[0], g[1], g[2], g[3]);
+        if (class_sums) {
+            const int c = (int)((i / HW4) % C);
+            const float s = (l[0] + l[1]) + (l[2] + l[3]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == c) cs[k] += s;
+        }
+    }
+    if (class_sums) {
+        const int w = threadIdx.x >> 5;
+        for (int c = 0; c < C && c < 8; ++c) {
+            double d = cs[c];
+            for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            if ((threadIdx.x & 31) == 0) sm[c][w] = d;
+        }
+        __syncthreads();
+        if (threadIdx.x < C && threadIdx.x < 8) {
+            double d = 0;
+            for (int k = 0; k < 8; ++k) d += sm[threadIdx.x][k];
+            atomicAdd(class_sums + threadIdx.x, d);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights: fp32 parameter layout <-> packed bf16 K-major GEMM operand / fp32 wgrad result
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+    int T, C, Kp, n_valid, n_rows;
+    long long ktot, sn, sc;
+    int tap_off[DMM_MAX_TAPS];
+};
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
+                                                           const PackArgs a) {
+    const long long total = (long long)a.n_rows * a.ktot;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / a.ktot);
+        const long long k = i - (long long)n * a.ktot;
+        const int t = (int)(k / a.Kp);
+        const int c = (int)(k - (long long)t * a.Kp);
+        float v = 0.f;
+        if (n < a.n_valid && c < a.C && t < a.T) v = w[(long long)n * a.sn + (long long)c * a.sc + a.tap_off[t]];
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+// grad[n*sn + m*sc + tap_off[t]] (=|+=) dw[(t*M + m)*ldw + n]
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, long long ldw, int M, int N,
+                                                           float* __restrict__ grad, const PackArgs a, int accumulate) {
+    const long long total = (long long)a.T * M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N);
+        const long long r = i / N;
+        const int m = (int)(r % M);
+        const int t = (int)(r / M);
+        const float v = dw[((long long)t * M + m) * ldw + n];
+        float* gp = grad + (long long)n * a.sn + (long long)m * a.sc + a.tap_off[t];
+        *gp = accumulate ? *gp + v : v;
+    }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+                                                   float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+// batched forms: one launch for all weight tensors of the network (job tables live in device memory)
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pack_job_t* __restrict__ jobs) {
+    const dmm_pack_job_t& j = jobs[blockIdx.y];
+    const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
+    const long long ktot = (long long)Kp * j.T;
+    const long long total = (long long)j.n_rows * ktot;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / ktot);
+        const long long k = i - (long long)n * ktot;
+        const int t = (int)(k / Kp);
+        const int c = (int)(k - (long long)t * Kp);
+        float v = 0.f;
+        if (n < j.n_valid && c < j.C) v = j.w[(long long)n * j.sn + (long long)c * j.sc + j.tap_off[t]];
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unpack_job_t* __restrict__ jobs) {
+    const dmm_unpack_job_t& j = jobs[blockIdx.y];
+    const long long total = (long long)j.T * j.M * j.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % j.N);
+        const long long r = i / j.N;
+        const int m = (int)(r % j.M);
+        const int t = (int)(r / j.M);
+        const float v = j.dw[((long long)t * j.Mld + m) * j.ldw + n];
+        float* gp = j.grad + (long long)n * j.sn + (long long)m * j.sc + j.tap_off[t];
+        *gp = j.accumulate ? *gp + v : v;
+    }
+}
+
+static unsigned flat_grid(long long total, int threads) {
+    long long g = (total + threads - 1) / threads;
+    const long long cap = (long long)kNumSm * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace dmm
+
+using namespace dmm;
+
+extern "C" int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DMM_CHECK(d && d->x && d->y, "dmm_bn_relu_apply: null pointer");
+    DMM_CHECK(d->C > 0 && d->C % 8 == 0, "dmm_bn_relu_apply: C=%d must be a positive multiple of 8", d->C);
+    DMM_CHECK(d->ldx % 8 == 0 && d->ldy % 8 == 0, "dmm_bn_relu_apply: row pitches must be multiples of 8");
+    DMM_CHECK(d->pool >= 0 && d->pool <= 2, "dmm_bn_relu_apply: pool=%d", d->pool);
+    DMM_CHECK(d->bn.training ? (d->bn.stats != nullptr && d->bn.count > 0) : (d->bn.running_mean && d->bn.running_var),
+              "dmm_bn_relu_apply: missing statistics");
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    int OH = d->H, OW = d->W;
+    if (d->pool == 1) { OH = d->H / 2; OW = d->W / 2; }
+    if (d->pool == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
+    if (OH <= 0 || OW <= 0) return 0;
+    ColCfg k = col_cfg(d->C, (long long)d->B * OH * OW);
+    if (d->pool == 0) bn_relu_apply_kernel<0><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
+    else if (d->pool == 1) bn_relu_apply_kernel<1><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
+    else bn_relu_apply_kernel<2><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
+    DMM_LAUNCH_CHECK("bn_relu_apply_kernel");
+    return 0;
+}
+
+template <int PASS>
+static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
+    DMM_CHECK(d && d->x && d->g, "dmm_bn_relu_bwd: null pointer");
+    DMM_CHECK(d->C > 0 && d->C % 8 == 0, "dmm_bn_relu_bwd: C=%d must be a positive multiple of 8", d->C);
+    DMM_CHECK(d->ldx % 8 == 0 && d->ldg % 8 == 0 && d->ldo % 8 == 0, "dmm_bn_relu_bwd: row pitches must be multiples of 8");
+    DMM_CHECK(d->gmode >= 0 && d->gmode <= 2, "dmm_bn_relu_bwd: gmode=%d", d->gmode);
+    DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd && d->bn.count > 0, "dmm_bn_relu_bwd: missing BN state");
+    DMM_CHECK(d->out_mode >= 0 && d->out_mode <= 2, "dmm_bn_relu_bwd: out_mode=%d", d->out_mode);
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    int OH = d->H, OW = d->W;
+    if (d->gmode == 1) { OH = d->H / 2; OW = d->W / 2; }
+    if (d->gmode == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
+    ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W);
+#define DMM_BWD_LAUNCH(GM, GT)                                                                      \
+    do {                                                                                            \
+        if (PASS == 0) bn_relu_bwd_reduce_kernel<GM, GT><<<k.grid, k.block, 0, stream>>>(*d, OH, OW); \
+        else bn_relu_bwd_apply_kernel<GM, GT><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);           \
+    } while (0)
+    if (d->g_is_f32) {
+        if (d->gmode == 0) DMM_BWD_LAUNCH(0, float);
+        else if (d->gmode == 1) DMM_BWD_LAUNCH(1, float);
+        else DMM_BWD_LAUNCH(2, float);
+    } else {
+        if (d->gmode == 0) DMM_BWD_LAUNCH(0, __nv_bfloat16);
+        else if (d->gmode == 1) DMM_BWD_LAUNCH(1, __nv_bfloat16);
+        else DMM_BWD_LAUNCH(2, __nv_bfloat16);
+    }
+#undef DMM_BWD_LAUNCH
+    DMM_LAUNCH_CHECK("bn_relu_bwd kernel");
+    return 0;
+}
+
+extern "C" int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream) {
+    return launch_bn_bwd<0>(d, (cudaStream_t)stream);
+}
+extern "C" int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream) {
+    return launch_bn_bwd<1>(d, (cudaStream_t)stream);
+}
+
+extern "C" int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H,
+                                int32_t W, void* out, int32_t kpad, void* stream) {
+    DMM_CHECK(x1 && out && C1 > 0 && C2 >= 0 && (C2 == 0 || x2), "dmm_im2col_7x7s2: bad inputs");
+    DMM_CHECK(kpad % 8 == 0 && kpad >= (C1 + C2) * 49, "dmm_im2col_7x7s2: kpad=%d too small / not a multiple of 8", kpad);
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+    const long long total = (long long)B * OH * OW * (kpad / 8);
+    im2col_7x7s2_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x1, C1, x2, C2, B, H, W, OH, OW, reinterpret_cast<__nv_bfloat16*>(out), kpad);
+    DMM_LAUNCH_CHECK("im2col_7x7s2_kernel");
+    return 0;
+}
+
+extern "C" int dmm_nchw_stats(const float* x, int32_t B, int32_t C, int64_t HW, double* stats, int32_t stats_ld,
+                              int32_t stats_off, void* stream) {
+    DMM_CHECK(x && stats && C > 0, "dmm_nchw_stats: bad inputs");
+    if (B <= 0 || HW <= 0) return 0;
+    int splits = (int)((HW + 65535) / 65536);
+    if (splits < 1) splits = 1;
+    nchw_stats_kernel<<<(unsigned)(B * C * splits), 256, 0, (cudaStream_t)stream>>>(x, C, HW, stats, stats_ld, stats_off, splits);
+    DMM_LAUNCH_CHECK("nchw_stats_kernel");
+    return 0;
+}
+
+extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
+    DMM_CHECK(d && d->u && d->x1 && d->out, "dmm_head_input: null pointer");
+    DMM_CHECK(d->Cu % 8 == 0 && d->ldu % 8 == 0 && d->ldo % 8 == 0, "dmm_head_input: Cu / pitches must be multiples of 8");
+    DMM_CHECK(d->ldo >= d->Cu + d->C1 + d->C2, "dmm_head_input: ldo too small");
+    DMM_CHECK(d->H % 2 == 0 && d->W % 2 == 0, "dmm_head_input: H and W must be even (nn.Upsample x2 of the decoder output)");
+    DMM_CHECK(d->C2 == 0 || d->x2, "dmm_head_input: x2 missing");
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    const int chunks = (int)(d->ldo / 8);
+    const long long total = (long long)d->B * d->H * d->W * chunks;
+    const size_t smem = (size_t)2 * chunks * 8 * sizeof(float);
+    head_input_kernel<<<flat_grid(total, 256), 256, smem, (cudaStream_t)stream>>>(*d);
+    DMM_LAUNCH_CHECK("head_input_kernel");
+    return 0;
+}
+
+template <int PASS>
+static int launch_head_bwd(const dmm_head_bwd_t* d, cudaStream_t stream) {
+    DMM_CHECK(d && d->u && d->x1 && d->g, "dmm_head_input_bwd: null pointer");
+    DMM_CHECK(d->Cu % 8 == 0 && d->ldu % 8 == 0 && d->ldg % 8 == 0, "dmm_head_input_bwd: Cu / pitches must be multiples of 8");
+    DMM_CHECK(d->H % 2 == 0 && d->W % 2 == 0, "dmm_head_input_bwd: H and W must be even");
+    DMM_CHECK(PASS == 0 || (d->du && d->lddu % 8 == 0), "dmm_head_input_bwd_apply: du missing");
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    const int Ct = d->Cu + d->C1 + d->C2;
+    const int chunks = (Ct + 7) / 8;
+    DMM_CHECK(d->ldg >= chunks * 8, "dmm_head_input_bwd: ldg too small");
+    const int nch = PASS == 0 ? chunks : d->Cu / 8;
+    const long long total = (long long)d->B * (d->H / 2) * (d->W / 2) * nch;
+    const size_t smem = (size_t)6 * chunks * 8 * sizeof(float);
+    head_input_bwd_kernel<PASS><<<flat_grid(total, 256), 256, smem, stream>>>(*d);
+    DMM_LAUNCH_CHECK("head_input_bwd_kernel");
+    return 0;
+}
+extern "C" int dmm_head_input_bwd_reduce(const dmm_head_bwd_t* d, void* stream) {
+    return launch_head_bwd<0>(d, (cudaStream_t)stream);
+}
+extern "C" int dmm_head_input_bwd_apply(const dmm_head_bwd_t* d, void* stream) {
+    return launch_head_bwd<1>(d, (cudaStream_t)stream);
+}
+
+extern "C" int dmm_nchw_to_nhwc_bf16(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, void* out,
+                                     int64_t ldo, void* stream) {
+    DMM_CHECK(x && out && C > 0 && ldo % 8 == 0 && ldo >= C, "dmm_nchw_to_nhwc_bf16: bad arguments");
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const long long total = (long long)B * H * W * (ldo / 8);
+    nchw_to_rows_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, B, C, (long long)H * W, reinterpret_cast<__nv_bfloat16*>(out), (int)ldo);
+    DMM_LAUNCH_CHECK("nchw_to_rows_kernel");
+    return 0;
+}
+
+extern "C" int dmm_rows_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t P, int32_t C,
+                                    void* stream) {
+    DMM_CHECK(src && dst && C > 0 && C % 8 == 0 && lds % 4 == 0 && ldd % 8 == 0, "dmm_rows_f32_to_bf16: bad arguments");
+    DMM_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "dmm_rows_f32_to_bf16: pointers must be 16-byte aligned");
+    if (P <= 0) return 0;
+    rows_f32_to_bf16_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, P, C);
+    DMM_LAUNCH_CHECK("rows_f32_to_bf16_kernel");
+    return 0;
+}
+
+extern "C" int dmm_bce_logits(const float* logits, const float* target, int64_t n, int32_t C, int64_t HW, float* loss,
+                              float* grad, double* class_sums, void* stream) {
+    DMM_CHECK(logits && target, "dmm_bce_logits: null input");
+    DMM_CHECK(n % 4 == 0 && HW % 4 == 0, "dmm_bce_logits: element counts must be multiples of 4 (n=%lld HW=%lld)", (long long)n,
+              (long long)HW);
+    DMM_CHECK(class_sums == nullptr || (C >= 1 && C <= 8), "dmm_bce_logits: per-class sums support at most 8 classes");
+    if (n <= 0) return 0;
+    bce_logits_kernel<<<flat_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(logits, target, n / 4, C, HW / 4, loss, grad,
+                                                                              class_sums);
+    DMM_LAUNCH_CHECK("bce_logits_kernel");
+    return 0;
+}
+
+static int fill_pack_args(PackArgs& a, int32_t n_valid, int32_t n_rows, int32_t C, int32_t kwidth, int32_t T,
+                          const int32_t* tap_off, int64_t sn, int64_t sc) {
+    DMM_CHECK(T >= 1 && T <= DMM_MAX_TAPS && tap_off, "weights: bad tap count %d", T);
+    DMM_CHECK(kwidth > 0 && C > 0 && n_valid > 0 && n_rows >= n_valid, "weights: bad sizes");
+    a.T = T;
+    a.C = C;
+    a.Kp = (C + kwidth - 1) / kwidth * kwidth;
+    a.n_valid = n_valid;
+    a.n_rows = n_rows;
+    a.ktot = (long long)a.Kp * T;
+    a.sn = sn;
+    a.sc = sc;
+    for (int t = 0; t < T; ++t) a.tap_off[t] = tap_off[t];
+    return 0;
+}
+
+extern "C" int dmm_pack_weights(const float* w, void* dst, int32_t n_valid, int32_t n_rows, int32_t C, int32_t kwidth,
+                                int32_t T, const int32_t* tap_off, int64_t sn, int64_t sc, void* stream) {
+    DMM_CHECK(w && dst, "dmm_pack_weights: null pointer");
+    PackArgs a;
+    int rc = fill_pack_args(a, n_valid, n_rows, C, kwidth, T, tap_off, sn, sc);
+    if (rc) return rc;
+    pack_weights_kernel<<<flat_grid((long long)n_rows * a.ktot, 256), 256, 0, (cudaStream_t)stream>>>(
+        w, reinterpret_cast<__nv_bfloat16*>(dst), a);
+    DMM_LAUNCH_CHECK("pack_weights_kernel");
+    return 0;
+}
+
+extern "C" int dmm_unpack_wgrad(const float* dw, int64_t ldw, int32_t M, int32_t N, float* grad, int32_t T,
+                                const int32_t* tap_off, int64_t sn, int64_t sc, int32_t accumulate, void* stream) {
+    DMM_CHECK(dw && grad, "dmm_unpack_wgrad: null pointer");
+    PackArgs a;
+    int rc = fill_pack_args(a, N, N, M, 1, T, tap_off, sn, sc);
+    if (rc) return rc;
+    unpack_wgrad_kernel<<<flat_grid((long long)T * M * N, 256), 256, 0, (cudaStream_t)stream>>>(dw, ldw, M, N, grad, a,
+                                                                                                accumulate);
+    DMM_LAUNCH_CHECK("unpack_wgrad_kernel");
+    return 0;
+}
+
+extern "C" int dmm_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+    DMM_CHECK(param && grad && exp_avg && exp_avg_sq && step >= 1, "dmm_adam_flat: bad arguments");
+    if (n <= 0) return 0;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2 = 1.f - powf(beta2, (float)step);
+    adam_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                    weight_decay, bc1, sqrtf(bc2));
+    DMM_LAUNCH_CHECK("adam_kernel");
+    return 0;
+}
+
+extern "C" int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream) {
+    DMM_CHECK(njobs >= 0 && (njobs == 0 || jobs_device), "dmm_pack_weights_batched: bad arguments");
+    if (njobs == 0) return 0;
+    pack_weights_batched_kernel<<<dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream>>>(jobs_device);
+    DMM_LAUNCH_CHECK("pack_weights_batched_kernel");
+    return 0;
+}
+
+extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream) {
+    DMM_CHECK(njobs >= 0 && (njobs == 0 || jobs_device), "dmm_unpack_wgrad_batched: bad arguments");
+    if (njobs == 0) return 0;
+    unpack_wgrad_batched_kernel<<<dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream>>>(jobs_device);
+    DMM_LAUNCH_CHECK("unpack_wgrad_batched_kernel");
+    return 0;
+}

@@ -1,0 +1,223 @@
+// Integer scatter kernels (bit-exact with the reference's sequential Python loops):
+//   LiDAR points -> image-like range tensor  (Dense_U_Net_lidar_helper.py:493-515)
+//   range transform + (20,10) max-pool        (helper:446-491)
+//   bounding boxes -> class heat-map masks    (helper:233-305)
+//   k x k pooling                             (helper:430-444)
+// "Last writer wins" is made deterministic by an atomicMax of the writer's sequence number per
+// pixel into an int32 scratch image, followed by a resolve pass that paints the winner's value.
+#include "common.cuh"
+#include "../../include/dmmfods_b200.h"
+
+namespace dmm {
+
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t* p, long long n, int32_t v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// python slice lo:hi on an axis of length n (negative bounds wrap once, then clip)
+__device__ __forceinline__ void py_slice(int lo, int hi, int n, int& a, int& b) {
+    if (lo < 0) lo = max(lo + n, 0);
+    if (hi < 0) hi = max(hi + n, 0);
+    lo = min(lo, n);
+    hi = min(hi, n);
+    a = lo;
+    b = max(hi, lo);
+}
+
+// float -> int like Python's int(): truncation toward zero (saturating for huge magnitudes; NaN -> 0)
+__device__ __forceinline__ int py_int(float v) { return __float2int_rz(v); }
+
+// one warp per point: paints the point's index into scratch with atomicMax
+__global__ void __launch_bounds__(256) lidar_mark_kernel(const float* __restrict__ pts, int n, int H, int W, int shift,
+                                                         int32_t* scratch) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+        const float x = pts[3 * i + 0], y = pts[3 * i + 1];
+        const float fs = (float)shift;
+        int min_y = py_int(__fsub_rn(y, fs));
+        if (min_y < 0) min_y = 0;
+        int max_y = py_int(__fadd_rn(__fadd_rn(y, fs), 1.f));
+        if (max_y > H - 1) max_y = H - 1;
+        int min_x = py_int(__fsub_rn(x, fs));
+        if (min_x < 0) min_x = 0;
+        int max_x = py_int(__fadd_rn(__fadd_rn(x, fs), 1.f));
+        if (max_x > W - 1) max_x = W - 1;
+        int y0, y1, x0, x1;
+        py_slice(min_y, max_y, H, y0, y1);
+        py_slice(min_x, max_x, W, x0, x1);
+        const int rw = x1 - x0;
+        const long long area = (long long)rw * (y1 - y0);
+        for (long long k = lane; k < area; k += 32) {
+            const int ry = (int)(k / rw), rx = (int)(k - (long long)ry * rw);
+            atomicMax(scratch + (long long)(y0 + ry) * W + (x0 + rx), i);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) lidar_resolve_kernel(const float* __restrict__ pts, const int32_t* __restrict__ scratch,
+                                                            long long n, float* __restrict__ img) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int32_t w = scratch[i];
+        img[i] = w < 0 ? -1.0f : pts[3 * (long long)w + 2];
+    }
+}
+
+__device__ __forceinline__ float lidar_value_transform(float v) {
+    // helper:472-481, sequential masked updates; separate (non-fused) fp32 multiply and add like ATen
+    if (v > 75.0f) v = 75.0f;
+    if (v == -1.0f) v = 76.0f;
+    if (v <= 25.f) v = __fadd_rn(__fmul_rn(v, -6.2f), 255.f);
+    if (v > 25.f && v <= 76.0f) v = __fadd_rn(__fmul_rn(v, -2.f), 150.f);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) lidar_pool_kernel(const float* __restrict__ img, int H, int W, int OH, int OW,
+                                                         float* __restrict__ out) {
+    // out has OH+1 rows: row OH replicates row OH-1 (F.pad mode='replicate'), negatives -> 0
+    const long long total = (long long)(OH + 1) * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW);
+        int oy = (int)(i / OW);
+        if (oy == OH) oy = OH - 1;
+        float m = -INFINITY;
+        for (int dy = 0; dy < 20; ++dy) {
+            const float* row = img + (long long)(oy * 10 + dy) * W + ox * 10;
+#pragma unroll
+            for (int dx = 0; dx < 10; ++dx) {
+                const float v = lidar_value_transform(row[dx]);
+                m = (v > m || v != v) ? v : m;   // torch max_pool2d: NaN propagates
+            }
+        }
+        out[i] = m < 0.f ? 0.f : m;
+    }
+}
+
+// boxes: int32 rows [type, x, y, w, h]; one block per box paints its index with atomicMax
+__global__ void __launch_bounds__(256) heatmap_mark_kernel(const int32_t* __restrict__ boxes, int n, int H, int W,
+                                                           int32_t* scratch) {
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int type = boxes[5 * i + 0];
+        if (!(type == 1 || type == 2 || type == 4)) continue;
+        const int cls = type == 1 ? 0 : (type == 2 ? 1 : 2);
+        const int x = boxes[5 * i + 1], y = boxes[5 * i + 2], w = boxes[5 * i + 3], h = boxes[5 * i + 4];
+        const int x0 = max(x, 0), y0 = max(y, 0), x1 = min(x + w, W), y1 = min(y + h, H);
+        if (x1 <= x0 || y1 <= y0) continue;
+        const int rw = x1 - x0;
+        const long long area = (long long)rw * (y1 - y0);
+        for (long long k = threadIdx.x; k < area; k += blockDim.x) {
+            const int ry = (int)(k / rw), rx = (int)(k - (long long)ry * rw);
+            atomicMax(scratch + ((long long)cls * H + (y0 + ry)) * W + (x0 + rx), i);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) heatmap_resolve_kernel(const int32_t* __restrict__ boxes,
+                                                              const int32_t* __restrict__ scratch, int H, int W,
+                                                              float* __restrict__ maps) {
+    const long long n = 3ll * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int32_t b = scratch[i];
+        float v = 0.f;
+        if (b >= 0) {
+            v = 1.f;
+            const int type = boxes[5 * b + 0];
+            if (type == 2) {   // pedestrian silhouette, rules applied in the reference's order (helper:238-250)
+                const int px = (int)(i % W), py = (int)((i / W) % H);
+                const int c = px - boxes[5 * b + 1], r = py - boxes[5 * b + 2];
+                const int w = boxes[5 * b + 3], h = boxes[5 * b + 4];
+                const int hf = h / 5, wf = w / 4;
+                if (r < hf && c < wf) v = 0.3f;
+                if (r < hf && c >= 3 * wf) v = 0.3f;
+                if (r >= 3 * hf && c < wf) v = 0.5f;
+                if (r >= 3 * hf && c >= 3 * wf) v = 0.5f;
+                if (r >= 3 * hf && c >= wf && c < 3 * wf) v = 0.75f;
+            }
+        }
+        maps[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) pool_kxk_kernel(const float* __restrict__ img, int C, int H, int W, int k, int OH,
+                                                       int OW, int is_max, float* __restrict__ out) {
+    const long long total = (long long)C * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW);
+        const long long t = i / OW;
+        const int oy = (int)(t % OH);
+        const int c = (int)(t / OH);
+        const float* base = img + ((long long)c * H + (long long)oy * k) * W + (long long)ox * k;
+        if (is_max) {
+            float m = -INFINITY;
+            for (int dy = 0; dy < k; ++dy)
+                for (int dx = 0; dx < k; ++dx) {
+                    const float v = base[(long long)dy * W + dx];
+                    m = (v > m || v != v) ? v : m;
+                }
+            out[i] = m;
+        } else {
+            float s = 0.f;   // ATen avg_pool2d: sequential fp32 sum in row-major order, then one division
+            for (int dy = 0; dy < k; ++dy)
+                for (int dx = 0; dx < k; ++dx) s = __fadd_rn(s, base[(long long)dy * W + dx]);
+            out[i] = __fdiv_rn(s, (float)(k * k));
+        }
+    }
+}
+
+static unsigned grid_for(long long total) {
+    long long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace dmm
+
+using namespace dmm;
+
+extern "C" int dmm_lidar_splat(const float* points, int32_t n_points, int32_t H, int32_t W, int32_t kernel_size,
+                               int32_t* scratch, float* img, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DMM_CHECK(img && scratch && H > 0 && W > 0 && kernel_size >= 1 && n_points >= 0, "dmm_lidar_splat: bad arguments");
+    DMM_CHECK(n_points == 0 || points, "dmm_lidar_splat: null points");
+    const long long n = (long long)H * W;
+    fill_i32_kernel<<<grid_for(n), 256, 0, stream>>>(scratch, n, -1);
+    if (n_points > 0) {
+        unsigned g = (unsigned)((n_points + 7) / 8);
+        if (g > 148 * 16) g = 148 * 16;
+        lidar_mark_kernel<<<g, 256, 0, stream>>>(points, n_points, H, W, (kernel_size - 1) / 2, scratch);
+    }
+    lidar_resolve_kernel<<<grid_for(n), 256, 0, stream>>>(points, scratch, n, img);
+    DMM_LAUNCH_CHECK("lidar_splat kernels");
+    return 0;
+}
+
+extern "C" int dmm_lidar_pool(const float* img, int32_t H, int32_t W, float* out, void* stream) {
+    DMM_CHECK(img && out && H >= 20 && W >= 10, "dmm_lidar_pool: bad arguments (needs H >= 20, W >= 10)");
+    const int OH = (H - 20) / 10 + 1, OW = (W - 10) / 10 + 1;
+    lidar_pool_kernel<<<grid_for((long long)(OH + 1) * OW), 256, 0, (cudaStream_t)stream>>>(img, H, W, OH, OW, out);
+    DMM_LAUNCH_CHECK("lidar_pool_kernel");
+    return 0;
+}
+
+extern "C" int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t H, int32_t W, int32_t* scratch,
+                                 float* maps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DMM_CHECK(maps && scratch && H > 0 && W > 0 && n_boxes >= 0, "dmm_heatmap_boxes: bad arguments");
+    DMM_CHECK(n_boxes == 0 || boxes, "dmm_heatmap_boxes: null boxes");
+    const long long n = 3ll * H * W;
+    fill_i32_kernel<<<grid_for(n), 256, 0, stream>>>(scratch, n, -1);
+    if (n_boxes > 0) heatmap_mark_kernel<<<(unsigned)(n_boxes < 148 * 8 ? n_boxes : 148 * 8), 256, 0, stream>>>(boxes, n_boxes, H, W, scratch);
+    heatmap_resolve_kernel<<<grid_for(n), 256, 0, stream>>>(boxes, scratch, H, W, maps);
+    DMM_LAUNCH_CHECK("heatmap kernels");
+    return 0;
+}
+
+extern "C" int dmm_pool_kxk(const float* img, int32_t C, int32_t H, int32_t W, int32_t k, int32_t is_max, float* out,
+                            void* stream) {
+    DMM_CHECK(img && out && C > 0 && k >= 1 && H >= k && W >= k, "dmm_pool_kxk: bad arguments");
+    const int OH = H / k, OW = W / k;
+    pool_kxk_kernel<<<grid_for((long long)C * OH * OW), 256, 0, (cudaStream_t)stream>>>(img, C, H, W, k, OH, OW, is_max, out);
+    DMM_LAUNCH_CHECK("pool_kxk_kernel");
+    return 0;
+}

@@ -1,0 +1,106 @@
+"""Host-side mirror of the pre-processing helpers of dmmfods/utils/Dense_U_Net_lidar_helper.py that sit on
+the hot path (same names, argument meaning and error behaviour), backed by the CUDA integer-scatter
+kernels in csrc/scatter.cu.  Results are bit-identical to the reference's CPU functions.
+
+    lidar_array_to_image_like_tensor   helper:493-515
+    pool_lidar_tensor                  helper:446-491
+    create_ground_truth_maps           helper:276-305 (+ templates :233-274)
+    maxpool_tensor / avgpool_tensor    helper:430-444
+
+Inputs may be numpy arrays / python dicts (as in the reference) or CUDA tensors; outputs are CUDA
+float32 tensors.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import (EasyDict, create_config, get_config, load_config, load_json_file, save_config,  # noqa: F401
+                     save_json_file, set_current_run)
+from .ops import _ptr, _stream, require_device
+
+
+def _dev():
+    require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def lidar_array_to_image_like_tensor(lidar_array, shape=(1, 1280, 1920), kernel_size=5):
+    """(N,3) rows [x, y, d] -> (1,H,W) float32 image, -1 where no point, kernel_size^2 splat, the LAST
+    point in array order wins (helper:493-515, incl. its clamping and slice semantics)."""
+    dev = _dev()
+    if isinstance(lidar_array, torch.Tensor):
+        pts = lidar_array.to(device=dev, dtype=torch.float32).reshape(-1, 3).contiguous()
+    else:
+        pts = torch.from_numpy(np.ascontiguousarray(np.asarray(lidar_array, dtype=np.float32).reshape(-1, 3))).to(dev)
+    _, H, W = shape
+    img = torch.empty(shape, dtype=torch.float32, device=dev)
+    scratch = torch.empty(H * W, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().dmm_lidar_splat(_ptr(pts) if pts.numel() else None, pts.shape[0], H, W, kernel_size,
+                                           _ptr(scratch), _ptr(img), _stream()), "dmm_lidar_splat")
+    return img
+
+
+def pool_lidar_tensor(lidar_tensor):
+    """(1,H,W) range image -> inverted [0,255] intensities, MaxPool2d((20,10), stride 10), one replicated
+    bottom row, negatives -> 0 (helper:446-491).  Like the reference this leaves the input transformed
+    semantics aside: the input tensor is NOT modified here."""
+    dev = _dev()
+    x = lidar_tensor.to(device=dev, dtype=torch.float32).contiguous()
+    assert x.dim() == 3 and x.shape[0] == 1
+    _, H, W = x.shape
+    out = torch.empty((1, (H - 20) // 10 + 2, (W - 10) // 10 + 1), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().dmm_lidar_pool(_ptr(x), H, W, _ptr(out), _stream()), "dmm_lidar_pool")
+    return out
+
+
+def boxes_from_ground_truth(ground_truth, width_img, height_img):
+    """dict of {type,x,y,width,height} -> int32 (N,5) rows [type,x,y,w,h] in dict (= paint) order.
+    Raises like the reference does: TypeError never (unknown classes are skipped, helper:295),
+    ValueError for boxes that do not lie inside the image (numpy broadcast error in the reference)."""
+    rows = []
+    for elem in ground_truth.values():
+        c = elem["type"]
+        if c == 1 or c == 2 or c == 4:
+            w, h, x, y = int(elem["width"]), int(elem["height"]), int(elem["x"]), int(elem["y"])
+            if x < 0 or y < 0 or w < 0 or h < 0 or x + w > width_img or y + h > height_img:
+                raise ValueError("could not broadcast input array from shape (%d,%d) into the image" % (h, w))
+            rows.append((c, x, y, w, h))
+    return np.asarray(rows, dtype=np.int32).reshape(-1, 5)
+
+
+def create_ground_truth_maps(ground_truth, width_img=1920, height_img=1280):
+    """label dict (or int32 (N,5) box tensor) -> (3,H,W) float32 class heat maps; vehicles / cyclists are
+    filled rectangles, pedestrians the 0.3/0.5/0.75/1 silhouette; later boxes overwrite earlier ones
+    of the same class (helper:233-305)."""
+    dev = _dev()
+    if isinstance(ground_truth, torch.Tensor):
+        boxes = ground_truth.to(device=dev, dtype=torch.int32).reshape(-1, 5).contiguous()
+    else:
+        boxes = torch.from_numpy(boxes_from_ground_truth(ground_truth, width_img, height_img)).to(dev)
+    maps = torch.empty((3, height_img, width_img), dtype=torch.float32, device=dev)
+    scratch = torch.empty(3 * height_img * width_img, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().dmm_heatmap_boxes(_ptr(boxes) if boxes.numel() else None, boxes.shape[0], height_img,
+                                             width_img, _ptr(scratch), _ptr(maps), _stream()), "dmm_heatmap_boxes")
+    return maps
+
+
+def _pool(img_tensor, k, is_max):
+    dev = _dev()
+    x = img_tensor.to(device=dev, dtype=torch.float32).contiguous()
+    assert x.dim() == 3
+    Cc, H, W = x.shape
+    out = torch.empty((Cc, H // k, W // k), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().dmm_pool_kxk(_ptr(x), Cc, H, W, k, 1 if is_max else 0, _ptr(out), _stream()), "dmm_pool_kxk")
+    return out
+
+
+def maxpool_tensor(img_tensor):
+    """torch.nn.MaxPool2d(10, stride=10) (helper:438-444)."""
+    return _pool(img_tensor, 10, True)
+
+
+def avgpool_tensor(img_tensor):
+    """torch.nn.AvgPool2d(10, stride=10) (helper:430-436)."""
+    return _pool(img_tensor, 10, False)

@@ -1,0 +1,358 @@
+"""Thin host-side wrappers: torch tensors (device memory, streams) -> C-ABI calls.
+
+Every function only enqueues kernels on torch's current CUDA stream.  Activations are pixel-major
+bf16 matrices `[P = B*H*W, ld]` (`Mat`).  Nothing here computes on the CPU or falls back to torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (MAX_SRC, MAX_TAPS, STATS_SLOTS, Bn, BnApply, BnBwd, BnBwdArgs, Head, HeadBwd, Igemm, View,
+                   Wgrad, check)
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+KWIDTH = 64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, byte_offset=0):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr() + byte_offset)
+
+
+def require_device():
+    lib = _lib.load()
+    if not torch.cuda.is_available() or not lib.dmm_device_ok():
+        raise RuntimeError("dmmfods_b200 needs an sm_100 (B200) CUDA device; there is no CPU fallback")
+    return lib
+
+
+def ceil_to(v, m):
+    return (v + m - 1) // m * m
+
+
+class Mat:
+    """bf16 pixel-major activation matrix [B*H*W, ld] living in `t` (2-D bf16 tensor)."""
+
+    def __init__(self, t, B, H, W):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.is_contiguous()
+        assert t.shape[0] == B * H * W, (t.shape, B, H, W)
+        self.t, self.B, self.H, self.W = t, B, H, W
+        self.ld = t.shape[1]
+
+    @property
+    def P(self):
+        return self.B * self.H * self.W
+
+    def ptr(self, c0=0):
+        return C.c_void_p(self.t.data_ptr() + 2 * c0)
+
+    def view(self, c0=0, C_=None):
+        """dmm_view_t of channels [c0, c0+C_)."""
+        C_ = self.ld - c0 if C_ is None else C_
+        assert c0 % 8 == 0 and c0 + C_ <= self.ld
+        v = View()
+        v.ptr = self.t.data_ptr() + 2 * c0
+        v.C, v.W, v.H, v.B = C_, self.W, self.H, self.B
+        v.sw, v.sh, v.sb = self.ld, self.ld * self.W, self.ld * self.W * self.H
+        return v
+
+    def phase_view(self, py, px, c0=0, C_=None):
+        """view of the pixels (2i+py, 2j+px) - sub-pixel phase of a stride-2 transposed conv output."""
+        C_ = self.ld - c0 if C_ is None else C_
+        v = View()
+        v.ptr = self.t.data_ptr() + 2 * ((py * self.W + px) * self.ld + c0)
+        v.C, v.W, v.H, v.B = C_, (self.W - px + 1) // 2, (self.H - py + 1) // 2, self.B
+        v.sw, v.sh, v.sb = 2 * self.ld, 2 * self.ld * self.W, self.ld * self.W * self.H
+        return v
+
+
+def new_mat(B, H, W, ld, device="cuda", zero=False):
+    f = torch.zeros if zero else torch.empty
+    return Mat(f((B * H * W, ld), dtype=torch.bfloat16, device=device), B, H, W)
+
+
+class Stats:
+    """double[STATS_SLOTS][2][ld] accumulator rows living inside a flat float64 tensor."""
+
+    def __init__(self, buf, offset, ld):
+        self.buf, self.offset, self.ld = buf, offset, ld
+
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + 8 * self.offset)
+
+    @staticmethod
+    def size(ld):
+        return STATS_SLOTS * 2 * ld
+
+    def totals(self):
+        """(sum, sumsq) per channel as float64 tensors (debug / tests)."""
+        v = self.buf[self.offset:self.offset + self.size(self.ld)].view(STATS_SLOTS, 2, self.ld).sum(0)
+        return v[0], v[1]
+
+
+def pick_tile_w(W, H, pixels):
+    """tile_w in {pixels, pixels/2, ..., 8} minimising the zero-padded area (ties: the squarest tile)."""
+    best = None
+    tw = pixels
+    while tw >= 8:
+        th = pixels // tw
+        area = ceil_to(W, tw) * ceil_to(H, th)
+        key = (area, abs(tw - th))
+        if best is None or key < best[0]:
+            best = (key, tw)
+        tw //= 2
+    return best[1]
+
+
+def pick_n_tile(N):
+    if N <= 256:
+        return ceil_to(N, 16)
+    return 256 if N % 256 == 0 or N > 512 else 128
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution tap tables
+# ------------------------------------------------------------------------------------------------
+class ConvGeom:
+    """Tap tables + weight (un)packing strides for one reference convolution.
+
+    fwd_taps / dgrad_taps: lists of (src, dy, dx); *_off: offset of the tap inside the kh*kw plane.
+    Weight tensor layouts: Conv2d (Cout, Cin, K, K); ConvTranspose2d (Cin, Cout, 3, 3)."""
+
+
+def conv_taps(K, pad):
+    """stride-1 Conv2d: forward taps, data-gradient taps (flipped), offsets kh*K+kw."""
+    fwd, dg, off = [], [], []
+    for kh in range(K):
+        for kw in range(K):
+            fwd.append((0, kh - pad, kw - pad))
+            dg.append((0, pad - kh, pad - kw))
+            off.append(kh * K + kw)
+    return fwd, dg, off
+
+
+def convt_phase_taps(py, px):
+    """ConvTranspose2d(3, stride 2, padding 1): taps feeding output phase (py, px).
+    out[2i+py, 2j+px] += x[i+dy, j+dx] * w[kh, kw] with kh = py+1-2dy, kw = px+1-2dx."""
+    taps, off = [], []
+    for dy in ((0,) if py == 0 else (0, 1)):
+        for dx in ((0,) if px == 0 else (0, 1)):
+            kh, kw = py + 1 - 2 * dy, px + 1 - 2 * dx
+            taps.append((0, dy, dx))
+            off.append(kh * 3 + kw)
+    return taps, off
+
+
+def convt_dgrad_taps():
+    """dx[i,j] = sum_{kh,kw} dout[2i-1+kh, 2j-1+kw] * w[kh,kw]: source = phase view (py*2+px), shifted."""
+    taps, off = [], []
+    for kh in range(3):
+        for kw in range(3):
+            py, dy = (0, 0) if kh == 1 else (1, -1 if kh == 0 else 0)
+            px, dx = (0, 0) if kw == 1 else (1, -1 if kw == 0 else 0)
+            taps.append((py * 2 + px, dy, dx))
+            off.append(kh * 3 + kw)
+    return taps, off
+
+
+def convt_wgrad_taps():
+    """dw[kh,kw] = sum_pix X(pix + shift) * dout_phase(pix): (ysrc, dy, dx) with the shift applied to X."""
+    taps, off = [], []
+    for kh in range(3):
+        for kw in range(3):
+            py, dy = (0, 0) if kh == 1 else (1, 1 if kh == 0 else 0)
+            px, dx = (0, 0) if kw == 1 else (1, 1 if kw == 0 else 0)
+            taps.append((py * 2 + px, dy, dx))
+            off.append(kh * 3 + kw)
+    return taps, off
+
+
+# ------------------------------------------------------------------------------------------------
+# descriptor builders (the returned ctypes structs can be re-launched any number of times)
+# ------------------------------------------------------------------------------------------------
+def make_igemm(srcs, taps, weights, ktot, n_rows, W, H, B, N, out_ptr, ldo, coff=0, out_mode=0, stats=None,
+               stats_off=0, out_stride=(1, 1), out_phase=(0, 0), out_hw=None, n_tile=None, tile_w=None,
+               kwidth=KWIDTH):
+    d = Igemm()
+    assert 1 <= len(srcs) <= MAX_SRC and 1 <= len(taps) <= MAX_TAPS
+    for i, v in enumerate(srcs):
+        d.src[i] = v
+    d.num_src = len(srcs)
+    d.num_taps = len(taps)
+    for i, (s, dy, dx) in enumerate(taps):
+        d.tap_src[i], d.tap_dy[i], d.tap_dx[i] = s, dy, dx
+    d.weights = weights.data_ptr() if isinstance(weights, torch.Tensor) else weights
+    d.ktot, d.n_rows, d.kwidth = ktot, n_rows, kwidth
+    d.W, d.H, d.B = W, H, B
+    d.tile_w = tile_w or pick_tile_w(W, H, 128)
+    d.N = N
+    d.n_tile = n_tile or pick_n_tile(N)
+    d.out = out_ptr.value if isinstance(out_ptr, C.c_void_p) else out_ptr
+    d.out_mode, d.ldo, d.coff = out_mode, ldo, coff
+    d.out_sy, d.out_sx = out_stride
+    d.out_py, d.out_px = out_phase
+    d.OH, d.OW = out_hw if out_hw is not None else (H, W)
+    if stats is not None:
+        d.stats = stats.ptr().value
+        d.stats_ld, d.stats_off = stats.ld, stats_off
+    return d
+
+
+def run_igemm(d):
+    check(_lib.load().dmm_conv_igemm(C.byref(d), _stream()), "dmm_conv_igemm")
+
+
+def make_wgrad(x, ys, taps, W, H, B, M, N, dw, ldw, n_tile=None, tile_w=None, splits=0):
+    d = Wgrad()
+    d.x = x
+    assert 1 <= len(ys) <= MAX_SRC and 1 <= len(taps) <= MAX_TAPS
+    for i, v in enumerate(ys):
+        d.y[i] = v
+    d.num_ysrc = len(ys)
+    d.num_taps = len(taps)
+    for i, (s, dy, dx) in enumerate(taps):
+        d.tap_ysrc[i], d.tap_dy[i], d.tap_dx[i] = s, dy, dx
+    d.W, d.H, d.B = W, H, B
+    d.tile_w = tile_w or pick_tile_w(W, H, 64)
+    d.M, d.N = M, N
+    d.n_tile = n_tile or min(pick_n_tile(N), 256)
+    d.splits = splits
+    d.dw = dw.data_ptr() if isinstance(dw, torch.Tensor) else dw
+    d.ldw = ldw
+    return d
+
+
+def run_wgrad(d):
+    check(_lib.load().dmm_conv_wgrad(C.byref(d), _stream()), "dmm_conv_wgrad")
+
+
+def _i32arr(vals):
+    return (C.c_int32 * len(vals))(*vals)
+
+
+def pack_weights(w, dst, n_valid, n_rows, C_, T, tap_off, sn, sc, kwidth=KWIDTH):
+    check(_lib.load().dmm_pack_weights(_ptr(w), _ptr(dst), n_valid, n_rows, C_, kwidth, T, _i32arr(tap_off), sn, sc,
+                                       _stream()), "dmm_pack_weights")
+
+
+def unpack_wgrad(dw, ldw, M, N, grad, T, tap_off, sn, sc, accumulate=False):
+    check(_lib.load().dmm_unpack_wgrad(_ptr(dw), ldw, M, N, _ptr(grad), T, _i32arr(tap_off), sn, sc,
+                                       1 if accumulate else 0, _stream()), "dmm_unpack_wgrad")
+
+
+def make_bn(stats, stats_off, count, gamma, beta, running_mean=None, running_var=None, save_mean=None,
+            save_invstd=None, training=True, rep=1.0, c0=0, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """dmm_bn_t for channels [c0, c0+C) of one BatchNorm2d; tensors are the module's full fp32 vectors."""
+    b = Bn()
+    if stats is not None:
+        b.stats = stats.ptr().value
+        b.stats_ld, b.stats_off = stats.ld, stats_off
+    b.count, b.rep = float(count), float(rep)
+    o = 4 * c0
+    b.gamma = gamma.data_ptr() + o
+    b.beta = beta.data_ptr() + o
+    if running_mean is not None:
+        b.running_mean = running_mean.data_ptr() + o
+        b.running_var = running_var.data_ptr() + o
+    if save_mean is not None:
+        b.save_mean = save_mean.data_ptr() + o
+        b.save_invstd = save_invstd.data_ptr() + o
+    b.eps, b.momentum, b.training = eps, momentum, 1 if training else 0
+    return b
+
+
+def make_bn_apply(x, c0, C_, bn, y, yc0, pool=0, ystats=None, ystats_off=0):
+    """x, y: Mat.  Normalises channels [c0, c0+C_) of x into channels [yc0, ...) of y."""
+    d = BnApply()
+    d.x, d.ldx = x.ptr(c0).value, x.ld
+    d.B, d.H, d.W, d.C = x.B, x.H, x.W, C_
+    d.bn = bn
+    d.pool = pool
+    d.y, d.ldy = y.ptr(yc0).value, y.ld
+    if ystats is not None:
+        d.ystats = ystats.ptr().value
+        d.ystats_ld, d.ystats_off = ystats.ld, ystats_off
+    return d
+
+
+def run_bn_apply(d):
+    check(_lib.load().dmm_bn_relu_apply(C.byref(d), _stream()), "dmm_bn_relu_apply")
+
+
+def make_bn_bwd(sums, sums_off, count, gamma, beta, save_mean, save_invstd, dgamma=None, dbeta=None, c0=0):
+    b = BnBwd()
+    b.sums = sums.ptr().value
+    b.sums_ld, b.sums_off = sums.ld, sums_off
+    b.count = float(count)
+    o = 4 * c0
+    b.gamma = gamma.data_ptr() + o
+    b.beta = beta.data_ptr() + o
+    b.save_mean = save_mean.data_ptr() + o
+    b.save_invstd = save_invstd.data_ptr() + o
+    if dgamma is not None:
+        b.dgamma = dgamma.data_ptr() + o
+        b.dbeta = dbeta.data_ptr() + o
+    return b
+
+
+def make_bn_bwd_args(x, c0, C_, g_ptr, ldg, bn, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False):
+    d = BnBwdArgs()
+    d.x, d.ldx = x.ptr(c0).value, x.ld
+    d.g = g_ptr.value if isinstance(g_ptr, C.c_void_p) else g_ptr
+    d.ldg = ldg
+    d.g_is_f32 = 1 if g_is_f32 else 0
+    d.gmode = gmode
+    d.B, d.H, d.W, d.C = x.B, x.H, x.W, C_
+    d.bn = bn
+    d.out = (out_ptr.value if isinstance(out_ptr, C.c_void_p) else out_ptr) if out_ptr is not None else None
+    d.ldo, d.out_mode = ldo, out_mode
+    return d
+
+
+def run_bn_bwd(d):
+    lib = _lib.load()
+    check(lib.dmm_bn_relu_bwd_reduce(C.byref(d), _stream()), "dmm_bn_relu_bwd_reduce")
+    check(lib.dmm_bn_relu_bwd_apply(C.byref(d), _stream()), "dmm_bn_relu_bwd_apply")
+
+
+def im2col_7x7s2(x1, x2, out):
+    """x1 (B,C1,H,W) fp32, x2 optional; out: Mat at half resolution with ld = kpad."""
+    B, C1, H, W = x1.shape
+    C2 = 0 if x2 is None else x2.shape[1]
+    check(_lib.load().dmm_im2col_7x7s2(_ptr(x1), C1, _ptr(x2), C2, B, H, W, out.ptr(), out.ld, _stream()),
+          "dmm_im2col_7x7s2")
+
+
+def nchw_stats(x, stats, off):
+    B, C_, H, W = x.shape
+    check(_lib.load().dmm_nchw_stats(_ptr(x), B, C_, H * W, stats.ptr(), stats.ld, off, _stream()), "dmm_nchw_stats")
+
+
+def nchw_to_nhwc_bf16(x, out):
+    B, C_, H, W = x.shape
+    check(_lib.load().dmm_nchw_to_nhwc_bf16(_ptr(x), B, C_, H, W, out.ptr(), out.ld, _stream()), "dmm_nchw_to_nhwc_bf16")
+
+
+def rows_f32_to_bf16(src, c0, C_, dst):
+    """src: fp32 [P, lds] tensor, channels [c0, c0+C_) -> dst Mat columns [0, C_)."""
+    check(_lib.load().dmm_rows_f32_to_bf16(C.c_void_p(src.data_ptr() + 4 * c0), src.shape[1], dst.ptr(), dst.ld,
+                                           src.shape[0], C_, _stream()), "dmm_rows_f32_to_bf16")
+
+
+def bce_logits(logits, target, loss=None, grad=None, class_sums=None):
+    B, C_, H, W = logits.shape
+    assert logits.is_contiguous() and target.is_contiguous() and target.shape == logits.shape
+    check(_lib.load().dmm_bce_logits(_ptr(logits), _ptr(target), logits.numel(), C_, H * W, _ptr(loss), _ptr(grad),
+                                     _ptr(class_sums), _stream()), "dmm_bce_logits")
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step):
+    check(_lib.load().dmm_adam_flat(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1,
+                                    beta2, eps, weight_decay, step, _stream()), "dmm_adam_flat")

@@ -14,7 +14,8 @@
  *   - activations are NHWC ("pixel-major") bf16 matrices [P = B*H*W rows, ld elements per row];
  *     a dmm_view_t describes a channel slice of such a buffer (concat-free dense-block buffers:
  *     replaces torch.cat at tv:48, tv:124, Dense_U_Net_lidar.py:228-231,244,258,264).
- *   - batch-norm statistics are accumulated in double: stats[slot][2][C] (sum, sum of squares).
+ *   - batch-norm statistics are accumulated in double: stats[slot][2][ld] (sum, sum of squares),
+ *     DMM_STATS_SLOTS slots spread the atomics; consumers add the slots up.  Caller zero-fills.
  */
 #ifndef DMMFODS_B200_H
 #define DMMFODS_B200_H
@@ -80,115 +81,185 @@ typedef struct {
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 
 /* Weight-gradient GEMM on tcgen05 (both operands pixel-major = MN-major UMMA descriptors):
- *   dw[t][m][n] += sum_{b,y,x} X[xsrc[t]](b, y + dy[t], x + dx[t], m) * Y[ysrc[t]](b, y, x, n)
+ *   dw[t][m][n] += sum_{b,y,x} X(b, y + dy[t], x + dx[t], m) * Y[ysrc[t]](b, y, x, n)
  * fp32 atomic accumulation into dw (caller zero-fills), layout dw[(t*M + m)*ldw + n].
  * Replaces the weight-gradient half of aten::convolution_backward for every Conv2d /
- * ConvTranspose2d above (47% of the reference's CPU time). */
+ * ConvTranspose2d above (47% of the reference's CPU time).  Several Y views are
+ * needed for ConvTranspose2d only (the four sub-pixel phases of the output gradient). */
 typedef struct {
-    dmm_view_t x[DMM_MAX_SRC];
+    dmm_view_t x;
     dmm_view_t y[DMM_MAX_SRC];
+    int32_t num_ysrc;
     int32_t num_taps;
-    int8_t tap_xsrc[DMM_MAX_TAPS];
     int8_t tap_ysrc[DMM_MAX_TAPS];
     int8_t tap_dy[DMM_MAX_TAPS];
     int8_t tap_dx[DMM_MAX_TAPS];
-    int32_t W, H, B;         /* pixel domain (of Y; X is read shifted) */
+    int32_t W, H, B;         /* pixel domain (of Y; X is read shifted, zero outside its view) */
     int32_t tile_w;          /* 64 / 32 / 16 / 8; tile_h = 64 / tile_w */
     int32_t M, N;            /* channels of X (rows of dw) and of Y (columns of dw) */
     int32_t n_tile;          /* multiple of 16, <= 256 */
-    int32_t splits;          /* pixel-chunk splits per (tap, m-tile, n-tile); 0 = auto */
+    int32_t splits;          /* pixel-range splits per (tap, m-tile, n-tile); 0 = auto */
     float* dw;
     int64_t ldw;
 } dmm_wgrad_t;
 int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream);
 
-/* dst[n][kb*kwidth + c] (bf16, row length ktot) <- w[n*sn + (c0 + c)*sc + off] for the k-block
- * groups listed; zero padding elsewhere.  Converts fp32 parameter tensors (Conv2d (Cout,Cin,kh,kw),
- * ConvTranspose2d (Cin,Cout,kh,kw)) into the K-major operand of dmm_conv_igemm for fprop or dgrad. */
+/* dst[n][t*Kp + c] (bf16, row length T*Kp, Kp = C rounded up to kwidth) <- w[n*sn + c*sc + tap_off[t]]
+ * for n < n_valid, c < C; zero elsewhere (rows up to n_rows).  Converts fp32 parameter tensors
+ * (Conv2d (Cout,Cin,kh,kw), ConvTranspose2d (Cin,Cout,kh,kw)) into the K-major B operand of
+ * dmm_conv_igemm for forward or data-gradient use. */
+int dmm_pack_weights(const float* w, void* dst, int32_t n_valid, int32_t n_rows, int32_t C, int32_t kwidth,
+                     int32_t T, const int32_t* tap_off, int64_t sn, int64_t sc, void* stream);
+/* grad[n*sn + m*sc + tap_off[t]] (= or +=) dw[(t*M + m)*ldw + n]: dmm_conv_wgrad result -> parameter layout. */
+int dmm_unpack_wgrad(const float* dw, int64_t ldw, int32_t M, int32_t N, float* grad, int32_t T,
+                     const int32_t* tap_off, int64_t sn, int64_t sc, int32_t accumulate, void* stream);
+
+/* Batched forms of the two calls above: the job tables live in DEVICE memory (built once per
+ * model), one launch per training step covers every weight tensor of the network.
+ * Mld = row count used to index dw per tap (the M the wgrad was launched with; may exceed M). */
 typedef struct {
-    int64_t sn, sc, off;     /* element strides/offset into w for (n, c) */
-    int32_t c0, cnt;         /* channel range of this group */
-    int32_t nblk;            /* k-blocks occupied = ceil(cnt / kwidth) */
-} dmm_pack_group_t;
-int dmm_pack_weights(const float* w, void* dst, int32_t n, int32_t n_rows_padded, int64_t ktot,
-                     int32_t kwidth, const dmm_pack_group_t* groups, int32_t num_groups, void* stream);
-/* grad[n*sn + (c0+c)*sc + off] (fp32, parameter layout) <- or += packed dw[(g*M + m)*ldw + n'] ;
- * inverse of the packing for the fp32 weight-gradient produced by dmm_conv_wgrad.
- * rows_are_n: 1 if dw rows index the parameter's "n" (stride sn) and columns its "c"; 0 if swapped. */
-int dmm_unpack_wgrad(const float* dw, int64_t ldw, int32_t M, int32_t N, float* grad,
-                     const dmm_pack_group_t* groups, int32_t num_groups, int32_t rows_are_n,
-                     int32_t accumulate, void* stream);
+    const float* w;
+    void* dst;
+    int32_t n_valid, n_rows, C, kwidth, T;
+    int32_t tap_off[DMM_MAX_TAPS];
+    int64_t sn, sc;
+} dmm_pack_job_t;
+typedef struct {
+    const float* dw;
+    float* grad;
+    int64_t ldw;
+    int32_t M, Mld, N, T, accumulate;
+    int32_t tap_off[DMM_MAX_TAPS];
+    int64_t sn, sc;
+} dmm_unpack_job_t;
+int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream);
+int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream);
 
-/* ---- batch-norm pieces (nn.BatchNorm2d semantics) ------------------------------- */
-/* column sums / sums of squares of a [P, C] bf16 view into stats[slot][2][stats_ld] at stats_off. */
-int dmm_col_stats(const void* x, int64_t ldx, int64_t P, int32_t C, double* stats, int32_t stats_ld,
-                  int32_t stats_off, void* stream);
-/* per-plane sums of an fp32 NCHW tensor (B, C, H, W) -> stats (raw network inputs, head BN). */
-int dmm_nchw_stats(const float* x, int32_t B, int32_t C, int64_t HW, double* stats, int32_t stats_ld,
-                   int32_t stats_off, void* stream);
-/* From accumulated stats (all slots are summed): mean, invstd (biased var, eps), then for ONE
- * BatchNorm module over channels [0,C) of that statistics row: scale = gamma*invstd,
- * shift = beta - mean*scale, running_mean/var momentum update with the unbiased variance
- * (count*rep/(count*rep-1); rep = replication factor of nn.Upsample), num_batches_tracked += 1.
- * running_* / nbt may be NULL (no update).  training=0: scale/shift from the running stats. */
-int dmm_bn_finalize(const double* stats, int32_t stats_ld, int32_t stats_off, int32_t C, double count,
-                    double rep, const float* gamma, const float* beta, float eps, float momentum,
-                    float* running_mean, float* running_var, int64_t* nbt, int32_t training,
-                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* ---- batch norm (nn.BatchNorm2d semantics) ---------------------------------------- */
+/* Forward-side description of ONE BatchNorm2d (or a channel slice of one; all pointers already
+ * offset to the slice's first channel).  training=1: batch statistics are taken from the
+ * accumulated column sums stats[slot][2][stats_ld] at stats_off (all slots summed; `count` elements
+ * per channel): normalise with mean / BIASED variance, save mean/invstd for backward, update
+ * running stats with momentum and the UNBIASED variance over count*rep elements (rep = replication
+ * factor of nn.Upsample, else 1).  training=0: running statistics. */
+typedef struct {
+    const double* stats;
+    int32_t stats_ld, stats_off;
+    double count, rep;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;     /* nullable in training mode (no update) */
+    float* running_var;
+    float* save_mean;        /* nullable */
+    float* save_invstd;
+    float eps, momentum;
+    int32_t training;
+} dmm_bn_t;
 
-/* y[p, c] = relu(scale[c]*x[p, c] + shift[c])  (BN-ReLU prologue, materialised bf16 operand)
+/* y = relu(bn(x)), bf16 pixel-major [B*H*W, C] (tv:47-50,90; Dense_U_Net_lidar.py:75-76,108-115).
  * pool: 0 none; 1 = then AvgPool2d(2,2) (tv:133 moved in front of the 1x1 conv - they commute);
  *       2 = then MaxPool2d(3, stride 2, padding 1) (Dense_U_Net_lidar.py:77).
- * stats (nullable): column stats of the OUTPUT (needed when the output is a raw feature). */
-int dmm_bn_relu_apply(const void* x, int64_t ldx, int32_t B, int32_t H, int32_t W, int32_t C,
-                      const float* scale, const float* shift, int32_t pool, void* y, int64_t ldy,
-                      double* stats, int32_t stats_ld, int32_t stats_off, void* stream);
+ * ystats (nullable): column sums / sums of squares of the stored OUTPUT are added at ystats_off. */
+typedef struct {
+    const void* x;
+    int64_t ldx;
+    int32_t B, H, W, C;
+    dmm_bn_t bn;
+    int32_t pool;
+    void* y;
+    int64_t ldy;
+    double* ystats;
+    int32_t ystats_ld, ystats_off;
+} dmm_bn_apply_t;
+int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream);
 
-/* Backward of BN-ReLU (threshold_backward + native_batch_norm_backward), two passes.
- * The incoming gradient g of the ACTIVATED tensor is addressed through `gmode`:
- *   0: g[p, c] same resolution;  1: avg-pool parent: 0.25 * g[parent(p), c];
- *   2: max-pool 3x3/s2/p1 parents (gradient routed to the first maximum of each window).
- * pass 1 (reduce): sums[slot][2][C] += (sum dz, sum dz*xhat), dz = g * [scale*x+shift > 0].
- * pass 2 (apply): dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat));
- *   out_mode 0: store bf16; 1: accumulate into bf16 (out += dx). */
-int dmm_bn_relu_bwd_reduce(const void* x, int64_t ldx, const void* g, int64_t ldg, int32_t gmode,
-                           int32_t B, int32_t H, int32_t W, int32_t C, const float* mean,
-                           const float* invstd, const float* scale, const float* shift, double* sums,
-                           int32_t sums_ld, int32_t sums_off, void* stream);
-int dmm_bn_bwd_finalize(const double* sums, int32_t sums_ld, int32_t sums_off, int32_t C, double count,
-                        const float* gamma, const float* invstd, float* dgamma, float* dbeta,
-                        float* c1, float* c2, int32_t accumulate, void* stream);
-int dmm_bn_relu_bwd_apply(const void* x, int64_t ldx, const void* g, int64_t ldg, int32_t gmode,
-                          int32_t B, int32_t H, int32_t W, int32_t C, const float* mean,
-                          const float* invstd, const float* scale, const float* shift,
-                          const float* c1, const float* c2, void* out, int64_t ldo, int32_t out_mode,
-                          void* stream);
+/* Backward of BN-ReLU (aten::threshold_backward + native_batch_norm_backward), two passes:
+ *   dz = g' * [bn(x) > 0], g' = gradient of the activated tensor addressed through gmode
+ *        (0: same pixel; 1: avg-pool parent, 0.25*g[parent]; 2: max-pool 3x3/s2/p1, the gradient
+ *         of each window goes to its FIRST maximum like ATen);
+ *   reduce: sums[slot][2][sums_ld] += (sum dz, sum dz*xhat);
+ *   apply : dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dgamma = sum dz*xhat, dbeta = sum dz.
+ * out_mode 0: store bf16; 1: store fp32; 2: accumulate into fp32.  out may be NULL (only dgamma/dbeta). */
+typedef struct {
+    double* sums;
+    int32_t sums_ld, sums_off;
+    double count;
+    const float* gamma;
+    const float* beta;
+    const float* save_mean;
+    const float* save_invstd;
+    float* dgamma;           /* nullable */
+    float* dbeta;
+} dmm_bn_bwd_t;
+typedef struct {
+    const void* x;           /* raw (pre-BN) bf16 input of the forward pass */
+    int64_t ldx;
+    const void* g;
+    int64_t ldg;
+    int32_t g_is_f32;
+    int32_t gmode;
+    int32_t B, H, W, C;      /* geometry of x */
+    dmm_bn_bwd_t bn;
+    void* out;
+    int64_t ldo;
+    int32_t out_mode;
+} dmm_bn_bwd_args_t;
+int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
+int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
 
 /* ---- stem / head data movement ------------------------------------------------------------- */
-/* im2col for conv0 (7x7, stride 2, padding 3): fp32 NCHW (B,Cin,H,W) -> bf16 [B*OH*OW, kpad],
- * k = (kh*7 + kw)*Cin + ci, zero padded to kpad.  c_off/c_cnt select input channels; a second
- * tensor x2 (nullable) supplies channels after x1's (early fusion cat, :228-229). */
+/* im2col for conv0 (7x7, stride 2, padding 3; Dense_U_Net_lidar.py:73-74,157-158): fp32 NCHW
+ * (B,C1[+C2],H,W) -> bf16 [B*OH*OW, kpad], k = ci*49 + kh*7 + kw (the flattened Conv2d weight
+ * order), zero padded to kpad.  x2 (nullable) supplies the channels after x1's (early fusion cat,
+ * :228-229). */
 int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H,
                      int32_t W, void* out, int32_t kpad, void* stream);
-/* head input: a0 = relu(bn0(cat(upsample2x(u), x1, x2))) as bf16 [B*H*W, ldo]
- * (nn.Upsample :120, torch.cat :264, dec_out_to_heat_maps.norm0/relu0 :124-125). */
-int dmm_head_input(const void* u, int64_t ldu, int32_t Cu, const float* x1, int32_t C1,
-                   const float* x2, int32_t C2, int32_t B, int32_t H, int32_t W, const float* scale,
-                   const float* shift, void* out, int64_t ldo, void* stream);
-/* backward of the above for the Cu up-sampled channels (sum over the 2x2 children), two passes as
- * for dmm_bn_relu_bwd_*; channels >= Cu (raw inputs) only contribute to the BN sums. */
-int dmm_head_input_bwd_reduce(const void* u, int64_t ldu, int32_t Cu, const float* x1, int32_t C1,
-                              const float* x2, int32_t C2, const void* g, int64_t ldg, int32_t B,
-                              int32_t H, int32_t W, const float* mean, const float* invstd,
-                              const float* scale, const float* shift, double* sums, int32_t sums_ld,
-                              void* stream);
-int dmm_head_input_bwd_apply(const void* u, int64_t ldu, int32_t Cu, const void* g, int64_t ldg,
-                             int32_t B, int32_t H, int32_t W, const float* mean, const float* invstd,
-                             const float* scale, const float* shift, const float* c1, const float* c2,
-                             void* du, int64_t lddu, void* stream);
+/* per-plane sums of an fp32 NCHW tensor (B, C, H*W) -> stats (raw network inputs feeding the head BN). */
+int dmm_nchw_stats(const float* x, int32_t B, int32_t C, int64_t HW, double* stats, int32_t stats_ld,
+                   int32_t stats_off, void* stream);
+/* head input: out = relu(bn0(cat(upsample2x(u), x1, x2))) as bf16 [B*H*W, ldo], zero beyond Cu+C1+C2
+ * (nn.Upsample :120, torch.cat :264, dec_out_to_heat_maps.norm0/relu0 :124-125).
+ * bn_u: the BN slice of the Cu decoder channels (statistics of u, rep = 4); bn_x: the slice of
+ * the C1+C2 raw input channels (statistics from dmm_nchw_stats). */
+typedef struct {
+    const void* u;
+    int64_t ldu;
+    int32_t Cu;
+    const float* x1;
+    int32_t C1;
+    const float* x2;
+    int32_t C2;
+    int32_t B, H, W;         /* full (output) resolution; u is (B, H/2, W/2) */
+    dmm_bn_t bn_u, bn_x;
+    void* out;
+    int64_t ldo;
+} dmm_head_t;
+int dmm_head_input(const dmm_head_t* d, void* stream);
+/* backward of the above: reduce over all channels, apply for the Cu decoder channels
+ * (du[parent] = sum of dx over the 2x2 children, bf16). */
+typedef struct {
+    const void* u;
+    int64_t ldu;
+    int32_t Cu;
+    const float* x1;
+    int32_t C1;
+    const float* x2;
+    int32_t C2;
+    int32_t B, H, W;
+    const void* g;           /* bf16 [B*H*W, ldg] gradient of the head input */
+    int64_t ldg;
+    dmm_bn_bwd_t bn_u, bn_x;
+    void* du;
+    int64_t lddu;
+} dmm_head_bwd_t;
+int dmm_head_input_bwd_reduce(const dmm_head_bwd_t* d, void* stream);
+int dmm_head_input_bwd_apply(const dmm_head_bwd_t* d, void* stream);
 /* fp32 NCHW (B,C,H,W) -> bf16 NHWC [B*H*W, ldo] (channels >= C zero) : d(logits) for refine1. */
 int dmm_nchw_to_nhwc_bf16(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, void* out,
                           int64_t ldo, void* stream);
+/* fp32 rows [P, C] (pitch lds) -> bf16 rows (pitch ldd): slices of the fp32 dense-block gradient buffer. */
+int dmm_rows_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t P, int32_t C,
+                         void* stream);
 
 /* ---- loss: torch.nn.BCEWithLogitsLoss(reduction='none') + its gradient for a ones cotangent
  * (Agent:54,247,264): loss = max(x,0) - x*t + log1p(exp(-|x|)); grad = sigmoid(x) - t.
@@ -205,9 +276,10 @@ int dmm_lidar_splat(const float* points, int32_t n_points, int32_t H, int32_t W,
  * pad of one bottom row, negatives -> 0.  (1,H,W) -> (1,(H-20)/10+2,(W-10)/10+1). */
 int dmm_lidar_pool(const float* img, int32_t H, int32_t W, float* out, void* stream);
 /* helper:233-305 create_ground_truth_maps: boxes int32 (N,5) rows [type,x,y,w,h] in dict order ->
- * maps (3,H,W) float32; last box wins per class channel; pedestrian silhouette template. */
-int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t H, int32_t W, float* maps,
-                      void* stream);
+ * maps (3,H,W) float32; last box wins per class channel; pedestrian silhouette template.
+ * scratch: int32[3*H*W]. */
+int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t H, int32_t W, int32_t* scratch,
+                      float* maps, void* stream);
 /* helper:438-444 maxpool_tensor / helper:430-436 avgpool_tensor: (C,H,W) -> (C,H/k,W/k). */
 int dmm_pool_kxk(const float* img, int32_t C, int32_t H, int32_t W, int32_t k, int32_t is_max,
                  float* out, void* stream);

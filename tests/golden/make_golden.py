@@ -1,0 +1,173 @@
+"""Generates the committed golden vectors by executing the UNMODIFIED reference (/root/reference) through
+oracle/ref_shim.py on deterministic synthetic inputs.  Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Outputs (small, committed):
+    tests/golden/lidar_heatmap.npz   integer-scatter helpers (helper:233-305, 430-515)
+    tests/golden/tiny_unet_<fusion>.npz  a small Dense_U_Net_lidar (growth 16, blocks (2,2,2,2)):
+                                     state_dict, inputs, logits, loss, gradients (fp32 run + fp64 run)
+    tests/golden/dn121_mid_probe.npz DenseNet-121 mid-fusion (cb=3), seed-123 init: logits / loss / gradient
+                                     probes and per-tensor parameter checksums (state_dict too large to commit)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+from dmmfods_b200 import synthetic  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def lidar_heatmap():
+    _, helper = ref_shim.ref_modules()
+    out = {}
+    cases = [("full", 1280, 1920, 30000), ("small", 64, 96, 400), ("edge", 40, 50, 0)]
+    for name, H, W, n in cases:
+        pts = synthetic.lidar_points(n, H, W, seed=7 + n)
+        if name == "small":   # hand-made edge cases: borders, far out of range (python slice wrap), duplicates
+            extra = np.array([[0, 0, 1.5], [W - 1, H - 1, 2.5], [W - 2, H - 2, 3.5], [W + 10, 5, 4.5], [5, H + 10, 5.5],
+                              [-1, -1, 6.5], [-3, 10, 7.5], [10, -3, 8.5], [-30, -30, 9.5], [3.7, 4.2, 10.5],
+                              [20, 20, 80.0], [20, 20, 25.0], [21, 21, 25.000002], [40, 30, 75.5], [41, 30, 0.0]],
+                             dtype=np.float32)
+            pts = np.concatenate([pts, extra], 0)
+        img = helper.lidar_array_to_image_like_tensor(pts, shape=(1, H, W), kernel_size=5)
+        out["%s_points" % name] = pts
+        out["%s_shape" % name] = np.array([1, H, W])
+        if name == "full":
+            # full-size image is 9.8 MB: keep a checksum + a crop, and the pooled output
+            out["full_img_crop"] = img[:, 600:700, 900:1100].numpy().copy()
+            out["full_img_sum"] = np.array([img.double().sum().item(), (img.double() ** 2).sum().item()])
+        else:
+            out["%s_img" % name] = img.numpy().copy()
+        if H >= 20:
+            out["%s_pooled" % name] = helper.pool_lidar_tensor(img.clone()).numpy().copy()
+        labels = synthetic.boxes(None if name == "full" else 12, H, W, seed=11 + n)
+        if name == "small":
+            labels["p0"] = {"type": 2, "x": 1, "y": 2, "width": 3, "height": 4}
+            labels["p1"] = {"type": 2, "x": 10, "y": 12, "width": 4, "height": 3}
+            labels["p2"] = {"type": 2, "x": 30, "y": 20, "width": 17, "height": 23}
+            labels["p3"] = {"type": 2, "x": 32, "y": 25, "width": 9, "height": 11}
+            labels["v0"] = {"type": 1, "x": 0, "y": 0, "width": W, "height": 1}
+            labels["c0"] = {"type": 4, "x": W - 5, "y": H - 6, "width": 5, "height": 6}
+            labels["u0"] = {"type": 3, "x": 0, "y": 0, "width": 5, "height": 5}
+        maps = helper.create_ground_truth_maps(labels, width_img=W, height_img=H)
+        boxes = np.array([[e["type"], e["x"], e["y"], e["width"], e["height"]] for e in labels.values()], dtype=np.int32)
+        out["%s_boxes" % name] = boxes.reshape(-1, 5)
+        if name == "full":
+            out["full_maps_pooled"] = helper.maxpool_tensor(maps).numpy().copy()
+            out["full_maps_sum"] = np.array([maps.double().sum().item(), (maps.double() ** 2).sum().item()])
+        else:
+            out["%s_maps" % name] = maps.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "lidar_heatmap.npz"), **out)
+    print("lidar_heatmap.npz", {k: v.shape for k, v in out.items()})
+
+
+def _train_step(model, x1, x2, tgt, dtype):
+    model = model.to(dtype)
+    model.train()
+    model.zero_grad()
+    logits = model(x1.to(dtype), x2.to(dtype))
+    loss = torch.nn.BCEWithLogitsLoss(reduction="none")(logits, tgt.to(dtype))
+    loss.backward(torch.ones_like(loss))
+    return logits.detach(), loss.detach()
+
+
+def tiny_unet(fusion):
+    import copy
+    model_mod, _ = ref_shim.ref_modules()
+    c2, cb = {"no": (0, 1), "early": (1, 1), "mid": (1, 3)}[fusion]
+    cfg = ref_shim.ref_config(stream_2_in_channels=c2, concat_before_block_num=cb, growth_rate=16,
+                              block_config=(2, 2, 2, 2), num_init_features=32, bn_size=2)
+    torch.manual_seed(123)
+    model = model_mod.Dense_U_Net_lidar(cfg)
+    # make the problem well conditioned: random BN affine parameters (at the gamma=1, beta=0 init the
+    # gradient of every BN weight that feeds another BN is exactly zero in exact arithmetic - SURVEY App. D)
+    g = torch.Generator().manual_seed(5)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=g) + 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=g) * 0.2
+    B, H, W = 2, 64, 96
+    x1 = torch.from_numpy(synthetic.rgb_image(B, H, W, seed=31))
+    x2 = torch.from_numpy(synthetic.lidar_image(B, H, W, seed=32))
+    tgt = torch.from_numpy(synthetic.target_maps(B, H, W, seed=33))
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    out = {"x1": x1.numpy(), "x2": x2.numpy(), "target": tgt.numpy(),
+           "model_cfg": np.array([16, 2, 2, 2, 2, 32, 2, c2, cb])}
+    for k, v in sd0.items():
+        out["sd/" + k] = v.numpy()
+    m32 = copy.deepcopy(model)
+    logits, loss = _train_step(m32, x1, x2, tgt, torch.float32)
+    out["logits32"] = logits.numpy()
+    out["loss32"] = loss.numpy()
+    for k, p in m32.named_parameters():
+        out["grad32/" + k] = p.grad.numpy()
+    for k, v in m32.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out["new/" + k] = v.numpy()
+    m64 = copy.deepcopy(model)
+    logits, loss = _train_step(m64, x1, x2, tgt, torch.float64)
+    out["logits64"] = logits.float().numpy()
+    out["loss64_sum"] = np.array([loss.sum().item()])
+    for k, p in m64.named_parameters():
+        out["grad64/" + k] = p.grad.float().numpy()
+    # eval-mode forward with the updated running stats (fp64)
+    m64.eval()
+    with torch.no_grad():
+        out["eval_logits64"] = m64(x1.double(), x2.double()).float().numpy()
+    # the reference's own bf16 yard-stick: CPU autocast(bfloat16) vs fp64 (SURVEY 8(c) protocol item 5)
+    mbf = copy.deepcopy(model)
+    mbf.train()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        lg = mbf(x1, x2)
+        ls = torch.nn.BCEWithLogitsLoss(reduction="none")(lg.float(), tgt)
+    ls.backward(torch.ones_like(ls))
+    out["logits_bf16_autocast"] = lg.detach().float().numpy()
+    for k, p in mbf.named_parameters():
+        out["gradbf16/" + k] = p.grad.float().numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_unet_%s.npz" % fusion), **out)
+    print("tiny_unet_%s.npz" % fusion, len(out), "arrays; params", sum(p.numel() for p in model.parameters()))
+
+
+def dn121_probe():
+    model_mod, _ = ref_shim.ref_modules()
+    cfg = ref_shim.ref_config(stream_2_in_channels=1, concat_before_block_num=3)
+    torch.manual_seed(123)
+    model = model_mod.densenet121_u_lidar(pretrained=False, config=cfg)
+    B, H, W = 1, 64, 96
+    x1 = torch.from_numpy(synthetic.rgb_image(B, H, W, seed=41))
+    x2 = torch.from_numpy(synthetic.lidar_image(B, H, W, seed=42))
+    tgt = torch.from_numpy(synthetic.target_maps(B, H, W, seed=43))
+    out = {}
+    names, sums, asums = [], [], []
+    for k, v in model.state_dict().items():
+        if v.is_floating_point():
+            names.append(k)
+            sums.append(v.double().sum().item())
+            asums.append(v.double().abs().sum().item())
+    out["param_names"] = np.array(names)
+    out["param_sum"] = np.array(sums)
+    out["param_abs_sum"] = np.array(asums)
+    logits, loss = _train_step(model, x1, x2, tgt, torch.float32)
+    out["logits32"] = logits.numpy()
+    out["loss32_per_class"] = loss.double().sum(dim=(0, 2, 3)).numpy()
+    gn = {k: p.grad.double().norm().item() for k, p in model.named_parameters()}
+    out["grad_names"] = np.array(list(gn.keys()))
+    out["grad_norm32"] = np.array(list(gn.values()))
+    out["grad_refine1"] = dict(model.named_parameters())["dec_out_to_heat_maps.refine1.weight"].grad.numpy()
+    out["num_params"] = np.array([model.num_params])
+    np.savez_compressed(os.path.join(OUT, "dn121_mid_probe.npz"), **out)
+    print("dn121_mid_probe.npz num_params", model.num_params)
+
+
+if __name__ == "__main__":
+    lidar_heatmap()
+    for f in ("no", "early", "mid"):
+        tiny_unet(f)
+    dn121_probe()

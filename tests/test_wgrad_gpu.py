@@ -1,0 +1,85 @@
+"""Parity of the tcgen05 weight-gradient GEMM (dmm_conv_wgrad + dmm_unpack_wgrad) with the weight
+gradients torch autograd computes for nn.Conv2d / nn.ConvTranspose2d (aten::convolution_backward),
+fp64 on identical bf16-rounded inputs.  fp32 accumulation: relL2 <= 1e-4."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from dmmfods_b200 import ops
+from gpu_util import bf16_round, rel_l2, to_mat
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _conv_wgrad_case(B, Cin, Cout, H, W, K, seed, n_tile=None, splits=0):
+    torch.manual_seed(seed)
+    pad = (K - 1) // 2
+    x = bf16_round(torch.randn(B, Cin, H, W))
+    g = bf16_round(torch.randn(B, Cout, H, W))
+    w = torch.zeros(Cout, Cin, K, K, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, padding=pad).backward(g.double())
+    ref = w.grad
+    xm = to_mat(x, ld=ops.ceil_to(Cin, 8))
+    N = ops.ceil_to(Cout, 16)
+    gm = to_mat(g, ld=N)
+    fwd, _, off = ops.conv_taps(K, pad)
+    T = K * K
+    dw = torch.zeros(T, Cin, N, dtype=torch.float32, device="cuda")
+    d = ops.make_wgrad(xm.view(0, Cin), [gm.view(0, N)], fwd, W, H, B, Cin, N, dw, N, n_tile=n_tile, splits=splits)
+    ops.run_wgrad(d)
+    grad = torch.full((Cout, Cin, K, K), float("nan"), dtype=torch.float32, device="cuda")
+    ops.unpack_wgrad(dw, N, Cin, Cout, grad, T, off, Cin * K * K, K * K)
+    torch.cuda.synchronize()
+    err = rel_l2(grad.cpu(), ref)
+    assert err < TOL, "wgrad K=%d Cin=%d Cout=%d n_tile=%s: relL2 %.3e" % (K, Cin, Cout, n_tile, err)
+
+
+@pytest.mark.parametrize("Cin,Cout,n_tile", [(128, 128, None), (256, 128, 64), (96, 128, 128), (64, 64, 64),
+                                             (1024, 256, 256), (136, 64, None)])
+def test_wgrad_1x1(Cin, Cout, n_tile):
+    _conv_wgrad_case(2, Cin, Cout, 12, 20, 1, seed=Cin + Cout, n_tile=n_tile)
+
+
+@pytest.mark.parametrize("n_tile", [32, 64])
+def test_wgrad_3x3_growth(n_tile):
+    """conv2 of a dense layer: X = 128 bottleneck channels, Y = 32 growth channels (narrow N)."""
+    _conv_wgrad_case(2, 128, 32, 12, 20, 3, seed=21, n_tile=n_tile)
+
+
+def test_wgrad_3x3_odd_sizes_and_head():
+    _conv_wgrad_case(1, 128, 32, 7, 9, 3, seed=22, n_tile=64)
+    _conv_wgrad_case(2, 132, 64, 10, 14, 3, seed=23)
+
+
+def test_wgrad_5x5_three_classes():
+    _conv_wgrad_case(2, 64, 3, 12, 16, 5, seed=24)
+
+
+def test_wgrad_many_tiles_split():
+    _conv_wgrad_case(4, 256, 128, 64, 96, 1, seed=25, splits=0)
+    _conv_wgrad_case(4, 128, 32, 32, 48, 3, seed=26, splits=7)
+
+
+@pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (64, 5, 7, 9, 13)])
+def test_wgrad_conv_transpose(C, H, W, OH, OW):
+    torch.manual_seed(C + OH)
+    B = 2
+    x = bf16_round(torch.randn(B, C, H, W))
+    g = bf16_round(torch.randn(B, C, OH, OW))
+    oph, opw = OH - ((H - 1) * 2 - 2 + 3), OW - ((W - 1) * 2 - 2 + 3)
+    w = torch.zeros(C, C, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv_transpose2d(x.double(), w, stride=2, padding=1, output_padding=(oph, opw)).backward(g.double())
+    ref = w.grad
+    xm = to_mat(x)
+    gm = to_mat(g)
+    taps, off = ops.convt_wgrad_taps()
+    ys = [gm.phase_view(py, px) for py in range(2) for px in range(2)]
+    dw = torch.zeros(9, C, C, dtype=torch.float32, device="cuda")
+    d = ops.make_wgrad(xm.view(), ys, taps, W, H, B, C, C, dw, C)
+    ops.run_wgrad(d)
+    grad = torch.full((C, C, 3, 3), float("nan"), dtype=torch.float32, device="cuda")
+    ops.unpack_wgrad(dw, C, C, C, grad, 9, off, 9, C * 9)      # weight (Cin=m, Cout=n, kh, kw)
+    torch.cuda.synchronize()
+    err = rel_l2(grad.cpu(), ref)
+    assert err < TOL, "convT wgrad relL2 %.3e" % err
