@@ -84,12 +84,15 @@ SIGNATURES = {
     "dmm_last_error": (C.c_char_p, []),
     "dmm_version": (C.c_int, []),
     "dmm_device_ok": (C.c_int, []),
+    "dmm_sizeof": (C.c_int, [C.c_int]),
     "dmm_conv_igemm": (C.c_int, [C.POINTER(Igemm), c_void_p]),
     "dmm_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), c_void_p]),
     "dmm_pack_weights": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                    C.POINTER(c_int32), c_int64, c_int64, c_void_p]),
     "dmm_unpack_wgrad": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, C.POINTER(c_int32),
                                    c_int64, c_int64, c_int32, c_void_p]),
+    "dmm_pack_weights_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
+    "dmm_unpack_wgrad_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_bn_relu_apply": (C.c_int, [C.POINTER(BnApply), c_void_p]),
     "dmm_bn_relu_bwd_reduce": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),
     "dmm_bn_relu_bwd_apply": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),

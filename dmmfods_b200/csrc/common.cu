@@ -98,3 +98,21 @@ extern "C" int dmm_device_ok(void) {
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
     return prop.major == 10 ? 1 : 0;
 }
+
+/* sizeof() of every struct that crosses the C-ABI, so that a binding can verify its own layout. */
+extern "C" int dmm_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(dmm_view_t);
+        case 1: return (int)sizeof(dmm_igemm_t);
+        case 2: return (int)sizeof(dmm_wgrad_t);
+        case 3: return (int)sizeof(dmm_bn_t);
+        case 4: return (int)sizeof(dmm_bn_apply_t);
+        case 5: return (int)sizeof(dmm_bn_bwd_t);
+        case 6: return (int)sizeof(dmm_bn_bwd_args_t);
+        case 7: return (int)sizeof(dmm_head_t);
+        case 8: return (int)sizeof(dmm_head_bwd_t);
+        case 9: return (int)sizeof(dmm_pack_job_t);
+        case 10: return (int)sizeof(dmm_unpack_job_t);
+        default: return -1;
+    }
+}

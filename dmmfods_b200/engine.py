@@ -1,0 +1,714 @@
+"""Execution engine of the Dense-U-Net hot path: turns the reference graph
+(Dense_U_Net_lidar.forward, dmmfods/graphs/models/Dense_U_Net_lidar.py:210-267, with torchvision's
+_DenseLayer/_DenseBlock/_Transition, tv:31-133) into two static programs of C-ABI kernel launches
+(forward, backward) over preallocated HBM buffers.
+
+Data layout in HBM (all per engine = per (B, H, W)):
+  * dense-block buffers: one bf16 matrix [P_b, C_total_b] per block; every layer's conv2 writes its
+    `growth_rate` channels in place at its channel offset (no torch.cat); the same buffer is the U-Net skip.
+  * per dense layer: a1 = relu(norm1(concat)) [P, C_i], z1 = conv1 output [P, 4k], a2 = relu(norm2(z1))
+    [P, 4k] - kept for backward (11 + 6 + 6 GB at BASELINE config 3; 180 GB HBM makes recompute unnecessary).
+  * batch statistics: double[8 slots][2][C] rows accumulated by the producing kernel's epilogue; a raw
+    channel's statistics are computed ONCE and shared by every later BatchNorm that normalises it.
+  * gradients w.r.t. block buffers: fp32 [P_b, C_total_b] (accumulated over all consuming layers);
+    every other activation gradient is a bf16 matrix; weight gradients: fp32 split-K accumulators that
+    are scattered into a flat fp32 gradient buffer in parameter layout.
+All launches go to torch's current stream, there is no host synchronisation and no allocation after
+construction, so a whole step can be captured in a CUDA graph.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import Head, HeadBwd
+from .ops import Mat, Stats, ceil_to
+
+
+class Op:
+    __slots__ = ("fn", "arg", "gbuf", "name")
+
+    def __init__(self, fn, arg, name, gbuf=None):
+        self.fn, self.arg, self.name, self.gbuf = fn, arg, name, gbuf
+
+
+class _Arena:
+    """bump allocator over one torch tensor (zeroed in one memset per step)."""
+
+    def __init__(self, numel, dtype, device):
+        self.buf = torch.zeros(numel, dtype=dtype, device=device)
+        self.used = 0
+
+    def take(self, n, align=64):
+        off = ceil_to(self.used, align)
+        if off + n > self.buf.numel():
+            raise RuntimeError("dmmfods_b200: arena exhausted (%d + %d > %d)" % (off, n, self.buf.numel()))
+        self.used = off + n
+        return off
+
+    def zero_used(self):
+        self.buf[:self.used].zero_()
+
+
+class _BNInfo:
+    def __init__(self, eng, prefix, C_):
+        self.prefix, self.C = prefix, C_
+        self.gamma = eng.p[prefix + ".weight"]
+        self.beta = eng.p[prefix + ".bias"]
+        self.rm = eng.p[prefix + ".running_mean"]
+        self.rv = eng.p[prefix + ".running_var"]
+        off = eng._save.take(2 * C_, 4)
+        self.save_mean = eng._save.buf[off:off + C_]
+        self.save_invstd = eng._save.buf[off + C_:off + 2 * C_]
+        self.dgamma = eng.grad[prefix + ".weight"]
+        self.dbeta = eng.grad[prefix + ".bias"]
+
+
+class Engine:
+    def __init__(self, params, model_cfg, B, H, W, training=True, need_backward=True, plan_only=False):
+        """params: dict name -> CUDA tensor with the reference's state_dict keys (parameters fp32, BN buffers);
+        model_cfg: mapping with the keys of helper:111-123.  plan_only=True builds the launch programs without a
+        GPU (host-logic tests); such an engine cannot run."""
+        self.lib = _lib.load() if plan_only else ops.require_device()
+        self.plan_only = plan_only
+        self.p = params
+        self.training = training
+        self.need_backward = need_backward and training
+        any_p = next(iter(params.values()))
+        self.dev = any_p.device
+        self.B, self.H, self.W = B, H, W
+        m = model_cfg
+        self.k = int(m["growth_rate"])
+        self.block_config = tuple(int(v) for v in m["block_config"])
+        self.nif = int(m["num_init_features"])
+        self.bnk = int(m["bn_size"]) * self.k
+        self.c1 = int(m["stream_1_in_channels"])
+        self.c2 = int(m["stream_2_in_channels"])
+        self.cb = int(m["concat_before_block_num"])
+        self.ncls = int(m["num_classes"])
+        nb = len(self.block_config)
+        if self.cb == 1 and self.c2 == 0:
+            self.fusion = "no"
+        elif self.cb == 1 and self.c2 > 0:
+            self.fusion = "early"
+        elif 1 < self.cb <= nb:
+            self.fusion = "mid"
+        else:
+            raise AttributeError("invalid fusion configuration")
+        if m.get("drop_rate", 0):
+            raise NotImplementedError("drop_rate > 0 is not supported by the CUDA path (reference default is 0)")
+        for v in (self.k, self.nif, self.bnk):
+            if v % 8:
+                raise ValueError("channel counts must be multiples of 8 for the bf16 pixel-major layout (got %d)" % v)
+        if H % 2 or W % 2:
+            raise ValueError("input height/width must be even (the reference's final torch.cat fails otherwise)")
+
+        # ---- flat gradient buffer (fp32, parameter layout) -------------------------------------------
+        self.param_names = [k for k, v in params.items() if v.is_floating_point() and "running_" not in k]
+        total = sum(params[k].numel() for k in self.param_names)
+        self.gflat = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.grad = {}
+        off = 0
+        for k in self.param_names:
+            n = params[k].numel()
+            self.grad[k] = self.gflat[off:off + n].view(params[k].shape)
+            off += n
+
+        self._stats = _Arena(4 << 20, torch.float64, self.dev)
+        self._sums = _Arena(4 << 20, torch.float64, self.dev)
+        self._save = _Arena(1 << 20, torch.float32, self.dev)
+        self._dw = None          # sized after planning
+        self._wpk = None
+        self._dw_req = []
+        self._wpk_req = []
+        self._pack_jobs = []
+        self._unpack_jobs = []
+        self._tmp = {}
+        self.fwd = []
+        self._bwd_stages = []
+        self.nbt_keys = [k for k in params if k.endswith("num_batches_tracked")]
+        self.mem_bytes = 0
+
+        self.in1 = torch.zeros(B, self.c1, H, W, dtype=torch.float32, device=self.dev)
+        self.in2 = torch.zeros(B, max(self.c2, 1), H, W, dtype=torch.float32, device=self.dev)
+        self.logits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
+        self.dlogits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
+        self.class_sums = torch.zeros(self.ncls, dtype=torch.float64, device=self.dev)
+
+        self._plan()
+        self._finalize()
+
+    # ------------------------------------------------------------------------------------------------
+    # small allocation helpers
+    # ------------------------------------------------------------------------------------------------
+    def _mat(self, B, H, W, ld):
+        self.mem_bytes += B * H * W * ld * 2
+        return Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self.dev), B, H, W)
+
+    def _tmpmat(self, tag, B, H, W, ld):
+        key = (tag, B, H, W, ld)
+        if key not in self._tmp:
+            self._tmp[key] = self._mat(B, H, W, ld)
+        return self._tmp[key]
+
+    def _f32(self, rows, ld):
+        self.mem_bytes += rows * ld * 4
+        return torch.empty((rows, ld), dtype=torch.float32, device=self.dev)
+
+    def _new_stats(self, ld):
+        return Stats(self._stats.buf, self._stats.take(Stats.size(ld)), ld)
+
+    def _new_sums(self, ld):
+        return Stats(self._sums.buf, self._sums.take(Stats.size(ld)), ld)
+
+    # deferred arenas: record requests, resolve pointers in _finalize()
+    def _req_wpk(self, n_rows, ktot):
+        self._wpk_req.append(n_rows * ktot)
+        return len(self._wpk_req) - 1
+
+    def _req_dw(self, numel):
+        self._dw_req.append(numel)
+        return len(self._dw_req) - 1
+
+    # ------------------------------------------------------------------------------------------------
+    # op emitters
+    # ------------------------------------------------------------------------------------------------
+    def _emit(self, lst, fn, arg, name, gbuf=None):
+        lst.append(Op(fn, arg, name, gbuf))
+
+    def _conv_fwd(self, lst, name, wname, srcs, taps, tap_off, Cin, Cout, sn, sc, W, H, B, out, coff, stats, stats_off,
+                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None):
+        """emit pack job + igemm launch for a forward convolution (or one ConvTranspose phase)."""
+        T = len(taps)
+        Kp = ceil_to(Cin, ops.KWIDTH)
+        n_tile = ops.pick_n_tile(Cout)
+        n_rows = ceil_to(Cout, n_tile)
+        if not self.training:
+            stats = None
+        wid = self._req_wpk(n_rows, T * Kp)
+        self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cout, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off,
+                                    sn=sn, sc=sc))
+        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cout,
+                           out_ptr if out_ptr is not None else out.ptr(), 0 if out is None else out.ld, coff=coff,
+                           out_mode=out_mode, stats=stats, stats_off=stats_off, out_stride=out_stride,
+                           out_phase=out_phase, out_hw=out_hw, n_tile=n_tile)
+        self._emit(lst, self.lib.dmm_conv_igemm, d, name)
+        self._fix_w.append((d, wid))
+        return d
+
+    def _conv_dgrad(self, lst, name, wname, srcs, taps, tap_off, Cg, Cin, sn, sc, W, H, B, out):
+        """data gradient: igemm over the output-gradient views `srcs` (Cg channels) -> out [P, >=Cin]."""
+        T = len(taps)
+        Kp = ceil_to(Cg, ops.KWIDTH)
+        n_tile = ops.pick_n_tile(Cin)
+        n_rows = ceil_to(Cin, n_tile)
+        wid = self._req_wpk(n_rows, T * Kp)
+        self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cin, n_rows=n_rows, C=Cg, T=T, tap_off=tap_off,
+                                    sn=sn, sc=sc))
+        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cin, out.ptr(), out.ld, n_tile=n_tile)
+        self._emit(lst, self.lib.dmm_conv_igemm, d, name)
+        self._fix_w.append((d, wid))
+
+    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B):
+        """weight gradient: wgrad into a zeroed fp32 scratch + unpack job into the flat gradient buffer."""
+        T = len(taps)
+        did = self._req_dw(T * M * N)
+        d = ops.make_wgrad(x, ys, taps, W, H, B, M, N, 0, N)
+        self._emit(lst, self.lib.dmm_conv_wgrad, d, name)
+        self._fix_dw.append((d, did))
+        self._unpack_jobs.append(dict(did=did, grad=self.grad[wname], ldw=N, M=Mvalid, Mld=M, N=Nvalid, T=T,
+                                      tap_off=tap_off, sn=sn, sc=sc))
+
+    def _bn_fwd(self, bn, stats, stats_off, count, c0=0, rep=1.0):
+        return ops.make_bn(stats, stats_off, count, bn.gamma, bn.beta, bn.rm, bn.rv, bn.save_mean, bn.save_invstd,
+                           training=self.training, rep=rep, c0=c0)
+
+    def _apply(self, lst, name, bn, x, xc0, C_, stats, stats_off, y, yc0, pool=0, ystats=None, ystats_off=0, bn_c0=0,
+               count=None):
+        b = self._bn_fwd(bn, stats, stats_off, x.P if count is None else count, c0=bn_c0)
+        if not self.training:
+            ystats = None
+        d = ops.make_bn_apply(x, xc0, C_, b, y, yc0, pool=pool, ystats=ystats, ystats_off=ystats_off)
+        self._emit(lst, self.lib.dmm_bn_relu_apply, d, name)
+
+    def _bn_bwd(self, lst, name, bn, x, xc0, C_, g_ptr, ldg, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False, bn_c0=0,
+                gbuf=None):
+        sums = self._new_sums(C_)
+        b = ops.make_bn_bwd(sums, 0, x.P, bn.gamma, bn.beta, bn.save_mean, bn.save_invstd, bn.dgamma, bn.dbeta, c0=bn_c0)
+        d = ops.make_bn_bwd_args(x, xc0, C_, g_ptr, ldg, b, out_ptr, ldo, out_mode, gmode=gmode, g_is_f32=g_is_f32)
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce")
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d, name + ".apply", gbuf=gbuf)
+
+    def _cast(self, lst, name, src, c0, C_, dst):
+        def run(_arg, stream, src=src, c0=c0, C_=C_, dst=dst, lib=self.lib):
+            return lib.dmm_rows_f32_to_bf16(C.c_void_p(src.data_ptr() + 4 * c0), src.shape[1], dst.ptr(), dst.ld,
+                                            src.shape[0], C_, stream)
+        self._emit(lst, run, None, name)
+
+    # ------------------------------------------------------------------------------------------------
+    # the plan
+    # ------------------------------------------------------------------------------------------------
+    def _plan(self):
+        B, H, W = self.B, self.H, self.W
+        k, bnk = self.k, self.bnk
+        nb = len(self.block_config)
+        self._fix_w, self._fix_dw = [], []
+        fwd = self.fwd
+        H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        H4, W4 = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
+        res = [(H4, W4)]
+        for _ in range(nb - 1):
+            res.append((res[-1][0] // 2, res[-1][1] // 2))
+        if min(res[-1]) < 1:
+            raise ValueError("input %dx%d is too small for %d dense blocks" % (H, W, nb))
+        for b in range(nb - 1):
+            if res[b][0] % 2 or res[b][1] % 2:
+                raise ValueError("feature map %s of dense block %d is odd: the reference's ConvTranspose2d "
+                                 "output_size check fails for this input size" % (res[b], b + 1))
+
+        # channel bookkeeping (Dense_U_Net_lidar.py:81-100)
+        cin_blk, ctot_blk = [], []
+        nf = self.nif
+        for b, L in enumerate(self.block_config):
+            cin_blk.append(nf)
+            nf += L * k
+            ctot_blk.append(nf)
+            if b != nb - 1:
+                nf //= 2
+
+        class Blk:
+            pass
+
+        def new_block(b):
+            o = Blk()
+            o.H, o.W = res[b]
+            o.C0, o.Ct = cin_blk[b], ctot_blk[b]
+            o.buf = self._mat(B, o.H, o.W, o.Ct)
+            o.stats = self._new_stats(o.Ct)
+            o.G = self._f32(B * o.H * o.W, o.Ct) if self.need_backward else None
+            return o
+
+        conv1x1 = ops.conv_taps(1, 0)
+        conv3x3 = ops.conv_taps(3, 1)
+
+        # ---------------- stem (features.conv0/norm0/relu0/pool0) ----------------
+        def stem(prefix, x1, c1, x2, c2, blk):
+            cin = c1 + c2
+            kpad = ceil_to(cin * 49, 8)
+            col = self._mat(B, H2, W2, kpad)
+
+            def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
+                return lib.dmm_im2col_7x7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
+                                            B, H, W, col.ptr(), col.ld, stream)
+            self._emit(fwd, run_im2col, None, prefix + ".im2col")
+            z0 = self._mat(B, H2, W2, self.nif)
+            z0s = self._new_stats(self.nif)
+            self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
+                           cin * 49, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0)
+            bn0 = _BNInfo(self, prefix + ".norm0", self.nif)
+            self._apply(fwd, prefix + ".norm0+pool0", bn0, z0, 0, self.nif, z0s, 0, blk.buf, 0, pool=2, ystats=blk.stats)
+            if self.need_backward:
+                st = []
+                dz0 = self._tmpmat("dz0", B, H2, W2, self.nif)
+                self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, blk.G.data_ptr(), blk.Ct, dz0.ptr(), dz0.ld, 0,
+                             gmode=2, g_is_f32=True)
+                self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
+                                 [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
+                self._bwd_stages.append(st)
+
+        # ---------------- dense block ----------------
+        def dense_block(prefix, blk, L):
+            Hb, Wb = blk.H, blk.W
+            for i in range(L):
+                Ci = blk.C0 + i * k
+                lp = "%s.denselayer%d" % (prefix, i + 1)
+                bn1 = _BNInfo(self, lp + ".norm1", Ci)
+                bn2 = _BNInfo(self, lp + ".norm2", bnk)
+                a1 = self._mat(B, Hb, Wb, Ci)
+                z1 = self._mat(B, Hb, Wb, bnk)
+                a2 = self._mat(B, Hb, Wb, bnk)
+                z1s = self._new_stats(bnk)
+                self._apply(fwd, lp + ".norm1", bn1, blk.buf, 0, Ci, blk.stats, 0, a1, 0)
+                self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [a1.view()], conv1x1[0], conv1x1[2], Ci, bnk, Ci, 1,
+                               Wb, Hb, B, z1, 0, z1s, 0)
+                self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
+                self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [a2.view()], conv3x3[0], conv3x3[2], bnk, k,
+                               bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
+                if self.need_backward:
+                    st = []
+                    kk = ceil_to(k, 8)
+                    go = self._tmpmat("go", B, Hb, Wb, kk)
+                    da2 = self._tmpmat("da2", B, Hb, Wb, bnk)
+                    dz1 = self._tmpmat("dz1", B, Hb, Wb, bnk)
+                    da1 = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
+                    self._cast(st, lp + ".gout", blk.G, Ci, k, go)
+                    self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", a2.view(), [go.view(0, k)], conv3x3[0],
+                                     conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B)
+                    self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
+                                     k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
+                    self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0)
+                    self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", a1.view(), [dz1.view()], conv1x1[0],
+                                     conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B)
+                    self._conv_dgrad(st, lp + ".conv1.dgrad", lp + ".conv1.weight", [dz1.view()], conv1x1[1], conv1x1[2],
+                                     bnk, Ci, 1, Ci, Wb, Hb, B, da1)
+                    self._bn_bwd(st, lp + ".norm1.bwd", bn1, blk.buf, 0, Ci, da1.ptr(), da1.ld, blk.G.data_ptr(), blk.Ct, 2,
+                                 gbuf=blk)
+                    self._bwd_stages.append(st)
+
+        # ---------------- transition: BN-ReLU -> (avg-pool first) -> 1x1 conv ----------------
+        def transition(prefix, blk, out, out_stats, out_G, out_is_block):
+            """out: Mat receiving Ct/2 channels at column 0 (next block buffer or a concat-module input)."""
+            Ct, Co = blk.Ct, blk.Ct // 2
+            bn = _BNInfo(self, prefix + ".norm", Ct)
+            ap = self._mat(B, out.H, out.W, Ct)
+            self._apply(fwd, prefix + ".norm+pool", bn, blk.buf, 0, Ct, blk.stats, 0, ap, 0, pool=1)
+            self._conv_fwd(fwd, prefix + ".conv", prefix + ".conv.weight", [ap.view()], conv1x1[0], conv1x1[2], Ct, Co, Ct, 1,
+                           out.W, out.H, B, out, 0, out_stats, 0)
+            if self.need_backward:
+                st = []
+                if out_is_block:          # gradient lives in the fp32 block gradient buffer
+                    gt = self._tmpmat("gt", B, out.H, out.W, Co)
+                    self._cast(st, prefix + ".gout", out_G, 0, Co, gt)
+                else:                     # bf16 gradient matrix written by the concat module backward
+                    gt = out_G
+                dap = self._tmpmat("dap", B, out.H, out.W, Ct)
+                self._conv_wgrad(st, prefix + ".conv.wgrad", prefix + ".conv.weight", ap.view(), [gt.view(0, Co)], conv1x1[0],
+                                 conv1x1[2], Ct, Co, Ct, Co, Ct, 1, out.W, out.H, B)
+                self._conv_dgrad(st, prefix + ".conv.dgrad", prefix + ".conv.weight", [gt.view(0, Co)], conv1x1[1], conv1x1[2],
+                                 Co, Ct, 1, Ct, out.W, out.H, B, dap)
+                self._bn_bwd(st, prefix + ".norm.bwd", bn, blk.buf, 0, Ct, dap.ptr(), dap.ld, blk.G.data_ptr(), blk.Ct, 2,
+                             gmode=1, gbuf=blk)
+                self._bwd_stages.append(st)
+
+        # ================= encoder =================
+        s1_blocks = [new_block(b) for b in range(nb)]
+        x2 = self.in2 if self.fusion == "early" else None
+        stem("features", self.in1, self.c1, x2, self.c2 if self.fusion == "early" else 0, s1_blocks[0])
+
+        s2_t = None
+        if self.fusion == "mid":
+            s2_blocks = [new_block(b) for b in range(self.cb - 1)]
+            stem("stream_2_features", self.in2, self.c2, None, 0, s2_blocks[0])
+            Cc = ctot_blk[self.cb - 2] // 2
+            hc, wc = res[self.cb - 1]
+            t2 = self._mat(B, hc, wc, Cc)
+            t2s = self._new_stats(Cc)
+            dt2 = self._tmpmat("dt2", B, hc, wc, Cc) if self.need_backward else None
+            for b in range(self.cb - 1):
+                dense_block("stream_2_features.denseblock%d" % (b + 1), s2_blocks[b], self.block_config[b])
+                last = b == self.cb - 2
+                if last:
+                    transition("stream_2_features.transition%d" % (b + 1), s2_blocks[b], t2, t2s, dt2, False)
+                else:
+                    nxt = s2_blocks[b + 1]
+                    transition("stream_2_features.transition%d" % (b + 1), s2_blocks[b], nxt.buf, nxt.stats, nxt.G, True)
+            s2_t = (t2, t2s, dt2)
+
+        for b in range(nb):
+            blk = s1_blocks[b]
+            dense_block("features.denseblock%d" % (b + 1), blk, self.block_config[b])
+            if b == nb - 1:
+                break
+            nxt = s1_blocks[b + 1]
+            if self.fusion == "mid" and b + 1 == self.cb - 1:
+                Cc = blk.Ct // 2
+                t1 = self._mat(B, nxt.H, nxt.W, Cc)
+                t1s = self._new_stats(Cc)
+                dt1 = self._tmpmat("dt1", B, nxt.H, nxt.W, Cc) if self.need_backward else None
+                transition("features.transition%d" % (b + 1), blk, t1, t1s, dt1, False)
+                # concat_module: BN(2C) -> ReLU -> 1x1 conv 2C -> C over cat(stream_1, stream_2) (:186-192, :242-245)
+                t2, t2s, dt2 = s2_t
+                bn = _BNInfo(self, "concat_module.norm", 2 * Cc)
+                acat = self._mat(B, nxt.H, nxt.W, 2 * Cc)
+                self._apply(fwd, "concat_module.norm[s1]", bn, t1, 0, Cc, t1s, 0, acat, 0)
+                self._apply(fwd, "concat_module.norm[s2]", bn, t2, 0, Cc, t2s, 0, acat, Cc, bn_c0=Cc)
+                self._conv_fwd(fwd, "concat_module.conv", "concat_module.conv.weight", [acat.view()], conv1x1[0], conv1x1[2],
+                               2 * Cc, Cc, 2 * Cc, 1, nxt.W, nxt.H, B, nxt.buf, 0, nxt.stats, 0)
+                if self.need_backward:
+                    st = []
+                    gt = self._tmpmat("gt", B, nxt.H, nxt.W, Cc)
+                    dacat = self._tmpmat("dacat", B, nxt.H, nxt.W, 2 * Cc)
+                    self._cast(st, "concat_module.gout", nxt.G, 0, Cc, gt)
+                    self._conv_wgrad(st, "concat_module.conv.wgrad", "concat_module.conv.weight", acat.view(), [gt.view()],
+                                     conv1x1[0], conv1x1[2], 2 * Cc, Cc, 2 * Cc, Cc, 2 * Cc, 1, nxt.W, nxt.H, B)
+                    self._conv_dgrad(st, "concat_module.conv.dgrad", "concat_module.conv.weight", [gt.view()], conv1x1[1],
+                                     conv1x1[2], Cc, 2 * Cc, 1, 2 * Cc, nxt.W, nxt.H, B, dacat)
+                    self._bn_bwd(st, "concat_module.norm.bwd[s1]", bn, t1, 0, Cc, dacat.ptr(0), dacat.ld, dt1.ptr(), dt1.ld, 0)
+                    self._bn_bwd(st, "concat_module.norm.bwd[s2]", bn, t2, 0, Cc, dacat.ptr(Cc), dacat.ld, dt2.ptr(), dt2.ld, 0,
+                                 bn_c0=Cc)
+                    self._bwd_stages.append(st)
+            else:
+                transition("features.transition%d" % (b + 1), blk, nxt.buf, nxt.stats, nxt.G, True)
+
+        # ================= decoder (:105-120, :255-261) =================
+        fstack = [self.nif + 2 * k] + ctot_blk            # feature_size_stack (:81-82,95)
+        sizes = [(H2, W2)] + [res[b] for b in range(nb - 1)]
+        cur = s1_blocks[nb - 1]                            # raw input of Sequence_1 = block4 buffer
+        cur_raw, cur_stats, cur_C = cur.buf, cur.stats, cur.Ct
+        num_in = fstack.pop()
+        up_prev = None                                     # (u Mat, stats, du Mat) of the previous ConvTranspose
+        for kdec in range(1, nb + 1):
+            num_f = fstack.pop()
+            sp = "decoder.Transposed_Convolution_Sequence_%d" % kdec
+            cp = "decoder.Transposed_Convolution_%d" % kdec
+            bn0 = _BNInfo(self, sp + ".norm0", num_in)
+            bn1 = _BNInfo(self, sp + ".norm1", num_f)
+            if kdec == 1:
+                hk, wk = cur.H, cur.W
+                a = self._mat(B, hk, wk, num_in)
+                self._apply(fwd, sp + ".norm0", bn0, cur_raw, 0, num_in, cur_stats, 0, a, 0)
+                skip_blk = None
+            else:
+                u, us, du = up_prev
+                skip_blk = s1_blocks[nb - kdec]
+                hk, wk = skip_blk.H, skip_blk.W
+                Cu = u.ld
+                assert Cu + skip_blk.Ct == num_in
+                a = self._mat(B, hk, wk, num_in)
+                self._apply(fwd, sp + ".norm0[up]", bn0, u, 0, Cu, us, 0, a, 0)
+                self._apply(fwd, sp + ".norm0[skip]", bn0, skip_blk.buf, 0, skip_blk.Ct, skip_blk.stats, 0, a, Cu, bn_c0=Cu)
+            r = self._mat(B, hk, wk, num_f)
+            rs = self._new_stats(num_f)
+            self._conv_fwd(fwd, sp + ".conv_reduce", sp + ".conv_reduce.weight", [a.view()], conv1x1[0], conv1x1[2], num_in,
+                           num_f, num_in, 1, wk, hk, B, r, 0, rs, 0)
+            a1 = self._mat(B, hk, wk, num_f)
+            self._apply(fwd, sp + ".norm1", bn1, r, 0, num_f, rs, 0, a1, 0)
+            oh, ow = sizes.pop()
+            for dim_in, dim_out in ((hk, oh), (wk, ow)):
+                if not (2 * dim_in - 1 <= dim_out <= 2 * dim_in):
+                    raise ValueError("requested an output size of %s, but valid sizes range from %d to %d"
+                                     % ((oh, ow), 2 * dim_in - 1, 2 * dim_in))
+            unew = self._mat(B, oh, ow, num_f)
+            unews = self._new_stats(num_f)
+            for py in range(2):
+                for px in range(2):
+                    taps, off = ops.convt_phase_taps(py, px)
+                    self._conv_fwd(fwd, cp + "[%d%d]" % (py, px), cp + ".weight", [a1.view()], taps, off, num_f, num_f, 9,
+                                   num_f * 9, wk, hk, B, unew, 0, unews, 0, out_stride=(2, 2), out_phase=(py, px),
+                                   out_hw=(oh, ow))
+            dunew = self._mat(B, oh, ow, num_f) if self.need_backward else None
+            if self.need_backward:
+                st = []
+                da1 = self._tmpmat("dec_da1", B, hk, wk, num_f)
+                dr = self._tmpmat("dec_dr", B, hk, wk, num_f)
+                da = self._tmpmat("dec_da", B, hk, wk, num_in)
+                wt, woff = ops.convt_wgrad_taps()
+                dt, doff = ops.convt_dgrad_taps()
+                phases = [dunew.phase_view(py, px) for py in range(2) for px in range(2)]
+                self._conv_wgrad(st, cp + ".wgrad", cp + ".weight", a1.view(), phases, wt, woff, num_f, num_f, num_f, num_f, 9,
+                                 num_f * 9, wk, hk, B)
+                self._conv_dgrad(st, cp + ".dgrad", cp + ".weight", phases, dt, doff, num_f, num_f, num_f * 9, 9, wk, hk, B, da1)
+                self._bn_bwd(st, sp + ".norm1.bwd", bn1, r, 0, num_f, da1.ptr(), da1.ld, dr.ptr(), dr.ld, 0)
+                self._conv_wgrad(st, sp + ".conv_reduce.wgrad", sp + ".conv_reduce.weight", a.view(), [dr.view()], conv1x1[0],
+                                 conv1x1[2], num_in, num_f, num_in, num_f, num_in, 1, wk, hk, B)
+                self._conv_dgrad(st, sp + ".conv_reduce.dgrad", sp + ".conv_reduce.weight", [dr.view()], conv1x1[1], conv1x1[2],
+                                 num_f, num_in, 1, num_in, wk, hk, B, da)
+                if kdec == 1:
+                    self._bn_bwd(st, sp + ".norm0.bwd", bn0, cur_raw, 0, num_in, da.ptr(), da.ld, cur.G.data_ptr(), cur.Ct, 2,
+                                 gbuf=cur)
+                else:
+                    self._bn_bwd(st, sp + ".norm0.bwd[up]", bn0, u, 0, Cu, da.ptr(0), da.ld, du.ptr(), du.ld, 0)
+                    self._bn_bwd(st, sp + ".norm0.bwd[skip]", bn0, skip_blk.buf, 0, skip_blk.Ct, da.ptr(Cu), da.ld,
+                                 skip_blk.G.data_ptr(), skip_blk.Ct, 2, bn_c0=Cu, gbuf=skip_blk)
+                self._bwd_stages.append(st)
+            up_prev = (unew, unews, dunew)
+            num_in = num_f * 2
+
+        # ================= head (:120-132, :264-265) =================
+        u, us, du = up_prev
+        Cu = u.ld
+        cx = self.c1 + self.c2
+        Ct = Cu + cx
+        if (2 * u.H, 2 * u.W) != (H, W):
+            raise RuntimeError("Sizes of tensors must match except in dimension 1 (decoder output %dx%d vs input %dx%d)"
+                               % (2 * u.H, 2 * u.W, H, W))
+        hp = "dec_out_to_heat_maps"
+        bn0 = _BNInfo(self, hp + ".norm0", Ct)
+        nf2 = Cu // 2
+        bn1 = _BNInfo(self, hp + ".norm1", nf2)
+        xst = self._new_stats(8 if cx <= 8 else ceil_to(cx, 8))
+        ld0 = ceil_to(Ct, 8)
+        a0 = self._mat(B, H, W, ld0)
+
+        def run_xstats(_a, stream, lib=self.lib):
+            rc = lib.dmm_nchw_stats(C.c_void_p(self.in1.data_ptr()), B, self.c1, H * W, xst.ptr(), xst.ld, 0, stream)
+            if rc == 0 and self.c2:
+                rc = lib.dmm_nchw_stats(C.c_void_p(self.in2.data_ptr()), B, self.c2, H * W, xst.ptr(), xst.ld, self.c1, stream)
+            return rc
+        if self.training:
+            self._emit(fwd, run_xstats, None, hp + ".input_stats")
+        hd = Head()
+        hd.u, hd.ldu, hd.Cu = u.ptr().value, u.ld, Cu
+        hd.x1, hd.C1 = self.in1.data_ptr(), self.c1
+        hd.x2, hd.C2 = (self.in2.data_ptr() if self.c2 else None), self.c2
+        hd.B, hd.H, hd.W = B, H, W
+        hd.bn_u = self._bn_fwd(bn0, us, 0, u.P, rep=4.0)
+        hd.bn_x = self._bn_fwd(bn0, xst, 0, B * H * W, c0=Cu)
+        hd.out, hd.ldo = a0.ptr().value, a0.ld
+        self._emit(fwd, self.lib.dmm_head_input, hd, hp + ".upsample+cat+norm0")
+        r0 = self._mat(B, H, W, nf2)
+        r0s = self._new_stats(nf2)
+        self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
+                       W, H, B, r0, 0, r0s, 0)
+        a1h = self._mat(B, H, W, nf2)
+        self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
+        conv5 = ops.conv_taps(5, 2)
+        self._conv_fwd(fwd, hp + ".refine1", hp + ".refine1.weight", [a1h.view()], conv5[0], conv5[2], nf2, self.ncls, nf2 * 25,
+                       25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
+        if self.need_backward:
+            st = []
+            ncp = ceil_to(self.ncls, 16)
+            dl = self._mat(B, H, W, ncp)
+
+            def run_dl(_a, stream, lib=self.lib, dl=dl):
+                return lib.dmm_nchw_to_nhwc_bf16(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, dl.ptr(), dl.ld, stream)
+            self._emit(st, run_dl, None, hp + ".dlogits")
+            da1h = self._tmpmat("head_da1", B, H, W, nf2)
+            dr0 = self._tmpmat("head_dr0", B, H, W, nf2)
+            da0 = self._tmpmat("head_da0", B, H, W, ld0)
+            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view()], conv5[0], conv5[2], nf2,
+                             ncp, nf2, self.ncls, nf2 * 25, 25, W, H, B)
+            self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view()], conv5[1], conv5[2], ncp, nf2, 25,
+                             nf2 * 25, W, H, B, da1h)
+            # packed dgrad weights must only contain the ncls valid channels (C = ncp would read past the tensor)
+            self._pack_jobs[-1]["C"] = self.ncls
+            self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0)
+            self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
+                             conv3x3[2], Ct, nf2, Ct, nf2, Ct * 9, 9, W, H, B)
+            self._conv_dgrad(st, hp + ".refine0.dgrad", hp + ".refine0.weight", [dr0.view()], conv3x3[1], conv3x3[2], nf2, Ct, 9,
+                             Ct * 9, W, H, B, da0)
+            hb = HeadBwd()
+            hb.u, hb.ldu, hb.Cu = u.ptr().value, u.ld, Cu
+            hb.x1, hb.C1 = self.in1.data_ptr(), self.c1
+            hb.x2, hb.C2 = (self.in2.data_ptr() if self.c2 else None), self.c2
+            hb.B, hb.H, hb.W = B, H, W
+            hb.g, hb.ldg = da0.ptr().value, da0.ld
+            su, sx = self._new_sums(Cu), self._new_sums(8 if cx <= 8 else ceil_to(cx, 8))
+            hb.bn_u = ops.make_bn_bwd(su, 0, B * H * W, bn0.gamma, bn0.beta, bn0.save_mean, bn0.save_invstd, bn0.dgamma,
+                                      bn0.dbeta)
+            hb.bn_x = ops.make_bn_bwd(sx, 0, B * H * W, bn0.gamma, bn0.beta, bn0.save_mean, bn0.save_invstd, bn0.dgamma,
+                                      bn0.dbeta, c0=Cu)
+            hb.du, hb.lddu = du.ptr().value, du.ld
+            self._emit(st, self.lib.dmm_head_input_bwd_reduce, hb, hp + ".norm0.bwd.reduce")
+            self._emit(st, self.lib.dmm_head_input_bwd_apply, hb, hp + ".norm0.bwd.apply")
+            self._bwd_stages.append(st)
+
+    # ------------------------------------------------------------------------------------------------
+    def _finalize(self):
+        dev = self.dev
+        # packed weights arena
+        offs, tot = [], 0
+        for n in self._wpk_req:
+            offs.append(tot)
+            tot += ceil_to(n, 512)      # 1 KiB alignment for TMA
+        self._wpk = torch.zeros(max(tot, 1), dtype=torch.bfloat16, device=dev)
+        self.mem_bytes += tot * 2
+        base = self._wpk.data_ptr()
+        for d, wid in self._fix_w:
+            d.weights = base + 2 * offs[wid]
+        pj = np.zeros(len(self._pack_jobs), dtype=_PACK_DT)
+        for i, j in enumerate(self._pack_jobs):
+            pj[i]["w"] = j["w"].data_ptr()
+            pj[i]["dst"] = base + 2 * offs[j["wid"]]
+            pj[i]["n_valid"], pj[i]["n_rows"], pj[i]["C"], pj[i]["T"] = j["n_valid"], j["n_rows"], j["C"], j["T"]
+            pj[i]["kwidth"] = ops.KWIDTH
+            pj[i]["tap_off"][:j["T"]] = j["tap_off"]
+            pj[i]["sn"], pj[i]["sc"] = j["sn"], j["sc"]
+        self._pack_tab = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
+        self._n_pack = len(self._pack_jobs)
+        self._param_ptrs = [j["w"].data_ptr() for j in self._pack_jobs]
+        self._pack_src = [j["w"] for j in self._pack_jobs]
+        # weight-gradient scratch arena
+        offs, tot = [], 0
+        for n in self._dw_req:
+            offs.append(tot)
+            tot += ceil_to(n, 64)
+        self._dw = torch.zeros(max(tot, 1), dtype=torch.float32, device=dev)
+        self.mem_bytes += tot * 4
+        base = self._dw.data_ptr()
+        for d, did in self._fix_dw:
+            d.dw = base + 4 * offs[did]
+        uj = np.zeros(len(self._unpack_jobs), dtype=_UNPACK_DT)
+        for i, j in enumerate(self._unpack_jobs):
+            uj[i]["dw"] = base + 4 * offs[j["did"]]
+            uj[i]["grad"] = j["grad"].data_ptr()
+            uj[i]["ldw"], uj[i]["M"], uj[i]["Mld"], uj[i]["N"], uj[i]["T"] = j["ldw"], j["M"], j["Mld"], j["N"], j["T"]
+            uj[i]["accumulate"] = 0
+            uj[i]["tap_off"][:j["T"]] = j["tap_off"]
+            uj[i]["sn"], uj[i]["sc"] = j["sn"], j["sc"]
+        self._unpack_tab = torch.from_numpy(uj.view(np.uint8).copy()).to(dev)
+        self._n_unpack = len(self._unpack_jobs)
+        # backward program = stages in reverse forward order; first writer of a block gradient buffer stores
+        self.bwd = []
+        for st in reversed(self._bwd_stages):
+            self.bwd.extend(st)
+        seen = set()
+        for op in self.bwd:
+            if op.gbuf is not None:
+                op.arg.out_mode = 2 if id(op.gbuf) in seen else 1
+                seen.add(id(op.gbuf))
+        self.nbt = [self.p[k] for k in self.nbt_keys]
+
+    # ------------------------------------------------------------------------------------------------
+    def _run(self, program):
+        if self.plan_only:
+            raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        byref = C.byref
+        for op in program:
+            rc = op.fn(byref(op.arg), stream) if op.arg is not None else op.fn(None, stream)
+            if rc != 0:
+                raise RuntimeError("dmmfods_b200: %s failed (rc=%d): %s" % (op.name, rc, _lib.last_error()))
+
+    def check_param_pointers(self):
+        for t, ptr in zip(self._pack_src, self._param_ptrs):
+            if t.data_ptr() != ptr:
+                raise RuntimeError("dmmfods_b200: a parameter tensor was re-allocated after the engine was built")
+
+    def forward(self, x1, x2):
+        """logits (B, num_classes, H, W) fp32 - engine-owned buffer, valid until the next forward()."""
+        if self.plan_only:
+            raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
+        self.in1.copy_(x1)
+        if self.c2:
+            self.in2.copy_(x2)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if self.training:
+            self._stats.zero_used()
+        _lib.check(self.lib.dmm_pack_weights_batched(C.c_void_p(self._pack_tab.data_ptr()), self._n_pack, stream),
+                   "dmm_pack_weights_batched")
+        self._run(self.fwd)
+        if self.training and self.nbt:
+            torch._foreach_add_(self.nbt, 1)
+        return self.logits
+
+    def backward(self, dlogits=None):
+        """gradient of all parameters for the cotangent dlogits (defaults to the engine's own dlogits buffer, as
+        filled by loss()).  Results land in self.grad[name] (views of the flat fp32 buffer self.gflat)."""
+        if not self.need_backward:
+            raise RuntimeError("engine was built without backward support")
+        if dlogits is not None:
+            self.dlogits.copy_(dlogits)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._sums.zero_used()
+        self._dw.zero_()
+        self._run(self.bwd)
+        _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(self._unpack_tab.data_ptr()), self._n_unpack, stream),
+                   "dmm_unpack_wgrad_batched")
+        return self.grad
+
+    def loss(self, target, loss_out=None):
+        """BCEWithLogits(reduction='none') of the current logits; fills dlogits (= d sum(loss) / d logits) and
+        the per-class loss sums (Agent.py:247-249)."""
+        self.class_sums.zero_()
+        ops.bce_logits(self.logits, target, loss_out, self.dlogits, self.class_sums)
+        return self.class_sums
+
+
+_PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32), ("n_rows", np.int32), ("C", np.int32),
+                     ("kwidth", np.int32), ("T", np.int32), ("tap_off", np.int32, (32,)), ("sn", np.int64),
+                     ("sc", np.int64)], align=True)
+_UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("ldw", np.int64), ("M", np.int32), ("Mld", np.int32),
+                       ("N", np.int32), ("T", np.int32), ("accumulate", np.int32), ("tap_off", np.int32, (32,)),
+                       ("sn", np.int64), ("sc", np.int64)], align=True)

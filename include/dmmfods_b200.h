@@ -289,6 +289,11 @@ int dmm_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   void* stream);
 
+/* sizeof() of the structs above in declaration order (0 = dmm_view_t, 1 = dmm_igemm_t, 2 = dmm_wgrad_t,
+ * 3 = dmm_bn_t, 4 = dmm_bn_apply_t, 5 = dmm_bn_bwd_t, 6 = dmm_bn_bwd_args_t, 7 = dmm_head_t,
+ * 8 = dmm_head_bwd_t, 9 = dmm_pack_job_t, 10 = dmm_unpack_job_t) so a binding can verify its layout. */
+int dmm_sizeof(int which);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,7 +275,7 @@ def test_bce_logits_loss_and_grad():
     assert torch.allclose(cs.cpu(), ref.detach().sum(dim=(0, 2, 3)), rtol=1e-6)
     # the fp32 torch op the reference runs (Agent.py:54): agreement to fp32 round-off
     ref32 = F.binary_cross_entropy_with_logits(x, t, reduction="none")
-    assert torch.allclose(loss.cpu(), ref32, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(loss.cpu(), ref32, rtol=1e-5, atol=2e-6)   # |x| ~ 30: fp32 cancellation in x - x*t
 
 
 def test_layout_converters():

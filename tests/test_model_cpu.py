@@ -1,0 +1,148 @@
+"""CPU tests of the host-side mirror: module tree / state_dict contract, initialisation sequence, config
+defaults, error behaviour, and that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import pytest
+import torch
+
+from dmmfods_b200 import _lib, config as cfgmod
+from dmmfods_b200.model import Dense_U_Net_lidar, densenet121_u_lidar, densenet201_u_lidar
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(c2=1, cb=3, **kw):
+    c = cfgmod.get_config("/nonexistent")
+    c.model.stream_2_in_channels = c2
+    c.model.concat_before_block_num = cb
+    for k, v in kw.items():
+        setattr(c.model, k, v)
+    return c
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dmmfods_b200.h")).read()
+    declared = set(re.findall(r"\b(dmm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "symbol %s missing from libdmmfods_b200.so" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.dmm_version() >= 100
+
+
+def test_struct_layouts_match_header_sizes():
+    import ctypes
+    from dmmfods_b200 import engine
+    lib = _lib.load()
+    binding = [_lib.View, _lib.Igemm, _lib.Wgrad, _lib.Bn, _lib.BnApply, _lib.BnBwd, _lib.BnBwdArgs, _lib.Head,
+               _lib.HeadBwd]
+    for i, st in enumerate(binding):
+        assert ctypes.sizeof(st) == lib.dmm_sizeof(i), (st.__name__, ctypes.sizeof(st), lib.dmm_sizeof(i))
+    assert engine._PACK_DT.itemsize == lib.dmm_sizeof(9)
+    assert engine._UNPACK_DT.itemsize == lib.dmm_sizeof(10)
+
+
+def test_default_config_matches_reference_defaults():
+    c = cfgmod.get_config("/nonexistent")
+    assert c.model.growth_rate == 32 and tuple(c.model.block_config) == (6, 12, 24, 16)
+    assert c.model.concat_before_block_num == 2 and c.model.stream_2_in_channels == 1
+    assert c.agent.seed == 123 and c.optimizer.learning_rate == 1e-3
+    if ref_shim.reference_available():
+        _, helper = ref_shim.ref_modules()
+        r = helper.get_config("/nonexistent")
+        for sec in ("model", "loss", "loader", "optimizer", "dataset", "agent", "scripts"):
+            assert dict(c[sec]) == dict(r[sec]), sec
+
+
+@pytest.mark.parametrize("c2,cb,fusion", [(0, 1, "no"), (1, 1, "early"), (1, 2, "mid"), (1, 3, "mid"), (1, 4, "mid")])
+def test_fusion_modes_and_param_counts(c2, cb, fusion):
+    m = densenet121_u_lidar(pretrained=False, config=_cfg(c2, cb))
+    assert m.fusion == fusion
+    expect = {(0, 1): 22004102, (1, 1): 22007816, (1, 2): 22409544, (1, 3): 23560136}
+    if (c2, cb) in expect:
+        assert m.num_params == expect[(c2, cb)]       # SURVEY Appendix A [probe]
+    assert m.concat_after_module_idx == 3 + 2 * (cb - 1)
+
+
+def test_invalid_fusion_raises_attribute_error():
+    with pytest.raises(AttributeError):
+        Dense_U_Net_lidar(_cfg(1, 5))
+    with pytest.raises(AttributeError):
+        Dense_U_Net_lidar(_cfg(0, 0))
+
+
+def test_cpu_call_fails_loudly():
+    m = densenet121_u_lidar(pretrained=False, config=_cfg(0, 1))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 96), torch.zeros(1, 1, 64, 96))
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+@pytest.mark.parametrize("c2,cb", [(0, 1), (1, 1), (1, 2), (1, 3)])
+def test_state_dict_and_init_identical_to_reference(c2, cb):
+    model_mod, _ = ref_shim.ref_modules()
+    torch.manual_seed(123)
+    ref = model_mod.densenet121_u_lidar(pretrained=False, config=ref_shim.ref_config(c2, cb))
+    torch.manual_seed(123)
+    ours = densenet121_u_lidar(pretrained=False, config=_cfg(c2, cb))
+    sr, so = ref.state_dict(), ours.state_dict()
+    assert list(sr.keys()) == list(so.keys())
+    for k in sr:
+        assert sr[k].shape == so[k].shape and sr[k].dtype == so[k].dtype, k
+        assert torch.equal(sr[k], so[k]), "initial value of %s differs" % k
+    ours.load_state_dict(sr, strict=True)
+    ref.load_state_dict(so, strict=True)
+    assert [k for k, _ in ref.named_parameters()] == [k for k, _ in ours.named_parameters()]
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_densenet201_keys_match_reference():
+    model_mod, _ = ref_shim.ref_modules()
+    with torch.device("meta"):
+        ref = model_mod.densenet201_u_lidar(pretrained=False, config=ref_shim.ref_config(1, 3))
+        ours = densenet201_u_lidar(pretrained=False, config=_cfg(1, 3))
+    assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == \
+           {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+    assert ours.num_params == 57346504
+
+
+@pytest.mark.parametrize("c2,cb", [(0, 1), (1, 1), (1, 2), (1, 3), (1, 4)])
+def test_engine_plan_covers_every_parameter(c2, cb):
+    """host logic without a GPU: the launch programs are built for every fusion mode, every convolution weight
+    has a pack job (forward + data gradient) and an unpack job (weight gradient), every BatchNorm a backward."""
+    from dmmfods_b200.engine import Engine
+    c = _cfg(c2, cb, growth_rate=16, block_config=(2, 3, 2, 2), num_init_features=32, bn_size=2)
+    m = Dense_U_Net_lidar(c)
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    eng = Engine(params, m.model_cfg(), 2, 64, 96, plan_only=True)
+    conv_w = {k for k, v in params.items() if v.dim() == 4}
+    bn_w = {k for k, v in params.items() if v.dim() == 1 and k.endswith(".weight")}
+    unpacked = {id(j["grad"]) for j in eng._unpack_jobs}
+    assert unpacked == {id(eng.grad[k]) for k in conv_w}
+    names = [op.name for op in eng.bwd]
+    for k in bn_w:
+        pre = k[:-len(".weight")]
+        assert any(n.startswith(pre + ".bwd") for n in names), pre
+    assert len({op.name for op in eng.fwd}) == len(eng.fwd)
+    # first writer of each block-gradient buffer stores, later ones accumulate
+    seen = {}
+    for op in eng.bwd:
+        if op.gbuf is not None:
+            assert op.arg.out_mode == (2 if id(op.gbuf) in seen else 1)
+            seen[id(op.gbuf)] = True
+    with pytest.raises(RuntimeError):
+        eng.forward(torch.zeros(2, 3, 64, 96), torch.zeros(2, 1, 64, 96))
+
+
+def test_engine_rejects_sizes_the_reference_rejects():
+    from dmmfods_b200.engine import Engine
+    c = _cfg(1, 3, growth_rate=16, block_config=(2, 2, 2, 2), num_init_features=32, bn_size=2)
+    m = Dense_U_Net_lidar(c)
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    with pytest.raises(ValueError):
+        Engine(params, m.model_cfg(), 1, 72, 96, plan_only=True)     # 72/4 = 18 -> 9 is odd at block 2
+    with pytest.raises(ValueError):
+        Engine(params, m.model_cfg(), 1, 63, 96, plan_only=True)
