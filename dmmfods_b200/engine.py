@@ -17,6 +17,7 @@ All launches go to torch's current stream, there is no host synchronisation and 
 construction, so a whole step can be captured in a CUDA graph.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -125,6 +126,7 @@ class Engine:
         self._pack_jobs = []
         self._unpack_jobs = []
         self._tmp = {}
+        self._keep = []
         self.fwd = []
         self._bwd_stages = []
         self.nbt_keys = [k for k in params if k.endswith("num_batches_tracked")]
@@ -144,7 +146,9 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     def _mat(self, B, H, W, ld):
         self.mem_bytes += B * H * W * ld * 2
-        return Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self.dev), B, H, W)
+        m = Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self.dev), B, H, W)
+        self._keep.append(m)      # launch descriptors hold raw addresses only
+        return m
 
     def _tmpmat(self, tag, B, H, W, ld):
         key = (tag, B, H, W, ld)
@@ -154,7 +158,9 @@ class Engine:
 
     def _f32(self, rows, ld):
         self.mem_bytes += rows * ld * 4
-        return torch.empty((rows, ld), dtype=torch.float32, device=self.dev)
+        t = torch.empty((rows, ld), dtype=torch.float32, device=self.dev)
+        self._keep.append(t)
+        return t
 
     def _new_stats(self, ld):
         return Stats(self._stats.buf, self._stats.take(Stats.size(ld)), ld)
@@ -276,6 +282,11 @@ class Engine:
             ctot_blk.append(nf)
             if b != nb - 1:
                 nf //= 2
+
+        for c in cin_blk + ctot_blk + [v // 2 for v in ctot_blk[:-1]]:
+            if c % 8:
+                raise ValueError("dense-block channel count %d is not a multiple of 8 (bf16 pixel-major layout needs "
+                                 "16-byte channel groups); choose growth_rate / block_config accordingly" % c)
 
         class Blk:
             pass
@@ -656,10 +667,16 @@ class Engine:
             raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         byref = C.byref
+        debug = bool(os.environ.get("DMM_DEBUG_SYNC"))
         for op in program:
             rc = op.fn(byref(op.arg), stream) if op.arg is not None else op.fn(None, stream)
             if rc != 0:
                 raise RuntimeError("dmmfods_b200: %s failed (rc=%d): %s" % (op.name, rc, _lib.last_error()))
+            if debug:
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:      # noqa: BLE001
+                    raise RuntimeError("dmmfods_b200: kernel of op %s faulted: %s" % (op.name, e))
 
     def check_param_pointers(self):
         for t, ptr in zip(self._pack_src, self._param_ptrs):

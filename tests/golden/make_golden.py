@@ -78,7 +78,16 @@ def _train_step(model, x1, x2, tgt, dtype):
     return logits.detach(), loss.detach()
 
 
-def tiny_unet(fusion):
+def _gerr(a_params, b_params):
+    num = sum(((p.grad.double() - q.grad.double()) ** 2).sum().item() for p, q in zip(a_params, b_params))
+    den = sum((q.grad.double() ** 2).sum().item() for q in b_params)
+    return (num / den) ** 0.5
+
+
+def tiny_unet(fusion, B=2, H=64, W=96, tag=None, store_sd=True):
+    """golden for a small Dense_U_Net_lidar.  Stored: state_dict, inputs (small case) or their seeds + checksum
+    (large case), fp64 logits / loss / gradients / updated BN buffers, and the ERROR LEVELS of the reference's own
+    fp32 run and of its own torch.autocast(bfloat16) run against fp64 (the bf16 yard-stick)."""
     import copy
     model_mod, _ = ref_shim.ref_modules()
     c2, cb = {"no": (0, 1), "early": (1, 1), "mid": (1, 3)}[fusion]
@@ -93,46 +102,50 @@ def tiny_unet(fusion):
         if isinstance(m, torch.nn.BatchNorm2d):
             m.weight.data = torch.rand(m.weight.shape, generator=g) + 0.5
             m.bias.data = torch.randn(m.bias.shape, generator=g) * 0.2
-    B, H, W = 2, 64, 96
     x1 = torch.from_numpy(synthetic.rgb_image(B, H, W, seed=31))
     x2 = torch.from_numpy(synthetic.lidar_image(B, H, W, seed=32))
     tgt = torch.from_numpy(synthetic.target_maps(B, H, W, seed=33))
-    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
-    out = {"x1": x1.numpy(), "x2": x2.numpy(), "target": tgt.numpy(),
+    out = {"shape": np.array([B, H, W]), "seeds": np.array([31, 32, 33]),
+           "input_checksum": np.array([x1.double().sum().item(), x2.double().sum().item(), tgt.double().sum().item()]),
            "model_cfg": np.array([16, 2, 2, 2, 2, 32, 2, c2, cb])}
-    for k, v in sd0.items():
-        out["sd/" + k] = v.numpy()
-    m32 = copy.deepcopy(model)
-    logits, loss = _train_step(m32, x1, x2, tgt, torch.float32)
-    out["logits32"] = logits.numpy()
-    out["loss32"] = loss.numpy()
-    for k, p in m32.named_parameters():
-        out["grad32/" + k] = p.grad.numpy()
-    for k, v in m32.state_dict().items():
-        if "running" in k or "num_batches" in k:
-            out["new/" + k] = v.numpy()
+    if store_sd:
+        for k, v in model.state_dict().items():
+            out["sd/" + k] = v.numpy()
     m64 = copy.deepcopy(model)
-    logits, loss = _train_step(m64, x1, x2, tgt, torch.float64)
-    out["logits64"] = logits.float().numpy()
-    out["loss64_sum"] = np.array([loss.sum().item()])
+    logits64, loss64 = _train_step(m64, x1, x2, tgt, torch.float64)
+    out["logits64"] = logits64.float().numpy()
+    out["loss64_sum"] = np.array([loss64.sum().item()])
+    out["loss64_per_class"] = loss64.sum(dim=(0, 2, 3)).numpy()
     for k, p in m64.named_parameters():
         out["grad64/" + k] = p.grad.float().numpy()
-    # eval-mode forward with the updated running stats (fp64)
-    m64.eval()
-    with torch.no_grad():
-        out["eval_logits64"] = m64(x1.double(), x2.double()).float().numpy()
-    # the reference's own bf16 yard-stick: CPU autocast(bfloat16) vs fp64 (SURVEY 8(c) protocol item 5)
+    for k, v in m64.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out["new/" + k] = v.float().numpy() if v.is_floating_point() else v.numpy()
+    # the reference's own fp32 run
+    m32 = copy.deepcopy(model)
+    logits32, loss32 = _train_step(m32, x1, x2, tgt, torch.float32)
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    out["ref_fp32_err"] = np.array([rel(logits32, logits64), _gerr(list(m32.parameters()), list(m64.parameters()))])
+    if H * W <= 64 * 96:
+        out["logits32"] = logits32.numpy()
+        out["loss32"] = loss32.numpy()
+    # the reference's own bf16 yard-stick: CPU autocast(bfloat16) vs fp64
     mbf = copy.deepcopy(model)
     mbf.train()
     with torch.autocast("cpu", dtype=torch.bfloat16):
         lg = mbf(x1, x2)
-        ls = torch.nn.BCEWithLogitsLoss(reduction="none")(lg.float(), tgt)
+    ls = torch.nn.BCEWithLogitsLoss(reduction="none")(lg.float(), tgt)
     ls.backward(torch.ones_like(ls))
-    out["logits_bf16_autocast"] = lg.detach().float().numpy()
-    for k, p in mbf.named_parameters():
-        out["gradbf16/" + k] = p.grad.float().numpy()
-    np.savez_compressed(os.path.join(OUT, "tiny_unet_%s.npz" % fusion), **out)
-    print("tiny_unet_%s.npz" % fusion, len(out), "arrays; params", sum(p.numel() for p in model.parameters()))
+    out["ref_bf16_autocast_err"] = np.array([rel(lg.detach().float(), logits64),
+                                             _gerr(list(mbf.parameters()), list(m64.parameters()))])
+    # eval-mode forward with the updated running stats (fp64)
+    m64.eval()
+    with torch.no_grad():
+        out["eval_logits64"] = m64(x1.double(), x2.double()).float().numpy()
+    name = "tiny_unet_%s.npz" % (tag or fusion)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, len(out), "arrays; params", sum(p.numel() for p in model.parameters()),
+          "ref fp32 err", out["ref_fp32_err"], "ref bf16 err", out["ref_bf16_autocast_err"])
 
 
 def dn121_probe():
@@ -170,4 +183,5 @@ if __name__ == "__main__":
     lidar_heatmap()
     for f in ("no", "early", "mid"):
         tiny_unet(f)
+    tiny_unet("mid", B=2, H=256, W=384, tag="mid_large", store_sd=False)     # BASELINE config-1 resolution
     dn121_probe()
