@@ -38,6 +38,7 @@ struct IgemmKParams {
 };
 
 constexpr int kThreads = 192;
+constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
 template <int OUT_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -328,13 +329,15 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
 
     const size_t smem = (size_t)stages * stage_bytes + 256 + (size_t)8 * d->n_tile * sizeof(float) + 1024;
     dim3 grid((unsigned)((long long)p.tiles_x * p.tiles_y * d->B), (unsigned)ceil_div(d->N, d->n_tile), 1);
-    if (d->out_mode == 0) {
-        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        igemm_kernel<0><<<grid, kThreads, smem, stream>>>(p);
-    } else {
-        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        igemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    static bool attr_set = false;      // opt in to the full 227 KB of shared memory once (not a stream operation)
+    if (!attr_set) {
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        attr_set = true;
     }
+    DMM_CHECK(smem <= (size_t)kMaxSmem, "dmm_conv_igemm: %zu bytes of shared memory requested", smem);
+    if (d->out_mode == 0) igemm_kernel<0><<<grid, kThreads, smem, stream>>>(p);
+    else igemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
     DMM_LAUNCH_CHECK("igemm_kernel");
     return 0;
 }

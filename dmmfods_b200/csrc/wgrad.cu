@@ -207,7 +207,12 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
     p.splits = (int)splits;
 
     const size_t smem = (size_t)stages * stage_bytes + 256 + 1024;
-    DMM_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMM_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set = true;
+    }
+    DMM_CHECK(smem <= 232448, "dmm_conv_wgrad: %zu bytes of shared memory requested", smem);
     dim3 grid((unsigned)p.splits, (unsigned)(p.m_tiles * n_tiles), (unsigned)d->num_taps);
     wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(p);
     DMM_LAUNCH_CHECK("wgrad_kernel");

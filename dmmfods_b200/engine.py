@@ -28,10 +28,13 @@ from .ops import Mat, Stats, ceil_to
 
 
 class Op:
-    __slots__ = ("fn", "arg", "gbuf", "name")
+    """one C-ABI launch.  kind / flops / bytes: kernel family and ALGORITHMIC work of the launch (each distinct
+    input element read once + each output written once; 2*M*N*K of the reference operator) for roofline reports."""
+    __slots__ = ("fn", "arg", "gbuf", "name", "kind", "flops", "bytes")
 
-    def __init__(self, fn, arg, name, gbuf=None):
+    def __init__(self, fn, arg, name, gbuf=None, kind="misc", flops=0.0, nbytes=0.0):
         self.fn, self.arg, self.name, self.gbuf = fn, arg, name, gbuf
+        self.kind, self.flops, self.bytes = kind, float(flops), float(nbytes)
 
 
 class _Arena:
@@ -67,7 +70,8 @@ class _BNInfo:
 
 
 class Engine:
-    def __init__(self, params, model_cfg, B, H, W, training=True, need_backward=True, plan_only=False):
+    def __init__(self, params, model_cfg, B, H, W, training=True, need_backward=True, plan_only=False,
+                 bucket_bytes=32 << 20):
         """params: dict name -> CUDA tensor with the reference's state_dict keys (parameters fp32, BN buffers);
         model_cfg: mapping with the keys of helper:111-123.  plan_only=True builds the launch programs without a
         GPU (host-logic tests); such an engine cannot run."""
@@ -105,48 +109,89 @@ class Engine:
         if H % 2 or W % 2:
             raise ValueError("input height/width must be even (the reference's final torch.cat fails otherwise)")
 
-        # ---- flat gradient buffer (fp32, parameter layout) -------------------------------------------
-        self.param_names = [k for k, v in params.items() if v.is_floating_point() and "running_" not in k]
-        total = sum(params[k].numel() for k in self.param_names)
+        # ---- flat gradient buffer (fp32): parameters ordered by the backward stage that finalises their
+        # gradient, so that gradient buckets (all-reduce overlap) are contiguous ranges --------------------
+        float_names = [k for k, v in params.items() if v.is_floating_point() and "running_" not in k]
+        self.nbt_keys = [k for k in params if k.endswith("num_batches_tracked")]
+        self.bucket_bytes = int(bucket_bytes)
+        self._dry = True
+        self._alloc_dev = torch.device("meta")
+        self.gflat = None
+        self.grad = {k: params[k] for k in float_names}       # placeholders for the dry pass (addresses unused)
+        self._reset_plan_state()
+        self._plan()
+        order, seen = [], set()
+        for st in reversed(self._bwd_stages):
+            for n in self._stage_params.get(id(st), []):
+                if n not in seen:
+                    seen.add(n)
+                    order.append(n)
+        if not self.need_backward:
+            order = list(float_names)
+        missing = [k for k in float_names if k not in set(order)]
+        if missing:
+            raise RuntimeError("dmmfods_b200: no backward stage produces the gradient of %s" % missing[:4])
+        self.param_names = order
+        total = sum(params[k].numel() for k in order)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=self.dev)
-        self.grad = {}
+        self.grad, self.grad_offset = {}, {}
         off = 0
-        for k in self.param_names:
+        for k in order:
             n = params[k].numel()
             self.grad[k] = self.gflat[off:off + n].view(params[k].shape)
+            self.grad_offset[k] = off
             off += n
 
-        self._stats = _Arena(4 << 20, torch.float64, self.dev)
-        self._sums = _Arena(4 << 20, torch.float64, self.dev)
-        self._save = _Arena(1 << 20, torch.float32, self.dev)
+        self._dry = False
+        self._alloc_dev = self.dev
+        self._reset_plan_state()
+        self.in1 = torch.zeros(B, self.c1, H, W, dtype=torch.float32, device=self.dev)
+        self.in2 = torch.zeros(B, max(self.c2, 1), H, W, dtype=torch.float32, device=self.dev)
+        self.logits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
+        self.dlogits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
+        self.class_sums = torch.zeros(self.ncls, dtype=torch.float64, device=self.dev)
+        self._plan()
+        self._finalize()
+
+    @staticmethod
+    def gradient_order(params, model_cfg, B, H, W):
+        """parameter names in the order of the engine's flat gradient buffer (= backward completion order)."""
+        e = Engine.__new__(Engine)
+        Engine.__init__(e, params, model_cfg, B, H, W, plan_only=True)
+        return list(e.param_names)
+
+    def _reset_plan_state(self):
+        if self._dry:      # meta arenas: only offsets matter
+            self._stats = _Arena(1 << 40, torch.float64, "meta")
+            self._sums = _Arena(1 << 40, torch.float64, "meta")
+            self._save = _Arena(1 << 34, torch.float32, "meta")
+        else:
+            self._stats = _Arena(4 << 20, torch.float64, self.dev)
+            self._sums = _Arena(4 << 20, torch.float64, self.dev)
+            self._save = _Arena(1 << 20, torch.float32, self.dev)
         self._dw = None          # sized after planning
         self._wpk = None
         self._dw_req = []
         self._wpk_req = []
         self._pack_jobs = []
         self._unpack_jobs = []
+        self._stage_params = {}
         self._tmp = {}
         self._keep = []
+        self.named = {}          # name -> Mat of the main raw activations (debugging / per-stage parity tests)
         self.fwd = []
         self._bwd_stages = []
-        self.nbt_keys = [k for k in params if k.endswith("num_batches_tracked")]
         self.mem_bytes = 0
-
-        self.in1 = torch.zeros(B, self.c1, H, W, dtype=torch.float32, device=self.dev)
-        self.in2 = torch.zeros(B, max(self.c2, 1), H, W, dtype=torch.float32, device=self.dev)
-        self.logits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
-        self.dlogits = torch.zeros(B, self.ncls, H, W, dtype=torch.float32, device=self.dev)
-        self.class_sums = torch.zeros(self.ncls, dtype=torch.float64, device=self.dev)
-
-        self._plan()
-        self._finalize()
+        if self._dry:
+            z = torch.empty(1, device="meta")
+            self.in1 = self.in2 = self.logits = self.dlogits = self.class_sums = z
 
     # ------------------------------------------------------------------------------------------------
     # small allocation helpers
     # ------------------------------------------------------------------------------------------------
     def _mat(self, B, H, W, ld):
         self.mem_bytes += B * H * W * ld * 2
-        m = Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self.dev), B, H, W)
+        m = Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self._alloc_dev), B, H, W)
         self._keep.append(m)      # launch descriptors hold raw addresses only
         return m
 
@@ -158,7 +203,7 @@ class Engine:
 
     def _f32(self, rows, ld):
         self.mem_bytes += rows * ld * 4
-        t = torch.empty((rows, ld), dtype=torch.float32, device=self.dev)
+        t = torch.empty((rows, ld), dtype=torch.float32, device=self._alloc_dev)
         self._keep.append(t)
         return t
 
@@ -180,8 +225,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------------
     # op emitters
     # ------------------------------------------------------------------------------------------------
-    def _emit(self, lst, fn, arg, name, gbuf=None):
-        lst.append(Op(fn, arg, name, gbuf))
+    def _emit(self, lst, fn, arg, name, gbuf=None, kind="misc", flops=0.0, nbytes=0.0):
+        lst.append(Op(fn, arg, name, gbuf, kind, flops, nbytes))
 
     def _conv_fwd(self, lst, name, wname, srcs, taps, tap_off, Cin, Cout, sn, sc, W, H, B, out, coff, stats, stats_off,
                   out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None):
@@ -199,7 +244,10 @@ class Engine:
                            out_ptr if out_ptr is not None else out.ptr(), 0 if out is None else out.ld, coff=coff,
                            out_mode=out_mode, stats=stats, stats_off=stats_off, out_stride=out_stride,
                            out_phase=out_phase, out_hw=out_hw, n_tile=n_tile)
-        self._emit(lst, self.lib.dmm_conv_igemm, d, name)
+        P = B * H * W
+        osz = 4 if out_mode == 1 else 2
+        self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_fprop", flops=2.0 * P * Cout * Cin * T,
+                   nbytes=P * (Cin * 2 + Cout * osz) + Cout * Cin * T * 2)
         self._fix_w.append((d, wid))
         return d
 
@@ -213,7 +261,9 @@ class Engine:
         self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cin, n_rows=n_rows, C=Cg, T=T, tap_off=tap_off,
                                     sn=sn, sc=sc))
         d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cin, out.ptr(), out.ld, n_tile=n_tile)
-        self._emit(lst, self.lib.dmm_conv_igemm, d, name)
+        P = B * H * W
+        self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_dgrad", flops=2.0 * P * Cin * Cg * T,
+                   nbytes=P * (Cg * 2 * (4 if len(srcs) == 4 else 1) + Cin * 2) + Cg * Cin * T * 2)
         self._fix_w.append((d, wid))
 
     def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B):
@@ -221,10 +271,13 @@ class Engine:
         T = len(taps)
         did = self._req_dw(T * M * N)
         d = ops.make_wgrad(x, ys, taps, W, H, B, M, N, 0, N)
-        self._emit(lst, self.lib.dmm_conv_wgrad, d, name)
+        P = B * H * W
+        self._emit(lst, self.lib.dmm_conv_wgrad, d, name, kind="wgrad", flops=2.0 * P * Mvalid * Nvalid * T,
+                   nbytes=P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4)
         self._fix_dw.append((d, did))
         self._unpack_jobs.append(dict(did=did, grad=self.grad[wname], ldw=N, M=Mvalid, Mld=M, N=Nvalid, T=T,
-                                      tap_off=tap_off, sn=sn, sc=sc))
+                                      tap_off=tap_off, sn=sn, sc=sc, stage=id(lst)))
+        self._stage_params.setdefault(id(lst), []).append(wname)
 
     def _bn_fwd(self, bn, stats, stats_off, count, c0=0, rep=1.0):
         return ops.make_bn(stats, stats_off, count, bn.gamma, bn.beta, bn.rm, bn.rv, bn.save_mean, bn.save_invstd,
@@ -236,21 +289,26 @@ class Engine:
         if not self.training:
             ystats = None
         d = ops.make_bn_apply(x, xc0, C_, b, y, yc0, pool=pool, ystats=ystats, ystats_off=ystats_off)
-        self._emit(lst, self.lib.dmm_bn_relu_apply, d, name)
+        self._emit(lst, self.lib.dmm_bn_relu_apply, d, name, kind="bn_relu_apply", nbytes=(x.P + y.P) * C_ * 2)
 
     def _bn_bwd(self, lst, name, bn, x, xc0, C_, g_ptr, ldg, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False, bn_c0=0,
                 gbuf=None):
+        self._stage_params.setdefault(id(lst), []).extend([bn.prefix + ".weight", bn.prefix + ".bias"])
         sums = self._new_sums(C_)
         b = ops.make_bn_bwd(sums, 0, x.P, bn.gamma, bn.beta, bn.save_mean, bn.save_invstd, bn.dgamma, bn.dbeta, c0=bn_c0)
         d = ops.make_bn_bwd_args(x, xc0, C_, g_ptr, ldg, b, out_ptr, ldo, out_mode, gmode=gmode, g_is_f32=g_is_f32)
-        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce")
-        self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d, name + ".apply", gbuf=gbuf)
+        pg = x.P if gmode == 0 else (x.P // 4)
+        rd = x.P * C_ * 2 + pg * C_ * (4 if g_is_f32 else 2)
+        wr = x.P * C_ * (2 if out_mode == 0 else (4 if gbuf is None else 8))
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce", kind="bn_relu_bwd_reduce", nbytes=rd)
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d, name + ".apply", gbuf=gbuf, kind="bn_relu_bwd_apply",
+                   nbytes=rd + wr)
 
     def _cast(self, lst, name, src, c0, C_, dst):
         def run(_arg, stream, src=src, c0=c0, C_=C_, dst=dst, lib=self.lib):
             return lib.dmm_rows_f32_to_bf16(C.c_void_p(src.data_ptr() + 4 * c0), src.shape[1], dst.ptr(), dst.ld,
                                             src.shape[0], C_, stream)
-        self._emit(lst, run, None, name)
+        self._emit(lst, run, None, name, kind="cast_f32_bf16", nbytes=src.shape[0] * C_ * 6)
 
     # ------------------------------------------------------------------------------------------------
     # the plan
@@ -300,6 +358,8 @@ class Engine:
             o.G = self._f32(B * o.H * o.W, o.Ct) if self.need_backward else None
             return o
 
+        self._blk_cls = Blk
+
         conv1x1 = ops.conv_taps(1, 0)
         conv3x3 = ops.conv_taps(3, 1)
 
@@ -312,9 +372,11 @@ class Engine:
             def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
                 return lib.dmm_im2col_7x7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
                                             B, H, W, col.ptr(), col.ld, stream)
-            self._emit(fwd, run_im2col, None, prefix + ".im2col")
+            self._emit(fwd, run_im2col, None, prefix + ".im2col", kind="im2col",
+                       nbytes=B * H * W * cin * 4 + B * H2 * W2 * kpad * 2)
             z0 = self._mat(B, H2, W2, self.nif)
             z0s = self._new_stats(self.nif)
+            self.named[prefix + ".conv0"] = z0
             self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
                            cin * 49, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0)
             bn0 = _BNInfo(self, prefix + ".norm0", self.nif)
@@ -394,12 +456,16 @@ class Engine:
 
         # ================= encoder =================
         s1_blocks = [new_block(b) for b in range(nb)]
+        for b, o in enumerate(s1_blocks):
+            self.named["features.denseblock%d" % (b + 1)] = o.buf
         x2 = self.in2 if self.fusion == "early" else None
         stem("features", self.in1, self.c1, x2, self.c2 if self.fusion == "early" else 0, s1_blocks[0])
 
         s2_t = None
         if self.fusion == "mid":
             s2_blocks = [new_block(b) for b in range(self.cb - 1)]
+            for b, o in enumerate(s2_blocks):
+                self.named["stream_2_features.denseblock%d" % (b + 1)] = o.buf
             stem("stream_2_features", self.in2, self.c2, None, 0, s2_blocks[0])
             Cc = ctot_blk[self.cb - 2] // 2
             hc, wc = res[self.cb - 1]
@@ -492,6 +558,8 @@ class Engine:
                                      % ((oh, ow), 2 * dim_in - 1, 2 * dim_in))
             unew = self._mat(B, oh, ow, num_f)
             unews = self._new_stats(num_f)
+            self.named["decoder.%d" % kdec] = unew
+            self.named["decoder.%d.reduce" % kdec] = r
             for py in range(2):
                 for px in range(2):
                     taps, off = ops.convt_phase_taps(py, px)
@@ -548,7 +616,7 @@ class Engine:
                 rc = lib.dmm_nchw_stats(C.c_void_p(self.in2.data_ptr()), B, self.c2, H * W, xst.ptr(), xst.ld, self.c1, stream)
             return rc
         if self.training:
-            self._emit(fwd, run_xstats, None, hp + ".input_stats")
+            self._emit(fwd, run_xstats, None, hp + ".input_stats", kind="nchw_stats", nbytes=B * H * W * cx * 4)
         hd = Head()
         hd.u, hd.ldu, hd.Cu = u.ptr().value, u.ld, Cu
         hd.x1, hd.C1 = self.in1.data_ptr(), self.c1
@@ -557,9 +625,12 @@ class Engine:
         hd.bn_u = self._bn_fwd(bn0, us, 0, u.P, rep=4.0)
         hd.bn_x = self._bn_fwd(bn0, xst, 0, B * H * W, c0=Cu)
         hd.out, hd.ldo = a0.ptr().value, a0.ld
-        self._emit(fwd, self.lib.dmm_head_input, hd, hp + ".upsample+cat+norm0")
+        self._emit(fwd, self.lib.dmm_head_input, hd, hp + ".upsample+cat+norm0", kind="head_input",
+                   nbytes=u.P * Cu * 2 + B * H * W * (cx * 4 + ld0 * 2))
         r0 = self._mat(B, H, W, nf2)
         r0s = self._new_stats(nf2)
+        self.named["head.a0"] = a0
+        self.named["head.refine0"] = r0
         self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
                        W, H, B, r0, 0, r0s, 0)
         a1h = self._mat(B, H, W, nf2)
@@ -574,7 +645,7 @@ class Engine:
 
             def run_dl(_a, stream, lib=self.lib, dl=dl):
                 return lib.dmm_nchw_to_nhwc_bf16(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, dl.ptr(), dl.ld, stream)
-            self._emit(st, run_dl, None, hp + ".dlogits")
+            self._emit(st, run_dl, None, hp + ".dlogits", kind="nchw_to_nhwc", nbytes=B * H * W * (self.ncls * 4 + ncp * 2))
             da1h = self._tmpmat("head_da1", B, H, W, nf2)
             dr0 = self._tmpmat("head_dr0", B, H, W, nf2)
             da0 = self._tmpmat("head_da0", B, H, W, ld0)
@@ -601,8 +672,12 @@ class Engine:
             hb.bn_x = ops.make_bn_bwd(sx, 0, B * H * W, bn0.gamma, bn0.beta, bn0.save_mean, bn0.save_invstd, bn0.dgamma,
                                       bn0.dbeta, c0=Cu)
             hb.du, hb.lddu = du.ptr().value, du.ld
-            self._emit(st, self.lib.dmm_head_input_bwd_reduce, hb, hp + ".norm0.bwd.reduce")
-            self._emit(st, self.lib.dmm_head_input_bwd_apply, hb, hp + ".norm0.bwd.apply")
+            self._stage_params.setdefault(id(st), []).extend([hp + ".norm0.weight", hp + ".norm0.bias"])
+            hb_rd = u.P * Cu * 2 + B * H * W * (cx * 4 + ld0 * 2)
+            self._emit(st, self.lib.dmm_head_input_bwd_reduce, hb, hp + ".norm0.bwd.reduce", kind="head_input_bwd",
+                       nbytes=hb_rd)
+            self._emit(st, self.lib.dmm_head_input_bwd_apply, hb, hp + ".norm0.bwd.apply", kind="head_input_bwd",
+                       nbytes=u.P * Cu * 4 + B * H * W * Cu * 2)
             self._bwd_stages.append(st)
 
     # ------------------------------------------------------------------------------------------------
@@ -630,6 +705,11 @@ class Engine:
         self._n_pack = len(self._pack_jobs)
         self._param_ptrs = [j["w"].data_ptr() for j in self._pack_jobs]
         self._pack_src = [j["w"] for j in self._pack_jobs]
+        # backward program = stages in reverse forward order, cut into SEGMENTS whose parameter gradients form one
+        # contiguous range of the flat gradient buffer (a gradient bucket, >= bucket_bytes) each
+        stages = list(reversed(self._bwd_stages))
+        stage_rank = {id(st): i for i, st in enumerate(stages)}
+        self._unpack_jobs.sort(key=lambda j: stage_rank[j["stage"]])
         # weight-gradient scratch arena
         offs, tot = [], 0
         for n in self._dw_req:
@@ -650,10 +730,28 @@ class Engine:
             uj[i]["sn"], uj[i]["sc"] = j["sn"], j["sc"]
         self._unpack_tab = torch.from_numpy(uj.view(np.uint8).copy()).to(dev)
         self._n_unpack = len(self._unpack_jobs)
-        # backward program = stages in reverse forward order; first writer of a block gradient buffer stores
         self.bwd = []
-        for st in reversed(self._bwd_stages):
+        self.segments = []       # (ops, first unpack job, number of unpack jobs, flat_lo, flat_hi)
+        seg_ops, seg_names, job_lo, job_i = [], [], 0, 0
+        done = set()
+        for si, st in enumerate(stages):
+            seg_ops.extend(st)
             self.bwd.extend(st)
+            for n in self._stage_params.get(id(st), []):
+                if n not in done:
+                    done.add(n)
+                    seg_names.append(n)
+            while job_i < len(self._unpack_jobs) and stage_rank[self._unpack_jobs[job_i]["stage"]] <= si:
+                job_i += 1
+            nbytes = 4 * sum(self.p[n].numel() for n in seg_names)
+            if nbytes >= self.bucket_bytes or si == len(stages) - 1:
+                if seg_names:
+                    lo = self.grad_offset[seg_names[0]]
+                    hi = self.grad_offset[seg_names[-1]] + self.p[seg_names[-1]].numel()
+                else:
+                    lo = hi = 0
+                self.segments.append((seg_ops, job_lo, job_i - job_lo, lo, hi))
+                seg_ops, seg_names, job_lo = [], [], job_i
         seen = set()
         for op in self.bwd:
             if op.gbuf is not None:
@@ -687,9 +785,9 @@ class Engine:
         """logits (B, num_classes, H, W) fp32 - engine-owned buffer, valid until the next forward()."""
         if self.plan_only:
             raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
-        self.in1.copy_(x1)
+        self.in1.copy_(x1, non_blocking=True)
         if self.c2:
-            self.in2.copy_(x2)
+            self.in2.copy_(x2, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.training:
             self._stats.zero_used()
@@ -700,9 +798,10 @@ class Engine:
             torch._foreach_add_(self.nbt, 1)
         return self.logits
 
-    def backward(self, dlogits=None):
+    def backward(self, dlogits=None, on_bucket=None):
         """gradient of all parameters for the cotangent dlogits (defaults to the engine's own dlogits buffer, as
-        filled by loss()).  Results land in self.grad[name] (views of the flat fp32 buffer self.gflat)."""
+        filled by loss()).  Results land in self.grad[name] (views of the flat fp32 buffer self.gflat).
+        on_bucket(i, flat_range) is called as soon as the i-th gradient bucket is final (stream-ordered)."""
         if not self.need_backward:
             raise RuntimeError("engine was built without backward support")
         if dlogits is not None:
@@ -710,9 +809,14 @@ class Engine:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         self._sums.zero_used()
         self._dw.zero_()
-        self._run(self.bwd)
-        _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(self._unpack_tab.data_ptr()), self._n_unpack, stream),
-                   "dmm_unpack_wgrad_batched")
+        tab = self._unpack_tab.data_ptr()
+        for i, (seg_ops, job_lo, njobs, lo, hi) in enumerate(self.segments):
+            self._run(seg_ops)
+            if njobs:
+                _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab + job_lo * _UNPACK_DT.itemsize), njobs, stream),
+                           "dmm_unpack_wgrad_batched")
+            if on_bucket is not None and hi > lo:
+                on_bucket(i, self.gflat[lo:hi])
         return self.grad
 
     def loss(self, target, loss_out=None):

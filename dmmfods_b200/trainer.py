@@ -1,0 +1,113 @@
+"""Training step driver: forward + BCE heat-map loss + backward (+ bucketed NCCL gradient all-reduce overlapped
+with backward) + fused flat Adam - the per-iteration work of Dense_U_Net_lidar_Agent.train_one_epoch
+(Agent.py:244-265) without its logging.  One process per GPU; BatchNorm statistics stay per process (the reference
+uses plain nn.BatchNorm2d), gradients are SUMMED over ranks (the reference back-propagates the sum over all samples,
+Agent.py:264).
+"""
+import torch
+
+from . import ops
+from .engine import Engine
+
+
+class Trainer:
+    def __init__(self, model, B, H, W, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, distributed=None,
+                 bucket_bytes=32 << 20, use_graph=False):
+        import torch.distributed as dist
+        self.model = model.train()
+        self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized()
+                                                                          and dist.get_world_size() > 1)) else None
+        named = dict(model.named_parameters())
+        sd = model.state_dict(keep_vars=True)
+        params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in sd.items()}
+        dev = next(iter(params.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("dmmfods_b200.Trainer: the model must live on a CUDA device (no CPU path)")
+        # flatten the parameters in the engine's gradient order so that Adam and the all-reduce see flat ranges
+        order = Engine.gradient_order(params, model.model_cfg(), B, H, W)
+        total = sum(named[n].numel() for n in order)
+        self.pflat = torch.empty(total, dtype=torch.float32, device=dev)
+        off = 0
+        for n in order:
+            p = named[n]
+            view = self.pflat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            off += p.numel()
+        self.eng = model.engine(B, H, W)
+        assert self.eng.param_names == order
+        self.eng.bucket_bytes = bucket_bytes
+        self.exp_avg = torch.zeros_like(self.pflat)
+        self.exp_avg_sq = torch.zeros_like(self.pflat)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.steps = 0
+        self.side = torch.cuda.Stream(device=dev) if self.dist is not None else None
+        self.use_graph = bool(use_graph) and self.dist is None
+        self.graph = None
+        self._static_target = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _on_bucket(self, i, flat):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
+
+    def _fwd_loss_bwd(self, target):
+        eng = self.eng
+        eng.loss(target)
+        eng.backward(on_bucket=self._on_bucket if self.dist is not None else None)
+        if self.dist is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+    def step(self, x1, x2, target):
+        """one optimisation step; x1/x2/target: CUDA tensors or pinned host tensors (copied asynchronously).
+        Returns the per-class loss sums (float64 CUDA tensor of num_classes entries, Agent.py:248)."""
+        eng = self.eng
+        if not target.is_cuda:
+            if self._static_target is None:
+                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
+            self._static_target.copy_(target, non_blocking=True)
+            target = self._static_target
+        if self.use_graph:
+            if self._static_target is None:
+                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
+            if target is not self._static_target:
+                self._static_target.copy_(target, non_blocking=True)
+            eng.in1.copy_(x1, non_blocking=True)
+            if eng.c2:
+                eng.in2.copy_(x2, non_blocking=True)
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            eng.forward(x1, x2)
+            self._fwd_loss_bwd(target)
+        self.steps += 1
+        ops.adam_flat(self.pflat, eng.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, self.steps)
+        return eng.class_sums
+
+    def _capture(self):
+        """CUDA graph of forward + loss + backward over the engine's static buffers (launch-bound otherwise)."""
+        eng = self.eng
+        # warm-up on a side stream as torch's capture rules require, then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            eng.forward(eng.in1, eng.in2)
+            self._fwd_loss_bwd(self._static_target)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.forward(eng.in1, eng.in2)
+            self._fwd_loss_bwd(self._static_target)
+        self.graph = g
+
+    def launches_per_step(self):
+        """number of this library's kernel launches in one step."""
+        eng = self.eng
+        n = len(eng.fwd) + len(eng.bwd) + 1 + len([s for s in eng.segments if s[2]]) + 1 + 1   # + pack, unpacks, bce, adam
+        n += sum(1 for op in eng.fwd if op.kind == "nchw_stats" and eng.c2)                     # second input tensor
+        return n

@@ -114,7 +114,7 @@ def test_engine_plan_covers_every_parameter(c2, cb):
     """host logic without a GPU: the launch programs are built for every fusion mode, every convolution weight
     has a pack job (forward + data gradient) and an unpack job (weight gradient), every BatchNorm a backward."""
     from dmmfods_b200.engine import Engine
-    c = _cfg(c2, cb, growth_rate=16, block_config=(2, 3, 2, 2), num_init_features=32, bn_size=2)
+    c = _cfg(c2, cb, growth_rate=16, block_config=(2, 4, 2, 2), num_init_features=32, bn_size=2)
     m = Dense_U_Net_lidar(c)
     params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
     eng = Engine(params, m.model_cfg(), 2, 64, 96, plan_only=True)
@@ -135,6 +135,17 @@ def test_engine_plan_covers_every_parameter(c2, cb):
             seen[id(op.gbuf)] = True
     with pytest.raises(RuntimeError):
         eng.forward(torch.zeros(2, 3, 64, 96), torch.zeros(2, 1, 64, 96))
+    # gradient buckets: contiguous, ordered, covering the whole flat gradient buffer, in backward order
+    small = Engine(params, m.model_cfg(), 2, 64, 96, plan_only=True, bucket_bytes=100 << 10)
+    assert len(small.segments) > 2
+    pos = 0
+    for ops_, job_lo, njobs, lo, hi in small.segments:
+        assert lo == pos and hi >= lo
+        pos = hi
+    assert pos == small.gflat.numel() == sum(p.numel() for p in m.parameters())
+    assert sum(s[2] for s in small.segments) == len(small._unpack_jobs)
+    assert small.param_names[0].startswith("dec_out_to_heat_maps")      # the head finishes first in backward
+    assert Engine.gradient_order(params, m.model_cfg(), 2, 64, 96) == eng.param_names
 
 
 def test_engine_rejects_sizes_the_reference_rejects():
