@@ -135,7 +135,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def kernel_breakdown(trainer, x1, x2, tgt):
+def kernel_breakdown(trainer, x1, x2, tgt, dump=None):
     """one instrumented step: CUDA events around every launch, grouped by kernel family."""
     import torch
     eng = trainer.eng
@@ -160,6 +160,10 @@ def kernel_breakdown(trainer, x1, x2, tgt):
         torch.cuda.synchronize()
     finally:
         eng._run = orig_run
+    if dump:
+        rows = [dict(name=op.name, kind=op.kind, ms=e0.elapsed_time(e1), flops=op.flops, bytes=op.bytes) for op, e0, e1 in recs]
+        with open(dump, "w") as fh:
+            json.dump(rows, fh)
     fam = {}
     for op, e0, e1 in recs:
         f = fam.setdefault(op.kind, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
@@ -182,6 +186,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="capture fwd+loss+bwd in a CUDA graph (single GPU)")
+    ap.add_argument("--dump-ops", default=None, help="write the per-launch CUDA-event timings of one instrumented step (json)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the timed region run ONE more step between cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -269,7 +276,15 @@ def main():
     h2d = hx1.numel() * 4 + hx2.numel() * 4 + htg.numel() * 4
     loss_per_class = [float(v) for v in loss_host]
 
-    fam = kernel_breakdown(trainer, x1, x2, tg)
+    fam = kernel_breakdown(trainer, x1, x2, tg, dump=args.dump_ops if rank == 0 else None)
+    if args.profile_step and rank == 0:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.eng.forward(x1, x2)
+        trainer.eng.loss(tg)
+        trainer.eng.backward()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     if rank != 0:
         if world > 1:
             dist.barrier()

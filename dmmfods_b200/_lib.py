@@ -34,11 +34,20 @@ class Igemm(C.Structure):
                 ("stats_ld", c_int32), ("stats_off", c_int32)]
 
 
+WG_MAX_A = 8
+WG_MAX_B = 25
+
+
+class WgSlot(C.Structure):
+    _fields_ = [("src", c_int8), ("dy", c_int8), ("dx", c_int8), ("pad_", c_int8), ("ch0", c_int32), ("out0", c_int32)]
+
+
 class Wgrad(C.Structure):
-    _fields_ = [("x", View), ("y", View * MAX_SRC), ("num_ysrc", c_int32), ("num_taps", c_int32),
-                ("tap_ysrc", c_int8 * MAX_TAPS), ("tap_dy", c_int8 * MAX_TAPS), ("tap_dx", c_int8 * MAX_TAPS),
-                ("W", c_int32), ("H", c_int32), ("B", c_int32), ("tile_w", c_int32), ("M", c_int32),
-                ("N", c_int32), ("n_tile", c_int32), ("splits", c_int32), ("dw", c_void_p), ("ldw", c_int64)]
+    _fields_ = [("a_src", View * MAX_SRC), ("b_src", View * MAX_SRC), ("num_a_src", c_int32), ("num_b_src", c_int32),
+                ("a", WgSlot * WG_MAX_A), ("b", WgSlot * WG_MAX_B), ("num_a", c_int32), ("num_b", c_int32),
+                ("n_tile", c_int32), ("ya", c_int32), ("yb", c_int32), ("a_step", c_int32), ("b_step", c_int32),
+                ("W", c_int32), ("H", c_int32), ("B", c_int32), ("kpx", c_int32), ("tile_w", c_int32),
+                ("splits", c_int32), ("dw", c_void_p), ("ld", c_int64)]
 
 
 class Bn(C.Structure):
@@ -63,7 +72,8 @@ class BnBwd(C.Structure):
 class BnBwdArgs(C.Structure):
     _fields_ = [("x", c_void_p), ("ldx", c_int64), ("g", c_void_p), ("ldg", c_int64), ("g_is_f32", c_int32),
                 ("gmode", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
-                ("bn", BnBwd), ("out", c_void_p), ("ldo", c_int64), ("out_mode", c_int32)]
+                ("bn", BnBwd), ("out", c_void_p), ("ldo", c_int64), ("out_mode", c_int32), ("dz_out", c_void_p),
+                ("lddz", c_int64)]
 
 
 class Head(C.Structure):
@@ -89,8 +99,8 @@ SIGNATURES = {
     "dmm_conv_wgrad": (C.c_int, [C.POINTER(Wgrad), c_void_p]),
     "dmm_pack_weights": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                    C.POINTER(c_int32), c_int64, c_int64, c_void_p]),
-    "dmm_unpack_wgrad": (C.c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int32, C.POINTER(c_int32),
-                                   c_int64, c_int64, c_int32, c_void_p]),
+    "dmm_unpack_wgrad": (C.c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p, c_int32,
+                                   C.POINTER(c_int32), c_int64, c_int64, c_int32, c_void_p]),
     "dmm_pack_weights_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_unpack_wgrad_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_bn_relu_apply": (C.c_int, [C.POINTER(BnApply), c_void_p]),

@@ -351,6 +351,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_reduce_kernel(const dm
         for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += (long long)gridDim.x * ry) {
             float xr[8], dz[8];
             bn_relu_dz<GMODE, GT>(p, x, g, row, chunk, sc, sh, OH, OW, xr, dz);
+            if (p.dz_out) {   // keep the masked, pool-routed gradient so that the apply pass can run with gmode 0
+                const uint4 packed = pack8(dz);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz_out) + row * p.lddz + chunk * 8) = packed;
+                unpack8(packed, dz);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += dz[j];
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
     float* sft = sm + 3 * Cpad;
     float* k1 = sm + 4 * Cpad;   // PASS 0: block sums of dz        PASS 1: c1
     float* k2 = sm + 5 * Cpad;   // PASS 0: block sums of dz*xhat   PASS 1: c2
-    for (int c = threadIdx.x; c < Cpad; c += blockDim.x) {
+    for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < Cpad; c += blockDim.x * blockDim.y) {
         float m = 0.f, is = 0.f, sc = 0.f, sh = 0.f, a1 = 0.f, a2 = 0.f;
         if (c < Ct) {
             const dmm_bn_bwd_t& bn = c < p.Cu ? p.bn_u : p.bn_x;
@@ -605,21 +610,24 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
     const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g);
     const int UH = p.H >> 1, UW = p.W >> 1;
     const long long HW = (long long)p.H * p.W;
-    const int nch = PASS == 0 ? chunks : (p.Cu >> 3);
-    const long long total = (long long)p.B * UH * UW * nch;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % nch);
-        const long long up = i / nch;
+    // block = (chunk lanes, pixel rows): a thread keeps ONE 8-channel chunk and walks over up-sampled-source pixels
+    const int ch = threadIdx.x;
+    const int ry = blockDim.y;
+    const long long rows = (long long)p.B * UH * UW;
+    float tot1[8], tot2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot1[j] = tot2[j] = 0.f;
+    const bool all_u = ch * 8 + 8 <= p.Cu;
+    for (long long up = (long long)blockIdx.x * ry + threadIdx.y; up < rows; up += (long long)gridDim.x * ry) {
         const int ux = (int)(up % UW);
         const long long t = up / UW;
         const int uy = (int)(t % UH);
         const int b = (int)(t / UH);
         float xu[8];
-        const bool all_u = ch * 8 + 8 <= p.Cu;
         if (all_u) unpack8(ldg16(u + up * p.ldu + ch * 8), xu);
-        float acc1[8], acc2[8];
+        float acc1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc1[j] = acc2[j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc1[j] = 0.f;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
@@ -647,20 +655,14 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
                     const float dz = (z > 0.f && c < Ct) ? gg[j] : 0.f;
                     const float xh = (xv - mean[c]) * istd[c];
                     if (PASS == 0) {
-                        acc1[j] += dz;
-                        acc2[j] += dz * xh;
+                        tot1[j] += dz;
+                        tot2[j] += dz * xh;
                     } else {
                         acc1[j] += dz - k1[c] - xh * k2[c];
                     }
                 }
             }
-        if (PASS == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                atomicAdd(&k1[ch * 8 + j], acc1[j]);
-                atomicAdd(&k2[ch * 8 + j], acc2[j]);
-            }
-        } else {
+        if (PASS == 1) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -672,9 +674,14 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
         }
     }
     if (PASS == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&k1[ch * 8 + j], tot1[j]);     // one shared-memory atomic per thread and channel, at the very end
+            atomicAdd(&k2[ch * 8 + j], tot2[j]);
+        }
         __syncthreads();
         const int slot = blockIdx.x % DMM_STATS_SLOTS;
-        for (int c = threadIdx.x; c < Ct; c += blockDim.x) {
+        for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < Ct; c += blockDim.x * blockDim.y) {
             const dmm_bn_bwd_t& bn = c < p.Cu ? p.bn_u : p.bn_x;
             const int cc = c < p.Cu ? c : c - p.Cu;
             atomicAdd(bn.sums + ((size_t)slot * 2 + 0) * bn.sums_ld + bn.sums_off + cc, (double)k1[c]);
@@ -790,16 +797,17 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
         dst[i] = __float2bfloat16_rn(v);
     }
 }
-// grad[n*sn + m*sc + tap_off[t]] (=|+=) dw[(t*M + m)*ldw + n]
-__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, long long ldw, int M, int N,
-                                                           float* __restrict__ grad, const PackArgs a, int accumulate) {
+// grad[n*sn + m*sc + tap_off[t]] (=|+=) dw[t*dt + m*dm + n*dn]
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, long long dt, long long dm,
+                                                           long long dn, int M, int N, float* __restrict__ grad,
+                                                           const PackArgs a, int accumulate) {
     const long long total = (long long)a.T * M * N;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i % N);
         const long long r = i / N;
         const int m = (int)(r % M);
         const int t = (int)(r / M);
-        const float v = dw[((long long)t * M + m) * ldw + n];
+        const float v = dw[(long long)t * dt + (long long)m * dm + (long long)n * dn];
         float* gp = grad + (long long)n * a.sn + (long long)m * a.sc + a.tap_off[t];
         *gp = accumulate ? *gp + v : v;
     }
@@ -846,7 +854,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unp
         const long long r = i / j.N;
         const int m = (int)(r % j.M);
         const int t = (int)(r / j.M);
-        const float v = j.dw[((long long)t * j.Mld + m) * j.ldw + n];
+        const float v = j.dw[(long long)t * j.dt + (long long)m * j.dm + (long long)n * j.dn];
         float* gp = j.grad + (long long)n * j.sn + (long long)m * j.sc + j.tap_off[t];
         *gp = j.accumulate ? *gp + v : v;
     }
@@ -974,9 +982,13 @@ static int launch_head_bwd(const dmm_head_bwd_t* d, cudaStream_t stream) {
     const int chunks = (Ct + 7) / 8;
     DMM_CHECK(d->ldg >= chunks * 8, "dmm_head_input_bwd: ldg too small");
     const int nch = PASS == 0 ? chunks : d->Cu / 8;
-    const long long total = (long long)d->B * (d->H / 2) * (d->W / 2) * nch;
+    DMM_CHECK(nch >= 1 && nch <= 128, "dmm_head_input_bwd: %d channel chunks (supported: 1..128)", nch);
+    const int ry = 256 / nch > 0 ? 256 / nch : 1;
+    const long long rows = (long long)d->B * (d->H / 2) * (d->W / 2);
+    long long gx = (rows + ry - 1) / ry;
+    if (gx > 148 * 8) gx = 148 * 8;
     const size_t smem = (size_t)6 * chunks * 8 * sizeof(float);
-    head_input_bwd_kernel<PASS><<<flat_grid(total, 256), 256, smem, stream>>>(*d);
+    head_input_bwd_kernel<PASS><<<dim3((unsigned)gx), dim3((unsigned)nch, (unsigned)ry), smem, stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_bwd_kernel");
     return 0;
 }
@@ -1051,13 +1063,13 @@ extern "C" int dmm_pack_weights(const float* w, void* dst, int32_t n_valid, int3
     return 0;
 }
 
-extern "C" int dmm_unpack_wgrad(const float* dw, int64_t ldw, int32_t M, int32_t N, float* grad, int32_t T,
-                                const int32_t* tap_off, int64_t sn, int64_t sc, int32_t accumulate, void* stream) {
+extern "C" int dmm_unpack_wgrad(const float* dw, int64_t dt, int64_t dm, int64_t dn, int32_t M, int32_t N, float* grad,
+                                int32_t T, const int32_t* tap_off, int64_t sn, int64_t sc, int32_t accumulate, void* stream) {
     DMM_CHECK(dw && grad, "dmm_unpack_wgrad: null pointer");
     PackArgs a;
     int rc = fill_pack_args(a, N, N, M, 1, T, tap_off, sn, sc);
     if (rc) return rc;
-    unpack_wgrad_kernel<<<flat_grid((long long)T * M * N, 256), 256, 0, (cudaStream_t)stream>>>(dw, ldw, M, N, grad, a,
+    unpack_wgrad_kernel<<<flat_grid((long long)T * M * N, 256), 256, 0, (cudaStream_t)stream>>>(dw, dt, dm, dn, M, N, grad, a,
                                                                                                 accumulate);
     DMM_LAUNCH_CHECK("unpack_wgrad_kernel");
     return 0;

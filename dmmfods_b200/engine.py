@@ -267,16 +267,20 @@ class Engine:
         self._fix_w.append((d, wid))
 
     def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B):
-        """weight gradient: wgrad into a zeroed fp32 scratch + unpack job into the flat gradient buffer."""
+        """weight gradient: wgrad launches into a zeroed fp32 scratch matrix + unpack job into the flat gradient
+        buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x."""
         T = len(taps)
-        did = self._req_dw(T * M * N)
-        d = ops.make_wgrad(x, ys, taps, W, H, B, M, N, 0, N)
+        plan = ops.plan_conv_wgrad(x, ys, taps, M, N)
+        did = self._req_dw(plan["rows"] * plan["ld"])
         P = B * H * W
-        self._emit(lst, self.lib.dmm_conv_wgrad, d, name, kind="wgrad", flops=2.0 * P * Mvalid * Nvalid * T,
-                   nbytes=P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4)
-        self._fix_dw.append((d, did))
-        self._unpack_jobs.append(dict(did=did, grad=self.grad[wname], ldw=N, M=Mvalid, Mld=M, N=Nvalid, T=T,
-                                      tap_off=tap_off, sn=sn, sc=sc, stage=id(lst)))
+        nl = len(plan["launches"])
+        for i, kw in enumerate(plan["launches"]):
+            d = ops.make_wgrad(W=W, H=H, B=B, dw=0, ld=plan["ld"], **kw)
+            self._emit(lst, self.lib.dmm_conv_wgrad, d, name + ("[%d]" % i if nl > 1 else ""), kind="wgrad",
+                       flops=2.0 * P * Mvalid * Nvalid * T / nl, nbytes=(P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4) / nl)
+            self._fix_dw.append((d, did))
+        self._unpack_jobs.append(dict(did=did, grad=self.grad[wname], dt=plan["dt"], dm=plan["dm"], dn=plan["dn"], M=Mvalid,
+                                      N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst)))
         self._stage_params.setdefault(id(lst), []).append(wname)
 
     def _bn_fwd(self, bn, stats, stats_off, count, c0=0, rep=1.0):
@@ -292,7 +296,9 @@ class Engine:
         self._emit(lst, self.lib.dmm_bn_relu_apply, d, name, kind="bn_relu_apply", nbytes=(x.P + y.P) * C_ * 2)
 
     def _bn_bwd(self, lst, name, bn, x, xc0, C_, g_ptr, ldg, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False, bn_c0=0,
-                gbuf=None):
+                gbuf=None, dz_tmp=None):
+        """BN-ReLU backward = reduce pass + apply pass.  dz_tmp (Mat): the reduce pass stores the masked, pool-routed
+        gradient there and the apply pass reads it back with gmode 0 (max-pool routing is evaluated once)."""
         self._stage_params.setdefault(id(lst), []).extend([bn.prefix + ".weight", bn.prefix + ".bias"])
         sums = self._new_sums(C_)
         b = ops.make_bn_bwd(sums, 0, x.P, bn.gamma, bn.beta, bn.save_mean, bn.save_invstd, bn.dgamma, bn.dbeta, c0=bn_c0)
@@ -300,9 +306,17 @@ class Engine:
         pg = x.P if gmode == 0 else (x.P // 4)
         rd = x.P * C_ * 2 + pg * C_ * (4 if g_is_f32 else 2)
         wr = x.P * C_ * (2 if out_mode == 0 else (4 if gbuf is None else 8))
-        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce", kind="bn_relu_bwd_reduce", nbytes=rd)
-        self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d, name + ".apply", gbuf=gbuf, kind="bn_relu_bwd_apply",
-                   nbytes=rd + wr)
+        d2 = d
+        if dz_tmp is not None:
+            d.dz_out, d.lddz = dz_tmp.ptr().value, dz_tmp.ld
+            d2 = ops.make_bn_bwd_args(x, xc0, C_, dz_tmp.ptr(), dz_tmp.ld, b, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False)
+            rd2 = x.P * C_ * 4
+        else:
+            rd2 = rd
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce", kind="bn_relu_bwd_reduce",
+                   nbytes=rd + (x.P * C_ * 2 if dz_tmp is not None else 0))
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d2, name + ".apply", gbuf=gbuf, kind="bn_relu_bwd_apply",
+                   nbytes=rd2 + wr)
 
     def _cast(self, lst, name, src, c0, C_, dst):
         def run(_arg, stream, src=src, c0=c0, C_=C_, dst=dst, lib=self.lib):
@@ -384,8 +398,9 @@ class Engine:
             if self.need_backward:
                 st = []
                 dz0 = self._tmpmat("dz0", B, H2, W2, self.nif)
+                dzr = self._tmpmat("dz0_routed", B, H2, W2, self.nif)
                 self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, blk.G.data_ptr(), blk.Ct, dz0.ptr(), dz0.ld, 0,
-                             gmode=2, g_is_f32=True)
+                             gmode=2, g_is_f32=True, dz_tmp=dzr)
                 self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
                                  [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
                 self._bwd_stages.append(st)
@@ -724,7 +739,8 @@ class Engine:
         for i, j in enumerate(self._unpack_jobs):
             uj[i]["dw"] = base + 4 * offs[j["did"]]
             uj[i]["grad"] = j["grad"].data_ptr()
-            uj[i]["ldw"], uj[i]["M"], uj[i]["Mld"], uj[i]["N"], uj[i]["T"] = j["ldw"], j["M"], j["Mld"], j["N"], j["T"]
+            uj[i]["dt"], uj[i]["dm"], uj[i]["dn"] = j["dt"], j["dm"], j["dn"]
+            uj[i]["M"], uj[i]["N"], uj[i]["T"] = j["M"], j["N"], j["T"]
             uj[i]["accumulate"] = 0
             uj[i]["tap_off"][:j["T"]] = j["tap_off"]
             uj[i]["sn"], uj[i]["sc"] = j["sn"], j["sc"]
@@ -830,6 +846,6 @@ class Engine:
 _PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32), ("n_rows", np.int32), ("C", np.int32),
                      ("kwidth", np.int32), ("T", np.int32), ("tap_off", np.int32, (32,)), ("sn", np.int64),
                      ("sc", np.int64)], align=True)
-_UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("ldw", np.int64), ("M", np.int32), ("Mld", np.int32),
-                       ("N", np.int32), ("T", np.int32), ("accumulate", np.int32), ("tap_off", np.int32, (32,)),
-                       ("sn", np.int64), ("sc", np.int64)], align=True)
+_UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("dt", np.int64), ("dm", np.int64), ("dn", np.int64),
+                       ("M", np.int32), ("N", np.int32), ("T", np.int32), ("accumulate", np.int32),
+                       ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64)], align=True)

@@ -209,28 +209,95 @@ def run_igemm(d):
     check(_lib.load().dmm_conv_igemm(C.byref(d), _stream()), "dmm_conv_igemm")
 
 
-def make_wgrad(x, ys, taps, W, H, B, M, N, dw, ldw, n_tile=None, tile_w=None, splits=0):
+def make_wgrad(a_srcs, b_srcs, a_slots, b_slots, n_tile, W, H, B, dw, ld, ya=1, yb=1, a_step=0, b_step=0, kpx=None,
+               tile_w=None, splits=0):
+    """dmm_wgrad_t.  a_slots / b_slots: lists of (src, dy, dx, ch0, out0)."""
     d = Wgrad()
-    d.x = x
-    assert 1 <= len(ys) <= MAX_SRC and 1 <= len(taps) <= MAX_TAPS
-    for i, v in enumerate(ys):
-        d.y[i] = v
-    d.num_ysrc = len(ys)
-    d.num_taps = len(taps)
-    for i, (s, dy, dx) in enumerate(taps):
-        d.tap_ysrc[i], d.tap_dy[i], d.tap_dx[i] = s, dy, dx
+    assert 1 <= len(a_srcs) <= MAX_SRC and 1 <= len(b_srcs) <= MAX_SRC
+    assert 1 <= len(a_slots) <= _lib.WG_MAX_A and 1 <= len(b_slots) <= _lib.WG_MAX_B
+    for i, v in enumerate(a_srcs):
+        d.a_src[i] = v
+    for i, v in enumerate(b_srcs):
+        d.b_src[i] = v
+    d.num_a_src, d.num_b_src = len(a_srcs), len(b_srcs)
+    for i, (s, dy, dx, ch0, out0) in enumerate(a_slots):
+        d.a[i].src, d.a[i].dy, d.a[i].dx, d.a[i].ch0, d.a[i].out0 = s, dy, dx, ch0, out0
+    for i, (s, dy, dx, ch0, out0) in enumerate(b_slots):
+        d.b[i].src, d.b[i].dy, d.b[i].dx, d.b[i].ch0, d.b[i].out0 = s, dy, dx, ch0, out0
+    d.num_a, d.num_b = len(a_slots), len(b_slots)
+    d.n_tile = n_tile
+    d.ya, d.yb, d.a_step, d.b_step = ya, yb, a_step, b_step
     d.W, d.H, d.B = W, H, B
-    d.tile_w = tile_w or pick_tile_w(W, H, 64)
-    d.M, d.N = M, N
-    d.n_tile = n_tile or min(pick_n_tile(N), 256)
+    if kpx is None:      # keep >= 3 pipeline stages in 200 KB of shared memory
+        na = (len(a_slots) + 1) // 2
+        bw = 64 if n_tile >= 64 else n_tile
+        stage64 = 2 * na * 8192 + len(b_slots) * ceil_to(n_tile, bw) * 128
+        kpx = 64 if stage64 * 3 <= 200 * 1024 else 32
+    d.kpx = kpx
+    d.tile_w = tile_w or pick_tile_w(W, H, kpx)
     d.splits = splits
     d.dw = dw.data_ptr() if isinstance(dw, torch.Tensor) else dw
-    d.ldw = ldw
+    d.ld = ld
     return d
 
 
 def run_wgrad(d):
     check(_lib.load().dmm_conv_wgrad(C.byref(d), _stream()), "dmm_conv_wgrad")
+
+
+def plan_conv_wgrad(x, ys, taps, M, N):
+    """Launch plan for  dw[t][m][n] = sum_pix X(pix + tap_t)[m] * Y[ysrc_t](pix)[n]   (t < T, m < M, n < N).
+
+    x: View with M channels; ys: list of Views with N channels; taps: list of (ysrc, dy, dx).
+    Returns dict(launches=[kwargs for make_wgrad without dw], rows, ld, dt, dm, dn): the scratch matrix has
+    `rows` x `ld` fp32 entries and element (t, m, n) lives at dw[t*dt + m*dm + n*dn]."""
+    T = len(taps)
+    mch = (M + 63) // 64                     # 64-channel chunks of X
+    if N <= 64:
+        nt = 16 if N <= 16 else (32 if N <= 32 else 64)
+        if T * nt <= 512:
+            # A = activation (loaded once), B = one group per tap: the output gradient shifted by -tap
+            na = max(1, min(4, 512 // (T * nt), (mch + 1) // 2))
+            n_slots = min(2 * na, mch)
+            ya = (mch + 2 * na - 1) // (2 * na)
+            ld = T * nt
+            a_slots = [(0, 0, 0, 64 * i, 64 * i) for i in range(n_slots)]
+            b_slots = [(ys_i, -dy, -dx, 0, t * nt) for t, (ys_i, dy, dx) in enumerate(taps)]
+            launch = dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=b_slots, n_tile=nt, ya=ya, yb=1,
+                          a_step=128 * na, b_step=0)
+            return dict(launches=[launch], rows=mch * 64, ld=ld, dt=nt, dm=ld, dn=1)
+        if M <= 256:
+            # roles swapped: A = shifted output-gradient chunks (rows = (tap, n)), B = the activation (columns = m)
+            nt = 16 if M <= 16 else (32 if M <= 32 else (64 if M <= 64 else ceil_to(M, 16)))
+            nch = (N + 63) // 64
+            npad = nch * 64
+            max_chunks = min(_lib.WG_MAX_A, 2 * (512 // nt))
+            taps_per = max(1, max_chunks // nch)
+            launches = []
+            for t0 in range(0, T, taps_per):
+                a_slots = []
+                for t in range(t0, min(T, t0 + taps_per)):
+                    ys_i, dy, dx = taps[t]
+                    for j in range(nch):
+                        a_slots.append((ys_i, -dy, -dx, 64 * j, t * npad + 64 * j))
+                launches.append(dict(a_srcs=list(ys), b_srcs=[x], a_slots=a_slots, b_slots=[(0, 0, 0, 0, 0)], n_tile=nt,
+                                     ya=1, yb=1, a_step=0, b_step=0))
+            return dict(launches=launches, rows=T * npad, ld=nt, dt=npad * nt, dm=1, dn=nt)
+    # general: one launch per tap, A = activation shifted by +tap, B = output gradient in 128-channel groups
+    nb = 1 if N <= 128 else 2
+    na = max(1, min(4 // nb, (mch + 1) // 2))
+    n_slots = min(2 * na, mch)
+    npad = ceil_to(N, 128)
+    ya = (mch + 2 * na - 1) // (2 * na)
+    yb = (N + 128 * nb - 1) // (128 * nb)
+    ld = T * npad
+    launches = []
+    for t, (ys_i, dy, dx) in enumerate(taps):
+        a_slots = [(0, dy, dx, 64 * i, 64 * i) for i in range(n_slots)]
+        b_slots = [(ys_i, 0, 0, 128 * g, t * npad + 128 * g) for g in range(nb)]
+        launches.append(dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=b_slots, n_tile=128, ya=ya, yb=yb,
+                             a_step=128 * na, b_step=128 * nb))
+    return dict(launches=launches, rows=mch * 64, ld=ld, dt=npad, dm=ld, dn=1)
 
 
 def _i32arr(vals):
@@ -242,8 +309,8 @@ def pack_weights(w, dst, n_valid, n_rows, C_, T, tap_off, sn, sc, kwidth=KWIDTH)
                                        _stream()), "dmm_pack_weights")
 
 
-def unpack_wgrad(dw, ldw, M, N, grad, T, tap_off, sn, sc, accumulate=False):
-    check(_lib.load().dmm_unpack_wgrad(_ptr(dw), ldw, M, N, _ptr(grad), T, _i32arr(tap_off), sn, sc,
+def unpack_wgrad(dw, dt, dm, dn, M, N, grad, T, tap_off, sn, sc, accumulate=False):
+    check(_lib.load().dmm_unpack_wgrad(_ptr(dw), dt, dm, dn, M, N, _ptr(grad), T, _i32arr(tap_off), sn, sc,
                                        1 if accumulate else 0, _stream()), "dmm_unpack_wgrad")
 
 

@@ -81,26 +81,41 @@ typedef struct {
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 
 /* Weight-gradient GEMM on tcgen05 (both operands pixel-major = MN-major UMMA descriptors):
- *   dw[t][m][n] += sum_{b,y,x} X(b, y + dy[t], x + dx[t], m) * Y[ysrc[t]](b, y, x, n)
- * fp32 atomic accumulation into dw (caller zero-fills), layout dw[(t*M + m)*ldw + n].
- * Replaces the weight-gradient half of aten::convolution_backward for every Conv2d /
- * ConvTranspose2d above (47% of the reference's CPU time).  Several Y views are
- * needed for ConvTranspose2d only (the four sub-pixel phases of the output gradient). */
+ *   dw[row*ld + col] += sum_{b,y,x} A_i(b, y + dy_i, x + dx_i, ch_i + r) * B_g(b, y + dy_g, x + dx_g, ch_g + c)
+ * for every A chunk i (64 channels: rows a[i].out0 + r, r < 64) and B group g (n_tile channels: columns
+ * b[g].out0 + c); views are zero outside their extent (pixels and channels).  fp32 atomic accumulation into the
+ * scratch matrix dw (caller zero-fills); dmm_unpack_wgrad(_batched) scatters it into the parameter layout.
+ * Replaces the weight-gradient half of aten::convolution_backward for every Conv2d / ConvTranspose2d of the model
+ * (47% of the reference's CPU time).  A KxK convolution is expressed either with A = the activation
+ * and one B group per tap (B = output gradient shifted by -tap), or with the roles swapped; several sources are
+ * needed for ConvTranspose2d (the four sub-pixel phases of the output gradient).
+ * One CTA owns ceil(num_a/2) x num_b accumulators of 128 x n_tile (<= 512 TMEM columns in total); the grid is
+ * (splits of the pixel tiles) x (ya x yb replicas, replica (ia, ib) adds ia*a_step / ib*b_step to the channel AND
+ * output offsets of the A / B side). */
+#define DMM_WG_MAX_A 8
+#define DMM_WG_MAX_B 25
 typedef struct {
-    dmm_view_t x;
-    dmm_view_t y[DMM_MAX_SRC];
-    int32_t num_ysrc;
-    int32_t num_taps;
-    int8_t tap_ysrc[DMM_MAX_TAPS];
-    int8_t tap_dy[DMM_MAX_TAPS];
-    int8_t tap_dx[DMM_MAX_TAPS];
-    int32_t W, H, B;         /* pixel domain (of Y; X is read shifted, zero outside its view) */
-    int32_t tile_w;          /* 64 / 32 / 16 / 8; tile_h = 64 / tile_w */
-    int32_t M, N;            /* channels of X (rows of dw) and of Y (columns of dw) */
-    int32_t n_tile;          /* multiple of 16, <= 256 */
-    int32_t splits;          /* pixel-range splits per (tap, m-tile, n-tile); 0 = auto */
+    int8_t src;              /* index into a_src / b_src */
+    int8_t dy, dx;
+    int8_t pad_;
+    int32_t ch0;             /* first channel inside the source view */
+    int32_t out0;            /* first dw row (A chunk) / column (B group) */
+} dmm_wg_slot_t;
+typedef struct {
+    dmm_view_t a_src[DMM_MAX_SRC];
+    dmm_view_t b_src[DMM_MAX_SRC];
+    int32_t num_a_src, num_b_src;
+    dmm_wg_slot_t a[DMM_WG_MAX_A];
+    dmm_wg_slot_t b[DMM_WG_MAX_B];
+    int32_t num_a, num_b;
+    int32_t n_tile;          /* 16, 32, or a multiple of 16 in [64, 256] */
+    int32_t ya, yb, a_step, b_step;
+    int32_t W, H, B;         /* pixel domain */
+    int32_t kpx;             /* pixels per pipeline stage: 64 or 32 */
+    int32_t tile_w;          /* power of two, 8 <= tile_w <= kpx; tile_h = kpx / tile_w */
+    int32_t splits;          /* pixel-range splits; 0 = auto */
     float* dw;
-    int64_t ldw;
+    int64_t ld;
 } dmm_wgrad_t;
 int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream);
 
@@ -110,13 +125,14 @@ int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream);
  * dmm_conv_igemm for forward or data-gradient use. */
 int dmm_pack_weights(const float* w, void* dst, int32_t n_valid, int32_t n_rows, int32_t C, int32_t kwidth,
                      int32_t T, const int32_t* tap_off, int64_t sn, int64_t sc, void* stream);
-/* grad[n*sn + m*sc + tap_off[t]] (= or +=) dw[(t*M + m)*ldw + n]: dmm_conv_wgrad result -> parameter layout. */
-int dmm_unpack_wgrad(const float* dw, int64_t ldw, int32_t M, int32_t N, float* grad, int32_t T,
+/* grad[n*sn + m*sc + tap_off[t]] (= or +=) dw[t*dt + m*dm + n*dn]: dmm_conv_wgrad scratch -> parameter layout
+ * (t < T taps, m < M input channels, n < N output channels of the reference weight tensor). */
+int dmm_unpack_wgrad(const float* dw, int64_t dt, int64_t dm, int64_t dn, int32_t M, int32_t N, float* grad, int32_t T,
                      const int32_t* tap_off, int64_t sn, int64_t sc, int32_t accumulate, void* stream);
 
 /* Batched forms of the two calls above: the job tables live in DEVICE memory (built once per
  * model), one launch per training step covers every weight tensor of the network.
- * Mld = row count used to index dw per tap (the M the wgrad was launched with; may exceed M). */
+ */
 typedef struct {
     const float* w;
     void* dst;
@@ -127,8 +143,8 @@ typedef struct {
 typedef struct {
     const float* dw;
     float* grad;
-    int64_t ldw;
-    int32_t M, Mld, N, T, accumulate;
+    int64_t dt, dm, dn;
+    int32_t M, N, T, accumulate;
     int32_t tap_off[DMM_MAX_TAPS];
     int64_t sn, sc;
 } dmm_unpack_job_t;
@@ -203,6 +219,8 @@ typedef struct {
     void* out;
     int64_t ldo;
     int32_t out_mode;
+    void* dz_out;            /* nullable: the reduce pass also stores dz as bf16 [B*H*W, lddz] (then run the apply */
+    int64_t lddz;            /* pass with g = dz_out, gmode = 0: the costly pool routing is done only once)       */
 } dmm_bn_bwd_args_t;
 int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);

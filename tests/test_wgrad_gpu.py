@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+def _run_plan(xv, yvs, taps, M, N, W, H, B, splits=0):
+    plan = ops.plan_conv_wgrad(xv, yvs, taps, M, N)
+    dw = torch.zeros(plan["rows"] * plan["ld"], dtype=torch.float32, device="cuda")
+    for kw in plan["launches"]:
+        ops.run_wgrad(ops.make_wgrad(W=W, H=H, B=B, dw=dw, ld=plan["ld"], splits=splits, **kw))
+    return plan, dw
+
+
 def _conv_wgrad_case(B, Cin, Cout, H, W, K, seed, n_tile=None, splits=0):
     torch.manual_seed(seed)
     pad = (K - 1) // 2
@@ -25,31 +33,30 @@ def _conv_wgrad_case(B, Cin, Cout, H, W, K, seed, n_tile=None, splits=0):
     gm = to_mat(g, ld=N)
     fwd, _, off = ops.conv_taps(K, pad)
     T = K * K
-    dw = torch.zeros(T, Cin, N, dtype=torch.float32, device="cuda")
-    d = ops.make_wgrad(xm.view(0, Cin), [gm.view(0, N)], fwd, W, H, B, Cin, N, dw, N, n_tile=n_tile, splits=splits)
-    ops.run_wgrad(d)
+    plan, dw = _run_plan(xm.view(0, Cin), [gm.view(0, N)], fwd, Cin, N, W, H, B, splits)
     grad = torch.full((Cout, Cin, K, K), float("nan"), dtype=torch.float32, device="cuda")
-    ops.unpack_wgrad(dw, N, Cin, Cout, grad, T, off, Cin * K * K, K * K)
+    ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], Cin, Cout, grad, T, off, Cin * K * K, K * K)
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
-    assert err < TOL, "wgrad K=%d Cin=%d Cout=%d n_tile=%s: relL2 %.3e" % (K, Cin, Cout, n_tile, err)
+    assert err < TOL, "wgrad K=%d Cin=%d Cout=%d: relL2 %.3e (%d launches)" % (K, Cin, Cout, err, len(plan["launches"]))
 
 
-@pytest.mark.parametrize("Cin,Cout,n_tile", [(128, 128, None), (256, 128, 64), (96, 128, 128), (64, 64, 64),
-                                             (1024, 256, 256), (136, 64, None)])
-def test_wgrad_1x1(Cin, Cout, n_tile):
-    _conv_wgrad_case(2, Cin, Cout, 12, 20, 1, seed=Cin + Cout, n_tile=n_tile)
+@pytest.mark.parametrize("Cin,Cout", [(128, 128), (256, 128), (96, 128), (64, 64), (1024, 256), (136, 64), (992, 128),
+                                      (2048, 512), (512, 256), (160, 32), (64, 16)])
+def test_wgrad_1x1(Cin, Cout):
+    _conv_wgrad_case(2, Cin, Cout, 12, 20, 1, seed=Cin + Cout)
 
 
-@pytest.mark.parametrize("n_tile", [32, 64])
-def test_wgrad_3x3_growth(n_tile):
-    """conv2 of a dense layer: X = 128 bottleneck channels, Y = 32 growth channels (narrow N)."""
-    _conv_wgrad_case(2, 128, 32, 12, 20, 3, seed=21, n_tile=n_tile)
+@pytest.mark.parametrize("Cout", [32, 16, 48])
+def test_wgrad_3x3_growth(Cout):
+    """conv2 of a dense layer: activation tile loaded once, 9 shifted copies of the narrow output gradient."""
+    _conv_wgrad_case(2, 128, Cout, 12, 20, 3, seed=21 + Cout)
 
 
 def test_wgrad_3x3_odd_sizes_and_head():
-    _conv_wgrad_case(1, 128, 32, 7, 9, 3, seed=22, n_tile=64)
-    _conv_wgrad_case(2, 132, 64, 10, 14, 3, seed=23)
+    _conv_wgrad_case(1, 128, 32, 7, 9, 3, seed=22)
+    _conv_wgrad_case(2, 132, 64, 10, 14, 3, seed=23)       # refine0: roles swapped, two launches
+    _conv_wgrad_case(2, 68, 32, 10, 14, 3, seed=27)
 
 
 def test_wgrad_5x5_three_classes():
@@ -59,9 +66,10 @@ def test_wgrad_5x5_three_classes():
 def test_wgrad_many_tiles_split():
     _conv_wgrad_case(4, 256, 128, 64, 96, 1, seed=25, splits=0)
     _conv_wgrad_case(4, 128, 32, 32, 48, 3, seed=26, splits=7)
+    _conv_wgrad_case(2, 64, 3, 64, 96, 5, seed=28)
 
 
-@pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (64, 5, 7, 9, 13)])
+@pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (64, 5, 7, 9, 13), (256, 6, 8, 12, 16), (512, 4, 6, 8, 12)])
 def test_wgrad_conv_transpose(C, H, W, OH, OW):
     torch.manual_seed(C + OH)
     B = 2
@@ -75,11 +83,9 @@ def test_wgrad_conv_transpose(C, H, W, OH, OW):
     gm = to_mat(g)
     taps, off = ops.convt_wgrad_taps()
     ys = [gm.phase_view(py, px) for py in range(2) for px in range(2)]
-    dw = torch.zeros(9, C, C, dtype=torch.float32, device="cuda")
-    d = ops.make_wgrad(xm.view(), ys, taps, W, H, B, C, C, dw, C)
-    ops.run_wgrad(d)
+    plan, dw = _run_plan(xm.view(), ys, taps, C, C, W, H, B)
     grad = torch.full((C, C, 3, 3), float("nan"), dtype=torch.float32, device="cuda")
-    ops.unpack_wgrad(dw, C, C, C, grad, 9, off, 9, C * 9)      # weight (Cin=m, Cout=n, kh, kw)
+    ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], C, C, grad, 9, off, 9, C * 9)      # weight (Cin=m, Cout=n, kh, kw)
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
     assert err < TOL, "convT wgrad relL2 %.3e" % err
