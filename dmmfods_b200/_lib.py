@@ -60,7 +60,7 @@ class Bn(C.Structure):
 class BnApply(C.Structure):
     _fields_ = [("x", c_void_p), ("ldx", c_int64), ("B", c_int32), ("H", c_int32), ("W", c_int32),
                 ("C", c_int32), ("bn", Bn), ("pool", c_int32), ("y", c_void_p), ("ldy", c_int64),
-                ("ystats", c_void_p), ("ystats_ld", c_int32), ("ystats_off", c_int32)]
+                ("ystats", c_void_p), ("ystats_ld", c_int32), ("ystats_off", c_int32), ("argmax", c_void_p), ("ldarg", c_int64)]
 
 
 class BnBwd(C.Structure):
@@ -73,7 +73,7 @@ class BnBwdArgs(C.Structure):
     _fields_ = [("x", c_void_p), ("ldx", c_int64), ("g", c_void_p), ("ldg", c_int64), ("g_is_f32", c_int32),
                 ("gmode", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
                 ("bn", BnBwd), ("out", c_void_p), ("ldo", c_int64), ("out_mode", c_int32), ("dz_out", c_void_p),
-                ("lddz", c_int64)]
+                ("lddz", c_int64), ("argmax", c_void_p), ("ldarg", c_int64)]
 
 
 class Head(C.Structure):
@@ -113,6 +113,7 @@ SIGNATURES = {
     "dmm_head_input_bwd_reduce": (C.c_int, [C.POINTER(HeadBwd), c_void_p]),
     "dmm_head_input_bwd_apply": (C.c_int, [C.POINTER(HeadBwd), c_void_p]),
     "dmm_nchw_to_nhwc_bf16": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "dmm_dlogits_im2col": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dmm_rows_f32_to_bf16": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "dmm_bce_logits": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),

@@ -194,8 +194,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
                 } else {
+                    uint32_t code[8];      // position (dy+1)*3 + (dx+1) of the FIRST maximum (ATen's max_pool2d rule)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] = -INFINITY;
+                    for (int j = 0; j < 8; ++j) {
+                        o[j] = -INFINITY;
+                        code[j] = 0;
+                    }
                     for (int dy = -1; dy <= 1; ++dy) {
                         const int iy = 2 * oy + dy;
                         if (iy < 0 || iy >= p.H) continue;
@@ -205,9 +209,22 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
                             const long long r = ((long long)b * p.H + iy) * p.W + ix;
                             float f[8];
                             unpack8(ldg16(x + r * p.ldx + chunk * 8), f);
+                            const uint32_t pos = (uint32_t)((dy + 1) * 3 + (dx + 1));
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f));
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                                if (a > o[j]) {
+                                    o[j] = a;
+                                    code[j] = pos;
+                                }
+                            }
                         }
+                    }
+                    if (p.argmax) {
+                        uint2 packed;
+                        packed.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+                        packed.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.argmax) + row * p.ldarg + chunk * 8) = packed;
                     }
                 }
             }
@@ -283,6 +300,20 @@ __device__ __forceinline__ void bn_relu_dz(const dmm_bn_bwd_args_t& p, const __n
                 if (oy >= OH) continue;
                 for (int ox = ox0; ox <= ox1; ++ox) {
                     if (ox >= OW) continue;
+                    if (p.argmax) {     // forward pass recorded the winner of every window: no neighbour scan
+                        const long long w = ((long long)b * OH + oy) * OW + ox;
+                        const uint2 cd = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.argmax) +
+                                                                              w * p.ldarg + chunk * 8));
+                        const uint32_t mine = (uint32_t)((yy - 2 * oy + 1) * 3 + (xx - 2 * ox + 1));
+                        float gg[8];
+                        load_g8<GT>(g, w * p.ldg + chunk * 8, gg);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t cj = ((j < 4 ? cd.x : cd.y) >> (8 * (j & 3))) & 0xffu;
+                            if (cj == mine) dz[j] += gg[j];
+                        }
+                        continue;
+                    }
                     bool arg[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) arg[j] = true;
@@ -427,6 +458,149 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_apply_kernel(const dmm
             }
             *reinterpret_cast<float4*>(of) = a;
             *reinterpret_cast<float4*>(of + 4) = b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lean same-pixel (gmode 0) variants: per-channel coefficients stay in shared memory, two rows per iteration
+// (4 independent 16-byte loads in flight per thread), <= 64 registers so that 4 blocks fit on an SM.
+//   reduce: s1 = sum dz, s2 = invstd * sum dz*(x - mean)
+//   apply : dx = A*dz + B*x + C with A = gamma*invstd, B = -A*invstd*c2, C = -A*c1 - B*mean
+// ---------------------------------------------------------------------------------------------
+template <typename GT>
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const dmm_bn_bwd_args_t p) {
+    __shared__ float sm[2 * kEwThreads * 8];
+    __shared__ __align__(16) float cf[4][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+        }
+    }
+    __syncthreads();
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+    const GT* g = reinterpret_cast<const GT*>(p.g) + chunk * 8;
+    const long long rows = (long long)p.B * p.H * p.W;
+    const long long step = (long long)gridDim.x * ry;
+    const float* csc = &cf[0][threadIdx.x * 8];
+    const float* csh = &cf[1][threadIdx.x * 8];
+    const float* cmu = &cf[2][threadIdx.x * 8];
+    if (active) {
+        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += 2 * step) {
+            const long long row2 = row + step;
+            const bool has2 = row2 < rows;
+            float xa[8], xb[8], ga[8], gb[8];
+            unpack8(ldg16(x + row * p.ldx), xa);
+            load_g8<GT>(g, row * p.ldg, ga);
+            if (has2) {
+                unpack8(ldg16(x + row2 * p.ldx), xb);
+                load_g8<GT>(g, row2 * p.ldg, gb);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sc = csc[j], sh = csh[j], mu = cmu[j];
+                const float dza = fmaf(xa[j], sc, sh) > 0.f ? ga[j] : 0.f;
+                s1[j] += dza;
+                s2[j] = fmaf(dza, xa[j] - mu, s2[j]);
+                if (has2) {
+                    const float dzb = fmaf(xb[j], sc, sh) > 0.f ? gb[j] : 0.f;
+                    s1[j] += dzb;
+                    s2[j] = fmaf(dzb, xb[j] - mu, s2[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
+    }
+    block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+}
+
+template <typename GT, int OUT_MODE>
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const dmm_bn_bwd_args_t p) {
+    __shared__ __align__(16) float cf[5][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            double a = 0.0, b = 0.0;
+#pragma unroll
+            for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+                const double* r = p.bn.sums + (size_t)s * 2 * p.bn.sums_ld + p.bn.sums_off + c;
+                a += r[0];
+                b += r[p.bn.sums_ld];
+            }
+            const float c1 = (float)(a / p.bn.count), c2 = (float)(b / p.bn.count);
+            const float A = (p.bn.gamma ? p.bn.gamma[c] : 1.f) * k.invstd;
+            const float Bc = -A * k.invstd * c2;
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = A; cf[3][tid] = Bc; cf[4][tid] = -A * c1 - Bc * k.mean;
+            if (blockIdx.x == 0) {
+                if (p.bn.dgamma) p.bn.dgamma[c] = (float)b;
+                if (p.bn.dbeta) p.bn.dbeta[c] = (float)a;
+            }
+        }
+    }
+    __syncthreads();
+    if (chunk >= nchunks || p.out == nullptr) return;
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+    const GT* g = reinterpret_cast<const GT*>(p.g) + chunk * 8;
+    const long long rows = (long long)p.B * p.H * p.W;
+    const long long step = (long long)gridDim.x * ry;
+    const int t8 = threadIdx.x * 8;
+    for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += 2 * step) {
+        float xv[2][8], gv[2][8];
+        float4 pa[2], pb[2];
+        const bool has2 = row0 + step < rows;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has2) break;
+            const long long row = row0 + u * step;
+            unpack8(ldg16(x + row * p.ldx), xv[u]);
+            load_g8<GT>(g, row * p.ldg, gv[u]);
+            if (OUT_MODE == 2) {
+                const float* of = reinterpret_cast<const float*>(p.out) + row * p.ldo + chunk * 8;
+                pa[u] = *reinterpret_cast<const float4*>(of);
+                pb[u] = *reinterpret_cast<const float4*>(of + 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has2) break;
+            const long long row = row0 + u * step;
+            float dx[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xx = xv[u][j];
+                const float dz = fmaf(xx, cf[0][t8 + j], cf[1][t8 + j]) > 0.f ? gv[u][j] : 0.f;
+                dx[j] = fmaf(cf[2][t8 + j], dz, fmaf(cf[3][t8 + j], xx, cf[4][t8 + j]));
+            }
+            const long long o = row * p.ldo + chunk * 8;
+            if (OUT_MODE == 0) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8(dx);
+            } else {
+                float* of = reinterpret_cast<float*>(p.out) + o;
+                float4 a = make_float4(dx[0], dx[1], dx[2], dx[3]);
+                float4 b = make_float4(dx[4], dx[5], dx[6], dx[7]);
+                if (OUT_MODE == 2) {
+                    a.x += pa[u].x; a.y += pa[u].y; a.z += pa[u].z; a.w += pa[u].w;
+                    b.x += pb[u].x; b.y += pb[u].y; b.z += pb[u].z; b.w += pb[u].w;
+                }
+                *reinterpret_cast<float4*>(of) = a;
+                *reinterpret_cast<float4*>(of + 4) = b;
+            }
         }
     }
 }
@@ -610,68 +784,49 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
     const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g);
     const int UH = p.H >> 1, UW = p.W >> 1;
     const long long HW = (long long)p.H * p.W;
-    // block = (chunk lanes, pixel rows): a thread keeps ONE 8-channel chunk and walks over up-sampled-source pixels
+    // block = (chunk lanes, pixel rows): a thread keeps ONE 8-channel chunk of the Cu up-sampled channels and walks over
+    // up-sampled-SOURCE pixels, reducing the 2x2 children in registers (the raw input channels are handled by
+    // head_raw_bwd_reduce_kernel).  rows < 2^31 (checked on the host): 32-bit index arithmetic.
     const int ch = threadIdx.x;
     const int ry = blockDim.y;
-    const long long rows = (long long)p.B * UH * UW;
+    const unsigned rows = (unsigned)p.B * (unsigned)UH * (unsigned)UW;
     float tot1[8], tot2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) tot1[j] = tot2[j] = 0.f;
-    const bool all_u = ch * 8 + 8 <= p.Cu;
-    for (long long up = (long long)blockIdx.x * ry + threadIdx.y; up < rows; up += (long long)gridDim.x * ry) {
-        const int ux = (int)(up % UW);
-        const long long t = up / UW;
-        const int uy = (int)(t % UH);
-        const int b = (int)(t / UH);
+    float c_sc[8], c_sh[8], c_mu[8], c_is[8], c_k1[8], c_k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        c_sc[j] = scl[c]; c_sh[j] = sft[c]; c_mu[j] = mean[c]; c_is[j] = istd[c]; c_k1[j] = k1[c]; c_k2[j] = k2[c];
+    }
+    for (unsigned up = blockIdx.x * ry + threadIdx.y; up < rows; up += gridDim.x * ry) {
+        const unsigned ux = up % (unsigned)UW;
+        const unsigned t = up / (unsigned)UW;
+        const unsigned uy = t % (unsigned)UH;
+        const unsigned b = t / (unsigned)UH;
         float xu[8];
-        if (all_u) unpack8(ldg16(u + up * p.ldu + ch * 8), xu);
-        float acc1[8];
+        unpack8(ldg16(u + (long long)up * p.ldu + ch * 8), xu);
+        const long long pix0 = ((long long)b * p.H + 2 * uy) * p.W + 2 * ux;
+        float g4[4][8];
+        unpack8(ldg16(g + pix0 * p.ldg + ch * 8), g4[0]);
+        unpack8(ldg16(g + (pix0 + 1) * p.ldg + ch * 8), g4[1]);
+        unpack8(ldg16(g + (pix0 + p.W) * p.ldg + ch * 8), g4[2]);
+        unpack8(ldg16(g + (pix0 + p.W + 1) * p.ldg + ch * 8), g4[3]);
+        float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc1[j] = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const int yy = 2 * uy + dy, xx = 2 * ux + dx;
-                const long long pix = ((long long)b * p.H + yy) * p.W + xx;
-                float gg[8];
-                unpack8(ldg16(g + pix * p.ldg + ch * 8), gg);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = ch * 8 + j;
-                    float xv;
-                    if (all_u) {
-                        xv = xu[j];
-                    } else if (c < p.Cu) {
-                        xv = __bfloat162float(u[up * p.ldu + c]);
-                    } else if (c < p.Cu + p.C1) {
-                        xv = __ldg(p.x1 + ((long long)b * p.C1 + (c - p.Cu)) * HW + (long long)yy * p.W + xx);
-                    } else if (c < Ct) {
-                        xv = __ldg(p.x2 + ((long long)b * p.C2 + (c - p.Cu - p.C1)) * HW + (long long)yy * p.W + xx);
-                    } else {
-                        xv = 0.f;
-                    }
-                    const float z = fmaf(xv, scl[c], sft[c]);
-                    const float dz = (z > 0.f && c < Ct) ? gg[j] : 0.f;
-                    const float xh = (xv - mean[c]) * istd[c];
-                    if (PASS == 0) {
-                        tot1[j] += dz;
-                        tot2[j] += dz * xh;
-                    } else {
-                        acc1[j] += dz - k1[c] - xh * k2[c];
-                    }
-                }
+        for (int j = 0; j < 8; ++j) {
+            const float gs = (g4[0][j] + g4[1][j]) + (g4[2][j] + g4[3][j]);      // the 4 children share x, hence the mask
+            const float dz = fmaf(xu[j], c_sc[j], c_sh[j]) > 0.f ? gs : 0.f;
+            const float xh = (xu[j] - c_mu[j]) * c_is[j];
+            if (PASS == 0) {
+                tot1[j] += dz;
+                tot2[j] = fmaf(dz, xh, tot2[j]);
+            } else {
+                const float gam = p.bn_u.gamma ? p.bn_u.gamma[ch * 8 + j] : 1.f;
+                o[j] = gam * c_is[j] * (dz - 4.f * (c_k1[j] + xh * c_k2[j]));
             }
-        if (PASS == 1) {
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = ch * 8 + j;
-                const float gam = p.bn_u.gamma ? p.bn_u.gamma[c] : 1.f;
-                o[j] = gam * istd[c] * acc1[j];
-            }
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.du) + up * p.lddu + ch * 8) = pack8(o);
         }
+        if (PASS == 1) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.du) + (long long)up * p.lddu + ch * 8) = pack8(o);
     }
     if (PASS == 0) {
 #pragma unroll
@@ -681,12 +836,99 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
         }
         __syncthreads();
         const int slot = blockIdx.x % DMM_STATS_SLOTS;
-        for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < Ct; c += blockDim.x * blockDim.y) {
-            const dmm_bn_bwd_t& bn = c < p.Cu ? p.bn_u : p.bn_x;
-            const int cc = c < p.Cu ? c : c - p.Cu;
-            atomicAdd(bn.sums + ((size_t)slot * 2 + 0) * bn.sums_ld + bn.sums_off + cc, (double)k1[c]);
-            atomicAdd(bn.sums + ((size_t)slot * 2 + 1) * bn.sums_ld + bn.sums_off + cc, (double)k2[c]);
+        for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < p.Cu; c += blockDim.x * blockDim.y) {
+            atomicAdd(p.bn_u.sums + ((size_t)slot * 2 + 0) * p.bn_u.sums_ld + p.bn_u.sums_off + c, (double)k1[c]);
+            atomicAdd(p.bn_u.sums + ((size_t)slot * 2 + 1) * p.bn_u.sums_ld + p.bn_u.sums_off + c, (double)k2[c]);
         }
+    }
+}
+
+// (sum dz, sum dz*xhat) of the C1+C2 (<= 8) RAW input channels of the head BatchNorm: one thread per pixel, the
+// fp32 planes are read coalesced, the 8 gradient columns [Cu, Cu+8) with one 16-byte load.
+__global__ void __launch_bounds__(256) head_raw_bwd_reduce_kernel(const dmm_head_bwd_t p) {
+    __shared__ float red[2][8][8];
+    const int Cx = p.C1 + p.C2;
+    float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = sh[j] = mu[j] = is[j] = s1[j] = s2[j] = 0.f;
+        if (j < Cx) {
+            BnCoef k = bn_coef_bwd(p.bn_x, j);
+            sc[j] = k.scale; sh[j] = k.shift; mu[j] = k.mean; is[j] = k.invstd;
+        }
+    }
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g);
+    const long long HW = (long long)p.H * p.W;
+    const long long total = (long long)p.B * HW;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const long long b = pix / HW, r = pix - b * HW;
+        float gg[8];
+        unpack8(ldg16(g + pix * p.ldg + p.Cu), gg);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < Cx) {
+                const float xv = j < p.C1 ? __ldg(p.x1 + (b * p.C1 + j) * HW + r) : __ldg(p.x2 + (b * p.C2 + (j - p.C1)) * HW + r);
+                const float dz = fmaf(xv, sc[j], sh[j]) > 0.f ? gg[j] : 0.f;
+                s1[j] += dz;
+                s2[j] = fmaf(dz, (xv - mu[j]) * is[j], s2[j]);
+            }
+        }
+    }
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float a = s1[j], c = s2[j];
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            red[0][j][w] = a;
+            red[1][j][w] = c;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int which = threadIdx.x >> 3, j = threadIdx.x & 7;
+        if (j < Cx) {
+            double d = 0.0;
+            for (int k = 0; k < 8; ++k) d += red[which][j][k];
+            const int slot = blockIdx.x % DMM_STATS_SLOTS;
+            atomicAdd(p.bn_x.sums + ((size_t)slot * 2 + which) * p.bn_x.sums_ld + p.bn_x.sums_off + j, d);
+        }
+    }
+}
+
+// dlogits (B, C, H, W) fp32 -> bf16 rows [B*H*W, ld]: column t*C + n = dlogits[n] at pixel (y - (kh - K/2), x - (kw - K/2)),
+// t = kh*K + kw (zero outside the image, zero beyond K*K*C).  This "im2col of the output gradient" turns both the
+// weight gradient and the data gradient of the N = num_classes KxK convolution (refine1) into plain 1x1 GEMMs.
+__global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int K,
+                                                             __nv_bfloat16* __restrict__ out, int ld) {
+    const int chunks = ld >> 3;
+    const long long total = (long long)B * H * W * chunks;
+    const int pad = K / 2;
+    const int KC = K * K * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % chunks);
+        const long long pix = i / chunks;
+        const int x = (int)(pix % W);
+        const long long t2 = pix / W;
+        const int y = (int)(t2 % H);
+        const int b = (int)(t2 / H);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = ch * 8 + j;
+            float v = 0.f;
+            if (col < KC) {
+                const int t = col / C, n = col - t * C;
+                const int kh = t / K, kw = t - kh * K;
+                const int yy = y - (kh - pad), xx = x - (kw - pad);
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(dl + (((long long)b * C + n) * H + yy) * W + xx);
+            }
+            f[j] = v;
+        }
+        *reinterpret_cast<uint4*>(out + pix * ld + ch * 8) = pack8(f);
     }
 }
 
@@ -842,7 +1084,10 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pac
         const int t = (int)(k / Kp);
         const int c = (int)(k - (long long)t * Kp);
         float v = 0.f;
-        if (n < j.n_valid && c < j.C) v = j.w[(long long)n * j.sn + (long long)c * j.sc + j.tap_off[t]];
+        if (n < j.n_valid && c < j.C) {
+            const int cdiv = j.cdiv > 0 ? j.cdiv : 1;
+            v = j.w[(long long)n * j.sn + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]];
+        }
         dst[i] = __float2bfloat16_rn(v);
     }
 }
@@ -906,6 +1151,24 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
     if (d->gmode == 1) { OH = d->H / 2; OW = d->W / 2; }
     if (d->gmode == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
     ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W);
+    if (d->gmode == 0 && d->dz_out == nullptr) {      // lean same-pixel kernels
+        if (PASS == 0) {
+            if (d->g_is_f32) bn_bwd_reduce_fast_kernel<float><<<k.grid, k.block, 0, stream>>>(*d);
+            else bn_bwd_reduce_fast_kernel<__nv_bfloat16><<<k.grid, k.block, 0, stream>>>(*d);
+        } else {
+#define DMM_APPLY_FAST(GT)                                                                              \
+    do {                                                                                                \
+        if (d->out_mode == 0) bn_bwd_apply_fast_kernel<GT, 0><<<k.grid, k.block, 0, stream>>>(*d);      \
+        else if (d->out_mode == 1) bn_bwd_apply_fast_kernel<GT, 1><<<k.grid, k.block, 0, stream>>>(*d); \
+        else bn_bwd_apply_fast_kernel<GT, 2><<<k.grid, k.block, 0, stream>>>(*d);                       \
+    } while (0)
+            if (d->g_is_f32) DMM_APPLY_FAST(float);
+            else DMM_APPLY_FAST(__nv_bfloat16);
+#undef DMM_APPLY_FAST
+        }
+        DMM_LAUNCH_CHECK("bn_bwd fast kernel");
+        return 0;
+    }
 #define DMM_BWD_LAUNCH(GM, GT)                                                                      \
     do {                                                                                            \
         if (PASS == 0) bn_relu_bwd_reduce_kernel<GM, GT><<<k.grid, k.block, 0, stream>>>(*d, OH, OW); \
@@ -981,14 +1244,18 @@ static int launch_head_bwd(const dmm_head_bwd_t* d, cudaStream_t stream) {
     const int Ct = d->Cu + d->C1 + d->C2;
     const int chunks = (Ct + 7) / 8;
     DMM_CHECK(d->ldg >= chunks * 8, "dmm_head_input_bwd: ldg too small");
-    const int nch = PASS == 0 ? chunks : d->Cu / 8;
+    const int nch = d->Cu / 8;
     DMM_CHECK(nch >= 1 && nch <= 128, "dmm_head_input_bwd: %d channel chunks (supported: 1..128)", nch);
+    DMM_CHECK(d->C1 + d->C2 <= 8, "dmm_head_input_bwd: at most 8 raw input channels are supported (got %d)", d->C1 + d->C2);
     const int ry = 256 / nch > 0 ? 256 / nch : 1;
     const long long rows = (long long)d->B * (d->H / 2) * (d->W / 2);
+    DMM_CHECK(rows < (1ll << 31), "dmm_head_input_bwd: too many pixels");
     long long gx = (rows + ry - 1) / ry;
     if (gx > 148 * 8) gx = 148 * 8;
     const size_t smem = (size_t)6 * chunks * 8 * sizeof(float);
     head_input_bwd_kernel<PASS><<<dim3((unsigned)gx), dim3((unsigned)nch, (unsigned)ry), smem, stream>>>(*d);
+    if (PASS == 0)
+        head_raw_bwd_reduce_kernel<<<flat_grid((long long)d->B * d->H * d->W, 256), 256, 0, stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_bwd_kernel");
     return 0;
 }
@@ -1100,5 +1367,17 @@ extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int
     if (njobs == 0) return 0;
     unpack_wgrad_batched_kernel<<<dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream>>>(jobs_device);
     DMM_LAUNCH_CHECK("unpack_wgrad_batched_kernel");
+    return 0;
+}
+
+extern "C" int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
+                                  int64_t ld, void* stream) {
+    DMM_CHECK(dlogits && out && C > 0 && K >= 1 && (K & 1) && ld % 8 == 0 && ld >= (int64_t)K * K * C,
+              "dmm_dlogits_im2col: bad arguments");
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const long long total = (long long)B * H * W * (ld / 8);
+    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, K,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(out), (int)ld);
+    DMM_LAUNCH_CHECK("dlogits_im2col_kernel");
     return 0;
 }

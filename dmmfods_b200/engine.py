@@ -394,13 +394,18 @@ class Engine:
             self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
                            cin * 49, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0)
             bn0 = _BNInfo(self, prefix + ".norm0", self.nif)
+            amax = torch.empty((B * blk.H * blk.W, self.nif), dtype=torch.uint8, device=self._alloc_dev)
+            self._keep.append(amax)
+            self.mem_bytes += amax.numel()
             self._apply(fwd, prefix + ".norm0+pool0", bn0, z0, 0, self.nif, z0s, 0, blk.buf, 0, pool=2, ystats=blk.stats)
+            fwd[-1].arg.argmax, fwd[-1].arg.ldarg = amax.data_ptr(), self.nif
             if self.need_backward:
                 st = []
                 dz0 = self._tmpmat("dz0", B, H2, W2, self.nif)
                 dzr = self._tmpmat("dz0_routed", B, H2, W2, self.nif)
                 self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, blk.G.data_ptr(), blk.Ct, dz0.ptr(), dz0.ld, 0,
                              gmode=2, g_is_f32=True, dz_tmp=dzr)
+                st[-2].arg.argmax, st[-2].arg.ldarg = amax.data_ptr(), self.nif
                 self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
                                  [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
                 self._bwd_stages.append(st)
@@ -655,21 +660,33 @@ class Engine:
                        25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
         if self.need_backward:
             st = []
-            ncp = ceil_to(self.ncls, 16)
-            dl = self._mat(B, H, W, ncp)
+            kk = 25 * self.ncls
+            ncp = ceil_to(kk, 16)
+            dl = self._mat(B, H, W, ncp)     # "im2col" of d(logits): column t*ncls + n = dlogits[n](pixel - tap_t)
 
             def run_dl(_a, stream, lib=self.lib, dl=dl):
-                return lib.dmm_nchw_to_nhwc_bf16(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, dl.ptr(), dl.ld, stream)
-            self._emit(st, run_dl, None, hp + ".dlogits", kind="nchw_to_nhwc", nbytes=B * H * W * (self.ncls * 4 + ncp * 2))
+                return lib.dmm_dlogits_im2col(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, 5, dl.ptr(), dl.ld, stream)
+            self._emit(st, run_dl, None, hp + ".dlogits_im2col", kind="dlogits_im2col", nbytes=B * H * W * (self.ncls * 4 + ncp * 2))
             da1h = self._tmpmat("head_da1", B, H, W, nf2)
             dr0 = self._tmpmat("head_dr0", B, H, W, nf2)
             da0 = self._tmpmat("head_da0", B, H, W, ld0)
-            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view()], conv5[0], conv5[2], nf2,
-                             ncp, nf2, self.ncls, nf2 * 25, 25, W, H, B)
-            self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view()], conv5[1], conv5[2], ncp, nf2, 25,
-                             nf2 * 25, W, H, B, da1h)
-            # packed dgrad weights must only contain the ncls valid channels (C = ncp would read past the tensor)
-            self._pack_jobs[-1]["C"] = self.ncls
+            # dW[t][m][n] = sum_q a1h(q)[m] * dl_im2col(q)[t*ncls + n]: one 1-tap weight-gradient GEMM with N = 25*ncls
+            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view()], [(0, 0, 0)], [0], nf2, ncp,
+                             nf2, kk, nf2 * 25, 25, W, H, B)
+            uj = self._unpack_jobs[-1]       # (t, m, n) lives at dw[m*ld + t*ncls + n]
+            uj.update(T=25, N=self.ncls, dt=self.ncls * uj["dn"], tap_off=list(range(25)), sn=nf2 * 25, sc=25)
+            st[-1].flops = 2.0 * B * H * W * nf2 * self.ncls * 25
+            # d(a1h)[p][c] = sum_col dl_im2col(p)[col] * w[n][c][t], col = t*ncls + n: a 1x1 convolution over 25*ncls columns
+            Kp = ceil_to(ncp, ops.KWIDTH)
+            n_tile = ops.pick_n_tile(nf2)
+            n_rows = ceil_to(nf2, n_tile)
+            wid = self._req_wpk(n_rows, Kp)
+            self._pack_jobs.append(dict(w=self.p[hp + ".refine1.weight"], wid=wid, n_valid=nf2, n_rows=n_rows, C=kk, T=1,
+                                        tap_off=[0], sn=25, sc=1, sc2=nf2 * 25, cdiv=self.ncls))
+            dd = ops.make_igemm([dl.view()], [(0, 0, 0)], 0, Kp, n_rows, W, H, B, nf2, da1h.ptr(), da1h.ld, n_tile=n_tile)
+            self._emit(st, self.lib.dmm_conv_igemm, dd, hp + ".refine1.dgrad", kind="igemm_dgrad",
+                       flops=2.0 * B * H * W * nf2 * self.ncls * 25, nbytes=B * H * W * (ncp + nf2) * 2)
+            self._fix_w.append((dd, wid))
             self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0)
             self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
                              conv3x3[2], Ct, nf2, Ct, nf2, Ct * 9, 9, W, H, B)
@@ -716,6 +733,7 @@ class Engine:
             pj[i]["kwidth"] = ops.KWIDTH
             pj[i]["tap_off"][:j["T"]] = j["tap_off"]
             pj[i]["sn"], pj[i]["sc"] = j["sn"], j["sc"]
+            pj[i]["sc2"], pj[i]["cdiv"] = j.get("sc2", 0), j.get("cdiv", 0)
         self._pack_tab = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
         self._n_pack = len(self._pack_jobs)
         self._param_ptrs = [j["w"].data_ptr() for j in self._pack_jobs]
@@ -845,7 +863,7 @@ class Engine:
 
 _PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32), ("n_rows", np.int32), ("C", np.int32),
                      ("kwidth", np.int32), ("T", np.int32), ("tap_off", np.int32, (32,)), ("sn", np.int64),
-                     ("sc", np.int64)], align=True)
+                     ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("pad_", np.int32)], align=True)
 _UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("dt", np.int64), ("dm", np.int64), ("dn", np.int64),
                        ("M", np.int32), ("N", np.int32), ("T", np.int32), ("accumulate", np.int32),
                        ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64)], align=True)

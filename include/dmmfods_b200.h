@@ -138,7 +138,10 @@ typedef struct {
     void* dst;
     int32_t n_valid, n_rows, C, kwidth, T;
     int32_t tap_off[DMM_MAX_TAPS];
-    int64_t sn, sc;
+    int64_t sn, sc;          /* source element of (n, c, t): w[n*sn + (c / cdiv)*sc + (c % cdiv)*sc2 + tap_off[t]] */
+    int64_t sc2;
+    int32_t cdiv;            /* 0 or 1: plain channel index */
+    int32_t pad_;
 } dmm_pack_job_t;
 typedef struct {
     const float* dw;
@@ -186,6 +189,8 @@ typedef struct {
     int64_t ldy;
     double* ystats;
     int32_t ystats_ld, ystats_off;
+    void* argmax;            /* pool == 2 only, nullable: uint8 [B*OH*OW, ldarg] position 0..8 of each window's */
+    int64_t ldarg;           /* first maximum, consumed by dmm_bn_relu_bwd_* (gmode 2)                           */
 } dmm_bn_apply_t;
 int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream);
 
@@ -221,6 +226,8 @@ typedef struct {
     int32_t out_mode;
     void* dz_out;            /* nullable: the reduce pass also stores dz as bf16 [B*H*W, lddz] (then run the apply */
     int64_t lddz;            /* pass with g = dz_out, gmode = 0: the costly pool routing is done only once)       */
+    const void* argmax;      /* gmode 2, nullable: window winners recorded by dmm_bn_relu_apply (else recomputed)  */
+    int64_t ldarg;
 } dmm_bn_bwd_args_t;
 int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
@@ -275,6 +282,11 @@ int dmm_head_input_bwd_apply(const dmm_head_bwd_t* d, void* stream);
 /* fp32 NCHW (B,C,H,W) -> bf16 NHWC [B*H*W, ldo] (channels >= C zero) : d(logits) for refine1. */
 int dmm_nchw_to_nhwc_bf16(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, void* out,
                           int64_t ldo, void* stream);
+/* d(logits) (B,C,H,W) fp32 -> bf16 rows [B*H*W, ld], column t*C + n = dlogits[n](y - (kh - K/2), x - (kw - K/2)),
+ * t = kh*K + kw, zero outside the image: turns the weight / data gradients of the KxK, N = num_classes head
+ * convolution (refine1, Dense_U_Net_lidar.py:130-131) into plain 1x1 GEMMs over K*K*C columns. */
+int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
+                       int64_t ld, void* stream);
 /* fp32 rows [P, C] (pitch lds) -> bf16 rows (pitch ldd): slices of the fp32 dense-block gradient buffer. */
 int dmm_rows_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t P, int32_t C,
                          void* stream);

@@ -310,3 +310,73 @@ def test_adam_flat_matches_torch_adam():
         ops.adam_flat(p, g.cuda(), m, v, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
     torch.cuda.synchronize()
     assert torch.allclose(p.cpu(), ref_p.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_maxpool_backward_with_recorded_argmax():
+    """stem path of the engine: forward records each window's winner, backward routes through the codes and the reduce
+    pass stores dz so that the apply pass runs with gmode 0."""
+    torch.manual_seed(51)
+    B, C, H, W = 2, 64, 18, 22
+    gamma, beta, rm, rv, sm, si = _bn_setup(C, 3)
+    x = bf16_round(torch.randn(B, C, H, W) * 1.5 + 0.2)
+    x[:, :, 4:8, 4:8] = x[:, :, 4:5, 4:5]                      # exact ties inside windows
+    xd = x.double().requires_grad_(True)
+    gd = gamma.cpu().double().requires_grad_(True)
+    bd = beta.cpu().double().requires_grad_(True)
+    a = F.max_pool2d(F.relu(F.batch_norm(xd, None, None, gd, bd, training=True, eps=1e-5)), 3, 2, 1)
+    g = torch.randn_like(a).float()
+    a.backward(g.double())
+    OH, OW = a.shape[2], a.shape[3]
+    xm = to_mat(x)
+    st = new_stats(C)
+    _col_stats(x, st)
+    y = ops.new_mat(B, OH, OW, C)
+    amax = torch.zeros(B * OH * OW, C, dtype=torch.uint8, device="cuda")
+    bn = ops.make_bn(st, 0, B * H * W, gamma, beta, rm, rv, sm, si, training=True)
+    d = ops.make_bn_apply(xm, 0, C, bn, y, 0, pool=2)
+    d.argmax, d.ldarg = amax.data_ptr(), C
+    ops.run_bn_apply(d)
+    torch.cuda.synchronize()
+    assert rel_l2(from_mat(y), a.detach()) < TOL_BF16
+    gt = g.permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda()
+    sums = new_stats(C)
+    dgam = torch.zeros(C, device="cuda")
+    dbet = torch.zeros(C, device="cuda")
+    bnb = ops.make_bn_bwd(sums, 0, B * H * W, gamma, beta, sm, si, dgam, dbet)
+    dz = ops.new_mat(B, H, W, C)
+    out = ops.new_mat(B, H, W, C)
+    d1 = ops.make_bn_bwd_args(xm, 0, C, gt.data_ptr(), C, bnb, out.ptr(), C, 0, gmode=2, g_is_f32=True)
+    d1.argmax, d1.ldarg = amax.data_ptr(), C
+    d1.dz_out, d1.lddz = dz.ptr().value, C
+    d2 = ops.make_bn_bwd_args(xm, 0, C, dz.ptr(), C, bnb, out.ptr(), C, 0, gmode=0)
+    import ctypes
+    from dmmfods_b200 import _lib
+    lib = _lib.load()
+    _lib.check(lib.dmm_bn_relu_bwd_reduce(ctypes.byref(d1), ops._stream()), "reduce")
+    _lib.check(lib.dmm_bn_relu_bwd_apply(ctypes.byref(d2), ops._stream()), "apply")
+    torch.cuda.synchronize()
+    err = rel_l2(from_mat(out), xd.grad)
+    assert err < 1e-2, "max-pool bwd via argmax codes relL2 %.3e" % err       # dz stored as bf16 in between
+    assert rel_l2(dgam.cpu(), gd.grad) < 5e-3
+    assert rel_l2(dbet.cpu(), bd.grad) < 5e-3
+
+
+def test_dlogits_im2col():
+    torch.manual_seed(52)
+    B, C, H, W, K = 2, 3, 9, 12, 5
+    dl = torch.randn(B, C, H, W)
+    ld = 80
+    out = ops.new_mat(B, H, W, ld)
+    import ctypes
+    from dmmfods_b200 import _lib
+    _lib.check(_lib.load().dmm_dlogits_im2col(ctypes.c_void_p(dl.cuda().data_ptr()), B, C, H, W, K, out.ptr(), ld, ops._stream()),
+               "dlogits_im2col")
+    torch.cuda.synchronize()
+    got = from_mat(out)                                        # (B, ld, H, W)
+    pad = K // 2
+    dp = F.pad(bf16_round(dl).double(), (pad, pad, pad, pad))
+    for t in range(K * K):
+        kh, kw = t // K, t % K
+        ref = dp[:, :, 2 * pad - kh:2 * pad - kh + H, 2 * pad - kw:2 * pad - kw + W]      # dl(y - (kh-pad), x - (kw-pad))
+        assert torch.equal(got[:, t * C:(t + 1) * C], ref), t
+    assert float(got[:, K * K * C:].abs().max()) == 0.0
