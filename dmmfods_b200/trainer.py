@@ -10,6 +10,39 @@ from . import ops
 from .engine import Engine
 
 
+class BucketReducer:
+    """SUM all-reduce of the gradient buckets as they become final during backward.
+
+    CUDA: every bucket is reduced on a side stream that waits for the event recorded on the compute stream when
+    the bucket was finalised, so NCCL overlaps the rest of backward; finish() makes the compute stream wait for
+    the side stream.  CPU tensors (gloo; host-logic tests): asynchronous work handles, finish() waits for them."""
+
+    def __init__(self, dist, device):
+        self.dist = dist
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if self.cuda else None
+        self.pending = []
+        self.ranges = []
+
+    def __call__(self, i, flat):
+        self.ranges.append((i, flat.numel()))
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
+        else:
+            self.pending.append(self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self):
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.side)
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+
 class Trainer:
     def __init__(self, model, B, H, W, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, distributed=None,
                  bucket_bytes=32 << 20, use_graph=False):
@@ -41,25 +74,18 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(self.pflat)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.steps = 0
-        self.side = torch.cuda.Stream(device=dev) if self.dist is not None else None
+        self.reducer = BucketReducer(self.dist, dev) if self.dist is not None else None
         self.use_graph = bool(use_graph) and self.dist is None
         self.graph = None
         self._static_target = None
 
     # ------------------------------------------------------------------------------------------------
-    def _on_bucket(self, i, flat):
-        ev = torch.cuda.Event()
-        ev.record()
-        self.side.wait_event(ev)
-        with torch.cuda.stream(self.side):
-            self.dist.all_reduce(flat, op=self.dist.ReduceOp.SUM)
-
     def _fwd_loss_bwd(self, target):
         eng = self.eng
         eng.loss(target)
-        eng.backward(on_bucket=self._on_bucket if self.dist is not None else None)
-        if self.dist is not None:
-            torch.cuda.current_stream().wait_stream(self.side)
+        eng.backward(on_bucket=self.reducer)
+        if self.reducer is not None:
+            self.reducer.finish()
 
     def step(self, x1, x2, target):
         """one optimisation step; x1/x2/target: CUDA tensors or pinned host tensors (copied asynchronously).
