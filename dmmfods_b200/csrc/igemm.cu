@@ -10,6 +10,8 @@
 #include "common.cuh"
 #include "../../include/dmmfods_b200.h"
 
+#include <stdlib.h>
+
 namespace dmm {
 
 struct IgemmKParams {
@@ -240,6 +242,8 @@ static uint32_t tmem_cols_for(int n) {
     return c;
 }
 
+int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream);
+
 int view_to_tmap(CUtensorMap* out, const dmm_view_t& v, int box_c, int box_w, int box_h, int swizzle) {
     uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.B};
     uint64_t strides[3] = {(uint64_t)v.sw, (uint64_t)v.sh, (uint64_t)v.sb};
@@ -266,6 +270,11 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     DMM_CHECK(d->N >= 1 && d->out != nullptr && d->weights != nullptr, "dmm_conv_igemm: bad output/weights");
     DMM_CHECK(d->out_mode == 0 || d->out_mode == 1, "dmm_conv_igemm: bad out_mode %d", d->out_mode);
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    {
+        // v2 (persistent, halo patches in shared memory) handles every kwidth-64 launch; DMM_IGEMM_V1=1 keeps v1
+        static const bool force_v1 = getenv("DMM_IGEMM_V1") != nullptr && atoi(getenv("DMM_IGEMM_V1")) != 0;
+        if (d->kwidth == 64 && !force_v1) return igemm2_launch(d, stream);
+    }
 
     IgemmKParams p;
     memset(&p, 0, sizeof(p));

@@ -1,0 +1,576 @@
+// Implicit-GEMM convolution v2 for sm_100a: persistent CTAs, halo patches in shared memory, TMA-store epilogue.
+//
+//   producer warp : per (source, 64-channel block) ONE TMA load of the halo patch of the CTA's pixel tile
+//                   ((TH + kh - 1) x (TW + kw - 1) pixels, each pixel a 128-byte row of the SWIZZLE_128B layout),
+//                   per (tap, block) one TMA load of the [n_tile x 64] weight slice (own ring).
+//   MMA warp      : every tap is a SHIFTED shared-memory descriptor into the patch (a tap moves the start address by
+//                   whole 128-byte pixel rows; the 8-row core-matrix groups are 8 consecutive pixels, the group
+//                   stride (SBO) is the patch row pitch), so an A element is fetched from L2 once per tile instead
+//                   of once per tap.  One weight stage feeds up to 4 sub-tiles of 128 pixels (msub accumulators).
+//                   Accumulators are double-buffered in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1.
+//   epilogue warps: tcgen05.ld -> bf16 -> swizzled smem staging -> TMA store (clips partial tiles and the channel
+//                   slice); BatchNorm column sums / sums of squares are read back from the staged bf16 tile and kept
+//                   in registers across the CTA's tiles.
+// Same C-ABI descriptor as v1 (dmm_conv_igemm, include/dmmfods_b200.h); kwidth must be 64.
+#include "common.cuh"
+#include "../../include/dmmfods_b200.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+namespace dmm {
+
+constexpr int kG2Threads = 192;
+constexpr int kMaxSub = 4;
+constexpr int kG2MaxSmem = 232448;
+constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
+
+struct Ig2Params {
+    CUtensorMap a_maps[DMM_MAX_SRC];
+    CUtensorMap b_map;
+    CUtensorMap o_map;
+    int num_src;
+    int src_nblk[DMM_MAX_SRC];
+    int src_lastk[DMM_MAX_SRC];
+    int src_ox[DMM_MAX_SRC], src_oy[DMM_MAX_SRC];
+    int src_tap0[DMM_MAX_SRC + 1];
+    uint32_t src_sbo[DMM_MAX_SRC];
+    uint32_t src_tx[DMM_MAX_SRC];
+    uint32_t sub_aoff[DMM_MAX_SRC][kMaxSub];
+    uint32_t tap_aoff[DMM_MAX_TAPS];
+    int tap_kb0[DMM_MAX_TAPS];
+    int sub_x[kMaxSub], sub_y[kMaxSub];
+    int msub, sub_w, sub_h;
+    int W, H, B, TW, TH, tiles_x, tiles_y, tiles_n;
+    long long total_tiles;
+    int n_tile, N;
+    int sa, sb;
+    uint32_t a_stage, b_stage, tmem_cols;
+    int desc_bo;
+    int Wv, Hv;
+    float* out32;
+    int OH, OW, out_sy, out_sx, out_py, out_px;
+    double* stats;
+    int stats_ld, stats_off;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+            reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct TileCoord {
+    int b, x0, y0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t) {
+    TileCoord c;
+    const int nt = (int)(t % p.tiles_n);
+    t /= p.tiles_n;
+    const int tx = (int)(t % p.tiles_x);
+    t /= p.tiles_x;
+    const int ty = (int)(t % p.tiles_y);
+    c.b = (int)(t / p.tiles_y);
+    c.x0 = tx * p.TW;
+    c.y0 = ty * p.TH;
+    c.n0 = nt * p.n_tile;
+    return c;
+}
+
+template <int NCH, int OUT_MODE>
+__global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
+    uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
+    uint8_t* tail = stg + (OUT_MODE == 0 ? 2 * kStageSlot : 0);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* a_empty = a_full + 8;
+    uint64_t* b_full = a_empty + 8;
+    uint64_t* b_empty = b_full + 8;
+    uint64_t* acc_full = b_empty + 8;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.sa; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < p.sb; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, p.tmem_cols);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
+        if (OUT_MODE == 0) tma_prefetch_desc(&p.o_map);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int ast = 0, bst = 0;
+            uint32_t aph = 0, bph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                for (int s = 0; s < p.num_src; ++s) {
+                    const int nblk = p.src_nblk[s];
+                    const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
+                    if (t0 == t1) continue;
+                    for (int cb = 0; cb < nblk; ++cb) {
+                        mbar_wait(&a_empty[ast], aph ^ 1);
+                        mbar_arrive_expect_tx(&a_full[ast], p.src_tx[s]);
+                        tma_load_4d(a_ring + (size_t)ast * p.a_stage, &p.a_maps[s], &a_full[ast], cb * 64, tc.x0 + p.src_ox[s],
+                                    tc.y0 + p.src_oy[s], tc.b);
+                        if (++ast == p.sa) { ast = 0; aph ^= 1; }
+                        for (int t = t0; t < t1; ++t) {
+                            mbar_wait(&b_empty[bst], bph ^ 1);
+                            mbar_arrive_expect_tx(&b_full[bst], p.b_stage);
+                            tma_load_2d(b_ring + (size_t)bst * p.b_stage, &p.b_map, &b_full[bst], (p.tap_kb0[t] + cb) * 64, tc.n0);
+                            if (++bst == p.sb) { bst = 0; bph ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
+        int ast = 0, bst = 0;
+        uint32_t aph = 0, bph = 0;
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, accph = (it >> 1) & 1;
+            mbar_wait(&acc_empty[as], accph ^ 1);
+            tc_fence_after();
+            bool first = true;
+            for (int s = 0; s < p.num_src; ++s) {
+                const int nblk = p.src_nblk[s];
+                const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
+                if (t0 == t1) continue;
+                const uint32_t sbo = p.src_sbo[s];
+                for (int cb = 0; cb < nblk; ++cb) {
+                    mbar_wait(&a_full[ast], aph);
+                    const uint32_t a_base = smem_u32(a_ring + (size_t)ast * p.a_stage);
+                    const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
+                    for (int t = t0; t < t1; ++t) {
+                        mbar_wait(&b_full[bst], bph);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t b_base = smem_u32(b_ring + (size_t)bst * p.b_stage);
+                            const uint32_t a_tap = a_base + p.tap_aoff[t];
+                            for (int sub = 0; sub < p.msub; ++sub) {
+                                const uint32_t a0 = a_tap + p.sub_aoff[s][sub];
+                                const uint32_t d_tmem = tmem_base + (as * p.msub + sub) * p.n_tile;
+                                for (int k = 0; k < ksteps; ++k) {
+                                    const uint32_t aa = a0 + k * 32;
+                                    uint64_t ad = make_smem_desc(aa, 16, sbo, 2);
+                                    if (p.desc_bo) ad |= (uint64_t)((aa >> 7) & 7) << 49;
+                                    const uint64_t bd = make_smem_desc(b_base + k * 32, 16, 1024, 2);
+                                    umma_bf16(d_tmem, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                                }
+                            }
+                            umma_commit(&b_empty[bst]);
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++bst == p.sb) { bst = 0; bph ^= 1; }
+                    }
+                    if (lane == 0) umma_commit(&a_empty[ast]);
+                    __syncwarp();
+                    if (++ast == p.sa) { ast = 0; aph ^= 1; }
+                }
+            }
+            if (lane == 0) umma_commit(&acc_full[as]);
+            __syncwarp();
+        }
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3;              // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;         // accumulator row = pixel within the sub-tile
+        const int px = r % p.sub_w, py = r / p.sub_w;
+        const bool do_stats = (OUT_MODE == 0) && (p.stats != nullptr);
+        const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
+        double sacc[NCH][4];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sacc[c][j] = 0.0;
+        uint32_t chunk_ctr = 0;
+        uint32_t it = 0;
+        int last_n0 = 0;
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const TileCoord tc = decode_tile(p, tile);
+            const uint32_t as = it & 1, accph = (it >> 1) & 1;
+            last_n0 = tc.n0;
+            mbar_wait(&acc_full[as], accph);
+            tc_fence_after();
+            for (int sub = 0; sub < p.msub; ++sub) {
+                const int x = tc.x0 + p.sub_x[sub] + px, y = tc.y0 + p.sub_y[sub] + py;
+                const bool valid = (x < p.Wv) && (y < p.Hv);
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * p.msub + sub) * p.n_tile;
+                if (OUT_MODE == 0) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int cols = min(64, p.n_tile - 64 * c);
+                        if (tc.n0 + 64 * c >= p.N) break;
+                        uint8_t* slot = stg + (chunk_ctr & 1) * kStageSlot;
+                        ++chunk_ctr;
+                        if (r == 0) bulk_wait_read1();
+                        epi_bar();
+                        uint8_t* srow = slot + r * 128;
+                        for (int g = 0; g < cols / 16; ++g) {
+                            uint32_t v[16];
+                            tmem_ld16(trow + c * 64 + g * 16, v);
+                            tmem_ld_wait();
+                            uint4 w0, w1;
+                            if (valid) {
+                                w0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                                w0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                                w0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+                                w0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+                                w1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+                                w1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+                                w1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+                                w1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+                            } else {
+                                w0 = make_uint4(0, 0, 0, 0);
+                                w1 = w0;
+                            }
+                            *reinterpret_cast<uint4*>(srow + (((2 * g) ^ (r & 7)) << 4)) = w0;
+                            *reinterpret_cast<uint4*>(srow + (((2 * g + 1) ^ (r & 7)) << 4)) = w1;
+                        }
+                        fence_proxy_async();
+                        epi_bar();
+                        if (r == 0) {
+                            tma_store_4d(&p.o_map, slot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
+                            bulk_commit();
+                        }
+                        if (do_stats) {
+                            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                            const uint8_t* base = slot + ((cp & 3) << 2);
+                            const int j = cp >> 2;
+#pragma unroll 8
+                            for (int i = 0; i < 32; ++i) {
+                                const int row = rq * 32 + i;
+                                const uint32_t u = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((j ^ (row & 7)) << 4));
+                                const float a = bf16_lo(u), b = bf16_hi(u);
+                                s1a += a; s1b += b;
+                                s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
+                            }
+                            sacc[c][0] += (double)s1a; sacc[c][1] += (double)s1b;
+                            sacc[c][2] += (double)s2a; sacc[c][3] += (double)s2b;
+                        }
+                    }
+                } else {
+                    // fp32 NCHW logits: out[((b*N + n)*OH + oy)*OW + ox], N <= 16
+                    uint32_t v[16];
+                    tmem_ld16(trow, v);
+                    tmem_ld_wait();
+                    const int oy = y * p.out_sy + p.out_py, ox = x * p.out_sx + p.out_px;
+                    if (valid && oy < p.OH && ox < p.OW) {
+                        const long long plane = (long long)p.OH * p.OW;
+                        float* o = p.out32 + ((long long)tc.b * p.N + tc.n0) * plane + (long long)oy * p.OW + ox;
+#pragma unroll
+                        for (int jn = 0; jn < 16; ++jn)
+                            if (tc.n0 + jn < p.N) o[jn * plane] = __uint_as_float(v[jn]);
+                    }
+                }
+            }
+            // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (do_stats && p.tiles_n > 1) {
+                double* st = p.stats + (size_t)(blockIdx.x % DMM_STATS_SLOTS) * 2 * p.stats_ld + p.stats_off;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int col = tc.n0 + c * 64 + 2 * cp;
+                    if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
+                        atomicAdd(st + col, sacc[c][0]);
+                        atomicAdd(st + p.stats_ld + col, sacc[c][2]);
+                        if (col + 1 < p.N) {
+                            atomicAdd(st + col + 1, sacc[c][1]);
+                            atomicAdd(st + p.stats_ld + col + 1, sacc[c][3]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sacc[c][j] = 0.0;
+                }
+            }
+        }
+        if (do_stats && p.tiles_n == 1 && it > 0) {
+            double* st = p.stats + (size_t)(blockIdx.x % DMM_STATS_SLOTS) * 2 * p.stats_ld + p.stats_off;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                const int col = last_n0 + c * 64 + 2 * cp;
+                if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
+                    atomicAdd(st + col, sacc[c][0]);
+                    atomicAdd(st + p.stats_ld + col, sacc[c][2]);
+                    if (col + 1 < p.N) {
+                        atomicAdd(st + col + 1, sacc[c][1]);
+                        atomicAdd(st + p.stats_ld + col + 1, sacc[c][3]);
+                    }
+                }
+            }
+        }
+        if (OUT_MODE == 0 && r == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+int view_to_tmap(CUtensorMap* out, const dmm_view_t& v, int box_c, int box_w, int box_h, int swizzle);
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+struct Tiling {
+    int msub, nsx, nsy, sub_w, sub_h, TW, TH, sa, sb;
+    uint32_t a_stage;
+    long long tiles;
+    double cost;
+};
+
+int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
+    DMM_CHECK(d->kwidth == 64, "igemm v2: kwidth must be 64");
+    DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
+    DMM_CHECK(d->out_mode == 0 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        DMM_CUDA(cudaGetDevice(&dev));
+        DMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static const int pitch8 = env_int("DMM_IGEMM_PITCH8", 0);
+    static const int desc_bo = env_int("DMM_IGEMM_DESC_BO", 0);
+    static const int force_msub = env_int("DMM_IGEMM_MSUB", 0);
+
+    Ig2Params p;
+    memset(&p, 0, sizeof(p));
+    // ---- taps grouped by source, halo extents ----
+    int mindx[DMM_MAX_SRC], maxdx[DMM_MAX_SRC], mindy[DMM_MAX_SRC], maxdy[DMM_MAX_SRC], ntap[DMM_MAX_SRC];
+    for (int s = 0; s < DMM_MAX_SRC; ++s) { mindx[s] = mindy[s] = 127; maxdx[s] = maxdy[s] = -128; ntap[s] = 0; }
+    for (int t = 0; t < d->num_taps; ++t) {
+        const int s = d->tap_src[t];
+        DMM_CHECK(s >= 0 && s < d->num_src, "igemm v2: tap %d bad source", t);
+        mindx[s] = d->tap_dx[t] < mindx[s] ? d->tap_dx[t] : mindx[s];
+        maxdx[s] = d->tap_dx[t] > maxdx[s] ? d->tap_dx[t] : maxdx[s];
+        mindy[s] = d->tap_dy[t] < mindy[s] ? d->tap_dy[t] : mindy[s];
+        maxdy[s] = d->tap_dy[t] > maxdy[s] ? d->tap_dy[t] : maxdy[s];
+        ++ntap[s];
+    }
+    int hx = 0, hy = 0;   // largest halo over the sources
+    long long ktot = 0;
+    int nkb_total = 0;    // (source, block) groups per tile
+    int nmma_steps = 0;   // sum over groups of taps * ksteps
+    for (int s = 0; s < d->num_src; ++s) {
+        const dmm_view_t& v = d->src[s];
+        DMM_CHECK(v.ptr != nullptr && v.C >= 1, "igemm v2: source %d empty", s);
+        p.src_nblk[s] = ceil_div(v.C, 64);
+        p.src_lastk[s] = ceil_div(v.C - (p.src_nblk[s] - 1) * 64, 16);
+        if (ntap[s] == 0) continue;
+        hx = (maxdx[s] - mindx[s]) > hx ? (maxdx[s] - mindx[s]) : hx;
+        hy = (maxdy[s] - mindy[s]) > hy ? (maxdy[s] - mindy[s]) : hy;
+        p.src_ox[s] = mindx[s];
+        p.src_oy[s] = mindy[s];
+        nkb_total += p.src_nblk[s];
+        nmma_steps += ntap[s] * ((p.src_nblk[s] - 1) * 4 + p.src_lastk[s]);
+    }
+    // taps sorted by source; k-block base of every tap in the (tap-major) packed weight matrix
+    {
+        int kb0[DMM_MAX_TAPS];
+        int kb = 0;
+        for (int t = 0; t < d->num_taps; ++t) {
+            kb0[t] = kb;
+            kb += p.src_nblk[d->tap_src[t]];
+        }
+        ktot = (long long)kb * 64;
+        int n = 0;
+        for (int s = 0; s < d->num_src; ++s) {
+            p.src_tap0[s] = n;
+            for (int t = 0; t < d->num_taps; ++t)
+                if (d->tap_src[t] == s) {
+                    p.tap_kb0[n] = kb0[t];
+                    p.tap_aoff[n] = (uint32_t)t;     // original index for now; byte offset filled below
+                    ++n;
+                }
+        }
+        for (int s = d->num_src; s <= DMM_MAX_SRC; ++s) p.src_tap0[s] = n;
+    }
+    DMM_CHECK(ktot == d->ktot, "dmm_conv_igemm: packed weight K (%lld) != tap table K (%lld)", (long long)d->ktot, ktot);
+    DMM_CHECK(d->n_rows >= d->N, "dmm_conv_igemm: weight rows %d < N %d", d->n_rows, d->N);
+
+    // ---- tiling ----
+    const bool xhalo = hx > 0;
+    const int staging = d->out_mode == 0 ? 2 * (int)kStageSlot : 0;
+    const int avail = kG2MaxSmem - 1024 - 512 - staging;
+    const uint32_t b_stage = (uint32_t)d->n_tile * 128u;
+    const int tiles_n = ceil_div(d->N, d->n_tile);
+    Tiling best;
+    best.msub = 0;
+    for (int m = kMaxSub; m >= 1; m >>= 1) {
+        if (2 * m * d->n_tile > 512) continue;
+        if (force_msub && m != force_msub && m != 1) continue;
+        for (int nsx = 1; nsx <= m; nsx <<= 1) {
+            const int nsy = m / nsx;
+            Tiling c;
+            c.msub = m; c.nsx = nsx; c.nsy = nsy;
+            if (xhalo) { c.sub_w = 8; c.sub_h = 16; }
+            else {
+                c.sub_w = d->tile_w; c.sub_h = 128 / d->tile_w;
+                if (c.sub_h == 1) { if (nsy != 1) continue; }       // one-row sub-tiles sit side by side
+                else if (nsx != 1) continue;                        // otherwise stacked (patch pitch == sub_w)
+            }
+            c.TW = c.sub_w * nsx; c.TH = c.sub_h * nsy;
+            int pw = c.TW + hx, ph = c.TH + hy;
+            if (pitch8 && xhalo) pw = (pw + 7) & ~7;
+            if (pw > 256 || ph > 256) continue;
+            c.a_stage = ((uint32_t)pw * ph * 128u + 1023u) & ~1023u;
+            c.sb = b_stage <= 8192 ? 6 : (b_stage <= 16384 ? 4 : 3);
+            int sa = (avail - c.sb * (int)b_stage) / (int)c.a_stage;
+            if (sa < 2) { c.sb = 2; sa = (avail - c.sb * (int)b_stage) / (int)c.a_stage; }
+            if (sa < 2) continue;
+            c.sa = sa > 6 ? 6 : sa;
+            c.tiles = (long long)ceil_div(d->W, c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
+            // crude per-tile time (cycles): L2 -> smem bytes at 32 B/cycle/SM vs MMA issue time
+            const double l2 = (double)nkb_total * pw * ph * 128.0 / 32.0;
+            double wbytes = 0;
+            for (int s = 0; s < d->num_src; ++s) wbytes += (double)ntap[s] * p.src_nblk[s] * b_stage;
+            const double mma_cyc = (double)m * nmma_steps * (d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4);
+            const double per_tile = (l2 + wbytes / 32.0 > mma_cyc ? l2 + wbytes / 32.0 : mma_cyc) + 1500.0;
+            const long long rounds = (c.tiles + num_sms - 1) / num_sms;
+            c.cost = (double)rounds * per_tile;
+            if (force_msub && m == force_msub) c.cost = -1.0;
+            if (best.msub == 0 || c.cost < best.cost) best = c;
+        }
+    }
+    DMM_CHECK(best.msub > 0, "igemm v2: no tiling fits in shared memory (n_tile %d, halo %dx%d)", d->n_tile, hx, hy);
+    p.msub = best.msub; p.sub_w = best.sub_w; p.sub_h = best.sub_h;
+    p.TW = best.TW; p.TH = best.TH;
+    p.sa = best.sa; p.sb = best.sb;
+    p.a_stage = best.a_stage; p.b_stage = b_stage;
+    p.tiles_x = ceil_div(d->W, p.TW);
+    p.tiles_y = ceil_div(d->H, p.TH);
+    p.tiles_n = tiles_n;
+    p.total_tiles = best.tiles;
+    p.W = d->W; p.H = d->H; p.B = d->B;
+    p.n_tile = d->n_tile; p.N = d->N;
+    p.num_src = d->num_src;
+    p.desc_bo = desc_bo;
+    for (int i = 0; i < p.msub; ++i) {
+        p.sub_x[i] = (i % best.nsx) * p.sub_w;
+        p.sub_y[i] = (i / best.nsx) * p.sub_h;
+    }
+    // ---- per-source patch geometry ----
+    for (int s = 0; s < d->num_src; ++s) {
+        if (ntap[s] == 0) continue;
+        int pw = p.TW + (maxdx[s] - mindx[s]), ph = p.TH + (maxdy[s] - mindy[s]);
+        if (pitch8 && xhalo) pw = (pw + 7) & ~7;
+        DMM_CHECK((uint32_t)pw * ph * 128u <= p.a_stage, "igemm v2: internal patch size error");
+        p.src_tx[s] = (uint32_t)pw * ph * 128u;
+        // 8-row groups: 8 consecutive pixels of one patch row.  sub_w == 8: next group = next patch row;
+        // otherwise the sub-tile's pixels are contiguous in the patch (pitch == sub_w or a single row).
+        if (p.sub_w == 8) p.src_sbo[s] = (uint32_t)pw * 128u;
+        else {
+            DMM_CHECK(pw == p.sub_w || p.sub_h == 1, "igemm v2: internal sub-tile layout error");
+            p.src_sbo[s] = 1024u;
+        }
+        for (int i = 0; i < p.msub; ++i) p.sub_aoff[s][i] = (uint32_t)(p.sub_y[i] * pw + p.sub_x[i]) * 128u;
+        for (int n = p.src_tap0[s]; n < p.src_tap0[s + 1]; ++n) {
+            const int t = (int)p.tap_aoff[n];
+            p.tap_aoff[n] = (uint32_t)((d->tap_dy[t] - mindy[s]) * pw + (d->tap_dx[t] - mindx[s])) * 128u;
+        }
+        int rc = view_to_tmap(&p.a_maps[s], d->src[s], 64, pw, ph, 128);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->n_rows};
+        uint64_t strides[1] = {(uint64_t)d->ktot};
+        uint32_t box[2] = {64u, (uint32_t)d->n_tile};
+        int rc = make_tmap_bf16(&p.b_map, d->weights, 2, dims, strides, box, 128);
+        if (rc) return rc;
+    }
+    const int osy = d->out_sy > 0 ? d->out_sy : 1, osx = d->out_sx > 0 ? d->out_sx : 1;
+    const int OH = d->OH > 0 ? d->OH : d->H, OW = d->OW > 0 ? d->OW : d->W;
+    DMM_CHECK(d->out_py < OH && d->out_px < OW, "igemm v2: output phase outside the output");
+    const int OHv = (OH - d->out_py + osy - 1) / osy, OWv = (OW - d->out_px + osx - 1) / osx;
+    p.Wv = d->W < OWv ? d->W : OWv;
+    p.Hv = d->H < OHv ? d->H : OHv;
+    p.OH = OH; p.OW = OW; p.out_sy = osy; p.out_sx = osx; p.out_py = d->out_py; p.out_px = d->out_px;
+    if (d->out_mode == 0) {
+        DMM_CHECK(d->ldo % 8 == 0 && d->coff % 8 == 0, "igemm v2: output pitch %lld / channel offset %d must be multiples of 8",
+                  (long long)d->ldo, d->coff);
+        dmm_view_t ov;
+        ov.ptr = reinterpret_cast<const uint16_t*>(d->out) + ((long long)d->out_py * OW + d->out_px) * d->ldo + d->coff;
+        ov.C = d->N; ov.W = OWv; ov.H = OHv; ov.B = d->B;
+        ov.sw = (long long)osx * d->ldo;
+        ov.sh = (long long)osy * OW * d->ldo;
+        ov.sb = (long long)OH * OW * d->ldo;
+        int rc = view_to_tmap(&p.o_map, ov, 64, p.sub_w, p.sub_h, 128);
+        if (rc) return rc;
+    } else {
+        p.out32 = reinterpret_cast<float*>(d->out);
+    }
+    p.stats = d->out_mode == 0 ? d->stats : nullptr;
+    p.stats_ld = d->stats_ld;
+    p.stats_off = d->stats_off;
+    uint32_t cols = 32;
+    while ((int)cols < 2 * p.msub * p.n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+
+    const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 512 + 1024;
+    DMM_CHECK(smem <= (size_t)kG2MaxSmem, "igemm v2: %zu bytes of shared memory requested", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    const int nch = ceil_div(p.n_tile, 64);
+    if (d->out_mode == 1) igemm2_kernel<1, 1><<<grid, kG2Threads, smem, stream>>>(p);
+    else if (nch == 1) igemm2_kernel<1, 0><<<grid, kG2Threads, smem, stream>>>(p);
+    else if (nch == 2) igemm2_kernel<2, 0><<<grid, kG2Threads, smem, stream>>>(p);
+    else if (nch == 3) igemm2_kernel<3, 0><<<grid, kG2Threads, smem, stream>>>(p);
+    else igemm2_kernel<4, 0><<<grid, kG2Threads, smem, stream>>>(p);
+    DMM_LAUNCH_CHECK("igemm2_kernel");
+    return 0;
+}
+
+}  // namespace dmm
