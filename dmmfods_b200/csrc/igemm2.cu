@@ -20,7 +20,7 @@
 
 namespace dmm {
 
-constexpr int kG2Threads = 192;
+constexpr int kG2Threads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps
 constexpr int kMaxSub = 4;
 constexpr int kG2MaxSmem = 232448;
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
@@ -45,9 +45,10 @@ struct Ig2Params {
     long long total_tiles;
     int n_tile, N;
     int sa, sb;
-    uint32_t a_stage, b_stage, tmem_cols;
-    int desc_bo;
+    uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
+    int tps;                                        // taps per weight stage
     int Wv, Hv;
+    long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
     float* out32;
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
@@ -62,10 +63,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
         : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
+// upper 32 bits of a K-major SWIZZLE_128B shared-memory descriptor (SBO, descriptor version 1, layout type 2); the
+// lower 32 bits are (address >> 4) | (LBO >> 4) << 16.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
 struct TileCoord {
     int b, x0, y0, n0;
 };
@@ -83,7 +87,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t
     return c;
 }
 
-template <int NCH, int OUT_MODE>
+template <int NCH, int OUT_MODE, int MSUB>
 __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);
+            mbar_init(&acc_empty[s], 8);
         }
         fence_mbar_init();
     }
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         if (lane == 0) {
             int ast = 0, bst = 0;
             uint32_t aph = 0, bph = 0;
+            long long w_a = 0, w_b = 0;
+            const long long t_begin = clock64();
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile);
                 for (int s = 0; s < p.num_src; ++s) {
@@ -143,71 +149,110 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                     const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
                     if (t0 == t1) continue;
                     for (int cb = 0; cb < nblk; ++cb) {
+                        long long c0 = clock64();
                         mbar_wait(&a_empty[ast], aph ^ 1);
+                        w_a += clock64() - c0;
                         mbar_arrive_expect_tx(&a_full[ast], p.src_tx[s]);
                         tma_load_4d(a_ring + (size_t)ast * p.a_stage, &p.a_maps[s], &a_full[ast], cb * 64, tc.x0 + p.src_ox[s],
                                     tc.y0 + p.src_oy[s], tc.b);
                         if (++ast == p.sa) { ast = 0; aph ^= 1; }
-                        for (int t = t0; t < t1; ++t) {
+                        for (int t = t0; t < t1; t += p.tps) {
+                            const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
+                            c0 = clock64();
                             mbar_wait(&b_empty[bst], bph ^ 1);
-                            mbar_arrive_expect_tx(&b_full[bst], p.b_stage);
-                            tma_load_2d(b_ring + (size_t)bst * p.b_stage, &p.b_map, &b_full[bst], (p.tap_kb0[t] + cb) * 64, tc.n0);
+                            w_b += clock64() - c0;
+                            mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nt * p.b_tap);
+                            uint8_t* bdst = b_ring + (size_t)bst * p.b_stage;
+                            for (int j = 0; j < nt; ++j)
+                                tma_load_2d(bdst + (size_t)j * p.b_tap, &p.b_map, &b_full[bst], (p.tap_kb0[t + j] + cb) * 64, tc.n0);
                             if (++bst == p.sb) { bst = 0; bph ^= 1; }
                         }
                     }
                 }
             }
+            if (p.prof) {
+                p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin;
+                p.prof[blockIdx.x * 16 + 1] = w_a;
+                p.prof[blockIdx.x * 16 + 2] = w_b;
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
+        // The issue block is guarded by elect.sync: nvcc then emits straight-line UTCHMMA (a `lane == 0` guard makes it
+        // wrap every MMA in an ELECT/BRA.U.ANY loop, ~45 instead of <40 cycles per instruction).  The tensor core needs
+        // (4096 + 32 N) / 128 cycles per M=128, K=16 instruction (operands stream from shared memory at 128 B/cycle,
+        // measured: scripts/ubench/mma_rate.cu), so the issue stream has to stay below ~40 cycles per MMA.
         const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+        const uint64_t bhi = (uint64_t)desc_hi(1024u) << 32;
         int ast = 0, bst = 0;
         uint32_t aph = 0, bph = 0;
         uint32_t it = 0;
+        long long w_a = 0, w_b = 0, w_acc = 0;
+        const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const uint32_t as = it & 1, accph = (it >> 1) & 1;
+            long long c0 = clock64();
             mbar_wait(&acc_empty[as], accph ^ 1);
+            w_acc += clock64() - c0;
             tc_fence_after();
-            bool first = true;
+            const uint32_t d0 = tmem_u + as * MSUB * p.n_tile;
+            uint32_t acc0 = 0;      // 0 only for the first MMA of every accumulator of this tile
             for (int s = 0; s < p.num_src; ++s) {
                 const int nblk = p.src_nblk[s];
                 const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
                 if (t0 == t1) continue;
-                const uint32_t sbo = p.src_sbo[s];
+                const uint64_t ahi = (uint64_t)desc_hi(p.src_sbo[s]) << 32;
+                uint32_t so[MSUB];
+#pragma unroll
+                for (int i = 0; i < MSUB; ++i) so[i] = p.sub_aoff[s][i] >> 4;
                 for (int cb = 0; cb < nblk; ++cb) {
+                    c0 = clock64();
                     mbar_wait(&a_full[ast], aph);
-                    const uint32_t a_base = smem_u32(a_ring + (size_t)ast * p.a_stage);
+                    w_a += clock64() - c0;
+                    const uint32_t a_lo = ((a_ring_u + (uint32_t)ast * p.a_stage) >> 4) | (1u << 16);
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
                     for (int t = t0; t < t1; ++t) {
+                        c0 = clock64();
                         mbar_wait(&b_full[bst], bph);
+                        w_b += clock64() - c0;
                         tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t b_base = smem_u32(b_ring + (size_t)bst * p.b_stage);
-                            const uint32_t a_tap = a_base + p.tap_aoff[t];
-                            for (int sub = 0; sub < p.msub; ++sub) {
-                                const uint32_t a0 = a_tap + p.sub_aoff[s][sub];
-                                const uint32_t d_tmem = tmem_base + (as * p.msub + sub) * p.n_tile;
-                                for (int k = 0; k < ksteps; ++k) {
-                                    const uint32_t aa = a0 + k * 32;
-                                    uint64_t ad = make_smem_desc(aa, 16, sbo, 2);
-                                    if (p.desc_bo) ad |= (uint64_t)((aa >> 7) & 7) << 49;
-                                    const uint64_t bd = make_smem_desc(b_base + k * 32, 16, 1024, 2);
-                                    umma_bf16(d_tmem, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
-                                }
+                        if (elect_one()) {
+                            const uint32_t b_lo = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
+                            const uint32_t a_tap = a_lo + (p.tap_aoff[t] >> 4);
+                            if (ksteps == 4) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                                    for (int sub = 0; sub < MSUB; ++sub)
+                                        umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
+                                                  k == 0 ? acc0 : 1u);
+                            } else {
+                                for (int k = 0; k < ksteps; ++k)
+#pragma unroll
+                                    for (int sub = 0; sub < MSUB; ++sub)
+                                        umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
+                                                  k == 0 ? acc0 : 1u);
                             }
                             umma_commit(&b_empty[bst]);
+                            if (t == t1 - 1) umma_commit(&a_empty[ast]);
                         }
                         __syncwarp();
-                        first = false;
+                        acc0 = 1;
                         if (++bst == p.sb) { bst = 0; bph ^= 1; }
                     }
-                    if (lane == 0) umma_commit(&a_empty[ast]);
-                    __syncwarp();
                     if (++ast == p.sa) { ast = 0; aph ^= 1; }
                 }
             }
-            if (lane == 0) umma_commit(&acc_full[as]);
+            if (elect_one()) umma_commit(&acc_full[as]);
             __syncwarp();
+        }
+        if (p.prof && lane == 0) {
+            p.prof[blockIdx.x * 16 + 4] = clock64() - t_begin;
+            p.prof[blockIdx.x * 16 + 5] = w_a;
+            p.prof[blockIdx.x * 16 + 6] = w_b;
+            p.prof[blockIdx.x * 16 + 7] = w_acc;
         }
     } else {
         // ================= epilogue =================
@@ -224,16 +269,20 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         uint32_t chunk_ctr = 0;
         uint32_t it = 0;
         int last_n0 = 0;
+        long long w_full = 0;
+        const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
             const uint32_t as = it & 1, accph = (it >> 1) & 1;
             last_n0 = tc.n0;
+            const long long c0 = clock64();
             mbar_wait(&acc_full[as], accph);
+            w_full += clock64() - c0;
             tc_fence_after();
-            for (int sub = 0; sub < p.msub; ++sub) {
+            for (int sub = 0; sub < MSUB; ++sub) {
                 const int x = tc.x0 + p.sub_x[sub] + px, y = tc.y0 + p.sub_y[sub] + py;
                 const bool valid = (x < p.Wv) && (y < p.Hv);
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * p.msub + sub) * p.n_tile;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * MSUB + sub) * p.n_tile;
                 if (OUT_MODE == 0) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
@@ -340,6 +389,10 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
             }
         }
         if (OUT_MODE == 0 && r == 0) bulk_wait_all();
+        if (p.prof && r == 0) {
+            p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
+            p.prof[blockIdx.x * 16 + 9] = w_full;
+        }
     }
 
     tc_fence_before();
@@ -374,8 +427,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         DMM_CUDA(cudaGetDevice(&dev));
         DMM_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    static const int pitch8 = env_int("DMM_IGEMM_PITCH8", 0);
-    static const int desc_bo = env_int("DMM_IGEMM_DESC_BO", 0);
     static const int force_msub = env_int("DMM_IGEMM_MSUB", 0);
 
     Ig2Params p;
@@ -456,7 +507,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             }
             c.TW = c.sub_w * nsx; c.TH = c.sub_h * nsy;
             int pw = c.TW + hx, ph = c.TH + hy;
-            if (pitch8 && xhalo) pw = (pw + 7) & ~7;
             if (pw > 256 || ph > 256) continue;
             c.a_stage = ((uint32_t)pw * ph * 128u + 1023u) & ~1023u;
             c.sb = b_stage <= 8192 ? 6 : (b_stage <= 16384 ? 4 : 3);
@@ -489,7 +539,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.W = d->W; p.H = d->H; p.B = d->B;
     p.n_tile = d->n_tile; p.N = d->N;
     p.num_src = d->num_src;
-    p.desc_bo = desc_bo;
     for (int i = 0; i < p.msub; ++i) {
         p.sub_x[i] = (i % best.nsx) * p.sub_w;
         p.sub_y[i] = (i / best.nsx) * p.sub_h;
@@ -498,7 +547,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     for (int s = 0; s < d->num_src; ++s) {
         if (ntap[s] == 0) continue;
         int pw = p.TW + (maxdx[s] - mindx[s]), ph = p.TH + (maxdy[s] - mindy[s]);
-        if (pitch8 && xhalo) pw = (pw + 7) & ~7;
         DMM_CHECK((uint32_t)pw * ph * 128u <= p.a_stage, "igemm v2: internal patch size error");
         p.src_tx[s] = (uint32_t)pw * ph * 128u;
         // 8-row groups: 8 consecutive pixels of one patch row.  sub_w == 8: next group = next patch row;
@@ -553,22 +601,47 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
 
     const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 512 + 1024;
     DMM_CHECK(smem <= (size_t)kG2MaxSmem, "igemm v2: %zu bytes of shared memory requested", smem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-        DMM_CUDA(cudaFuncSetAttribute(igemm2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-        attr_set = true;
-    }
     const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     const int nch = ceil_div(p.n_tile, 64);
-    if (d->out_mode == 1) igemm2_kernel<1, 1><<<grid, kG2Threads, smem, stream>>>(p);
-    else if (nch == 1) igemm2_kernel<1, 0><<<grid, kG2Threads, smem, stream>>>(p);
-    else if (nch == 2) igemm2_kernel<2, 0><<<grid, kG2Threads, smem, stream>>>(p);
-    else if (nch == 3) igemm2_kernel<3, 0><<<grid, kG2Threads, smem, stream>>>(p);
-    else igemm2_kernel<4, 0><<<grid, kG2Threads, smem, stream>>>(p);
+    typedef void (*KernelFn)(const Ig2Params);
+    KernelFn fn = nullptr;
+    if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4> : (p.msub == 2 ? igemm2_kernel<1, 1, 2> : igemm2_kernel<1, 1, 1>);
+    else if (nch == 1) fn = p.msub == 4 ? igemm2_kernel<1, 0, 4> : (p.msub == 2 ? igemm2_kernel<1, 0, 2> : igemm2_kernel<1, 0, 1>);
+    else if (nch == 2) fn = p.msub == 2 ? igemm2_kernel<2, 0, 2> : igemm2_kernel<2, 0, 1>;
+    else if (nch == 3) fn = igemm2_kernel<3, 0, 1>;
+    else fn = igemm2_kernel<4, 0, 1>;
+    DMM_CHECK(nch <= 2 || p.msub == 1, "igemm v2: internal msub error");
+    DMM_CHECK(nch <= 1 || p.msub <= 2, "igemm v2: internal msub error");
+    {
+        static KernelFn configured[16];
+        static int nconf = 0;
+        bool seen = false;
+        for (int i = 0; i < nconf; ++i) seen = seen || configured[i] == fn;
+        if (!seen) {
+            DMM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
+            if (nconf < 16) configured[nconf++] = fn;
+        }
+    }
+    static const int prof = env_int("DMM_IGEMM_PROF", 0);
+    static long long* prof_buf = nullptr;
+    if (prof) {
+        if (!prof_buf) DMM_CUDA(cudaMalloc(&prof_buf, 160 * 16 * sizeof(long long)));
+        DMM_CUDA(cudaMemsetAsync(prof_buf, 0, 160 * 16 * sizeof(long long), stream));
+        p.prof = prof_buf;
+    }
+    fn<<<grid, kG2Threads, smem, stream>>>(p);
+    if (prof) {
+        static long long h[160 * 16];
+        DMM_CUDA(cudaStreamSynchronize(stream));
+        DMM_CUDA(cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        double a[16] = {0};
+        for (unsigned i = 0; i < grid; ++i)
+            for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j] / grid;
+        fprintf(stderr,
+                "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
+                "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f (cycles, CTA average)\n",
+                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+    }
     DMM_LAUNCH_CHECK("igemm2_kernel");
     return 0;
 }

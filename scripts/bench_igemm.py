@@ -1,0 +1,59 @@
+"""micro-benchmark of dmm_conv_igemm on the layer shapes of BASELINE config 3 (CUDA events, L2 flushed by size)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dmmfods_b200 import ops
+
+CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
+    "refine0": (32, 640, 960, 132, 64, 3, 0),
+    "refine1": (32, 640, 960, 64, 3, 5, 1),
+    "refine0_dgrad": (32, 640, 960, 64, 132, 3, 0),
+    "b1_conv2": (32, 160, 240, 128, 32, 3, 0),
+    "b1_conv2_dgrad": (32, 160, 240, 32, 128, 3, 0),
+    "b1_conv1_k160": (32, 160, 240, 160, 128, 1, 0),
+    "b2_conv1_k320": (32, 80, 120, 320, 128, 1, 0),
+    "b2_conv2": (32, 80, 120, 128, 32, 3, 0),
+    "b3_conv2": (32, 40, 60, 128, 32, 3, 0),
+    "b3_conv1_k640": (32, 40, 60, 640, 128, 1, 0),
+    "reduce4": (32, 160, 240, 512, 128, 1, 0),
+    "convT4_phase11": (32, 160, 240, 128, 128, 2, 0),
+}
+
+def run(name, reps=5):
+    B, H, W, Cin, Cout, K, om = CASES[name]
+    torch.manual_seed(0)
+    ld = ops.ceil_to(Cin, 8)
+    a = ops.Mat((torch.randn(B * H * W, ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
+    if K == 2:
+        taps = [(0, dy, dx) for dy in (0, 1) for dx in (0, 1)]
+    else:
+        taps = ops.conv_taps(K, (K - 1) // 2)[0]
+    T = len(taps)
+    Kp = ops.ceil_to(Cin, 64)
+    n_tile = ops.pick_n_tile(Cout)
+    n_rows = ops.ceil_to(Cout, n_tile)
+    wp = (torch.randn(n_rows, T * Kp, device="cuda") * 0.05).to(torch.bfloat16)
+    if om == 0:
+        out = ops.new_mat(B, H, W, ops.ceil_to(Cout, 8))
+        st = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
+        d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.ptr(), out.ld,
+                           stats=ops.Stats(st, 0, out.ld), n_tile=n_tile)
+    else:
+        out = torch.zeros(B, Cout, H, W, device="cuda")
+        d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.data_ptr(), 0, out_mode=1, n_tile=n_tile)
+    ops.run_igemm(d)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.run_igemm(d); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    fl = 2.0 * B * H * W * Cin * Cout * T
+    by = B * H * W * (Cin + Cout) * 2
+    print("%-16s %8.3f ms %8.1f TF/s %8.0f GB/s" % (name, ms, fl / ms / 1e9, by / ms / 1e6), flush=True)
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        run(n)
