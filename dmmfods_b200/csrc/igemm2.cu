@@ -213,30 +213,37 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                     w_a += clock64() - c0;
                     const uint32_t a_lo = ((a_ring_u + (uint32_t)ast * p.a_stage) >> 4) | (1u << 16);
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
-                    for (int t = t0; t < t1; ++t) {
+                    for (int t = t0; t < t1; t += p.tps) {
+                        const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
                         c0 = clock64();
                         mbar_wait(&b_full[bst], bph);
                         w_b += clock64() - c0;
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t b_lo = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
-                            const uint32_t a_tap = a_lo + (p.tap_aoff[t] >> 4);
-                            if (ksteps == 4) {
+                            uint32_t b_lo = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
+                            uint32_t aoff = p.tap_aoff[t] >> 4;
+                            for (int j = 0; j < nt; ++j) {
+                                const uint32_t a_tap = a_lo + aoff;
+                                if (j + 1 < nt) aoff = p.tap_aoff[t + j + 1] >> 4;      // prefetch the next tap's offset
+                                if (ksteps == 4) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
+                                    for (int k = 0; k < 4; ++k)
 #pragma unroll
-                                    for (int sub = 0; sub < MSUB; ++sub)
-                                        umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
-                                                  k == 0 ? acc0 : 1u);
-                            } else {
-                                for (int k = 0; k < ksteps; ++k)
+                                        for (int sub = 0; sub < MSUB; ++sub)
+                                            umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
+                                                      k == 0 ? acc0 : 1u);
+                                } else {
+                                    for (int k = 0; k < ksteps; ++k)
 #pragma unroll
-                                    for (int sub = 0; sub < MSUB; ++sub)
-                                        umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
-                                                  k == 0 ? acc0 : 1u);
+                                        for (int sub = 0; sub < MSUB; ++sub)
+                                            umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
+                                                      k == 0 ? acc0 : 1u);
+                                }
+                                acc0 = 1;
+                                b_lo += p.b_tap >> 4;
                             }
                             umma_commit(&b_empty[bst]);
-                            if (t == t1 - 1) umma_commit(&a_empty[ast]);
+                            if (t + nt == t1) umma_commit(&a_empty[ast]);
                         }
                         __syncwarp();
                         acc0 = 1;
@@ -255,12 +262,15 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
             p.prof[blockIdx.x * 16 + 7] = w_acc;
         }
     } else {
-        // ================= epilogue =================
+        // ================= epilogue: two teams of 4 warps, alternating 64-column chunks =================
+        const int team = (warp - 2) >> 2;
         const int q = warp & 3;              // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;         // accumulator row = pixel within the sub-tile
         const int px = r % p.sub_w, py = r / p.sub_w;
         const bool do_stats = (OUT_MODE == 0) && (p.stats != nullptr);
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
+        uint8_t* slot = stg + team * kStageSlot;
+        uint8_t* srow = slot + r * 128;
         double sacc[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -286,36 +296,36 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                 if (OUT_MODE == 0) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-                        const int cols = min(64, p.n_tile - 64 * c);
                         if (tc.n0 + 64 * c >= p.N) break;
-                        uint8_t* slot = stg + (chunk_ctr & 1) * kStageSlot;
-                        ++chunk_ctr;
-                        if (r == 0) bulk_wait_read1();
-                        epi_bar();
-                        uint8_t* srow = slot + r * 128;
-                        for (int g = 0; g < cols / 16; ++g) {
-                            uint32_t v[16];
-                            tmem_ld16(trow + c * 64 + g * 16, v);
-                            tmem_ld_wait();
-                            uint4 w0, w1;
-                            if (valid) {
-                                w0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                                w0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                                w0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
-                                w0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
-                                w1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
-                                w1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
-                                w1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
-                                w1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
-                            } else {
-                                w0 = make_uint4(0, 0, 0, 0);
-                                w1 = w0;
+                        if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
+                        const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
+                        uint32_t v[4][16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
+                        if (r == 0) bulk_wait_read0();       // the team's previous TMA store has finished reading the slot
+                        tmem_ld_wait();
+                        epi_bar(team);
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (g < ngrp) {
+                                uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+                                if (valid) {
+                                    w0.x = pack_bf16x2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1]));
+                                    w0.y = pack_bf16x2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3]));
+                                    w0.z = pack_bf16x2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5]));
+                                    w0.w = pack_bf16x2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7]));
+                                    w1.x = pack_bf16x2(__uint_as_float(v[g][8]), __uint_as_float(v[g][9]));
+                                    w1.y = pack_bf16x2(__uint_as_float(v[g][10]), __uint_as_float(v[g][11]));
+                                    w1.z = pack_bf16x2(__uint_as_float(v[g][12]), __uint_as_float(v[g][13]));
+                                    w1.w = pack_bf16x2(__uint_as_float(v[g][14]), __uint_as_float(v[g][15]));
+                                }
+                                *reinterpret_cast<uint4*>(srow + (((2 * g) ^ (r & 7)) << 4)) = w0;
+                                *reinterpret_cast<uint4*>(srow + (((2 * g + 1) ^ (r & 7)) << 4)) = w1;
                             }
-                            *reinterpret_cast<uint4*>(srow + (((2 * g) ^ (r & 7)) << 4)) = w0;
-                            *reinterpret_cast<uint4*>(srow + (((2 * g + 1) ^ (r & 7)) << 4)) = w1;
                         }
                         fence_proxy_async();
-                        epi_bar();
+                        epi_bar(team);
                         if (r == 0) {
                             tma_store_4d(&p.o_map, slot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
@@ -337,7 +347,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                         }
                     }
                 } else {
-                    // fp32 NCHW logits: out[((b*N + n)*OH + oy)*OW + ox], N <= 16
+                    // fp32 NCHW logits: out[((b*N + n)*OH + oy)*OW + ox], N <= 16; the teams alternate sub-tiles
+                    if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
                     uint32_t v[16];
                     tmem_ld16(trow, v);
                     tmem_ld_wait();
@@ -351,7 +362,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                     }
                 }
             }
-            // all tcgen05.ld of this accumulator stage have completed: hand it back to the MMA warp
+            // all tcgen05.ld of this warp on this accumulator stage have completed: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
             }
         }
         if (OUT_MODE == 0 && r == 0) bulk_wait_all();
-        if (p.prof && r == 0) {
+        if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
         }
@@ -411,7 +422,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct Tiling {
-    int msub, nsx, nsy, sub_w, sub_h, TW, TH, sa, sb;
+    int msub, nsx, nsy, sub_w, sub_h, TW, TH, sa, sb, tps;
     uint32_t a_stage;
     long long tiles;
     double cost;
@@ -488,8 +499,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     const bool xhalo = hx > 0;
     const int staging = d->out_mode == 0 ? 2 * (int)kStageSlot : 0;
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
-    const uint32_t b_stage = (uint32_t)d->n_tile * 128u;
+    const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
+    int max_taps = 1;
+    for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
+    const int mma_hw = d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4;   // cycles per MMA (measured law)
     Tiling best;
     best.msub = 0;
     for (int m = kMaxSub; m >= 1; m >>= 1) {
@@ -509,17 +523,30 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             int pw = c.TW + hx, ph = c.TH + hy;
             if (pw > 256 || ph > 256) continue;
             c.a_stage = ((uint32_t)pw * ph * 128u + 1023u) & ~1023u;
-            c.sb = b_stage <= 8192 ? 6 : (b_stage <= 16384 ? 4 : 3);
-            int sa = (avail - c.sb * (int)b_stage) / (int)c.a_stage;
-            if (sa < 2) { c.sb = 2; sa = (avail - c.sb * (int)b_stage) / (int)c.a_stage; }
-            if (sa < 2) continue;
-            c.sa = sa > 6 ? 6 : sa;
+            // shared memory: 2 patch stages first, then weight stages of `tps` taps (the MMA warp pays ~300-400 cycles
+            // per stage hand-over, so a stage should carry many MMAs), then more patch stages with what is left
+            const int rest = avail - 2 * (int)c.a_stage;
+            if (rest < 2 * (int)b_tap) continue;
+            int tps_max = rest / (2 * (int)b_tap);
+            if (tps_max > max_taps) tps_max = max_taps;
+            if (tps_max * (int)b_tap > 48 * 1024) tps_max = (48 * 1024) / (int)b_tap > 0 ? (48 * 1024) / (int)b_tap : 1;
+            const int groups = ceil_div(max_taps, tps_max);
+            c.tps = ceil_div(max_taps, groups);
+            const int b_stage_c = c.tps * (int)b_tap;
+            c.sb = rest / b_stage_c;
+            if (c.sb > 4) c.sb = 4;
+            if (max_taps == 1 && b_stage_c <= 16384 && rest / b_stage_c >= 6) c.sb = 6;
+            int sa = (avail - c.sb * b_stage_c) / (int)c.a_stage;
+            c.sa = sa > 4 ? 4 : sa;
             c.tiles = (long long)ceil_div(d->W, c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
-            // crude per-tile time (cycles): L2 -> smem bytes at 32 B/cycle/SM vs MMA issue time
+            // crude per-tile time (cycles): L2 -> smem bytes at 32 B/cycle/SM vs MMA time + stage hand-overs
             const double l2 = (double)nkb_total * pw * ph * 128.0 / 32.0;
-            double wbytes = 0;
-            for (int s = 0; s < d->num_src; ++s) wbytes += (double)ntap[s] * p.src_nblk[s] * b_stage;
-            const double mma_cyc = (double)m * nmma_steps * (d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4);
+            double wbytes = 0, waits = 0;
+            for (int s = 0; s < d->num_src; ++s) {
+                wbytes += (double)ntap[s] * p.src_nblk[s] * b_tap;
+                if (ntap[s]) waits += (double)p.src_nblk[s] * (1 + ceil_div(ntap[s], c.tps));
+            }
+            const double mma_cyc = (double)m * nmma_steps * mma_hw + 350.0 * waits;
             const double per_tile = (l2 + wbytes / 32.0 > mma_cyc ? l2 + wbytes / 32.0 : mma_cyc) + 1500.0;
             const long long rounds = (c.tiles + num_sms - 1) / num_sms;
             c.cost = (double)rounds * per_tile;
@@ -531,7 +558,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.msub = best.msub; p.sub_w = best.sub_w; p.sub_h = best.sub_h;
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
-    p.a_stage = best.a_stage; p.b_stage = b_stage;
+    p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.b_stage = (uint32_t)best.tps * b_tap;
     p.tiles_x = ceil_div(d->W, p.TW);
     p.tiles_y = ceil_div(d->H, p.TH);
     p.tiles_n = tiles_n;
@@ -638,9 +665,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         for (unsigned i = 0; i < grid; ++i)
             for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j] / grid;
         fprintf(stderr,
-                "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
+                "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d tps %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
                 "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f (cycles, CTA average)\n",
-                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
     }
     DMM_LAUNCH_CHECK("igemm2_kernel");
     return 0;
