@@ -80,6 +80,26 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return 0;
 }
 
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems, uint32_t box_cols,
+                     uint32_t box_rows, int swizzle_bytes) {
+    EncodeTiledFn enc = get_encode();
+    DMM_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    DMM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "fp32 tensor map base %p is not 16-byte aligned", base);
+    DMM_CHECK((row_stride_elems * 4ull) % 16 == 0 && row_stride_elems > 0, "fp32 tensor map row stride %llu elements",
+              (unsigned long long)row_stride_elems);
+    DMM_CHECK(box_cols >= 1 && box_cols <= 256 && box_rows >= 1 && box_rows <= 256, "fp32 tensor map box %u x %u", box_cols, box_rows);
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {row_stride_elems * 4ull};
+    cuuint32_t bx[2] = {box_cols, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DMM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with CUresult %d (%llu x %llu, box %u x %u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, box_cols, box_rows);
+    return 0;
+}
+
 }  // namespace dmm
 
 extern "C" const char* dmm_last_error(void) { return dmm::g_err; }

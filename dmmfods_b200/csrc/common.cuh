@@ -36,6 +36,10 @@ int check_cuda(cudaError_t e, const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
 
+// fp32 2-D tensor map (row-major [rows][row_stride]) for TMA reduce-add epilogues; swizzle_bytes in {0, 128}.
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems, uint32_t box_cols,
+                     uint32_t box_rows, int swizzle_bytes);
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------------------------

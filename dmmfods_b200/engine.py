@@ -271,6 +271,7 @@ class Engine:
         buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x."""
         T = len(taps)
         plan = ops.plan_conv_wgrad(x, ys, taps, M, N)
+        tap_off = [tap_off[t] for t in plan["tap_order"]]
         did = self._req_dw(plan["rows"] * plan["ld"])
         P = B * H * W
         nl = len(plan["launches"])

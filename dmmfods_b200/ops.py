@@ -4,6 +4,7 @@ Every function only enqueues kernels on torch's current CUDA stream.  Activation
 bf16 matrices `[P = B*H*W, ld]` (`Mat`).  Nothing here computes on the CPU or falls back to torch ops.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -228,13 +229,31 @@ def make_wgrad(a_srcs, b_srcs, a_slots, b_slots, n_tile, W, H, B, dw, ld, ya=1, 
     d.n_tile = n_tile
     d.ya, d.yb, d.a_step, d.b_step = ya, yb, a_step, b_step
     d.W, d.H, d.B = W, H, B
-    if kpx is None:      # keep >= 3 pipeline stages in 200 KB of shared memory
-        na = (len(a_slots) + 1) // 2
-        bw = 64 if n_tile >= 64 else n_tile
-        stage64 = 2 * na * 8192 + len(b_slots) * ceil_to(n_tile, bw) * 128
-        kpx = 64 if stage64 * 3 <= 200 * 1024 else 32
+    na = (len(a_slots) + 1) // 2
+    bw = 64 if n_tile >= 64 else n_tile
+    # "family" (see wgrad.cu): every B group is a shifted view of one source -> one halo patch per stage, tile_w = 8
+    family = (len(b_slots) > 1 and n_tile <= 64 and yb == 1 and len({(s[0], s[3]) for s in b_slots}) == 1)
+    hx = max(s[2] for s in b_slots) - min(s[2] for s in b_slots)
+    hy = max(s[1] for s in b_slots) - min(s[1] for s in b_slots)
+
+    def stage_bytes(k):
+        a = 2 * na * k * 128
+        if family:
+            return a + (k // 8 + hy) * (8 + hx) * bw * 2
+        return a + len(b_slots) * ceil_to(n_tile, bw) * k * 2
+    if kpx is None:      # the MMA warp pays a few hundred cycles per stage hand-over: big stages, but >= 3 (else 2) of them
+        kpx = int(os.environ.get("DMM_WGRAD_KPX", "0")) or None
+    if kpx is None:
+        for need in (3, 2):
+            for k in (128, 64, 32):
+                if stage_bytes(k) * need <= 200 * 1024:
+                    kpx = k
+                    break
+            if kpx:
+                break
+        kpx = kpx or 32
     d.kpx = kpx
-    d.tile_w = tile_w or pick_tile_w(W, H, kpx)
+    d.tile_w = tile_w or (8 if family else pick_tile_w(W, H, kpx))
     d.splits = splits
     d.dw = dw.data_ptr() if isinstance(dw, torch.Tensor) else dw
     d.ld = ld
@@ -249,8 +268,10 @@ def plan_conv_wgrad(x, ys, taps, M, N):
     """Launch plan for  dw[t][m][n] = sum_pix X(pix + tap_t)[m] * Y[ysrc_t](pix)[n]   (t < T, m < M, n < N).
 
     x: View with M channels; ys: list of Views with N channels; taps: list of (ysrc, dy, dx).
-    Returns dict(launches=[kwargs for make_wgrad without dw], rows, ld, dt, dm, dn): the scratch matrix has
-    `rows` x `ld` fp32 entries and element (t, m, n) lives at dw[t*dt + m*dm + n*dn]."""
+    Returns dict(launches=[kwargs for make_wgrad without dw], rows, ld, dt, dm, dn, tap_order): the scratch matrix has
+    `rows` x `ld` fp32 entries and element (t', m, n) lives at dw[t'*dt + m*dm + n*dn], where t' is the position of tap
+    tap_order[t'] of the caller's list (the plan may reorder taps so that horizontally adjacent ones can share one wide
+    MMA; permute any per-tap table, e.g. the unpack offsets, with tap_order)."""
     T = len(taps)
     mch = (M + 63) // 64                     # 64-channel chunks of X
     if N <= 64:
@@ -262,10 +283,12 @@ def plan_conv_wgrad(x, ys, taps, M, N):
             ya = (mch + 2 * na - 1) // (2 * na)
             ld = T * nt
             a_slots = [(0, 0, 0, 64 * i, 64 * i) for i in range(n_slots)]
-            b_slots = [(ys_i, -dy, -dx, 0, t * nt) for t, (ys_i, dy, dx) in enumerate(taps)]
+            # B shift = -tap; ascending (source, row, x) order puts the taps of one kernel row next to each other
+            order = sorted(range(T), key=lambda t: (taps[t][0], -taps[t][1], -taps[t][2]))
+            b_slots = [(taps[t][0], -taps[t][1], -taps[t][2], 0, i * nt) for i, t in enumerate(order)]
             launch = dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=b_slots, n_tile=nt, ya=ya, yb=1,
                           a_step=128 * na, b_step=0)
-            return dict(launches=[launch], rows=mch * 64, ld=ld, dt=nt, dm=ld, dn=1)
+            return dict(launches=[launch], rows=mch * 64, ld=ld, dt=nt, dm=ld, dn=1, tap_order=order)
         if M <= 256:
             # roles swapped: A = shifted output-gradient chunks (rows = (tap, n)), B = the activation (columns = m)
             nt = 16 if M <= 16 else (32 if M <= 32 else (64 if M <= 64 else ceil_to(M, 16)))
@@ -282,7 +305,7 @@ def plan_conv_wgrad(x, ys, taps, M, N):
                         a_slots.append((ys_i, -dy, -dx, 64 * j, t * npad + 64 * j))
                 launches.append(dict(a_srcs=list(ys), b_srcs=[x], a_slots=a_slots, b_slots=[(0, 0, 0, 0, 0)], n_tile=nt,
                                      ya=1, yb=1, a_step=0, b_step=0))
-            return dict(launches=launches, rows=T * npad, ld=nt, dt=npad * nt, dm=1, dn=nt)
+            return dict(launches=launches, rows=T * npad, ld=nt, dt=npad * nt, dm=1, dn=nt, tap_order=list(range(T)))
     # general: one launch per tap, A = activation shifted by +tap, B = output gradient in 128-channel groups
     nb = 1 if N <= 128 else 2
     na = max(1, min(4 // nb, (mch + 1) // 2))
@@ -297,7 +320,7 @@ def plan_conv_wgrad(x, ys, taps, M, N):
         b_slots = [(ys_i, 0, 0, 128 * g, t * npad + 128 * g) for g in range(nb)]
         launches.append(dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=b_slots, n_tile=128, ya=ya, yb=yb,
                              a_step=128 * na, b_step=128 * nb))
-    return dict(launches=launches, rows=mch * 64, ld=ld, dt=npad, dm=ld, dn=1)
+    return dict(launches=launches, rows=mch * 64, ld=ld, dt=npad, dm=ld, dn=1, tap_order=list(range(T)))
 
 
 def _i32arr(vals):

@@ -35,6 +35,7 @@ def _conv_wgrad_case(B, Cin, Cout, H, W, K, seed, n_tile=None, splits=0):
     T = K * K
     plan, dw = _run_plan(xm.view(0, Cin), [gm.view(0, N)], fwd, Cin, N, W, H, B, splits)
     grad = torch.full((Cout, Cin, K, K), float("nan"), dtype=torch.float32, device="cuda")
+    off = [off[t] for t in plan["tap_order"]]
     ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], Cin, Cout, grad, T, off, Cin * K * K, K * K)
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
@@ -85,6 +86,7 @@ def test_wgrad_conv_transpose(C, H, W, OH, OW):
     ys = [gm.phase_view(py, px) for py in range(2) for px in range(2)]
     plan, dw = _run_plan(xm.view(), ys, taps, C, C, W, H, B)
     grad = torch.full((C, C, 3, 3), float("nan"), dtype=torch.float32, device="cuda")
+    off = [off[t] for t in plan["tap_order"]]
     ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], C, C, grad, 9, off, 9, C * 9)      # weight (Cin=m, Cout=n, kh, kw)
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
