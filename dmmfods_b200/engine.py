@@ -661,33 +661,20 @@ class Engine:
                        25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
         if self.need_backward:
             st = []
-            kk = 25 * self.ncls
-            ncp = ceil_to(kk, 16)
-            dl = self._mat(B, H, W, ncp)     # "im2col" of d(logits): column t*ncls + n = dlogits[n](pixel - tap_t)
+            dl = self._mat(B, H, W, 16)      # d(logits) as a pixel-major bf16 matrix (channels >= num_classes are zero)
 
             def run_dl(_a, stream, lib=self.lib, dl=dl):
-                return lib.dmm_dlogits_im2col(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, 5, dl.ptr(), dl.ld, stream)
-            self._emit(st, run_dl, None, hp + ".dlogits_im2col", kind="dlogits_im2col", nbytes=B * H * W * (self.ncls * 4 + ncp * 2))
+                return lib.dmm_nchw_to_nhwc_bf16(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, dl.ptr(), dl.ld, stream)
+            self._emit(st, run_dl, None, hp + ".dlogits_nhwc", kind="nchw_to_nhwc", nbytes=B * H * W * (self.ncls * 4 + 16 * 2))
             da1h = self._tmpmat("head_da1", B, H, W, nf2)
             dr0 = self._tmpmat("head_dr0", B, H, W, nf2)
             da0 = self._tmpmat("head_da0", B, H, W, ld0)
-            # dW[t][m][n] = sum_q a1h(q)[m] * dl_im2col(q)[t*ncls + n]: one 1-tap weight-gradient GEMM with N = 25*ncls
-            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view()], [(0, 0, 0)], [0], nf2, ncp,
-                             nf2, kk, nf2 * 25, 25, W, H, B)
-            uj = self._unpack_jobs[-1]       # (t, m, n) lives at dw[m*ld + t*ncls + n]
-            uj.update(T=25, N=self.ncls, dt=self.ncls * uj["dn"], tap_off=list(range(25)), sn=nf2 * 25, sc=25)
-            st[-1].flops = 2.0 * B * H * W * nf2 * self.ncls * 25
-            # d(a1h)[p][c] = sum_col dl_im2col(p)[col] * w[n][c][t], col = t*ncls + n: a 1x1 convolution over 25*ncls columns
-            Kp = ceil_to(ncp, ops.KWIDTH)
-            n_tile = ops.pick_n_tile(nf2)
-            n_rows = ceil_to(nf2, n_tile)
-            wid = self._req_wpk(n_rows, Kp)
-            self._pack_jobs.append(dict(w=self.p[hp + ".refine1.weight"], wid=wid, n_valid=nf2, n_rows=n_rows, C=kk, T=1,
-                                        tap_off=[0], sn=25, sc=1, sc2=nf2 * 25, cdiv=self.ncls))
-            dd = ops.make_igemm([dl.view()], [(0, 0, 0)], 0, Kp, n_rows, W, H, B, nf2, da1h.ptr(), da1h.ld, n_tile=n_tile)
-            self._emit(st, self.lib.dmm_conv_igemm, dd, hp + ".refine1.dgrad", kind="igemm_dgrad",
-                       flops=2.0 * B * H * W * nf2 * self.ncls * 25, nbytes=B * H * W * (ncp + nf2) * 2)
-            self._fix_w.append((dd, wid))
+            # refine1 (5x5, 64 -> num_classes): weight gradient = activation x 25 shifted views of d(logits) (one halo patch,
+            # five wide MMAs per k-step); data gradient = a 25-tap convolution over the 16-channel d(logits) matrix
+            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)], conv5[0], conv5[2],
+                             nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B)
+            self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1], conv5[2],
+                             self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
             self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0)
             self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
                              conv3x3[2], Ct, nf2, Ct, nf2, Ct * 9, 9, W, H, B)

@@ -289,6 +289,27 @@ def plan_conv_wgrad(x, ys, taps, M, N):
             launch = dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=b_slots, n_tile=nt, ya=ya, yb=1,
                           a_step=128 * na, b_step=0)
             return dict(launches=[launch], rows=mch * 64, ld=ld, dt=nt, dm=ld, dn=1, tap_order=order)
+        kw_max = max(sum(1 for t in taps if (t[0], t[1]) == r) for r in {(t[0], t[1]) for t in taps})
+        if kw_max * nt <= 512:
+            # same, but too many taps for the 512 TMEM columns: one launch per group of kernel rows
+            na = max(1, min(4, 512 // (kw_max * nt), (mch + 1) // 2))
+            n_slots = min(2 * na, mch)
+            ya = (mch + 2 * na - 1) // (2 * na)
+            order = sorted(range(T), key=lambda t: (taps[t][0], -taps[t][1], -taps[t][2]))
+            a_slots = [(0, 0, 0, 64 * i, 64 * i) for i in range(n_slots)]
+            launches, cur, cur_rows = [], [], []
+            for i, t in enumerate(order):
+                row = (taps[t][0], taps[t][1])
+                if row not in cur_rows and na * (len(cur) + kw_max) * nt > 512 and cur:
+                    launches.append(cur)
+                    cur, cur_rows = [], []
+                if row not in cur_rows:
+                    cur_rows.append(row)
+                cur.append((taps[t][0], -taps[t][1], -taps[t][2], 0, i * nt))
+            launches.append(cur)
+            launches = [dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=bs, n_tile=nt, ya=ya, yb=1, a_step=128 * na,
+                             b_step=0) for bs in launches]
+            return dict(launches=launches, rows=mch * 64, ld=T * nt, dt=nt, dm=T * nt, dn=1, tap_order=order)
         if M <= 256:
             # roles swapped: A = shifted output-gradient chunks (rows = (tap, n)), B = the activation (columns = m)
             nt = 16 if M <= 16 else (32 if M <= 32 else (64 if M <= 64 else ceil_to(M, 16)))
