@@ -273,10 +273,11 @@ __device__ __forceinline__ void bn_relu_dz(const dmm_bn_bwd_args_t& p, const __n
     if (GMODE == 0) {
         load_g8<GT>(g, row * p.ldg + chunk * 8, dz);
     } else {
-        const int xx = (int)(row % p.W);
-        const long long t = row / p.W;
-        const int yy = (int)(t % p.H);
-        const int b = (int)(t / p.H);
+        const unsigned r32 = (unsigned)row;          // host guarantees B*H*W < 2^31 for the pooled modes
+        const int xx = (int)(r32 % (unsigned)p.W);
+        const unsigned t = r32 / (unsigned)p.W;
+        const int yy = (int)(t % (unsigned)p.H);
+        const int b = (int)(t / (unsigned)p.H);
         if (GMODE == 1) {
             const int oy = yy >> 1, ox = xx >> 1;
             if (oy < OH && ox < OW) {
@@ -606,39 +607,170 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lean avg-pool-parent (gmode 1, bf16 gradient, even H and W) variants: one thread per (pooled pixel, 8-channel chunk),
+// the parent gradient is loaded once and the four children are independent 16-byte loads; blockIdx.x walks pooled rows,
+// so there is no per-element division.  PASS 0 = reduce, PASS 1 = apply.
+// ---------------------------------------------------------------------------------------------
+template <int PASS, int OUT_MODE>
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_pool_fast_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    __shared__ float sm[PASS == 0 ? 2 * kEwThreads * 8 : 1];
+    __shared__ __align__(16) float cf[5][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            if (PASS == 0) {
+                cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+            } else {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+                    const double* r = p.bn.sums + (size_t)s * 2 * p.bn.sums_ld + p.bn.sums_off + c;
+                    a += r[0];
+                    b += r[p.bn.sums_ld];
+                }
+                const float c1 = (float)(a / p.bn.count), c2 = (float)(b / p.bn.count);
+                const float A = (p.bn.gamma ? p.bn.gamma[c] : 1.f) * k.invstd;
+                const float Bc = -A * k.invstd * c2;
+                cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = A; cf[3][tid] = Bc; cf[4][tid] = -A * c1 - Bc * k.mean;
+                if (blockIdx.x == 0) {
+                    if (p.bn.dgamma) p.bn.dgamma[c] = (float)b;
+                    if (p.bn.dbeta) p.bn.dbeta[c] = (float)a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    const int t8 = threadIdx.x * 8;
+    if (active && (PASS == 0 || p.out != nullptr)) {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g) + chunk * 8;
+        const int prow_total = p.B * OH;
+        for (int pr = blockIdx.x; pr < prow_total; pr += gridDim.x) {
+            const int b = pr / OH, oy = pr - b * OH;
+            const long long xrow0 = ((long long)b * p.H + 2 * oy) * p.W;
+            const long long grow = (long long)pr * OW;
+            for (int ox = threadIdx.y; ox < OW; ox += ry) {
+                float gv[8], xv[4][8];
+                unpack8(ldg16(g + (grow + ox) * p.ldg), gv);
+                const long long r00 = xrow0 + 2 * ox;
+                const long long rr[4] = {r00, r00 + 1, r00 + p.W, r00 + p.W + 1};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) unpack8(ldg16(x + rr[u] * p.ldx), xv[u]);
+                float4 pa[4], pb[4];
+                if (PASS == 1 && OUT_MODE == 2) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float* of = reinterpret_cast<const float*>(p.out) + rr[u] * p.ldo + chunk * 8;
+                        pa[u] = *reinterpret_cast<const float4*>(of);
+                        pb[u] = *reinterpret_cast<const float4*>(of + 4);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float dx[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float xx = xv[u][j];
+                        const float dz = fmaf(xx, cf[0][t8 + j], cf[1][t8 + j]) > 0.f ? 0.25f * gv[j] : 0.f;
+                        if (PASS == 0) {
+                            s1[j] += dz;
+                            s2[j] = fmaf(dz, xx - cf[2][t8 + j], s2[j]);
+                        } else {
+                            dx[j] = fmaf(cf[2][t8 + j], dz, fmaf(cf[3][t8 + j], xx, cf[4][t8 + j]));
+                        }
+                    }
+                    if (PASS == 1) {
+                        const long long o = rr[u] * p.ldo + chunk * 8;
+                        if (OUT_MODE == 0) {
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8(dx);
+                        } else {
+                            float* of = reinterpret_cast<float*>(p.out) + o;
+                            float4 a = make_float4(dx[0], dx[1], dx[2], dx[3]);
+                            float4 bq = make_float4(dx[4], dx[5], dx[6], dx[7]);
+                            if (OUT_MODE == 2) {
+                                a.x += pa[u].x; a.y += pa[u].y; a.z += pa[u].z; a.w += pa[u].w;
+                                bq.x += pb[u].x; bq.y += pb[u].y; bq.z += pb[u].z; bq.w += pb[u].w;
+                            }
+                            *reinterpret_cast<float4*>(of) = a;
+                            *reinterpret_cast<float4*>(of + 4) = bq;
+                        }
+                    }
+                }
+            }
+        }
+        if (PASS == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s2[j] *= cf[3][t8 + j];
+        }
+    }
+    if (PASS == 0) block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+}
+
+// ---------------------------------------------------------------------------------------------
 // stem im2col: fp32 NCHW (B,C1[+C2],H,W) -> bf16 [B*OH*OW, kpad], k = ci*49 + kh*7 + kw
 // (same k order as the flattened Conv2d weight (Cout, Cin*7*7)), zero padded.
 // ---------------------------------------------------------------------------------------------
+// One block = one output row segment of kIm2colPx pixels: the 7 input rows x (2*px+5) columns x C channels it needs are
+// staged in shared memory with coalesced loads, a k -> patch-offset table replaces the per-element divisions, and every
+// thread then emits 16-byte chunks of im2col rows.
+constexpr int kIm2colPx = 64;
 __global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ x1, int C1,
                                                            const float* __restrict__ x2, int C2, int B, int H, int W,
                                                            int OH, int OW, __nv_bfloat16* __restrict__ out, int kpad) {
+    extern __shared__ float im_sm[];                 // [C][7][PW] patch, then int koff[kpad]
+    const int C = C1 + C2;
+    const int PW = 2 * kIm2colPx + 5;
+    float* patch = im_sm;
+    int* koff = reinterpret_cast<int*>(im_sm + C * 7 * PW);
+    const int K = C * 49;
+    const int segs = (OW + kIm2colPx - 1) / kIm2colPx;
+    const int seg = blockIdx.x % segs;
+    const int row = blockIdx.x / segs;               // b * OH + oy
+    const int oy = row % OH, b = row / OH;
+    const int ox0 = seg * kIm2colPx;
+    const int ix0 = 2 * ox0 - 3, iy0 = 2 * oy - 3;
+    for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+        int o = -1;
+        if (k < K) {
+            const int ci = k / 49, tp = k - ci * 49;
+            const int kh = tp / 7, kw = tp - kh * 7;
+            o = (ci * 7 + kh) * PW + kw;
+        }
+        koff[k] = o;
+    }
+    for (int i = threadIdx.x; i < C * 7 * PW; i += blockDim.x) {
+        const int px = i % PW;
+        const int r = i / PW;
+        const int kh = r % 7, ci = r / 7;
+        const int iy = iy0 + kh, ix = ix0 + px;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = ci < C1 ? __ldg(x1 + (((long long)b * C1 + ci) * H + iy) * W + ix)
+                        : __ldg(x2 + (((long long)b * C2 + (ci - C1)) * H + iy) * W + ix);
+        patch[i] = v;
+    }
+    __syncthreads();
     const int chunks = kpad >> 3;
-    const long long total = (long long)B * OH * OW * chunks;
-    const int K = (C1 + C2) * 49;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % chunks);
-        const long long pix = i / chunks;
-        const int ox = (int)(pix % OW);
-        const long long t = pix / OW;
-        const int oy = (int)(t % OH);
-        const int b = (int)(t / OH);
+    const int npx = min(kIm2colPx, OW - ox0);
+    __nv_bfloat16* orow = out + ((long long)row * OW + ox0) * kpad;
+    for (int i = threadIdx.x; i < npx * chunks; i += blockDim.x) {
+        const int px = i / chunks, ch = i - px * chunks;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = ch * 8 + j;
-            float v = 0.f;
-            if (k < K) {
-                const int ci = k / 49, tp = k - ci * 49;
-                const int kh = tp / 7, kw = tp - kh * 7;
-                const int iy = 2 * oy - 3 + kh, ix = 2 * ox - 3 + kw;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                    v = ci < C1 ? __ldg(x1 + (((long long)b * C1 + ci) * H + iy) * W + ix)
-                                : __ldg(x2 + (((long long)b * C2 + (ci - C1)) * H + iy) * W + ix);
-                }
-            }
-            f[j] = v;
+            const int o = koff[ch * 8 + j];
+            f[j] = o >= 0 ? patch[o + 2 * px] : 0.f;
         }
-        *reinterpret_cast<uint4*>(out + pix * kpad + ch * 8) = pack8(f);
+        *reinterpret_cast<uint4*>(orow + (long long)px * kpad + ch * 8) = pack8(f);
     }
 }
 
@@ -685,6 +817,9 @@ __global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict
 // head input: out[p, :] = relu(bn0(cat(upsample2(u)[p], x1[p], x2[p]))), bf16 rows of pitch ldo
 // (columns >= Cu+C1+C2 are zero).  One thread per (pixel, 8-channel chunk).
 // ---------------------------------------------------------------------------------------------
+// One block = one output row (b, y); thread t owns chunk t % chunks for pixels t / chunks, t / chunks + ppb, ... so the
+// inner loop has no divisions, 16-byte stores of a row are contiguous, and every up-sampled source row is read by
+// exactly two blocks.
 __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
     extern __shared__ float coef[];   // [2][Cpad]
     const int Ct = p.Cu + p.C1 + p.C2;
@@ -702,41 +837,46 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
         coef[Cpad + c] = sh;
     }
     __syncthreads();
-    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(p.u);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-    const long long total = (long long)p.B * p.H * p.W * chunks;
-    const long long HW = (long long)p.H * p.W;
+    const int cu = p.Cu >> 3;                        // chunks that come from the up-sampled decoder output
+    const int yy = blockIdx.x % p.H, b = blockIdx.x / p.H;
     const int UH = p.H >> 1, UW = p.W >> 1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % chunks);
-        const long long pix = i / chunks;
-        const int xx = (int)(pix % p.W);
-        const long long t = pix / p.W;
-        const int yy = (int)(t % p.H);
-        const int b = (int)(t / p.H);
-        float f[8];
-        if (ch * 8 + 8 <= p.Cu) {
-            const long long up = ((long long)b * UH + (yy >> 1)) * UW + (xx >> 1);
-            unpack8(ldg16(u + up * p.ldu + ch * 8), f);
-        } else {
+    const long long HW = (long long)p.H * p.W;
+    __nv_bfloat16* orow0 = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + yy) * p.W * p.ldo;
+    // phase 1: thread t owns chunk t % cu for pixels t / cu, t / cu + ppb, ...: no divisions in the loop, contiguous 16-byte
+    // stores, every up-sampled source row is read by exactly two blocks
+    const int ppb = blockDim.x / cu;
+    if ((int)threadIdx.x < ppb * cu) {
+        const int ch = threadIdx.x % cu, px0 = threadIdx.x / cu;
+        const __nv_bfloat16* urow = reinterpret_cast<const __nv_bfloat16*>(p.u) + ((long long)b * UH + (yy >> 1)) * UW * p.ldu + ch * 8;
+        __nv_bfloat16* orow = orow0 + ch * 8;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = coef[ch * 8 + j]; sh[j] = coef[Cpad + ch * 8 + j]; }
+#pragma unroll 4
+        for (int xx = px0; xx < p.W; xx += ppb) {
+            float f[8];
+            unpack8(ldg16(urow + (long long)(xx >> 1) * p.ldu), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+            *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
+        }
+    }
+    // phase 2: the raw network inputs (fp32 NCHW planes, coalesced along x) fill the remaining chunks
+    const float* x1row = p.x1 + (long long)b * p.C1 * HW + (long long)yy * p.W;
+    const float* x2row = p.C2 ? p.x2 + (long long)b * p.C2 * HW + (long long)yy * p.W : nullptr;
+    for (int ch = cu; ch < chunks; ++ch) {
+        for (int xx = threadIdx.x; xx < p.W; xx += blockDim.x) {
+            float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = ch * 8 + j;
                 float v = 0.f;
-                if (c < p.Cu) {
-                    const long long up = ((long long)b * UH + (yy >> 1)) * UW + (xx >> 1);
-                    v = __bfloat162float(u[up * p.ldu + c]);
-                } else if (c < p.Cu + p.C1) {
-                    v = __ldg(p.x1 + ((long long)b * p.C1 + (c - p.Cu)) * HW + (long long)yy * p.W + xx);
-                } else if (c < Ct) {
-                    v = __ldg(p.x2 + ((long long)b * p.C2 + (c - p.Cu - p.C1)) * HW + (long long)yy * p.W + xx);
-                }
-                f[j] = v;
+                if (c < p.Cu + p.C1) v = __ldg(x1row + (long long)(c - p.Cu) * HW + xx);
+                else if (c < Ct) v = __ldg(x2row + (long long)(c - p.Cu - p.C1) * HW + xx);
+                f[j] = fmaxf(fmaf(v, coef[c], coef[Cpad + c]), 0.f);
             }
+            *reinterpret_cast<uint4*>(orow0 + (long long)xx * p.ldo + ch * 8) = pack8(f);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], coef[ch * 8 + j], coef[Cpad + ch * 8 + j]), 0.f);
-        *reinterpret_cast<uint4*>(out + pix * p.ldo + ch * 8) = pack8(f);
     }
 }
 
@@ -1147,6 +1287,7 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
     DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd && d->bn.count > 0, "dmm_bn_relu_bwd: missing BN state");
     DMM_CHECK(d->out_mode >= 0 && d->out_mode <= 2, "dmm_bn_relu_bwd: out_mode=%d", d->out_mode);
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    DMM_CHECK(d->gmode == 0 || (long long)d->B * d->H * d->W < (1ll << 31), "dmm_bn_relu_bwd: too many pixels for a pooled gradient mode");
     int OH = d->H, OW = d->W;
     if (d->gmode == 1) { OH = d->H / 2; OW = d->W / 2; }
     if (d->gmode == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
@@ -1167,6 +1308,19 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
 #undef DMM_APPLY_FAST
         }
         DMM_LAUNCH_CHECK("bn_bwd fast kernel");
+        return 0;
+    }
+    if (d->gmode == 1 && !d->g_is_f32 && d->dz_out == nullptr && d->H % 2 == 0 && d->W % 2 == 0) {      // lean pooled kernels
+        ColCfg kp = col_cfg(d->C, (long long)d->B * OH * OW);
+        unsigned gx = (unsigned)(d->B * OH);
+        const unsigned cap = (unsigned)(kNumSm * kMaxBlocksPerSm) / kp.grid.y;
+        if (gx > cap) gx = cap > 0 ? cap : 1;
+        kp.grid.x = gx;
+        if (PASS == 0) bn_bwd_pool_fast_kernel<0, 0><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
+        else if (d->out_mode == 0) bn_bwd_pool_fast_kernel<1, 0><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
+        else if (d->out_mode == 1) bn_bwd_pool_fast_kernel<1, 1><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
+        else bn_bwd_pool_fast_kernel<1, 2><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
+        DMM_LAUNCH_CHECK("bn_bwd pooled kernel");
         return 0;
     }
 #define DMM_BWD_LAUNCH(GM, GT)                                                                      \
@@ -1201,8 +1355,10 @@ extern "C" int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, in
     DMM_CHECK(kpad % 8 == 0 && kpad >= (C1 + C2) * 49, "dmm_im2col_7x7s2: kpad=%d too small / not a multiple of 8", kpad);
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
-    const long long total = (long long)B * OH * OW * (kpad / 8);
-    im2col_7x7s2_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const int segs = (OW + kIm2colPx - 1) / kIm2colPx;
+    const size_t smem = (size_t)(C1 + C2) * 7 * (2 * kIm2colPx + 5) * sizeof(float) + (size_t)kpad * sizeof(int);
+    DMM_CHECK(smem <= 48 * 1024, "dmm_im2col_7x7s2: %d input channels need %zu bytes of shared memory", C1 + C2, smem);
+    im2col_7x7s2_kernel<<<(unsigned)((long long)B * OH * segs), 256, smem, (cudaStream_t)stream>>>(
         x1, C1, x2, C2, B, H, W, OH, OW, reinterpret_cast<__nv_bfloat16*>(out), kpad);
     DMM_LAUNCH_CHECK("im2col_7x7s2_kernel");
     return 0;
@@ -1223,13 +1379,14 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     DMM_CHECK(d && d->u && d->x1 && d->out, "dmm_head_input: null pointer");
     DMM_CHECK(d->Cu % 8 == 0 && d->ldu % 8 == 0 && d->ldo % 8 == 0, "dmm_head_input: Cu / pitches must be multiples of 8");
     DMM_CHECK(d->ldo >= d->Cu + d->C1 + d->C2, "dmm_head_input: ldo too small");
+    DMM_CHECK(d->Cu >= 8 && d->Cu <= 2048, "dmm_head_input: Cu=%d out of range", d->Cu);
     DMM_CHECK(d->H % 2 == 0 && d->W % 2 == 0, "dmm_head_input: H and W must be even (nn.Upsample x2 of the decoder output)");
     DMM_CHECK(d->C2 == 0 || d->x2, "dmm_head_input: x2 missing");
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
     const int chunks = (int)(d->ldo / 8);
-    const long long total = (long long)d->B * d->H * d->W * chunks;
+    DMM_CHECK(chunks <= 256, "dmm_head_input: ldo %lld too large", (long long)d->ldo);
     const size_t smem = (size_t)2 * chunks * 8 * sizeof(float);
-    head_input_kernel<<<flat_grid(total, 256), 256, smem, (cudaStream_t)stream>>>(*d);
+    head_input_kernel<<<(unsigned)(d->B * d->H), 256, smem, (cudaStream_t)stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;
 }

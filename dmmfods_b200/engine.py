@@ -280,8 +280,29 @@ class Engine:
             self._emit(lst, self.lib.dmm_conv_wgrad, d, name + ("[%d]" % i if nl > 1 else ""), kind="wgrad",
                        flops=2.0 * P * Mvalid * Nvalid * T / nl, nbytes=(P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4) / nl)
             self._fix_dw.append((d, did))
-        self._unpack_jobs.append(dict(did=did, grad=self.grad[wname], dt=plan["dt"], dm=plan["dm"], dn=plan["dn"], M=Mvalid,
+        self._unpack_jobs.append(dict(wname=wname, did=did, grad=self.grad[wname], dt=plan["dt"], dm=plan["dm"], dn=plan["dn"], M=Mvalid,
                                       N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst)))
+        self._stage_params.setdefault(id(lst), []).append(wname)
+
+    def _conv_wgrad_tail(self, lst, name, wname, xtail, c_off, r, y, taps, tap_off, N, Nvalid, sn, sc, W, H, B):
+        """weight gradient of the LAST r (<= 16) input channels of a KxK convolution with few (<= 64) output channels, roles
+        swapped: A = the output gradient y (rows = output channels), B = one halo patch of the r-channel activation slice
+        xtail, every tap a shifted view of it (wgrad.cu family mode).  Keeps the odd channels of e.g. the head's 128+3+1
+        input out of the 128-row m-tiles of the main launch."""
+        T = len(taps)
+        order = sorted(range(T), key=lambda t: (taps[t][1], taps[t][2]))
+        nch = (N + 63) // 64
+        a_slots = [(0, 0, 0, 64 * j, 64 * j) for j in range(nch)]
+        b_slots = [(0, taps[t][1], taps[t][2], 0, i * 16) for i, t in enumerate(order)]
+        ld = T * 16
+        did = self._req_dw(nch * 64 * ld)
+        d = ops.make_wgrad(a_srcs=[y], b_srcs=[xtail], a_slots=a_slots, b_slots=b_slots, n_tile=16, W=W, H=H, B=B, dw=0, ld=ld)
+        P = B * H * W
+        self._emit(lst, self.lib.dmm_conv_wgrad, d, name, kind="wgrad", flops=2.0 * P * r * Nvalid * T, nbytes=P * (N + 8) * 2)
+        self._fix_dw.append((d, did))
+        g = self.grad[wname].view(-1)[c_off * sc:]
+        self._unpack_jobs.append(dict(wname=wname, did=did, grad=g, dt=16, dm=1, dn=ld, M=r, N=Nvalid, T=T, tap_off=[tap_off[t] for t in order],
+                                      sn=sn, sc=sc, stage=id(lst)))
         self._stage_params.setdefault(id(lst), []).append(wname)
 
     def _bn_fwd(self, bn, stats, stats_off, count, c0=0, rep=1.0):
@@ -676,8 +697,15 @@ class Engine:
             self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1], conv5[2],
                              self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
             self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0)
-            self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
-                             conv3x3[2], Ct, nf2, Ct, nf2, Ct * 9, 9, W, H, B)
+            if Cu % 64 == 0 and 0 < cx <= 16:
+                # the 128 decoder channels fill one 128-row m-tile exactly; the few raw input channels go through the tail path
+                self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Cu), [dr0.view()], conv3x3[0],
+                                 conv3x3[2], Cu, nf2, Cu, nf2, Ct * 9, 9, W, H, B)
+                self._conv_wgrad_tail(st, hp + ".refine0.wgrad[tail]", hp + ".refine0.weight", a0.view(Cu, ld0 - Cu), Cu, cx,
+                                      dr0.view(), conv3x3[0], conv3x3[2], nf2, nf2, Ct * 9, 9, W, H, B)
+            else:
+                self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
+                                 conv3x3[2], Ct, nf2, Ct, nf2, Ct * 9, 9, W, H, B)
             self._conv_dgrad(st, hp + ".refine0.dgrad", hp + ".refine0.weight", [dr0.view()], conv3x3[1], conv3x3[2], nf2, Ct, 9,
                              Ct * 9, W, H, B, da0)
             hb = HeadBwd()
