@@ -273,7 +273,16 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     {
         // v2 (persistent, halo patches in shared memory) handles every kwidth-64 launch; DMM_IGEMM_V1=1 keeps v1
         static const bool force_v1 = getenv("DMM_IGEMM_V1") != nullptr && atoi(getenv("DMM_IGEMM_V1")) != 0;
-        if (d->kwidth == 64 && !force_v1) return igemm2_launch(d, stream);
+        // (and the kwidth-16 launches whose single tapped source has <= 16 channels: four taps share a 64-wide K block)
+        bool packed16 = d->kwidth == 16;
+        int tapped = 0;
+        for (int s = 0; s < d->num_src && packed16; ++s) {
+            bool used = false;
+            for (int t = 0; t < d->num_taps; ++t) used = used || d->tap_src[t] == s;
+            if (used) { ++tapped; packed16 = d->src[s].C <= 16; }
+        }
+        packed16 = packed16 && tapped == 1;
+        if ((d->kwidth == 64 || packed16) && !force_v1) return igemm2_launch(d, stream);
     }
 
     IgemmKParams p;

@@ -47,6 +47,7 @@ struct Ig2Params {
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
     int tps;                                        // taps per weight stage
+    int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
     int Wv, Hv;
     long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
     float* out32;
@@ -161,10 +162,11 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                             c0 = clock64();
                             mbar_wait(&b_empty[bst], bph ^ 1);
                             w_b += clock64() - c0;
-                            mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nt * p.b_tap);
+                            const int nblk_b = (nt + p.tpk - 1) / p.tpk;
+                            mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nblk_b * p.b_tap);
                             uint8_t* bdst = b_ring + (size_t)bst * p.b_stage;
-                            for (int j = 0; j < nt; ++j)
-                                tma_load_2d(bdst + (size_t)j * p.b_tap, &p.b_map, &b_full[bst], (p.tap_kb0[t + j] + cb) * 64, tc.n0);
+                            for (int j = 0; j < nblk_b; ++j)
+                                tma_load_2d(bdst + (size_t)j * p.b_tap, &p.b_map, &b_full[bst], (p.tap_kb0[t + j * p.tpk] + cb) * 64, tc.n0);
                             if (++bst == p.sb) { bst = 0; bph ^= 1; }
                         }
                     }
@@ -220,10 +222,13 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                         w_b += clock64() - c0;
                         tc_fence_after();
                         if (elect_one()) {
-                            uint32_t b_lo = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
+                            const uint32_t b_lo0 = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
                             uint32_t aoff = p.tap_aoff[t] >> 4;
                             for (int j = 0; j < nt; ++j) {
                                 const uint32_t a_tap = a_lo + aoff;
+                                // weights of tap j: own 64-wide block, or (16-channel sources) a quarter of a shared block
+                                const uint32_t b_lo = b_lo0 + (p.tpk == 1 ? (uint32_t)j * (p.b_tap >> 4)
+                                                                          : (uint32_t)(j >> 2) * (p.b_tap >> 4) + (uint32_t)(j & 3) * 2u);
                                 if (j + 1 < nt) aoff = p.tap_aoff[t + j + 1] >> 4;      // prefetch the next tap's offset
                                 if (ksteps == 4) {
 #pragma unroll
@@ -240,7 +245,6 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                                                       k == 0 ? acc0 : 1u);
                                 }
                                 acc0 = 1;
-                                b_lo += p.b_tap >> 4;
                             }
                             umma_commit(&b_empty[bst]);
                             if (t + nt == t1) umma_commit(&a_empty[ast]);
@@ -429,7 +433,8 @@ struct Tiling {
 };
 
 int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
-    DMM_CHECK(d->kwidth == 64, "igemm v2: kwidth must be 64");
+    DMM_CHECK(d->kwidth == 64 || d->kwidth == 16, "igemm v2: kwidth must be 64 or 16");
+    const int tpk = d->kwidth == 16 ? 4 : 1;       // kwidth 16: sources of <= 16 channels, weights packed [n][tap*16 + c]
     DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
     DMM_CHECK(d->out_mode == 0 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
     static int num_sms = 0;
@@ -453,6 +458,15 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         mindy[s] = d->tap_dy[t] < mindy[s] ? d->tap_dy[t] : mindy[s];
         maxdy[s] = d->tap_dy[t] > maxdy[s] ? d->tap_dy[t] : maxdy[s];
         ++ntap[s];
+    }
+    if (tpk == 4) {
+        int tapped = 0;
+        for (int s = 0; s < d->num_src; ++s) {
+            if (ntap[s] == 0) continue;
+            ++tapped;
+            DMM_CHECK(d->src[s].C <= 16, "igemm v2: kwidth 16 needs sources of at most 16 channels (source %d has %d)", s, d->src[s].C);
+        }
+        DMM_CHECK(tapped == 1, "igemm v2: kwidth 16 supports a single tapped source");
     }
     int hx = 0, hy = 0;   // largest halo over the sources
     long long ktot = 0;
@@ -480,6 +494,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             kb += p.src_nblk[d->tap_src[t]];
         }
         ktot = (long long)kb * 64;
+        if (tpk == 4) {
+            // packed: tap t owns K columns [16 t, 16 t + 16): block t / 4 (the producer only uses taps that start a block)
+            for (int t = 0; t < d->num_taps; ++t) kb0[t] = t / 4;
+            ktot = (long long)d->num_taps * 16;
+        }
         int n = 0;
         for (int s = 0; s < d->num_src; ++s) {
             p.src_tap0[s] = n;
@@ -527,12 +546,13 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             // per stage hand-over, so a stage should carry many MMAs), then more patch stages with what is left
             const int rest = avail - 2 * (int)c.a_stage;
             if (rest < 2 * (int)b_tap) continue;
-            int tps_max = rest / (2 * (int)b_tap);
+            int blk_max = rest / (2 * (int)b_tap);                      // weight blocks per stage
+            if (blk_max * (int)b_tap > 48 * 1024) blk_max = (48 * 1024) / (int)b_tap > 0 ? (48 * 1024) / (int)b_tap : 1;
+            int tps_max = blk_max * tpk;
             if (tps_max > max_taps) tps_max = max_taps;
-            if (tps_max * (int)b_tap > 48 * 1024) tps_max = (48 * 1024) / (int)b_tap > 0 ? (48 * 1024) / (int)b_tap : 1;
             const int groups = ceil_div(max_taps, tps_max);
-            c.tps = ceil_div(max_taps, groups);
-            const int b_stage_c = c.tps * (int)b_tap;
+            c.tps = ceil_div(ceil_div(max_taps, groups), tpk) * tpk;
+            const int b_stage_c = ceil_div(c.tps, tpk) * (int)b_tap;
             c.sb = rest / b_stage_c;
             if (c.sb > 4) c.sb = 4;
             if (max_taps == 1 && b_stage_c <= 16384 && rest / b_stage_c >= 6) c.sb = 6;
@@ -543,7 +563,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             const double l2 = (double)nkb_total * pw * ph * 128.0 / 32.0;
             double wbytes = 0, waits = 0;
             for (int s = 0; s < d->num_src; ++s) {
-                wbytes += (double)ntap[s] * p.src_nblk[s] * b_tap;
+                wbytes += (double)ceil_div(ntap[s], tpk) * p.src_nblk[s] * b_tap;
                 if (ntap[s]) waits += (double)p.src_nblk[s] * (1 + ceil_div(ntap[s], c.tps));
             }
             const double mma_cyc = (double)m * nmma_steps * mma_hw + 350.0 * waits;
@@ -558,7 +578,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.msub = best.msub; p.sub_w = best.sub_w; p.sub_h = best.sub_h;
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
-    p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.b_stage = (uint32_t)best.tps * b_tap;
+    p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
+    p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
     p.tiles_x = ceil_div(d->W, p.TW);
     p.tiles_y = ceil_div(d->H, p.TH);
     p.tiles_n = tiles_n;

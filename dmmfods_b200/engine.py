@@ -254,13 +254,15 @@ class Engine:
     def _conv_dgrad(self, lst, name, wname, srcs, taps, tap_off, Cg, Cin, sn, sc, W, H, B, out):
         """data gradient: igemm over the output-gradient views `srcs` (Cg channels) -> out [P, >=Cin]."""
         T = len(taps)
-        Kp = ceil_to(Cg, ops.KWIDTH)
+        # a narrow (<= 16 channels) single gradient source: four taps share one 64-wide K block of the packed weights
+        kwidth = 16 if (Cg <= 16 and len(srcs) == 1 and T > 1) else ops.KWIDTH
+        Kp = ceil_to(Cg, kwidth)
         n_tile = ops.pick_n_tile(Cin)
         n_rows = ceil_to(Cin, n_tile)
         wid = self._req_wpk(n_rows, T * Kp)
         self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cin, n_rows=n_rows, C=Cg, T=T, tap_off=tap_off,
-                                    sn=sn, sc=sc))
-        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cin, out.ptr(), out.ld, n_tile=n_tile)
+                                    sn=sn, sc=sc, kwidth=kwidth))
+        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cin, out.ptr(), out.ld, n_tile=n_tile, kwidth=kwidth)
         P = B * H * W
         self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_dgrad", flops=2.0 * P * Cin * Cg * T,
                    nbytes=P * (Cg * 2 * (4 if len(srcs) == 4 else 1) + Cin * 2) + Cg * Cin * T * 2)
@@ -746,7 +748,7 @@ class Engine:
             pj[i]["w"] = j["w"].data_ptr()
             pj[i]["dst"] = base + 2 * offs[j["wid"]]
             pj[i]["n_valid"], pj[i]["n_rows"], pj[i]["C"], pj[i]["T"] = j["n_valid"], j["n_rows"], j["C"], j["T"]
-            pj[i]["kwidth"] = ops.KWIDTH
+            pj[i]["kwidth"] = j.get("kwidth", ops.KWIDTH)
             pj[i]["tap_off"][:j["T"]] = j["tap_off"]
             pj[i]["sn"], pj[i]["sc"] = j["sn"], j["sc"]
             pj[i]["sc2"], pj[i]["cdiv"] = j.get("sc2", 0), j.get("cdiv", 0)
