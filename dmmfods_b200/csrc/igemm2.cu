@@ -230,20 +230,15 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                                 const uint32_t b_lo = b_lo0 + (p.tpk == 1 ? (uint32_t)j * (p.b_tap >> 4)
                                                                           : (uint32_t)(j >> 2) * (p.b_tap >> 4) + (uint32_t)(j & 3) * 2u);
                                 if (j + 1 < nt) aoff = p.tap_aoff[t + j + 1] >> 4;      // prefetch the next tap's offset
-                                if (ksteps == 4) {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                                        for (int sub = 0; sub < MSUB; ++sub)
-                                            umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
-                                                      k == 0 ? acc0 : 1u);
-                                } else {
-                                    for (int k = 0; k < ksteps; ++k)
-#pragma unroll
-                                        for (int sub = 0; sub < MSUB; ++sub)
-                                            umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc,
-                                                      k == 0 ? acc0 : 1u);
-                                }
+                                // fully unrolled per k-step count: keeps the descriptor arithmetic in uniform registers
+#define DMM_ISSUE_TAP(KS)                                                                                                       \
+    _Pragma("unroll") for (int k = 0; k < KS; ++k) _Pragma("unroll") for (int sub = 0; sub < MSUB; ++sub)                      \
+        umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u)
+                                if (ksteps == 4) { DMM_ISSUE_TAP(4); }
+                                else if (ksteps == 1) { DMM_ISSUE_TAP(1); }
+                                else if (ksteps == 2) { DMM_ISSUE_TAP(2); }
+                                else { DMM_ISSUE_TAP(3); }
+#undef DMM_ISSUE_TAP
                                 acc0 = 1;
                             }
                             umma_commit(&b_empty[bst]);

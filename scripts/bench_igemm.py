@@ -17,6 +17,7 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "b3_conv1_k640": (32, 40, 60, 640, 128, 1, 0),
     "reduce4": (32, 160, 240, 512, 128, 1, 0),
     "convT4_phase11": (32, 160, 240, 128, 128, 2, 0),
+    "refine1_dgrad": (32, 640, 960, 3, 64, 5, 0),
 }
 
 def run(name, reps=5):
@@ -29,7 +30,8 @@ def run(name, reps=5):
     else:
         taps = ops.conv_taps(K, (K - 1) // 2)[0]
     T = len(taps)
-    Kp = ops.ceil_to(Cin, 64)
+    kwidth = 16 if (Cin <= 16 and T > 1) else 64
+    Kp = ops.ceil_to(Cin, kwidth)
     n_tile = ops.pick_n_tile(Cout)
     n_rows = ops.ceil_to(Cout, n_tile)
     wp = (torch.randn(n_rows, T * Kp, device="cuda") * 0.05).to(torch.bfloat16)
@@ -37,7 +39,7 @@ def run(name, reps=5):
         out = ops.new_mat(B, H, W, ops.ceil_to(Cout, 8))
         st = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.ptr(), out.ld,
-                           stats=ops.Stats(st, 0, out.ld), n_tile=n_tile)
+                           stats=ops.Stats(st, 0, out.ld), n_tile=n_tile, kwidth=kwidth)
     else:
         out = torch.zeros(B, Cout, H, W, device="cuda")
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.data_ptr(), 0, out_mode=1, n_tile=n_tile)
