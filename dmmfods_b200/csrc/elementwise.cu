@@ -245,6 +245,54 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Lean y = relu(bn(x)) (no pooling, no output statistics): four rows per iteration = four independent 16-byte loads in
+// flight per thread, coefficients in registers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads, 4) bn_apply_fast_kernel(const dmm_bn_apply_t p) {
+    __shared__ float cf[2][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_fwd(p.bn, c, blockIdx.x == 0);
+            cf[0][tid] = k.scale;
+            cf[1][tid] = k.shift;
+        }
+    }
+    __syncthreads();
+    if (chunk >= nchunks) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = cf[0][threadIdx.x * 8 + j];
+        sh[j] = cf[1][threadIdx.x * 8 + j];
+    }
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + chunk * 8;
+    const long long rows = (long long)p.B * p.H * p.W;
+    const long long step = (long long)gridDim.x * ry;
+    for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += 4 * step) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (row0 + u * step < rows) v[u] = ldg16(x + (row0 + u * step) * p.ldx);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (row0 + u * step < rows) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+                *reinterpret_cast<uint4*>(y + (row0 + u * step) * p.ldy) = pack8(f);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // BN-ReLU backward.  dz = g' * [bn(x) > 0] where g' is the gradient of the activated tensor,
 // addressed through gmode (0 same pixel, 1 avg-pool parent / 4, 2 max-pool 3x3 s2 p1 argmax).
 // ---------------------------------------------------------------------------------------------
@@ -1271,7 +1319,8 @@ extern "C" int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream_) {
     if (d->pool == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
     if (OH <= 0 || OW <= 0) return 0;
     ColCfg k = col_cfg(d->C, (long long)d->B * OH * OW);
-    if (d->pool == 0) bn_relu_apply_kernel<0><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
+    if (d->pool == 0 && d->ystats == nullptr) bn_apply_fast_kernel<<<k.grid, k.block, 0, stream>>>(*d);
+    else if (d->pool == 0) bn_relu_apply_kernel<0><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
     else if (d->pool == 1) bn_relu_apply_kernel<1><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
     else bn_relu_apply_kernel<2><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
     DMM_LAUNCH_CHECK("bn_relu_apply_kernel");
