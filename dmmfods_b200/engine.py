@@ -837,8 +837,9 @@ class Engine:
         """logits (B, num_classes, H, W) fp32 - engine-owned buffer, valid until the next forward()."""
         if self.plan_only:
             raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
-        self.in1.copy_(x1, non_blocking=True)
-        if self.c2:
+        if x1 is not self.in1:
+            self.in1.copy_(x1, non_blocking=True)
+        if self.c2 and x2 is not self.in2:
             self.in2.copy_(x2, non_blocking=True)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.training:

@@ -78,6 +78,7 @@ class Trainer:
         self.use_graph = bool(use_graph) and self.dist is None
         self.graph = None
         self._static_target = None
+        self._copy_stream, self._stage, self._staged, self._stage_ready, self._stage_free = None, None, None, None, None
 
     # ------------------------------------------------------------------------------------------------
     def _fwd_loss_bwd(self, target):
@@ -87,10 +88,52 @@ class Trainer:
         if self.reducer is not None:
             self.reducer.finish()
 
-    def step(self, x1, x2, target):
+    # ------------------------------------------------------------------------------------------------
+    def prefetch(self, x1, x2, target):
+        """start the host -> device copy of the NEXT step's (pinned) inputs on a copy stream while the current step
+        computes (the data-loader prefetch of a training loop).  step() called with the same tensor objects then only
+        does a device-to-device hand-over."""
+        dev = self.pflat.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in (x1, x2, target)]
+        cs = self._copy_stream
+        if self._stage_free is not None:
+            cs.wait_event(self._stage_free)          # the previous hand-over has finished reading the staging buffers
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage, (x1, x2, target)):
+                dst.copy_(src, non_blocking=True)
+            self._stage_ready = torch.cuda.Event()
+            self._stage_ready.record(cs)
+        self._staged = (x1, x2, target)
+
+    def _take_staged(self, x1, x2, target):
+        """if (x1, x2, target) are the tensors handed to prefetch(): wait for that copy and return the device copies."""
+        st = self._staged
+        if st is None or st[0] is not x1 or st[1] is not x2 or st[2] is not target:
+            return None
+        torch.cuda.current_stream().wait_event(self._stage_ready)
+        self._staged = None
+        return self._stage
+
+    def step(self, x1, x2, target, prefetch_next=None):
         """one optimisation step; x1/x2/target: CUDA tensors or pinned host tensors (copied asynchronously).
+        prefetch_next: optional (x1, x2, target) of the following step (see prefetch()).
         Returns the per-class loss sums (float64 CUDA tensor of num_classes entries, Agent.py:248)."""
         eng = self.eng
+        staged = self._take_staged(x1, x2, target)
+        if staged is not None:
+            # hand-over: device-to-device into the engine-owned buffers, then the staging buffers are free again and the
+            # next prefetch overlaps with this step's kernels
+            if self._static_target is None:
+                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
+            eng.in1.copy_(staged[0], non_blocking=True)
+            if eng.c2:
+                eng.in2.copy_(staged[1], non_blocking=True)
+            self._static_target.copy_(staged[2], non_blocking=True)
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+            x1, x2, target = eng.in1, eng.in2, self._static_target
         if not target.is_cuda:
             if self._static_target is None:
                 self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
@@ -101,8 +144,9 @@ class Trainer:
                 self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
             if target is not self._static_target:
                 self._static_target.copy_(target, non_blocking=True)
-            eng.in1.copy_(x1, non_blocking=True)
-            if eng.c2:
+            if x1 is not eng.in1:
+                eng.in1.copy_(x1, non_blocking=True)
+            if eng.c2 and x2 is not eng.in2:
                 eng.in2.copy_(x2, non_blocking=True)
             if self.graph is None:
                 self._capture()
@@ -110,6 +154,8 @@ class Trainer:
         else:
             eng.forward(x1, x2)
             self._fwd_loss_bwd(target)
+        if prefetch_next is not None:
+            self.prefetch(*prefetch_next)
         self.steps += 1
         ops.adam_flat(self.pflat, eng.gflat, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                       self.weight_decay, self.steps)
