@@ -31,7 +31,10 @@ class Igemm(C.Structure):
                 ("n_tile", c_int32), ("out", c_void_p), ("out_mode", c_int32), ("ldo", c_int64),
                 ("coff", c_int32), ("out_sy", c_int32), ("out_sx", c_int32), ("out_py", c_int32),
                 ("out_px", c_int32), ("OH", c_int32), ("OW", c_int32), ("stats", c_void_p),
-                ("stats_ld", c_int32), ("stats_off", c_int32)]
+                ("stats_ld", c_int32), ("stats_off", c_int32),
+                ("bnb_x", c_void_p), ("bnb_ldx", c_int64), ("bnb_gamma", c_void_p), ("bnb_beta", c_void_p),
+                ("bnb_mean", c_void_p), ("bnb_invstd", c_void_p), ("bnb_sums", c_void_p), ("bnb_sums_ld", c_int32),
+                ("bnb_sums_off", c_int32)]
 
 
 WG_MAX_A = 8

@@ -29,6 +29,7 @@ struct Ig2Params {
     CUtensorMap a_maps[DMM_MAX_SRC];
     CUtensorMap b_map;
     CUtensorMap o_map;
+    CUtensorMap x_map;             // bnb: raw input of the BatchNorm whose backward reduce is fused into the epilogue
     int num_src;
     int src_nblk[DMM_MAX_SRC];
     int src_lastk[DMM_MAX_SRC];
@@ -54,6 +55,11 @@ struct Ig2Params {
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
     int stats_ld, stats_off;
+    int bnb;
+    const float* bnb_gamma;
+    const float* bnb_beta;
+    const float* bnb_mean;
+    const float* bnb_invstd;
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
@@ -95,14 +101,16 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* tail = stg + (OUT_MODE == 0 ? 2 * kStageSlot : 0);
+    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * kStageSlot : 0);          // bnb: one x tile per epilogue team
+    uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
     uint64_t* b_full = a_empty + 8;
     uint64_t* b_empty = b_full + 8;
     uint64_t* acc_full = b_empty + 8;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* x_bar = acc_empty + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(x_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 8);
+            mbar_init(&x_bar[s], 1);
         }
         fence_mbar_init();
     }
@@ -130,6 +139,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         tma_prefetch_desc(&p.b_map);
         if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
         if (OUT_MODE == 0) tma_prefetch_desc(&p.o_map);
+        if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
     }
     tc_fence_before();
     __syncthreads();
@@ -270,6 +280,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
         uint8_t* slot = stg + team * kStageSlot;
         uint8_t* srow = slot + r * 128;
+        uint8_t* xslot = xstg + team * kStageSlot;
+        uint32_t x_phase = 0;
         double sacc[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -304,7 +316,11 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
                         if (r == 0) bulk_wait_read0();       // the team's previous TMA store has finished reading the slot
                         tmem_ld_wait();
-                        epi_bar(team);
+                        epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
+                        if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
+                            mbar_arrive_expect_tx(&x_bar[team], kStageSlot);
+                            tma_load_4d(xslot, &p.x_map, &x_bar[team], tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
+                        }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             if (g < ngrp) {
@@ -333,13 +349,44 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint8_t* base = slot + ((cp & 3) << 2);
                             const int j = cp >> 2;
+                            if (!p.bnb) {
 #pragma unroll 8
-                            for (int i = 0; i < 32; ++i) {
-                                const int row = rq * 32 + i;
-                                const uint32_t u = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((j ^ (row & 7)) << 4));
-                                const float a = bf16_lo(u), b = bf16_hi(u);
-                                s1a += a; s1b += b;
-                                s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
+                                for (int i = 0; i < 32; ++i) {
+                                    const int row = rq * 32 + i;
+                                    const uint32_t u = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((j ^ (row & 7)) << 4));
+                                    const float a = bf16_lo(u), b = bf16_hi(u);
+                                    s1a += a; s1b += b;
+                                    s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
+                                }
+                            } else {
+                                // fused BatchNorm-ReLU backward reduce: dz = g * [bn(x) > 0]; sums of dz and dz * (x - mean)
+                                const int col = tc.n0 + 64 * c + 2 * cp;
+                                float sc0 = 0.f, sh0 = 0.f, mu0 = 0.f, sc1 = 0.f, sh1 = 0.f, mu1 = 0.f;
+                                if (col < p.N) {
+                                    mu0 = __ldg(p.bnb_mean + col);
+                                    sc0 = (p.bnb_gamma ? __ldg(p.bnb_gamma + col) : 1.f) * __ldg(p.bnb_invstd + col);
+                                    sh0 = (p.bnb_beta ? __ldg(p.bnb_beta + col) : 0.f) - mu0 * sc0;
+                                }
+                                if (col + 1 < p.N) {
+                                    mu1 = __ldg(p.bnb_mean + col + 1);
+                                    sc1 = (p.bnb_gamma ? __ldg(p.bnb_gamma + col + 1) : 1.f) * __ldg(p.bnb_invstd + col + 1);
+                                    sh1 = (p.bnb_beta ? __ldg(p.bnb_beta + col + 1) : 0.f) - mu1 * sc1;
+                                }
+                                const uint8_t* xbase = xslot + ((cp & 3) << 2);
+                                mbar_wait(&x_bar[team], x_phase);
+                                x_phase ^= 1;
+#pragma unroll 8
+                                for (int i = 0; i < 32; ++i) {
+                                    const int row = rq * 32 + i;
+                                    const int o = row * 128 + ((j ^ (row & 7)) << 4);
+                                    const uint32_t u = *reinterpret_cast<const uint32_t*>(base + o);
+                                    const uint32_t xu = *reinterpret_cast<const uint32_t*>(xbase + o);
+                                    const float xa = bf16_lo(xu), xb = bf16_hi(xu);
+                                    const float a = fmaf(xa, sc0, sh0) > 0.f ? bf16_lo(u) : 0.f;
+                                    const float b = fmaf(xb, sc1, sh1) > 0.f ? bf16_hi(u) : 0.f;
+                                    s1a += a; s1b += b;
+                                    s2a = fmaf(a, xa - mu0, s2a); s2b = fmaf(b, xb - mu1, s2b);
+                                }
                             }
                             sacc[c][0] += (double)s1a; sacc[c][1] += (double)s1b;
                             sacc[c][2] += (double)s2a; sacc[c][3] += (double)s2b;
@@ -372,10 +419,10 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                     const int col = tc.n0 + c * 64 + 2 * cp;
                     if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
                         atomicAdd(st + col, sacc[c][0]);
-                        atomicAdd(st + p.stats_ld + col, sacc[c][2]);
+                        atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
                         if (col + 1 < p.N) {
                             atomicAdd(st + col + 1, sacc[c][1]);
-                            atomicAdd(st + p.stats_ld + col + 1, sacc[c][3]);
+                            atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                         }
                     }
 #pragma unroll
@@ -390,10 +437,10 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                 const int col = last_n0 + c * 64 + 2 * cp;
                 if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
                     atomicAdd(st + col, sacc[c][0]);
-                    atomicAdd(st + p.stats_ld + col, sacc[c][2]);
+                    atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
                     if (col + 1 < p.N) {
                         atomicAdd(st + col + 1, sacc[c][1]);
-                        atomicAdd(st + p.stats_ld + col + 1, sacc[c][3]);
+                        atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                     }
                 }
             }
@@ -511,7 +558,13 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
 
     // ---- tiling ----
     const bool xhalo = hx > 0;
-    const int staging = d->out_mode == 0 ? 2 * (int)kStageSlot : 0;
+    const bool bnb = d->bnb_sums != nullptr;
+    if (bnb) {
+        DMM_CHECK(d->out_mode == 0 && d->stats == nullptr, "igemm v2: fused BN backward reduce needs out_mode 0 and no forward statistics");
+        DMM_CHECK(d->out_sy <= 1 && d->out_sx <= 1 && d->out_py == 0 && d->out_px == 0, "igemm v2: fused BN backward reduce: no output stride");
+        DMM_CHECK(d->bnb_x && d->bnb_mean && d->bnb_invstd && d->bnb_ldx % 8 == 0, "igemm v2: fused BN backward reduce: missing inputs");
+    }
+    const int staging = d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : 0;
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
@@ -638,6 +691,17 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.stats = d->out_mode == 0 ? d->stats : nullptr;
     p.stats_ld = d->stats_ld;
     p.stats_off = d->stats_off;
+    if (bnb) {
+        dmm_view_t xv;
+        xv.ptr = d->bnb_x;
+        xv.C = d->N; xv.W = d->W; xv.H = d->H; xv.B = d->B;
+        xv.sw = d->bnb_ldx; xv.sh = (long long)d->W * d->bnb_ldx; xv.sb = (long long)d->H * d->W * d->bnb_ldx;
+        int rc = view_to_tmap(&p.x_map, xv, 64, p.sub_w, p.sub_h, 128);
+        if (rc) return rc;
+        p.bnb = 1;
+        p.bnb_gamma = d->bnb_gamma; p.bnb_beta = d->bnb_beta; p.bnb_mean = d->bnb_mean; p.bnb_invstd = d->bnb_invstd;
+        p.stats = d->bnb_sums; p.stats_ld = d->bnb_sums_ld; p.stats_off = d->bnb_sums_off;
+    }
     uint32_t cols = 32;
     while ((int)cols < 2 * p.msub * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;

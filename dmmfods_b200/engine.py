@@ -27,14 +27,19 @@ from ._lib import Head, HeadBwd
 from .ops import Mat, Stats, ceil_to
 
 
+# fuse the reduce pass of a BatchNorm-ReLU backward into the epilogue of the data-gradient convolution that produces its input
+FUSE_BN_BWD_REDUCE = os.environ.get("DMM_FUSE_BN_BWD_REDUCE", "1") != "0"
+
+
 class Op:
     """one C-ABI launch.  kind / flops / bytes: kernel family and ALGORITHMIC work of the launch (each distinct
     input element read once + each output written once; 2*M*N*K of the reference operator) for roofline reports."""
-    __slots__ = ("fn", "arg", "gbuf", "name", "kind", "flops", "bytes")
+    __slots__ = ("fn", "arg", "gbuf", "name", "kind", "flops", "bytes", "heavy")
 
     def __init__(self, fn, arg, name, gbuf=None, kind="misc", flops=0.0, nbytes=0.0):
         self.fn, self.arg, self.name, self.gbuf = fn, arg, name, gbuf
         self.kind, self.flops, self.bytes = kind, float(flops), float(nbytes)
+        self.heavy = False
 
 
 class _Arena:
@@ -267,6 +272,10 @@ class Engine:
         self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_dgrad", flops=2.0 * P * Cin * Cg * T,
                    nbytes=P * (Cg * 2 * (4 if len(srcs) == 4 else 1) + Cin * 2) + Cg * Cin * T * 2)
         self._fix_w.append((d, wid))
+        # "heavy": enough MMA work per output chunk that a longer epilogue stays hidden (KxK data gradients); the 1x1 data
+        # gradients of the dense layers are epilogue/HBM-bound and lose more than the separate reduce pass costs
+        lst[-1].heavy = T * ceil_to(Cg, 64) >= 512
+        return lst[-1]
 
     def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B):
         """weight gradient: wgrad launches into a zeroed fp32 scratch matrix + unpack job into the flat gradient
@@ -320,7 +329,7 @@ class Engine:
         self._emit(lst, self.lib.dmm_bn_relu_apply, d, name, kind="bn_relu_apply", nbytes=(x.P + y.P) * C_ * 2)
 
     def _bn_bwd(self, lst, name, bn, x, xc0, C_, g_ptr, ldg, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False, bn_c0=0,
-                gbuf=None, dz_tmp=None):
+                gbuf=None, dz_tmp=None, producer=None):
         """BN-ReLU backward = reduce pass + apply pass.  dz_tmp (Mat): the reduce pass stores the masked, pool-routed
         gradient there and the apply pass reads it back with gmode 0 (max-pool routing is evaluated once)."""
         self._stage_params.setdefault(id(lst), []).extend([bn.prefix + ".weight", bn.prefix + ".bias"])
@@ -337,8 +346,13 @@ class Engine:
             rd2 = x.P * C_ * 4
         else:
             rd2 = rd
-        self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce", kind="bn_relu_bwd_reduce",
-                   nbytes=rd + (x.P * C_ * 2 if dz_tmp is not None else 0))
+        if producer is not None and gmode == 0 and not g_is_f32 and dz_tmp is None and FUSE_BN_BWD_REDUCE and producer.heavy:
+            # the data-gradient launch that produces g also accumulates (sum dz, sum dz*xhat): no separate reduce pass
+            ops.fuse_bn_bwd_reduce(producer.arg, x, xc0, b)
+            producer.bytes += x.P * C_ * 2
+        else:
+            self._emit(lst, self.lib.dmm_bn_relu_bwd_reduce, d, name + ".reduce", kind="bn_relu_bwd_reduce",
+                       nbytes=rd + (x.P * C_ * 2 if dz_tmp is not None else 0))
         self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d2, name + ".apply", gbuf=gbuf, kind="bn_relu_bwd_apply",
                    nbytes=rd2 + wr)
 
@@ -462,15 +476,15 @@ class Engine:
                     self._cast(st, lp + ".gout", blk.G, Ci, k, go)
                     self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", a2.view(), [go.view(0, k)], conv3x3[0],
                                      conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B)
-                    self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
-                                     k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
-                    self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0)
+                    dg2 = self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
+                                           k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
+                    self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0, producer=dg2)
                     self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", a1.view(), [dz1.view()], conv1x1[0],
                                      conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B)
-                    self._conv_dgrad(st, lp + ".conv1.dgrad", lp + ".conv1.weight", [dz1.view()], conv1x1[1], conv1x1[2],
-                                     bnk, Ci, 1, Ci, Wb, Hb, B, da1)
+                    dg1 = self._conv_dgrad(st, lp + ".conv1.dgrad", lp + ".conv1.weight", [dz1.view()], conv1x1[1], conv1x1[2],
+                                           bnk, Ci, 1, Ci, Wb, Hb, B, da1)
                     self._bn_bwd(st, lp + ".norm1.bwd", bn1, blk.buf, 0, Ci, da1.ptr(), da1.ld, blk.G.data_ptr(), blk.Ct, 2,
-                                 gbuf=blk)
+                                 gbuf=blk, producer=dg1)
                     self._bwd_stages.append(st)
 
         # ---------------- transition: BN-ReLU -> (avg-pool first) -> 1x1 conv ----------------
@@ -621,8 +635,8 @@ class Engine:
                 phases = [dunew.phase_view(py, px) for py in range(2) for px in range(2)]
                 self._conv_wgrad(st, cp + ".wgrad", cp + ".weight", a1.view(), phases, wt, woff, num_f, num_f, num_f, num_f, 9,
                                  num_f * 9, wk, hk, B)
-                self._conv_dgrad(st, cp + ".dgrad", cp + ".weight", phases, dt, doff, num_f, num_f, num_f * 9, 9, wk, hk, B, da1)
-                self._bn_bwd(st, sp + ".norm1.bwd", bn1, r, 0, num_f, da1.ptr(), da1.ld, dr.ptr(), dr.ld, 0)
+                dgt = self._conv_dgrad(st, cp + ".dgrad", cp + ".weight", phases, dt, doff, num_f, num_f, num_f * 9, 9, wk, hk, B, da1)
+                self._bn_bwd(st, sp + ".norm1.bwd", bn1, r, 0, num_f, da1.ptr(), da1.ld, dr.ptr(), dr.ld, 0, producer=dgt)
                 self._conv_wgrad(st, sp + ".conv_reduce.wgrad", sp + ".conv_reduce.weight", a.view(), [dr.view()], conv1x1[0],
                                  conv1x1[2], num_in, num_f, num_in, num_f, num_in, 1, wk, hk, B)
                 self._conv_dgrad(st, sp + ".conv_reduce.dgrad", sp + ".conv_reduce.weight", [dr.view()], conv1x1[1], conv1x1[2],
@@ -696,9 +710,9 @@ class Engine:
             # five wide MMAs per k-step); data gradient = a 25-tap convolution over the 16-channel d(logits) matrix
             self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)], conv5[0], conv5[2],
                              nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B)
-            self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1], conv5[2],
-                             self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
-            self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0)
+            dgh = self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1], conv5[2],
+                                   self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
+            self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0, producer=dgh)
             if Cu % 64 == 0 and 0 < cx <= 16:
                 # the 128 decoder channels fill one 128-row m-tile exactly; the few raw input channels go through the tail path
                 self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Cu), [dr0.view()], conv3x3[0],

@@ -206,6 +206,16 @@ def make_igemm(srcs, taps, weights, ktot, n_rows, W, H, B, N, out_ptr, ldo, coff
     return d
 
 
+def fuse_bn_bwd_reduce(d, x, xc0, bn_bwd):
+    """make the data-gradient launch `d` also perform the reduce pass of the BatchNorm-ReLU backward that consumes its output
+    (x: Mat holding the raw BN input, channel n of the output <-> column xc0 + n; bn_bwd: the BnBwd of make_bn_bwd)."""
+    d.bnb_x, d.bnb_ldx = x.ptr(xc0).value, x.ld
+    d.bnb_gamma, d.bnb_beta = bn_bwd.gamma, bn_bwd.beta
+    d.bnb_mean, d.bnb_invstd = bn_bwd.save_mean, bn_bwd.save_invstd
+    d.bnb_sums, d.bnb_sums_ld, d.bnb_sums_off = bn_bwd.sums, bn_bwd.sums_ld, bn_bwd.sums_off
+    return d
+
+
 def run_igemm(d):
     check(_lib.load().dmm_conv_igemm(C.byref(d), _stream()), "dmm_conv_igemm")
 

@@ -77,6 +77,18 @@ typedef struct {
     int32_t out_sy, out_sx, out_py, out_px, OH, OW;
     double* stats;
     int32_t stats_ld, stats_off;
+    /* Optional (bnb_sums != NULL, out_mode 0, no output stride/phase, stats == NULL): the output g of this launch is the gradient
+     * of relu(bn(x)) (a data-gradient launch); the epilogue then also performs dmm_bn_relu_bwd_reduce for the BatchNorm whose
+     * input channel n is column n of bnb_x (same pixels): bnb_sums[slot][0][off + n] += sum_p dz,
+     * bnb_sums[slot][1][off + n] += invstd[n] * sum_p dz * (x - mean[n]), dz = g (as stored in bf16) * [gamma*invstd*(x-mean)+beta > 0]. */
+    const void* bnb_x;
+    int64_t bnb_ldx;
+    const float* bnb_gamma;
+    const float* bnb_beta;
+    const float* bnb_mean;
+    const float* bnb_invstd;
+    double* bnb_sums;
+    int32_t bnb_sums_ld, bnb_sums_off;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 

@@ -170,3 +170,38 @@ def test_igemm_large_pixel_count():
     """many tiles / 2 CTAs per SM, n_tile 128: exercises the pipeline for real."""
     _conv_case(4, 256, 128, 64, 96, 1, seed=11)
     _conv_case(2, 128, 32, 64, 96, 3, seed=12)
+
+
+@pytest.mark.parametrize("K,Cin,Cout,H,W", [(1, 128, 160, 20, 30), (3, 32, 128, 16, 24), (1, 128, 288, 9, 13)])
+def test_fused_bn_backward_reduce_matches_separate_pass(K, Cin, Cout, H, W):
+    """the epilogue-fused BatchNorm-ReLU backward reduce (dmm_igemm_t.bnb_*) must produce the sums of
+    dmm_bn_relu_bwd_reduce run on the stored bf16 output."""
+    torch.manual_seed(K * 7 + Cout)
+    B = 2
+    pad = (K - 1) // 2
+    g_in = bf16_round(torch.randn(B, Cin, H, W))
+    w = bf16_round(torch.randn(Cout, Cin, K, K) / (Cin * K * K) ** 0.5)
+    a = to_mat(g_in)
+    fwd, _, off = ops.conv_taps(K, pad)
+    wp, ktot, n_rows = _pack(w, Cout, Cin, K * K, off, Cin * K * K, K * K)
+    x = to_mat(bf16_round(torch.randn(B, Cout, H, W) * 2 + 0.3))          # raw BN input of the consumer
+    gamma = (torch.rand(Cout) + 0.5).cuda()
+    beta = (torch.randn(Cout) * 0.3).cuda()
+    mean = (torch.randn(Cout) * 0.2 + 0.3).cuda()
+    invstd = (torch.rand(Cout) * 0.5 + 0.4).cuda()
+    out = ops.new_mat(B, H, W, Cout, zero=True)
+    fused, sep = new_stats(Cout), new_stats(Cout)
+    bn_f = ops.make_bn_bwd(fused, 0, B * H * W, gamma, beta, mean, invstd)
+    d = ops.make_igemm([a.view(0, Cin)], fwd, wp, ktot, n_rows, W, H, B, Cout, out.ptr(), Cout)
+    ops.fuse_bn_bwd_reduce(d, x, 0, bn_f)
+    ops.run_igemm(d)
+    bn_s = ops.make_bn_bwd(sep, 0, B * H * W, gamma, beta, mean, invstd)
+    tmp = ops.new_mat(B, H, W, Cout)
+    args = ops.make_bn_bwd_args(x, 0, Cout, out.ptr(), out.ld, bn_s, tmp.ptr(), tmp.ld, 0)
+    ops.check(ops._lib.load().dmm_bn_relu_bwd_reduce(ops.C.byref(args), ops._stream()), "reduce")
+    torch.cuda.synchronize()
+    f1, f2 = fused.totals()
+    s1, s2 = sep.totals()
+    scale1, scale2 = s1.abs().max().item() + 1e-6, s2.abs().max().item() + 1e-6
+    assert (f1 - s1).abs().max().item() < 2e-4 * scale1 + 1e-3
+    assert (f2 - s2).abs().max().item() < 2e-4 * scale2 + 1e-3
