@@ -886,17 +886,27 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
     }
     __syncthreads();
     const int cu = p.Cu >> 3;                        // chunks that come from the up-sampled decoder output
+    const int Cx = p.C1 + p.C2;
     const int yy = blockIdx.x % p.H, b = blockIdx.x / p.H;
     const int UH = p.H >> 1, UW = p.W >> 1;
     const long long HW = (long long)p.H * p.W;
-    __nv_bfloat16* orow0 = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + yy) * p.W * p.ldo;
-    // phase 1: thread t owns chunk t % cu for pixels t / cu, t / cu + ppb, ...: no divisions in the loop, contiguous 16-byte
-    // stores, every up-sampled source row is read by exactly two blocks
-    const int ppb = blockDim.x / cu;
-    if ((int)threadIdx.x < ppb * cu) {
-        const int ch = threadIdx.x % cu, px0 = threadIdx.x / cu;
+    // the raw network inputs of this row (fp32 NCHW planes) are staged in shared memory with coalesced loads, already activated
+    float* xs = coef + 2 * Cpad;                     // [Cx][W]
+    for (int i = threadIdx.x; i < Cx * p.W; i += blockDim.x) {
+        const int c = i / p.W, xx = i - c * p.W;
+        const float v = c < p.C1 ? __ldg(p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W + xx)
+                                 : __ldg(p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + (long long)yy * p.W + xx);
+        xs[i] = fmaxf(fmaf(v, coef[p.Cu + c], coef[Cpad + p.Cu + c]), 0.f);
+    }
+    __syncthreads();
+    // thread t owns chunk t % chunks for pixels t / chunks, t / chunks + ppb, ...: no divisions in the loop and the 16-byte
+    // stores of the block form one contiguous stream (every chunk of every pixel of the row, in order)
+    const int ppb = blockDim.x / chunks;
+    if ((int)threadIdx.x >= ppb * chunks) return;
+    const int ch = threadIdx.x % chunks, px0 = threadIdx.x / chunks;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + yy) * p.W * p.ldo + ch * 8;
+    if (ch < cu) {
         const __nv_bfloat16* urow = reinterpret_cast<const __nv_bfloat16*>(p.u) + ((long long)b * UH + (yy >> 1)) * UW * p.ldu + ch * 8;
-        __nv_bfloat16* orow = orow0 + ch * 8;
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = coef[ch * 8 + j]; sh[j] = coef[Cpad + ch * 8 + j]; }
@@ -908,22 +918,13 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
             for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
             *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
         }
-    }
-    // phase 2: the raw network inputs (fp32 NCHW planes, coalesced along x) fill the remaining chunks
-    const float* x1row = p.x1 + (long long)b * p.C1 * HW + (long long)yy * p.W;
-    const float* x2row = p.C2 ? p.x2 + (long long)b * p.C2 * HW + (long long)yy * p.W : nullptr;
-    for (int ch = cu; ch < chunks; ++ch) {
-        for (int xx = threadIdx.x; xx < p.W; xx += blockDim.x) {
+    } else {
+        const int c0 = ch * 8 - p.Cu;                // first raw-input channel of this chunk
+        for (int xx = px0; xx < p.W; xx += ppb) {
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = ch * 8 + j;
-                float v = 0.f;
-                if (c < p.Cu + p.C1) v = __ldg(x1row + (long long)(c - p.Cu) * HW + xx);
-                else if (c < Ct) v = __ldg(x2row + (long long)(c - p.Cu - p.C1) * HW + xx);
-                f[j] = fmaxf(fmaf(v, coef[c], coef[Cpad + c]), 0.f);
-            }
-            *reinterpret_cast<uint4*>(orow0 + (long long)xx * p.ldo + ch * 8) = pack8(f);
+            for (int j = 0; j < 8; ++j) f[j] = (c0 + j < Cx) ? xs[(c0 + j) * p.W + xx] : 0.f;
+            *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
         }
     }
 }
@@ -1434,7 +1435,13 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
     const int chunks = (int)(d->ldo / 8);
     DMM_CHECK(chunks <= 256, "dmm_head_input: ldo %lld too large", (long long)d->ldo);
-    const size_t smem = (size_t)2 * chunks * 8 * sizeof(float);
+    const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * d->W) * sizeof(float);
+    DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: row of %d raw channels x %d pixels does not fit in shared memory", d->C1 + d->C2, d->W);
+    static bool head_attr = false;
+    if (!head_attr) {
+        DMM_CUDA(cudaFuncSetAttribute(head_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        head_attr = true;
+    }
     head_input_kernel<<<(unsigned)(d->B * d->H), 256, smem, (cudaStream_t)stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;
