@@ -92,6 +92,15 @@ class HeadBwd(C.Structure):
                 ("lddu", c_int64)]
 
 
+GATHER_MAX = 40
+
+
+class GradGather(C.Structure):
+    _fields_ = [("src", c_void_p * GATHER_MAX), ("ld", c_int64 * GATHER_MAX), ("nsrc", c_int32), ("nk", c_int32),
+                ("k1", c_void_p * GATHER_MAX), ("k2", c_void_p * GATHER_MAX), ("x", c_void_p), ("ldx", c_int64),
+                ("mean", c_void_p), ("rows", c_int64), ("C", c_int32), ("pad_", c_int32), ("out", c_void_p), ("ldo", c_int64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/dmmfods_b200.h
 SIGNATURES = {
     "dmm_last_error": (C.c_char_p, []),
@@ -109,6 +118,9 @@ SIGNATURES = {
     "dmm_bn_relu_apply": (C.c_int, [C.POINTER(BnApply), c_void_p]),
     "dmm_bn_relu_bwd_reduce": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),
     "dmm_bn_relu_bwd_apply": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),
+    "dmm_bn_relu_bwd_contrib": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),
+    "dmm_bn_bwd_finalize": (C.c_int, [C.POINTER(BnBwd), c_int32, c_void_p, c_void_p]),
+    "dmm_grad_gather": (C.c_int, [C.POINTER(GradGather), c_void_p]),
     "dmm_im2col_7x7s2": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_int32, c_void_p]),
     "dmm_nchw_stats": (C.c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32, c_int32, c_void_p]),

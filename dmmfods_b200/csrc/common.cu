@@ -133,6 +133,7 @@ extern "C" int dmm_sizeof(int which) {
         case 8: return (int)sizeof(dmm_head_bwd_t);
         case 9: return (int)sizeof(dmm_pack_job_t);
         case 10: return (int)sizeof(dmm_unpack_job_t);
+        case 11: return (int)sizeof(dmm_grad_gather_t);
         default: return -1;
     }
 }

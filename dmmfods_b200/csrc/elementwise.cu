@@ -655,6 +655,143 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-pass BN-ReLU backward "contribution" (see include/dmmfods_b200.h): sums like the reduce pass + bf16 slab A*dz.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_contrib_kernel(const dmm_bn_bwd_args_t p) {
+    __shared__ float sm[2 * kEwThreads * 8];
+    __shared__ __align__(16) float cf[5][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+            cf[4][tid] = (p.bn.gamma ? p.bn.gamma[c] : 1.f) * k.invstd;
+        }
+    }
+    __syncthreads();
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (active) {
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g) + chunk * 8;
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + chunk * 8;
+        const long long rows = (long long)p.B * p.H * p.W;
+        const long long step = (long long)gridDim.x * ry;
+        const int t8 = threadIdx.x * 8;
+        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += 2 * step) {
+            const long long row2 = row + step;
+            const bool has2 = row2 < rows;
+            float xa[8], xb[8], ga[8], gb[8], oa[8], ob[8];
+            unpack8(ldg16(x + row * p.ldx), xa);
+            unpack8(ldg16(g + row * p.ldg), ga);
+            if (has2) {
+                unpack8(ldg16(x + row2 * p.ldx), xb);
+                unpack8(ldg16(g + row2 * p.ldg), gb);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sc = cf[0][t8 + j], sh = cf[1][t8 + j], mu = cf[2][t8 + j], A = cf[4][t8 + j];
+                const float dza = fmaf(xa[j], sc, sh) > 0.f ? ga[j] : 0.f;
+                s1[j] += dza;
+                s2[j] = fmaf(dza, xa[j] - mu, s2[j]);
+                oa[j] = A * dza;
+                if (has2) {
+                    const float dzb = fmaf(xb[j], sc, sh) > 0.f ? gb[j] : 0.f;
+                    s1[j] += dzb;
+                    s2[j] = fmaf(dzb, xb[j] - mu, s2[j]);
+                    ob[j] = A * dzb;
+                }
+            }
+            *reinterpret_cast<uint4*>(out + row * p.ldo) = pack8(oa);
+            if (has2) *reinterpret_cast<uint4*>(out + row2 * p.ldo) = pack8(ob);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
+    }
+    block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const dmm_bn_bwd_t bn, int C, float* __restrict__ k) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+        const double* r = bn.sums + (size_t)s * 2 * bn.sums_ld + bn.sums_off + c;
+        a += r[0];
+        b += r[bn.sums_ld];
+    }
+    const float invstd = bn.save_invstd[c];
+    const float A = (bn.gamma ? bn.gamma[c] : 1.f) * invstd;
+    if (bn.dgamma) bn.dgamma[c] = (float)b;
+    if (bn.dbeta) bn.dbeta[c] = (float)a;
+    k[c] = A * (float)(a / bn.count);
+    k[C + c] = A * invstd * (float)(b / bn.count);
+}
+
+__global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_grad_gather_t p) {
+    __shared__ __align__(16) float ks[3][kEwThreads];       // sum k1, sum k2, mean of the block's channels
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            float a = 0.f, b = 0.f;
+            for (int j = 0; j < p.nk; ++j) {
+                a += __ldg(p.k1[j] + c);
+                b += __ldg(p.k2[j] + c);
+            }
+            ks[0][tid] = a; ks[1][tid] = b; ks[2][tid] = p.nk ? __ldg(p.mean + c) : 0.f;
+        }
+    }
+    __syncthreads();
+    if (chunk >= nchunks) return;
+    const int t8 = threadIdx.x * 8;
+    const long long step = (long long)gridDim.x * ry;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + chunk * 8;
+    for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < p.rows; row += step) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        int s = 0;
+        for (; s + 4 <= p.nsrc; s += 4) {        // four independent 16-byte loads in flight
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                v[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s + u]) + row * p.ld[s + u] + chunk * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        for (; s < p.nsrc; ++s) {
+            float f[8];
+            unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s]) + row * p.ld[s] + chunk * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+        if (p.nk) {
+            float xv[8];
+            unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + chunk * 8), xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] -= fmaf(xv[j] - ks[2][t8 + j], ks[1][t8 + j], ks[0][t8 + j]);
+        }
+        *reinterpret_cast<uint4*>(out + row * p.ldo) = pack8(acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Lean avg-pool-parent (gmode 1, bf16 gradient, even H and W) variants: one thread per (pooled pixel, 8-channel chunk),
 // the parent gradient is loaded once and the four children are independent 16-byte loads; blockIdx.x walks pooled rows,
 // so there is no per-element division.  PASS 0 = reduce, PASS 1 = apply.
@@ -1397,6 +1534,40 @@ extern "C" int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream) 
 }
 extern "C" int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream) {
     return launch_bn_bwd<1>(d, (cudaStream_t)stream);
+}
+
+extern "C" int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream) {
+    DMM_CHECK(d && d->x && d->g && d->out, "dmm_bn_relu_bwd_contrib: null pointer");
+    DMM_CHECK(d->C > 0 && d->C % 8 == 0, "dmm_bn_relu_bwd_contrib: C=%d must be a positive multiple of 8", d->C);
+    DMM_CHECK(d->ldx % 8 == 0 && d->ldg % 8 == 0 && d->ldo % 8 == 0, "dmm_bn_relu_bwd_contrib: row pitches must be multiples of 8");
+    DMM_CHECK(d->gmode == 0 && !d->g_is_f32, "dmm_bn_relu_bwd_contrib: same-pixel bf16 gradients only");
+    DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd, "dmm_bn_relu_bwd_contrib: missing BN state");
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
+    ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W);
+    bn_bwd_contrib_kernel<<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
+    DMM_LAUNCH_CHECK("bn_bwd_contrib_kernel");
+    return 0;
+}
+
+extern "C" int dmm_bn_bwd_finalize(const dmm_bn_bwd_t* bn, int32_t C, float* k, void* stream) {
+    DMM_CHECK(bn && k && bn->sums && bn->save_invstd && bn->count > 0, "dmm_bn_bwd_finalize: missing inputs");
+    if (C <= 0) return 0;
+    bn_bwd_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*bn, C, k);
+    DMM_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+    return 0;
+}
+
+extern "C" int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream) {
+    DMM_CHECK(d && d->out && d->nsrc >= 1 && d->nsrc <= DMM_GATHER_MAX && d->nk >= 0 && d->nk <= DMM_GATHER_MAX,
+              "dmm_grad_gather: bad descriptor");
+    DMM_CHECK(d->C > 0 && d->C % 8 == 0 && d->ldo % 8 == 0, "dmm_grad_gather: C / ldo must be multiples of 8");
+    DMM_CHECK(d->nk == 0 || (d->x && d->mean && d->ldx % 8 == 0), "dmm_grad_gather: corrections need x and mean");
+    for (int s = 0; s < d->nsrc; ++s) DMM_CHECK(d->src[s] && d->ld[s] % 8 == 0, "dmm_grad_gather: source %d", s);
+    if (d->rows <= 0) return 0;
+    ColCfg k = col_cfg(d->C, d->rows);
+    grad_gather_kernel<<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
+    DMM_LAUNCH_CHECK("grad_gather_kernel");
+    return 0;
 }
 
 extern "C" int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H,

@@ -356,6 +356,40 @@ class Engine:
         self._emit(lst, self.lib.dmm_bn_relu_bwd_apply, d2, name + ".apply", gbuf=gbuf, kind="bn_relu_bwd_apply",
                    nbytes=rd2 + wr)
 
+    def _slab_bwd(self, lst, name, bn, blk, C_, g_ptr, ldg, gmode=0, bn_c0=0):
+        """BatchNorm-ReLU backward of a consumer of dense-block buffer `blk` (transition / decoder skip) : the usual two
+        passes, dx stored as its own bf16 slab that the gradient gathers of the block sum up (no fp32 read-modify-write)."""
+        slab = self._mat(self.B, blk.H, blk.W, C_)
+        self._bn_bwd(lst, name, bn, blk.buf, 0, C_, g_ptr, ldg, slab.ptr(), slab.ld, 0, gmode=gmode, bn_c0=bn_c0)
+        blk.contribs.append(dict(mat=slab, C=C_, k=None, mean=None))
+
+    def _contrib_bwd(self, lst, name, bn, blk, C_, g):
+        """dense-layer norm1 backward in ONE pass (dmm_bn_relu_bwd_contrib): slab A*dz + sums; the per-channel correction
+        vectors k (dmm_bn_bwd_finalize) are applied when the block's channel gradients are gathered."""
+        self._stage_params.setdefault(id(lst), []).extend([bn.prefix + ".weight", bn.prefix + ".bias"])
+        sums = self._new_sums(C_)
+        b = ops.make_bn_bwd(sums, 0, blk.buf.P, bn.gamma, bn.beta, bn.save_mean, bn.save_invstd, bn.dgamma, bn.dbeta)
+        slab = self._mat(self.B, blk.H, blk.W, C_)
+        d = ops.make_bn_bwd_args(blk.buf, 0, C_, g.ptr(), g.ld, b, slab.ptr(), slab.ld, 0)
+        self._emit(lst, self.lib.dmm_bn_relu_bwd_contrib, d, name + ".contrib", kind="bn_relu_bwd_apply", nbytes=blk.buf.P * C_ * 6)
+        off = self._save.take(2 * C_, 4)
+        kvec = self._save.buf[off:off + 2 * C_]
+
+        def run_fin(_a, stream, b=b, C_=C_, kvec=kvec, lib=self.lib):
+            return lib.dmm_bn_bwd_finalize(C.byref(b), C_, C.c_void_p(kvec.data_ptr()), stream)
+        self._emit(lst, run_fin, None, name + ".finalize", kind="bn_finalize", nbytes=C_ * 150)
+        self._keep.append(b)
+        blk.contribs.append(dict(mat=slab, C=C_, k=kvec, mean=bn.save_mean))
+
+    def _gather(self, lst, name, blk, c0, C_, dst):
+        """gradient of channels [c0, c0+C_) of a block buffer = sum of the slabs of every consumer of those channels (all of
+        them run earlier in the backward program) minus the deferred BatchNorm corrections.  Sources are resolved in _finalize."""
+        d = _lib.GradGather()
+        d.rows, d.C = blk.buf.P, C_
+        d.out, d.ldo = dst.ptr().value, dst.ld
+        self._emit(lst, self.lib.dmm_grad_gather, d, name, kind="grad_gather", nbytes=0.0)
+        self._gathers.append((lst[-1], blk, c0, C_))
+
     def _cast(self, lst, name, src, c0, C_, dst):
         def run(_arg, stream, src=src, c0=c0, C_=C_, dst=dst, lib=self.lib):
             return lib.dmm_rows_f32_to_bf16(C.c_void_p(src.data_ptr() + 4 * c0), src.shape[1], dst.ptr(), dst.ld,
@@ -370,6 +404,7 @@ class Engine:
         k, bnk = self.k, self.bnk
         nb = len(self.block_config)
         self._fix_w, self._fix_dw = [], []
+        self._gathers = []
         fwd = self.fwd
         H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
         H4, W4 = (H2 - 1) // 2 + 1, (W2 - 1) // 2 + 1
@@ -407,7 +442,7 @@ class Engine:
             o.C0, o.Ct = cin_blk[b], ctot_blk[b]
             o.buf = self._mat(B, o.H, o.W, o.Ct)
             o.stats = self._new_stats(o.Ct)
-            o.G = self._f32(B * o.H * o.W, o.Ct) if self.need_backward else None
+            o.contribs = []      # backward: slabs written by the consumers of this buffer (see _gather)
             return o
 
         self._blk_cls = Blk
@@ -441,8 +476,10 @@ class Engine:
                 st = []
                 dz0 = self._tmpmat("dz0", B, H2, W2, self.nif)
                 dzr = self._tmpmat("dz0_routed", B, H2, W2, self.nif)
-                self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, blk.G.data_ptr(), blk.Ct, dz0.ptr(), dz0.ld, 0,
-                             gmode=2, g_is_f32=True, dz_tmp=dzr)
+                g0 = self._tmpmat("g_blockin", B, blk.H, blk.W, self.nif)
+                self._gather(st, prefix + ".gout", blk, 0, self.nif, g0)
+                self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, g0.ptr(), g0.ld, dz0.ptr(), dz0.ld, 0,
+                             gmode=2, dz_tmp=dzr)
                 st[-2].arg.argmax, st[-2].arg.ldarg = amax.data_ptr(), self.nif
                 self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
                                  [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
@@ -473,7 +510,7 @@ class Engine:
                     da2 = self._tmpmat("da2", B, Hb, Wb, bnk)
                     dz1 = self._tmpmat("dz1", B, Hb, Wb, bnk)
                     da1 = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
-                    self._cast(st, lp + ".gout", blk.G, Ci, k, go)
+                    self._gather(st, lp + ".gout", blk, Ci, k, go)
                     self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", a2.view(), [go.view(0, k)], conv3x3[0],
                                      conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B)
                     dg2 = self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
@@ -483,8 +520,7 @@ class Engine:
                                      conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B)
                     dg1 = self._conv_dgrad(st, lp + ".conv1.dgrad", lp + ".conv1.weight", [dz1.view()], conv1x1[1], conv1x1[2],
                                            bnk, Ci, 1, Ci, Wb, Hb, B, da1)
-                    self._bn_bwd(st, lp + ".norm1.bwd", bn1, blk.buf, 0, Ci, da1.ptr(), da1.ld, blk.G.data_ptr(), blk.Ct, 2,
-                                 gbuf=blk, producer=dg1)
+                    self._contrib_bwd(st, lp + ".norm1.bwd", bn1, blk, Ci, da1)
                     self._bwd_stages.append(st)
 
         # ---------------- transition: BN-ReLU -> (avg-pool first) -> 1x1 conv ----------------
@@ -500,7 +536,7 @@ class Engine:
                 st = []
                 if out_is_block:          # gradient lives in the fp32 block gradient buffer
                     gt = self._tmpmat("gt", B, out.H, out.W, Co)
-                    self._cast(st, prefix + ".gout", out_G, 0, Co, gt)
+                    self._gather(st, prefix + ".gout", out_G, 0, Co, gt)
                 else:                     # bf16 gradient matrix written by the concat module backward
                     gt = out_G
                 dap = self._tmpmat("dap", B, out.H, out.W, Ct)
@@ -508,8 +544,7 @@ class Engine:
                                  conv1x1[2], Ct, Co, Ct, Co, Ct, 1, out.W, out.H, B)
                 self._conv_dgrad(st, prefix + ".conv.dgrad", prefix + ".conv.weight", [gt.view(0, Co)], conv1x1[1], conv1x1[2],
                                  Co, Ct, 1, Ct, out.W, out.H, B, dap)
-                self._bn_bwd(st, prefix + ".norm.bwd", bn, blk.buf, 0, Ct, dap.ptr(), dap.ld, blk.G.data_ptr(), blk.Ct, 2,
-                             gmode=1, gbuf=blk)
+                self._slab_bwd(st, prefix + ".norm.bwd", bn, blk, Ct, dap.ptr(), dap.ld, gmode=1)
                 self._bwd_stages.append(st)
 
         # ================= encoder =================
@@ -537,7 +572,7 @@ class Engine:
                     transition("stream_2_features.transition%d" % (b + 1), s2_blocks[b], t2, t2s, dt2, False)
                 else:
                     nxt = s2_blocks[b + 1]
-                    transition("stream_2_features.transition%d" % (b + 1), s2_blocks[b], nxt.buf, nxt.stats, nxt.G, True)
+                    transition("stream_2_features.transition%d" % (b + 1), s2_blocks[b], nxt.buf, nxt.stats, nxt, True)
             s2_t = (t2, t2s, dt2)
 
         for b in range(nb):
@@ -564,7 +599,7 @@ class Engine:
                     st = []
                     gt = self._tmpmat("gt", B, nxt.H, nxt.W, Cc)
                     dacat = self._tmpmat("dacat", B, nxt.H, nxt.W, 2 * Cc)
-                    self._cast(st, "concat_module.gout", nxt.G, 0, Cc, gt)
+                    self._gather(st, "concat_module.gout", nxt, 0, Cc, gt)
                     self._conv_wgrad(st, "concat_module.conv.wgrad", "concat_module.conv.weight", acat.view(), [gt.view()],
                                      conv1x1[0], conv1x1[2], 2 * Cc, Cc, 2 * Cc, Cc, 2 * Cc, 1, nxt.W, nxt.H, B)
                     self._conv_dgrad(st, "concat_module.conv.dgrad", "concat_module.conv.weight", [gt.view()], conv1x1[1],
@@ -574,7 +609,7 @@ class Engine:
                                  bn_c0=Cc)
                     self._bwd_stages.append(st)
             else:
-                transition("features.transition%d" % (b + 1), blk, nxt.buf, nxt.stats, nxt.G, True)
+                transition("features.transition%d" % (b + 1), blk, nxt.buf, nxt.stats, nxt, True)
 
         # ================= decoder (:105-120, :255-261) =================
         fstack = [self.nif + 2 * k] + ctot_blk            # feature_size_stack (:81-82,95)
@@ -642,12 +677,10 @@ class Engine:
                 self._conv_dgrad(st, sp + ".conv_reduce.dgrad", sp + ".conv_reduce.weight", [dr.view()], conv1x1[1], conv1x1[2],
                                  num_f, num_in, 1, num_in, wk, hk, B, da)
                 if kdec == 1:
-                    self._bn_bwd(st, sp + ".norm0.bwd", bn0, cur_raw, 0, num_in, da.ptr(), da.ld, cur.G.data_ptr(), cur.Ct, 2,
-                                 gbuf=cur)
+                    self._slab_bwd(st, sp + ".norm0.bwd", bn0, cur, num_in, da.ptr(), da.ld)
                 else:
                     self._bn_bwd(st, sp + ".norm0.bwd[up]", bn0, u, 0, Cu, da.ptr(0), da.ld, du.ptr(), du.ld, 0)
-                    self._bn_bwd(st, sp + ".norm0.bwd[skip]", bn0, skip_blk.buf, 0, skip_blk.Ct, da.ptr(Cu), da.ld,
-                                 skip_blk.G.data_ptr(), skip_blk.Ct, 2, bn_c0=Cu, gbuf=skip_blk)
+                    self._slab_bwd(st, sp + ".norm0.bwd[skip]", bn0, skip_blk, skip_blk.Ct, da.ptr(Cu), da.ld, bn_c0=Cu)
                 self._bwd_stages.append(st)
             up_prev = (unew, unews, dunew)
             num_in = num_f * 2
@@ -818,6 +851,25 @@ class Engine:
                     lo = hi = 0
                 self.segments.append((seg_ops, job_lo, job_i - job_lo, lo, hi))
                 seg_ops, seg_names, job_lo = [], [], job_i
+        for op, blk, c0, C_ in self._gathers:
+            d = op.arg
+            srcs = [c for c in blk.contribs if c["C"] >= c0 + C_]
+            if not srcs or len(srcs) > _lib.GATHER_MAX:
+                raise RuntimeError("dmmfods_b200: %d gradient sources for channels [%d, %d) of a block buffer (%s)"
+                                   % (len(srcs), c0, c0 + C_, op.name))
+            nk = 0
+            for i, c in enumerate(srcs):
+                d.src[i] = c["mat"].ptr(c0).value
+                d.ld[i] = c["mat"].ld
+                if c["k"] is not None:
+                    d.k1[nk] = c["k"].data_ptr() + 4 * c0
+                    d.k2[nk] = c["k"].data_ptr() + 4 * (c["C"] + c0)
+                    d.mean = c["mean"].data_ptr() + 4 * c0
+                    nk += 1
+            d.nsrc, d.nk = len(srcs), nk
+            if nk:
+                d.x, d.ldx = blk.buf.ptr(c0).value, blk.buf.ld
+            op.bytes = float(blk.buf.P * C_ * 2 * (len(srcs) + 1 + (1 if nk else 0)))
         seen = set()
         for op in self.bwd:
             if op.gbuf is not None:

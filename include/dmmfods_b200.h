@@ -244,6 +244,36 @@ typedef struct {
 int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
 
+/* Dense-block gradient flow without read-modify-write (every dense layer contributes to ALL earlier channels).
+ * All BatchNorms that consume a dense-block buffer normalise the same raw channels with the same batch statistics, so
+ *   dx = A*dz - A*c1 - A*invstd*c2*(x - mean)         (A = gamma*invstd, c1 = mean(dz), c2 = mean(dz*xhat))
+ * splits into a per-pixel part A*dz and a per-channel affine correction that can be summed over the consumers:
+ *   dmm_bn_relu_bwd_contrib : ONE pass over (x, g): dz = g*[bn(x) > 0]; sums += (sum dz, invstd*sum dz*(x-mean)) like
+ *                             dmm_bn_relu_bwd_reduce, and the bf16 slab out = A*dz is stored (args: x, g (bf16), bn, out/ldo).
+ *   dmm_bn_bwd_finalize     : dgamma = sum dz*xhat, dbeta = sum dz, k[0][c] = A*c1, k[1][c] = A*invstd*c2 (k: float[2][C]).
+ *   dmm_grad_gather         : out = bf16( sum_s src_s - sum_j k1_j - (x - mean) * sum_j k2_j ): the gradient of a channel range
+ *                             of the block buffer from the slabs of all its consumers (those with a fully corrected dx pass no k). */
+int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream);
+int dmm_bn_bwd_finalize(const dmm_bn_bwd_t* bn, int32_t C, float* k, void* stream);
+#define DMM_GATHER_MAX 40
+typedef struct {
+    const void* src[DMM_GATHER_MAX];     /* bf16 rows, already offset to the first channel of the range */
+    int64_t ld[DMM_GATHER_MAX];
+    int32_t nsrc;
+    int32_t nk;
+    const float* k1[DMM_GATHER_MAX];     /* per-consumer correction vectors, offset to the first channel */
+    const float* k2[DMM_GATHER_MAX];
+    const void* x;                       /* raw block buffer (bf16), offset to the first channel; NULL if nk == 0 */
+    int64_t ldx;
+    const float* mean;                   /* batch mean of the channels (any consumer's save_mean slice) */
+    int64_t rows;
+    int32_t C;                           /* multiple of 8 */
+    int32_t pad_;
+    void* out;                           /* bf16 [rows, ldo] */
+    int64_t ldo;
+} dmm_grad_gather_t;
+int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream);
+
 /* ---- stem / head data movement ------------------------------------------------------------- */
 /* im2col for conv0 (7x7, stride 2, padding 3; Dense_U_Net_lidar.py:73-74,157-158): fp32 NCHW
  * (B,C1[+C2],H,W) -> bf16 [B*OH*OW, kpad], k = ci*49 + kh*7 + kw (the flattened Conv2d weight
@@ -333,7 +363,7 @@ int dmm_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_av
 
 /* sizeof() of the structs above in declaration order (0 = dmm_view_t, 1 = dmm_igemm_t, 2 = dmm_wgrad_t,
  * 3 = dmm_bn_t, 4 = dmm_bn_apply_t, 5 = dmm_bn_bwd_t, 6 = dmm_bn_bwd_args_t, 7 = dmm_head_t,
- * 8 = dmm_head_bwd_t, 9 = dmm_pack_job_t, 10 = dmm_unpack_job_t) so a binding can verify its layout. */
+ * 8 = dmm_head_bwd_t, 9 = dmm_pack_job_t, 10 = dmm_unpack_job_t, 11 = dmm_grad_gather_t) so a binding can verify its layout. */
 int dmm_sizeof(int which);
 
 #ifdef __cplusplus
