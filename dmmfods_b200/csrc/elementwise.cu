@@ -762,7 +762,20 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         int s = 0;
-        for (; s + 4 <= p.nsrc; s += 4) {        // four independent 16-byte loads in flight
+        for (; s + 8 <= p.nsrc; s += 8) {        // eight independent 16-byte loads in flight
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                v[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s + u]) + row * p.ld[s + u] + chunk * 8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        for (; s + 4 <= p.nsrc; s += 4) {
             uint4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)

@@ -594,7 +594,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             // per stage hand-over, so a stage should carry many MMAs), then more patch stages with what is left
             const int rest = avail - 2 * (int)c.a_stage;
             if (rest < 2 * (int)b_tap) continue;
-            int blk_max = rest / (2 * (int)b_tap);                      // weight blocks per stage
+            static const int min_sb = env_int("DMM_IGEMM_MIN_SB", 2);
+            int blk_max = rest / (min_sb * (int)b_tap);                 // weight blocks per stage
+            if (blk_max < 1) blk_max = rest / (2 * (int)b_tap);
             if (blk_max * (int)b_tap > 48 * 1024) blk_max = (48 * 1024) / (int)b_tap > 0 ? (48 * 1024) / (int)b_tap : 1;
             int tps_max = blk_max * tpk;
             if (tps_max > max_taps) tps_max = max_taps;
