@@ -29,6 +29,8 @@ from .ops import Mat, Stats, ceil_to
 
 # fuse the reduce pass of a BatchNorm-ReLU backward into the epilogue of the data-gradient convolution that produces its input
 FUSE_BN_BWD_REDUCE = os.environ.get("DMM_FUSE_BN_BWD_REDUCE", "1") != "0"
+# run the weight-gradient kernels on a second stream beside the data-gradient / BatchNorm-backward chain
+WGRAD_SIDE_STREAM = os.environ.get("DMM_WGRAD_SIDE_STREAM", "1") != "0"
 
 
 class Op:
@@ -834,6 +836,8 @@ class Engine:
         seg_ops, seg_names, job_lo, job_i = [], [], 0, 0
         done = set()
         for si, st in enumerate(stages):
+            marker = Op(None, None, "stage%d" % si, kind="stage_begin")
+            seg_ops.append(marker)
             seg_ops.extend(st)
             self.bwd.extend(st)
             for n in self._stage_params.get(id(st), []):
@@ -881,10 +885,27 @@ class Engine:
     def _run(self, program):
         if self.plan_only:
             raise RuntimeError("dmmfods_b200: plan-only engine cannot execute (no CUDA device)")
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        main = torch.cuda.current_stream()
+        stream = C.c_void_p(main.cuda_stream)
         byref = C.byref
         debug = bool(os.environ.get("DMM_DEBUG_SYNC"))
+        side = self._side_stream() if (WGRAD_SIDE_STREAM and not debug) else None
         for op in program:
+            if op.kind == "stage_begin":
+                # temporaries (go, dz1, ...) are re-written from here on: weight-gradient kernels of the previous stage that
+                # still read them on the side stream must have finished
+                self._join_side(main)
+                continue
+            if side is not None and op.kind == "wgrad":
+                # weight gradients feed nothing but the final unpack: they run beside the dgrad -> BN-backward chain
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                rc = op.fn(byref(op.arg), C.c_void_p(side.cuda_stream))
+                self._side_busy = True
+                if rc != 0:
+                    raise RuntimeError("dmmfods_b200: %s failed (rc=%d): %s" % (op.name, rc, _lib.last_error()))
+                continue
             rc = op.fn(byref(op.arg), stream) if op.arg is not None else op.fn(None, stream)
             if rc != 0:
                 raise RuntimeError("dmmfods_b200: %s failed (rc=%d): %s" % (op.name, rc, _lib.last_error()))
@@ -893,6 +914,19 @@ class Engine:
                     torch.cuda.synchronize()
                 except Exception as e:      # noqa: BLE001
                     raise RuntimeError("dmmfods_b200: kernel of op %s faulted: %s" % (op.name, e))
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+            self._side_busy = False
+        return self._side
+
+    def _join_side(self, main):
+        if getattr(self, "_side", None) is not None and self._side_busy:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            main.wait_event(ev)
+            self._side_busy = False
 
     def check_param_pointers(self):
         for t, ptr in zip(self._pack_src, self._param_ptrs):
@@ -931,6 +965,7 @@ class Engine:
         tab = self._unpack_tab.data_ptr()
         for i, (seg_ops, job_lo, njobs, lo, hi) in enumerate(self.segments):
             self._run(seg_ops)
+            self._join_side(torch.cuda.current_stream())
             if njobs:
                 _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab + job_lo * _UNPACK_DT.itemsize), njobs, stream),
                            "dmm_unpack_wgrad_batched")
