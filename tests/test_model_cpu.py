@@ -43,6 +43,7 @@ def test_struct_layouts_match_header_sizes():
         assert ctypes.sizeof(st) == lib.dmm_sizeof(i), (st.__name__, ctypes.sizeof(st), lib.dmm_sizeof(i))
     assert engine._PACK_DT.itemsize == lib.dmm_sizeof(9)
     assert engine._UNPACK_DT.itemsize == lib.dmm_sizeof(10)
+    assert ctypes.sizeof(_lib.GradGather) == lib.dmm_sizeof(11)
 
 
 def test_default_config_matches_reference_defaults():
