@@ -174,10 +174,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
             } else {
-                const int ox = (int)(row % OW);
-                const long long t = row / OW;
-                const int oy = (int)(t % OH);
-                const int b = (int)(t / OH);
+                const unsigned r32 = (unsigned)row;      // host guarantees B*OH*OW < 2^31 for the pooled modes
+                const int ox = (int)(r32 % (unsigned)OW);
+                const unsigned t = r32 / (unsigned)OW;
+                const int oy = (int)(t % (unsigned)OH);
+                const int b = (int)(t / (unsigned)OH);
                 if (POOL == 1) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = 0.f;
@@ -200,22 +201,25 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
                         o[j] = -INFINITY;
                         code[j] = 0;
                     }
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int iy = 2 * oy + dy;
-                        if (iy < 0 || iy >= p.H) continue;
-                        for (int dx = -1; dx <= 1; ++dx) {
-                            const int ix = 2 * ox + dx;
-                            if (ix < 0 || ix >= p.W) continue;
-                            const long long r = ((long long)b * p.H + iy) * p.W + ix;
+                    uint4 win[9];      // the nine window elements are independent loads: issue them all, then reduce
+                    bool ok[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int iy = 2 * oy + t / 3 - 1, ix = 2 * ox + t % 3 - 1;
+                        ok[t] = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        if (ok[t]) win[t] = ldg16(x + (((long long)b * p.H + iy) * p.W + ix) * p.ldx + chunk * 8);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        if (ok[t]) {
                             float f[8];
-                            unpack8(ldg16(x + r * p.ldx + chunk * 8), f);
-                            const uint32_t pos = (uint32_t)((dy + 1) * 3 + (dx + 1));
+                            unpack8(win[t], f);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
                                 if (a > o[j]) {
                                     o[j] = a;
-                                    code[j] = pos;
+                                    code[j] = (uint32_t)t;
                                 }
                             }
                         }
@@ -345,6 +349,34 @@ __device__ __forceinline__ void bn_relu_dz(const dmm_bn_bwd_args_t& p, const __n
             }
             const int oy0 = yy >> 1, oy1 = (yy + 1) >> 1;   // windows whose rows 2o-1..2o+1 contain yy
             const int ox0 = xx >> 1, ox1 = (xx + 1) >> 1;
+            if (p.argmax) {
+                // the forward pass recorded the winner of every window: all (up to four) windows are fetched at once
+                const int ny = (oy1 != oy0 && oy1 < OH) ? 2 : 1, nx = (ox1 != ox0 && ox1 < OW) ? 2 : 1;
+                uint2 cd[4];
+                float gg[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int a = q >> 1, bb = q & 1;
+                    if (a < ny && bb < nx) {
+                        const long long w = ((long long)b * OH + (a ? oy1 : oy0)) * OW + (bb ? ox1 : ox0);
+                        cd[q] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.argmax) + w * p.ldarg + chunk * 8));
+                        load_g8<GT>(g, w * p.ldg + chunk * 8, gg[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int a = q >> 1, bb = q & 1;
+                    if (a < ny && bb < nx) {
+                        const int oy = a ? oy1 : oy0, ox = bb ? ox1 : ox0;
+                        const uint32_t mine = (uint32_t)((yy - 2 * oy + 1) * 3 + (xx - 2 * ox + 1));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t cj = ((j < 4 ? cd[q].x : cd[q].y) >> (8 * (j & 3))) & 0xffu;
+                            if (cj == mine) dz[j] += gg[q][j];
+                        }
+                    }
+                }
+            } else
             for (int oy = oy0; oy <= oy1; ++oy) {
                 if (oy >= OH) continue;
                 for (int ox = ox0; ox <= ox1; ++ox) {
@@ -1469,6 +1501,7 @@ extern "C" int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream_) {
     if (d->pool == 1) { OH = d->H / 2; OW = d->W / 2; }
     if (d->pool == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
     if (OH <= 0 || OW <= 0) return 0;
+    DMM_CHECK(d->pool == 0 || (long long)d->B * d->H * d->W < (1ll << 31), "dmm_bn_relu_apply: too many pixels for a pooled mode");
     ColCfg k = col_cfg(d->C, (long long)d->B * OH * OW);
     if (d->pool == 0 && d->ystats == nullptr) bn_apply_fast_kernel<<<k.grid, k.block, 0, stream>>>(*d);
     else if (d->pool == 0) bn_relu_apply_kernel<0><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
