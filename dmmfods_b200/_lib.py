@@ -76,7 +76,8 @@ class BnBwdArgs(C.Structure):
     _fields_ = [("x", c_void_p), ("ldx", c_int64), ("g", c_void_p), ("ldg", c_int64), ("g_is_f32", c_int32),
                 ("gmode", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
                 ("bn", BnBwd), ("out", c_void_p), ("ldo", c_int64), ("out_mode", c_int32), ("dz_out", c_void_p),
-                ("lddz", c_int64), ("argmax", c_void_p), ("ldarg", c_int64)]
+                ("lddz", c_int64), ("argmax", c_void_p), ("ldarg", c_int64), ("out_gw", c_int32), ("pad_", c_int32),
+                ("out_plane", c_int64)]
 
 
 class Head(C.Structure):
@@ -96,7 +97,8 @@ GATHER_MAX = 40
 
 
 class GradGather(C.Structure):
-    _fields_ = [("src", c_void_p * GATHER_MAX), ("ld", c_int64 * GATHER_MAX), ("nsrc", c_int32), ("nk", c_int32),
+    _fields_ = [("src", c_void_p * GATHER_MAX), ("ld", c_int64 * GATHER_MAX), ("plane", c_int64 * GATHER_MAX),
+                ("gw", c_int32), ("pad0_", c_int32), ("nsrc", c_int32), ("nk", c_int32),
                 ("k1", c_void_p * GATHER_MAX), ("k2", c_void_p * GATHER_MAX), ("x", c_void_p), ("ldx", c_int64),
                 ("mean", c_void_p), ("rows", c_int64), ("C", c_int32), ("pad_", c_int32), ("out", c_void_p), ("ldo", c_int64)]
 

@@ -712,7 +712,17 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_contrib_kernel(const dmm
     if (active) {
         const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
         const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g) + chunk * 8;
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + chunk * 8;
+        // slab layout: row-major [rows, ldo], or planar = one contiguous [rows, gw] matrix per channel group (the gathers of
+        // the block then read whole cache lines instead of 64-byte pieces of wide rows)
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+        long long ldo = p.ldo;
+        if (p.out_gw > 0) {
+            const int c = chunk * 8;
+            out += (long long)(c / p.out_gw) * p.out_plane + (c % p.out_gw);
+            ldo = p.out_gw;
+        } else {
+            out += chunk * 8;
+        }
         const long long rows = (long long)p.B * p.H * p.W;
         const long long step = (long long)gridDim.x * ry;
         const int t8 = threadIdx.x * 8;
@@ -740,8 +750,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_contrib_kernel(const dmm
                     ob[j] = A * dzb;
                 }
             }
-            *reinterpret_cast<uint4*>(out + row * p.ldo) = pack8(oa);
-            if (has2) *reinterpret_cast<uint4*>(out + row2 * p.ldo) = pack8(ob);
+            *reinterpret_cast<uint4*>(out + row * ldo) = pack8(oa);
+            if (has2) *reinterpret_cast<uint4*>(out + row2 * ldo) = pack8(ob);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
@@ -789,6 +799,9 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
     const int t8 = threadIdx.x * 8;
     const long long step = (long long)gridDim.x * ry;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + chunk * 8;
+    // element offset of this thread's chunk inside a planar source (group plane + position in the group)
+    const int cg = p.gw > 0 ? (chunk * 8) / p.gw : 0, cw = p.gw > 0 ? (chunk * 8) % p.gw : 0;
+#define DMM_GSRC(S) (reinterpret_cast<const __nv_bfloat16*>(p.src[S]) + (p.plane[S] ? (long long)cg * p.plane[S] + cw : (long long)chunk * 8) + row * p.ld[S])
     for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < p.rows; row += step) {
         float acc[8];
 #pragma unroll
@@ -798,7 +811,7 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
             uint4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                v[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s + u]) + row * p.ld[s + u] + chunk * 8);
+                v[u] = ldg16(DMM_GSRC(s + u));
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 float f[8];
@@ -811,7 +824,7 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
             uint4 v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                v[u] = ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s + u]) + row * p.ld[s + u] + chunk * 8);
+                v[u] = ldg16(DMM_GSRC(s + u));
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float f[8];
@@ -822,10 +835,11 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
         }
         for (; s < p.nsrc; ++s) {
             float f[8];
-            unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(p.src[s]) + row * p.ld[s] + chunk * 8), f);
+            unpack8(ldg16(DMM_GSRC(s)), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
+#undef DMM_GSRC_UNUSED
         if (p.nk) {
             float xv[8];
             unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + chunk * 8), xv);
@@ -1586,6 +1600,7 @@ extern "C" int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream)
     DMM_CHECK(d && d->x && d->g && d->out, "dmm_bn_relu_bwd_contrib: null pointer");
     DMM_CHECK(d->C > 0 && d->C % 8 == 0, "dmm_bn_relu_bwd_contrib: C=%d must be a positive multiple of 8", d->C);
     DMM_CHECK(d->ldx % 8 == 0 && d->ldg % 8 == 0 && d->ldo % 8 == 0, "dmm_bn_relu_bwd_contrib: row pitches must be multiples of 8");
+    DMM_CHECK(d->out_gw == 0 || (d->out_gw % 8 == 0 && d->out_plane % 8 == 0 && d->out_plane > 0), "dmm_bn_relu_bwd_contrib: bad planar slab");
     DMM_CHECK(d->gmode == 0 && !d->g_is_f32, "dmm_bn_relu_bwd_contrib: same-pixel bf16 gradients only");
     DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd, "dmm_bn_relu_bwd_contrib: missing BN state");
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
@@ -1608,7 +1623,10 @@ extern "C" int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream) {
               "dmm_grad_gather: bad descriptor");
     DMM_CHECK(d->C > 0 && d->C % 8 == 0 && d->ldo % 8 == 0, "dmm_grad_gather: C / ldo must be multiples of 8");
     DMM_CHECK(d->nk == 0 || (d->x && d->mean && d->ldx % 8 == 0), "dmm_grad_gather: corrections need x and mean");
-    for (int s = 0; s < d->nsrc; ++s) DMM_CHECK(d->src[s] && d->ld[s] % 8 == 0, "dmm_grad_gather: source %d", s);
+    for (int s = 0; s < d->nsrc; ++s) {
+        DMM_CHECK(d->src[s] && d->ld[s] % 8 == 0, "dmm_grad_gather: source %d", s);
+        DMM_CHECK(d->plane[s] == 0 || (d->gw > 0 && d->gw % 8 == 0 && d->plane[s] % 8 == 0), "dmm_grad_gather: planar source %d", s);
+    }
     if (d->rows <= 0) return 0;
     ColCfg k = col_cfg(d->C, d->rows);
     grad_gather_kernel<<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);

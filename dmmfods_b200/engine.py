@@ -373,6 +373,11 @@ class Engine:
         b = ops.make_bn_bwd(sums, 0, blk.buf.P, bn.gamma, bn.beta, bn.save_mean, bn.save_invstd, bn.dgamma, bn.dbeta)
         slab = self._mat(self.B, blk.H, blk.W, C_)
         d = ops.make_bn_bwd_args(blk.buf, 0, C_, g.ptr(), g.ld, b, slab.ptr(), slab.ld, 0)
+        # planar slab: one contiguous [P, k] matrix per growth-rate-wide channel group, so that the gather of a layer's k
+        # channels reads whole cache lines (row-major slabs cost 1.5x the DRAM traffic: 64-byte pieces of wide rows)
+        gw = self.k if (self.k % 8 == 0 and C_ % self.k == 0 and blk.C0 % self.k == 0) else 0
+        if gw:
+            d.out_gw, d.out_plane = gw, blk.buf.P * gw
         self._emit(lst, self.lib.dmm_bn_relu_bwd_contrib, d, name + ".contrib", kind="bn_relu_bwd_apply", nbytes=blk.buf.P * C_ * 6)
         off = self._save.take(2 * C_, 4)
         kvec = self._save.buf[off:off + 2 * C_]
@@ -381,7 +386,7 @@ class Engine:
             return lib.dmm_bn_bwd_finalize(C.byref(b), C_, C.c_void_p(kvec.data_ptr()), stream)
         self._emit(lst, run_fin, None, name + ".finalize", kind="bn_finalize", nbytes=C_ * 150)
         self._keep.append(b)
-        blk.contribs.append(dict(mat=slab, C=C_, k=kvec, mean=bn.save_mean))
+        blk.contribs.append(dict(mat=slab, C=C_, k=kvec, mean=bn.save_mean, gw=gw))
 
     def _gather(self, lst, name, blk, c0, C_, dst):
         """gradient of channels [c0, c0+C_) of a block buffer = sum of the slabs of every consumer of those channels (all of
@@ -862,9 +867,20 @@ class Engine:
                 raise RuntimeError("dmmfods_b200: %d gradient sources for channels [%d, %d) of a block buffer (%s)"
                                    % (len(srcs), c0, c0 + C_, op.name))
             nk = 0
+            gws = {c.get("gw", 0) for c in srcs} - {0}
+            if len(gws) > 1 or any(c0 % g_ for g_ in gws):
+                raise RuntimeError("dmmfods_b200: inconsistent planar slab groups for %s" % op.name)
+            d.gw = gws.pop() if gws else 0
             for i, c in enumerate(srcs):
-                d.src[i] = c["mat"].ptr(c0).value
-                d.ld[i] = c["mat"].ld
+                if c.get("gw", 0):        # planar: group c0 / gw starts at that plane; the kernel adds further groups itself
+                    plane = blk.buf.P * c["gw"]
+                    d.src[i] = c["mat"].t.data_ptr() + 2 * (c0 // c["gw"]) * plane
+                    d.ld[i] = c["gw"]
+                    d.plane[i] = plane
+                else:
+                    d.src[i] = c["mat"].ptr(c0).value
+                    d.ld[i] = c["mat"].ld
+                    d.plane[i] = 0
                 if c["k"] is not None:
                     d.k1[nk] = c["k"].data_ptr() + 4 * c0
                     d.k2[nk] = c["k"].data_ptr() + 4 * (c["C"] + c0)

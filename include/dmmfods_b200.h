@@ -240,6 +240,9 @@ typedef struct {
     int64_t lddz;            /* pass with g = dz_out, gmode = 0: the costly pool routing is done only once)       */
     const void* argmax;      /* gmode 2, nullable: window winners recorded by dmm_bn_relu_apply (else recomputed)  */
     int64_t ldarg;
+    int32_t out_gw;          /* dmm_bn_relu_bwd_contrib only: > 0 = "planar" slab, channel group g = c / out_gw is its own */
+    int32_t pad_;            /* contiguous [rows, out_gw] matrix at out + g * out_plane (elements); ldo is ignored          */
+    int64_t out_plane;
 } dmm_bn_bwd_args_t;
 int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
@@ -259,6 +262,9 @@ int dmm_bn_bwd_finalize(const dmm_bn_bwd_t* bn, int32_t C, float* k, void* strea
 typedef struct {
     const void* src[DMM_GATHER_MAX];     /* bf16 rows, already offset to the first channel of the range */
     int64_t ld[DMM_GATHER_MAX];
+    int64_t plane[DMM_GATHER_MAX];       /* 0: row-major source; else planar (see dmm_bn_bwd_args_t.out_gw): group stride in elements */
+    int32_t gw;                          /* channel-group width of the planar sources (ld = gw for them) */
+    int32_t pad0_;
     int32_t nsrc;
     int32_t nk;
     const float* k1[DMM_GATHER_MAX];     /* per-consumer correction vectors, offset to the first channel */
