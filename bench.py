@@ -218,7 +218,7 @@ def main():
 
     torch.manual_seed(123)
     model = densenet121_u_lidar(pretrained=False, config=model_cfg(wl["c2"], wl["cb"])).cuda()
-    trainer = Trainer(model, B, H, W, lr=1e-3, use_graph=bool(args.graph) and world == 1)
+    trainer = Trainer(model, B, H, W, lr=1e-3, use_graph=bool(args.graph))
     seed = 123 + rank
     hx1 = torch.from_numpy(synthetic.rgb_image(B, H, W, seed=seed)).pin_memory()
     hx2 = torch.from_numpy(synthetic.lidar_image(B, H, W, seed=seed + 1000)).pin_memory()

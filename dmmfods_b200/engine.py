@@ -975,19 +975,31 @@ class Engine:
             raise RuntimeError("engine was built without backward support")
         if dlogits is not None:
             self.dlogits.copy_(dlogits)
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.backward_begin()
+        for i in range(len(self.segments)):
+            flat = self.backward_segment(i)
+            if on_bucket is not None and flat is not None:
+                on_bucket(i, flat)
+        return self.grad
+
+    def backward_begin(self):
+        """zero the backward accumulators (first half of backward(); separate so that a caller can capture the segments of
+        the backward program in individual CUDA graphs with the gradient all-reduce between them)."""
         self._sums.zero_used()
         self._dw.zero_()
-        tab = self._unpack_tab.data_ptr()
-        for i, (seg_ops, job_lo, njobs, lo, hi) in enumerate(self.segments):
-            self._run(seg_ops)
-            self._join_side(torch.cuda.current_stream())
-            if njobs:
-                _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab + job_lo * _UNPACK_DT.itemsize), njobs, stream),
-                           "dmm_unpack_wgrad_batched")
-            if on_bucket is not None and hi > lo:
-                on_bucket(i, self.gflat[lo:hi])
-        return self.grad
+
+    def backward_segment(self, i):
+        """run backward segment i (stages whose parameter gradients form gradient bucket i); returns the bucket's range
+        of the flat gradient buffer, final once the enqueued work completes, or None if the segment owns no parameters."""
+        seg_ops, job_lo, njobs, lo, hi = self.segments[i]
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self._run(seg_ops)
+        self._join_side(torch.cuda.current_stream())
+        if njobs:
+            tab = self._unpack_tab.data_ptr()
+            _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab + job_lo * _UNPACK_DT.itemsize), njobs, stream),
+                       "dmm_unpack_wgrad_batched")
+        return self.gflat[lo:hi] if hi > lo else None
 
     def loss(self, target, loss_out=None):
         """BCEWithLogits(reduction='none') of the current logits; fills dlogits (= d sum(loss) / d logits) and

@@ -75,8 +75,11 @@ class Trainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.steps = 0
         self.reducer = BucketReducer(self.dist, dev) if self.dist is not None else None
-        self.use_graph = bool(use_graph) and self.dist is None
+        # single GPU: one CUDA graph for forward + loss + backward.  Data parallel: one graph for forward + loss and one per
+        # backward segment, the bucket all-reduces are issued between them (NCCL calls stay outside the graphs)
+        self.use_graph = bool(use_graph)
         self.graph = None
+        self.seg_graphs = None
         self._static_target = None
         self._copy_stream, self._stage, self._staged, self._stage_ready, self._stage_free = None, None, None, None, None
 
@@ -151,6 +154,12 @@ class Trainer:
             if self.graph is None:
                 self._capture()
             self.graph.replay()
+            if self.seg_graphs is not None:
+                for i, (g, flat) in enumerate(self.seg_graphs):
+                    g.replay()
+                    if flat is not None:
+                        self.reducer(i, flat)
+                self.reducer.finish()
         else:
             eng.forward(x1, x2)
             self._fwd_loss_bwd(target)
@@ -172,9 +181,21 @@ class Trainer:
             self._fwd_loss_bwd(self._static_target)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            eng.forward(eng.in1, eng.in2)
-            self._fwd_loss_bwd(self._static_target)
+        if self.dist is None:
+            with torch.cuda.graph(g):
+                eng.forward(eng.in1, eng.in2)
+                self._fwd_loss_bwd(self._static_target)
+        else:
+            with torch.cuda.graph(g):
+                eng.forward(eng.in1, eng.in2)
+                eng.loss(self._static_target)
+                eng.backward_begin()
+            self.seg_graphs = []
+            for i in range(len(eng.segments)):
+                gi = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gi, pool=g.pool()):
+                    flat = eng.backward_segment(i)
+                self.seg_graphs.append((gi, flat))
         self.graph = g
 
     def launches_per_step(self):
