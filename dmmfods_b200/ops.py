@@ -254,12 +254,11 @@ def make_wgrad(a_srcs, b_srcs, a_slots, b_slots, n_tile, W, H, B, dw, ld, ya=1, 
     if kpx is None:      # the MMA warp pays a few hundred cycles per stage hand-over: big stages, but >= 3 (else 2) of them
         kpx = int(os.environ.get("DMM_WGRAD_KPX", "0")) or None
     if kpx is None:
-        for need in (3, 2):
-            for k in (128, 64, 32):
-                if stage_bytes(k) * need <= 200 * 1024:
-                    kpx = k
-                    break
-            if kpx:
+        # one tensor load costs the producer thread a few hundred cycles whatever its size: the largest k-block that still
+        # double-buffers wins (measured: K=512 conv_reduce wgrad 0.41 ms at kpx 32 x 5 stages, 0.25 ms at kpx 64 x 2 stages)
+        for k in (128, 64, 32):
+            if stage_bytes(k) * 2 <= 200 * 1024:
+                kpx = k
                 break
         kpx = kpx or 32
     d.kpx = kpx
