@@ -138,6 +138,7 @@ SIGNATURES = {
     "dmm_lidar_pool": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dmm_heatmap_boxes": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dmm_pool_kxk": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dmm_step_metrics": (C.c_int, [c_void_p, c_void_p, c_int32, c_int64, c_float, c_void_p, c_void_p]),
     "dmm_adam_flat": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                 c_float, c_float, c_int32, c_void_p]),
 }

@@ -213,6 +213,50 @@ extern "C" int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Step metrics (helper:311-401): thresholded intersection / union / agreement counts per (sample, class) plane in one pass
+// over (prediction, ground truth); integer counters, so IoU = I/U (nan for 0/0 like the reference) and accuracy = E/N are
+// reproduced exactly.  counts: int64 [planes][3] = (intersection, union, equal), caller zero-fills.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) step_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                           long long HW, float thr, int splits, unsigned long long* counts) {
+    __shared__ unsigned int sm[3][8];
+    const int plane = blockIdx.x / splits, sp = blockIdx.x - plane * splits;
+    const float* p = pred + (long long)plane * HW;
+    const float* g = gt + (long long)plane * HW;
+    const long long lo = HW * sp / splits, hi = HW * (sp + 1) / splits;
+    unsigned int ci = 0, cu = 0, ce = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const bool a = __ldg(p + i) >= thr, b = __ldg(g + i) >= thr;
+        ci += (a && b); cu += (a || b); ce += (a == b);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        ci += __shfl_xor_sync(0xffffffffu, ci, o);
+        cu += __shfl_xor_sync(0xffffffffu, cu, o);
+        ce += __shfl_xor_sync(0xffffffffu, ce, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sm[0][threadIdx.x >> 5] = ci; sm[1][threadIdx.x >> 5] = cu; sm[2][threadIdx.x >> 5] = ce;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += sm[threadIdx.x][w];
+        atomicAdd(counts + (long long)plane * 3 + threadIdx.x, t);
+    }
+}
+
+extern "C" int dmm_step_metrics(const float* pred, const float* gt, int32_t planes, int64_t HW, float threshold, int64_t* counts,
+                                void* stream) {
+    DMM_CHECK(pred && gt && counts && planes >= 0 && HW >= 0, "dmm_step_metrics: bad arguments");
+    if (planes == 0 || HW == 0) return 0;
+    int splits = (int)((HW + 65535) / 65536);
+    step_metrics_kernel<<<(unsigned)(planes * splits), 256, 0, (cudaStream_t)stream>>>(pred, gt, HW, threshold, splits,
+                                                                                       reinterpret_cast<unsigned long long*>(counts));
+    DMM_LAUNCH_CHECK("step_metrics_kernel");
+    return 0;
+}
+
 extern "C" int dmm_pool_kxk(const float* img, int32_t C, int32_t H, int32_t W, int32_t k, int32_t is_max, float* out,
                             void* stream) {
     DMM_CHECK(img && out && C > 0 && k >= 1 && H >= k && W >= k, "dmm_pool_kxk: bad arguments");

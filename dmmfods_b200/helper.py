@@ -6,6 +6,7 @@ kernels in csrc/scatter.cu.  Results are bit-identical to the reference's CPU fu
     pool_lidar_tensor                  helper:446-491
     create_ground_truth_maps           helper:276-305 (+ templates :233-274)
     maxpool_tensor / avgpool_tensor    helper:430-444
+    compute_IoU_whole_img_per_class / compute_IoU_whole_img_batch / compute_accuracy   helper:311-401 (fused counters)
 
 Inputs may be numpy arrays / python dicts (as in the reference) or CUDA tensors; outputs are CUDA
 float32 tensors.  There is no CPU fallback.
@@ -104,3 +105,45 @@ def maxpool_tensor(img_tensor):
 def avgpool_tensor(img_tensor):
     """torch.nn.AvgPool2d(10, stride=10) (helper:430-436)."""
     return _pool(img_tensor, 10, False)
+
+
+def _metric_counts(ground_truth, prediction, threshold):
+    """int64 [planes, 3] = (intersection, union, equal) of the thresholded maps, one fused pass (dmm_step_metrics)."""
+    dev = _dev()
+    gt = ground_truth.to(device=dev, dtype=torch.float32).contiguous()
+    pr = prediction.to(device=dev, dtype=torch.float32).contiguous()
+    if gt.shape != pr.shape:
+        raise RuntimeError("The size of tensor a %s must match the size of tensor b %s" % (tuple(pr.shape), tuple(gt.shape)))
+    H, W = gt.shape[-2:]
+    planes = gt.numel() // (H * W) if H * W else 0
+    counts = torch.zeros((planes, 3), dtype=torch.int64, device=dev)
+    _lib.check(_lib.load().dmm_step_metrics(_ptr(pr), _ptr(gt), planes, H * W, float(threshold), _ptr(counts), _stream()),
+               "dmm_step_metrics")
+    return counts
+
+
+def compute_IoU_whole_img_per_class(ground_truth_map, estimated_heat_map, threshold):
+    """(C,H,W) maps -> IoU per class, nan where the union is empty (helper:311-343)."""
+    c = _metric_counts(ground_truth_map, estimated_heat_map, threshold)
+    return c[:, 0].float() / c[:, 1].float()
+
+
+def compute_IoU_whole_img_batch(ground_truth_map_batch, estimated_heat_map_batch, threshold=0.7):
+    """(B,C,H,W) batches -> whole-image IoU per sample and class, nan for 0/0 (helper:345-367), without the reference's
+    per-sample Python loop."""
+    B, Cc = ground_truth_map_batch.shape[:2]
+    c = _metric_counts(ground_truth_map_batch, estimated_heat_map_batch, threshold).view(B, Cc, 3)
+    return c[:, :, 0].float() / c[:, :, 1].float()
+
+
+def compute_accuracy(ground_truth, prediction, threshold=0.7):
+    """class-wise (TP+TN)/all of the thresholded maps for one sample (C,H,W) or a batch (B,C,H,W) (helper:369-401)."""
+    if ground_truth.dim() == 3:
+        Cc = ground_truth.shape[0]
+        c = _metric_counts(ground_truth, prediction, threshold)[:, 2]
+    elif ground_truth.dim() == 4:
+        B, Cc = ground_truth.shape[:2]
+        c = _metric_counts(ground_truth, prediction, threshold).view(B, Cc, 3)[:, :, 2].sum(0)
+    else:
+        raise ValueError('Number of dimensions must be either 3 or 4, you gave ' + str(ground_truth.dim()))
+    return c / (ground_truth.numel() / Cc)

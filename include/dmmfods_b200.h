@@ -362,6 +362,12 @@ int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t H, int32_t 
 int dmm_pool_kxk(const float* img, int32_t C, int32_t H, int32_t W, int32_t k, int32_t is_max,
                  float* out, void* stream);
 
+/* ---- step metrics (helper:311-401 compute_IoU_whole_img_per_class / compute_accuracy) ---------------
+ * pred, gt: fp32 [planes][HW] (planes = samples * classes); counts: int64 [planes][3] += (|pred>=t & gt>=t|,
+ * |pred>=t | gt>=t|, |(pred>=t) == (gt>=t)|).  Caller zero-fills counts. */
+int dmm_step_metrics(const float* pred, const float* gt, int32_t planes, int64_t HW, float threshold, int64_t* counts,
+                     void* stream);
+
 /* ---- optimiser: fused Adam over a flat fp32 parameter/grad buffer ---------- */
 int dmm_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,

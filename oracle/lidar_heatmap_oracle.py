@@ -137,3 +137,29 @@ def avgpool(img, k=10):
     C, H, W = img.shape
     oh, ow = H // k, W // k
     return img[:, :oh * k, :ow * k].reshape(C, oh, k, ow, k).mean(axis=(2, 4), dtype=np.float32)
+
+
+# ---- step metrics (helper:311-401) --------------------------------------------------------------------------------
+def iou_whole_img_batch(ground_truth_map_batch, estimated_heat_map_batch, threshold=0.7):
+    """compute_IoU_whole_img_batch (helper:345-367) over compute_IoU_whole_img_per_class (:311-343): both maps are
+    thresholded with >=, IoU = |and| / |or| per (sample, class) as float32, nan where the union is empty."""
+    gt = np.asarray(ground_truth_map_batch) >= threshold
+    est = np.asarray(estimated_heat_map_batch) >= threshold
+    inter = (gt & est).sum(axis=(2, 3)).astype(np.float32)
+    union = (gt | est).sum(axis=(2, 3)).astype(np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return inter / union
+
+
+def accuracy(ground_truth, prediction, threshold=0.7):
+    """compute_accuracy (helper:369-401): class-wise fraction of positions whose thresholded values agree; (C,H,W) or
+    (B,C,H,W) inputs."""
+    gt = np.asarray(ground_truth)
+    pr = np.asarray(prediction)
+    if gt.ndim == 3:
+        axes, ncls = (1, 2), gt.shape[0]
+    elif gt.ndim == 4:
+        axes, ncls = (0, 2, 3), gt.shape[1]
+    else:
+        raise ValueError('Number of dimensions must be either 3 or 4, you gave ' + str(gt.ndim))
+    return ((pr >= threshold) == (gt >= threshold)).sum(axis=axes) / (gt.size / ncls)

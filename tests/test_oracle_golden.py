@@ -105,3 +105,24 @@ def test_unet_oracle_matches_live_reference():
     ref = model(x1, x2)
     got, _ = du.oracle_forward(model.state_dict(), dict(cfg.model), x1, x2, train=True)
     assert torch.allclose(got, ref.detach(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="/root/reference not present")
+def test_metric_oracle_matches_live_reference():
+    """numpy restatement of compute_IoU_whole_img_batch / compute_accuracy (helper:311-401) vs the reference itself."""
+    import numpy as np
+    from oracle import lidar_heatmap_oracle as orc
+    _, helper_mod = ref_shim.ref_modules()
+    rng = np.random.default_rng(7)
+    gt = rng.choice(np.array([0, 0.3, 0.5, 0.75, 1.0], dtype=np.float32), size=(3, 3, 24, 40), p=[0.6, 0.1, 0.1, 0.1, 0.1])
+    gt[1, 2] = 0                                        # a class without any box: IoU 0/0 = nan in the reference
+    pred = (rng.standard_normal((3, 3, 24, 40)) * 1.5).astype(np.float32)
+    pred[1, 2] = -5
+    ref_iou = helper_mod.compute_IoU_whole_img_batch(torch.from_numpy(gt), torch.from_numpy(pred), 0.7).numpy()
+    got = orc.iou_whole_img_batch(gt, pred, 0.7)
+    assert np.array_equal(np.isnan(ref_iou), np.isnan(got)) and np.isnan(got[1, 2])
+    assert np.array_equal(np.nan_to_num(ref_iou), np.nan_to_num(got))
+    ref_acc = helper_mod.compute_accuracy(torch.from_numpy(gt), torch.from_numpy(pred), 0.7).numpy()
+    assert np.allclose(ref_acc, orc.accuracy(gt, pred, 0.7), rtol=0, atol=1e-7)
+    ref_acc1 = helper_mod.compute_accuracy(torch.from_numpy(gt[0]), torch.from_numpy(pred[0]), 0.7).numpy()
+    assert np.allclose(ref_acc1, orc.accuracy(gt[0], pred[0], 0.7), rtol=0, atol=1e-7)

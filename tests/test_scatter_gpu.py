@@ -87,3 +87,23 @@ def test_idempotent_and_order_dependent():
     c = helper.lidar_array_to_image_like_tensor(pts[::-1].copy())
     assert not torch.equal(a, c)
     assert torch.equal(a != -1, c != -1)
+
+
+@pytest.mark.parametrize("seed,shape", [(1, (2, 3, 128, 192)), (2, (3, 3, 37, 53)), (3, (1, 3, 640, 960))])
+def test_step_metrics_match_oracle(seed, shape):
+    """fused IoU / accuracy counters (dmm_step_metrics) == the numpy restatement of helper:311-401, incl. nan for 0/0."""
+    rng = np.random.default_rng(seed)
+    gt = rng.choice(np.array([0, 0.3, 0.5, 0.75, 1.0], dtype=np.float32), size=shape, p=[0.7, 0.05, 0.05, 0.1, 0.1])
+    pred = (rng.standard_normal(shape) * 2).astype(np.float32)
+    gt[0, 1] = 0
+    pred[0, 1] = -3.0                                   # empty union -> nan
+    iou = helper.compute_IoU_whole_img_batch(torch.from_numpy(gt), torch.from_numpy(pred), 0.7).cpu().numpy()
+    want = orc.iou_whole_img_batch(gt, pred, 0.7)
+    assert np.array_equal(np.isnan(iou), np.isnan(want)) and np.isnan(iou[0, 1])
+    assert np.array_equal(np.nan_to_num(iou), np.nan_to_num(want))
+    acc = helper.compute_accuracy(torch.from_numpy(gt), torch.from_numpy(pred), 0.7).cpu().numpy()
+    assert np.allclose(acc, orc.accuracy(gt, pred, 0.7), rtol=0, atol=1e-7)
+    acc1 = helper.compute_accuracy(torch.from_numpy(gt[0]), torch.from_numpy(pred[0]), 0.7).cpu().numpy()
+    assert np.allclose(acc1, orc.accuracy(gt[0], pred[0], 0.7), rtol=0, atol=1e-7)
+    iou1 = helper.compute_IoU_whole_img_per_class(torch.from_numpy(gt[1]), torch.from_numpy(pred[1]), 0.5).cpu().numpy()
+    assert np.array_equal(np.nan_to_num(iou1), np.nan_to_num(orc.iou_whole_img_batch(gt[1:2], pred[1:2], 0.5)[0]))
