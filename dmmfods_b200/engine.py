@@ -78,7 +78,7 @@ class _BNInfo:
 
 class Engine:
     def __init__(self, params, model_cfg, B, H, W, training=True, need_backward=True, plan_only=False,
-                 bucket_bytes=32 << 20):
+                 bucket_bytes=32 << 20, _order_only=False):
         """params: dict name -> CUDA tensor with the reference's state_dict keys (parameters fp32, BN buffers);
         model_cfg: mapping with the keys of helper:111-123.  plan_only=True builds the launch programs without a
         GPU (host-logic tests); such an engine cannot run."""
@@ -139,6 +139,8 @@ class Engine:
         if missing:
             raise RuntimeError("dmmfods_b200: no backward stage produces the gradient of %s" % missing[:4])
         self.param_names = order
+        if _order_only:          # gradient_order(): the dry (meta-device) planning pass is all that is needed
+            return
         total = sum(params[k].numel() for k in order)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=self.dev)
         self.grad, self.grad_offset = {}, {}
@@ -164,7 +166,7 @@ class Engine:
     def gradient_order(params, model_cfg, B, H, W):
         """parameter names in the order of the engine's flat gradient buffer (= backward completion order)."""
         e = Engine.__new__(Engine)
-        Engine.__init__(e, params, model_cfg, B, H, W, plan_only=True)
+        Engine.__init__(e, params, model_cfg, B, H, W, plan_only=True, _order_only=True)
         return list(e.param_names)
 
     def _reset_plan_state(self):
