@@ -518,7 +518,10 @@ class Engine:
                     go = self._tmpmat("go", B, Hb, Wb, kk)
                     da2 = self._tmpmat("da2", B, Hb, Wb, bnk)
                     dz1 = self._tmpmat("dz1", B, Hb, Wb, bnk)
-                    da1 = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
+                    # shared scratch of the widest layer, re-pitched to this layer's channel count: dense rows for the
+                    # data-gradient store and the contribution pass (a [P, Ct] pitch would leave holes in every DRAM page)
+                    da1_full = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
+                    da1 = Mat(da1_full.t.view(-1)[:B * Hb * Wb * Ci].view(B * Hb * Wb, Ci), B, Hb, Wb)
                     self._gather(st, lp + ".gout", blk, Ci, k, go)
                     self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", a2.view(), [go.view(0, k)], conv3x3[0],
                                      conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B)
