@@ -23,6 +23,13 @@ class View(C.Structure):
                 ("sw", c_int64), ("sh", c_int64), ("sb", c_int64)]
 
 
+class Bn(C.Structure):
+    _fields_ = [("stats", c_void_p), ("stats_ld", c_int32), ("stats_off", c_int32), ("count", c_double),
+                ("rep", c_double), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
+                ("running_var", c_void_p), ("save_mean", c_void_p), ("save_invstd", c_void_p),
+                ("eps", c_float), ("momentum", c_float), ("training", c_int32)]
+
+
 class Igemm(C.Structure):
     _fields_ = [("src", View * MAX_SRC), ("num_src", c_int32), ("num_taps", c_int32),
                 ("tap_src", c_int8 * MAX_TAPS), ("tap_dy", c_int8 * MAX_TAPS), ("tap_dx", c_int8 * MAX_TAPS),
@@ -34,7 +41,7 @@ class Igemm(C.Structure):
                 ("stats_ld", c_int32), ("stats_off", c_int32),
                 ("bnb_x", c_void_p), ("bnb_ldx", c_int64), ("bnb_gamma", c_void_p), ("bnb_beta", c_void_p),
                 ("bnb_mean", c_void_p), ("bnb_invstd", c_void_p), ("bnb_sums", c_void_p), ("bnb_sums_ld", c_int32),
-                ("bnb_sums_off", c_int32)]
+                ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("pad2_", c_int32), ("pro_bn", Bn)]
 
 
 WG_MAX_A = 8
@@ -50,14 +57,8 @@ class Wgrad(C.Structure):
                 ("a", WgSlot * WG_MAX_A), ("b", WgSlot * WG_MAX_B), ("num_a", c_int32), ("num_b", c_int32),
                 ("n_tile", c_int32), ("ya", c_int32), ("yb", c_int32), ("a_step", c_int32), ("b_step", c_int32),
                 ("W", c_int32), ("H", c_int32), ("B", c_int32), ("kpx", c_int32), ("tile_w", c_int32),
-                ("splits", c_int32), ("dw", c_void_p), ("ld", c_int64)]
-
-
-class Bn(C.Structure):
-    _fields_ = [("stats", c_void_p), ("stats_ld", c_int32), ("stats_off", c_int32), ("count", c_double),
-                ("rep", c_double), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p),
-                ("running_var", c_void_p), ("save_mean", c_void_p), ("save_invstd", c_void_p),
-                ("eps", c_float), ("momentum", c_float), ("training", c_int32)]
+                ("splits", c_int32), ("dw", c_void_p), ("ld", c_int64), ("pro_enable", c_int32), ("pad_", c_int32),
+                ("pro_gamma", c_void_p), ("pro_beta", c_void_p), ("pro_mean", c_void_p), ("pro_invstd", c_void_p)]
 
 
 class BnApply(C.Structure):

@@ -30,49 +30,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-// ---------------------------------------------------------------------------------------------
-// Batch-norm coefficients for channel c of a dmm_bn_t (training: from accumulated sum / sumsq).
-// ---------------------------------------------------------------------------------------------
-struct BnCoef {
-    float mean, invstd, scale, shift;
-};
-
-__device__ __forceinline__ BnCoef bn_coef_fwd(const dmm_bn_t& bn, int c, bool writer) {
-    BnCoef k;
-    const float g = bn.gamma ? bn.gamma[c] : 1.f;
-    const float b = bn.beta ? bn.beta[c] : 0.f;
-    if (bn.training) {
-        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-        for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
-            const double* row = bn.stats + (size_t)s * 2 * bn.stats_ld + bn.stats_off + c;
-            s1 += row[0];
-            s2 += row[bn.stats_ld];
-        }
-        const double mean = s1 / bn.count;
-        double var = s2 / bn.count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        k.mean = (float)mean;
-        k.invstd = (float)(1.0 / sqrt(var + (double)bn.eps));
-        if (writer) {
-            if (bn.save_mean) bn.save_mean[c] = k.mean;
-            if (bn.save_invstd) bn.save_invstd[c] = k.invstd;
-            if (bn.running_mean) {
-                const double n = bn.count * bn.rep;   // nn.Upsample replicates every element `rep` times
-                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
-                bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * (float)mean;
-                bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * (float)unbiased;
-            }
-        }
-    } else {
-        k.mean = bn.running_mean[c];
-        k.invstd = 1.f / sqrtf(bn.running_var[c] + bn.eps);
-    }
-    k.scale = g * k.invstd;
-    k.shift = b - k.mean * k.scale;
-    return k;
-}
-
 __device__ __forceinline__ BnCoef bn_coef_bwd(const dmm_bn_bwd_t& bn, int c) {
     BnCoef k;
     k.mean = bn.save_mean[c];

@@ -55,6 +55,10 @@ struct Ig2Params {
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
     int stats_ld, stats_off;
+    int pro;                       // BN-ReLU prologue on the A tiles of source 0 (1x1 convolutions)
+    int pro_kp;                    // padded channel count of source 0 (multiple of 64)
+    int pro_c;                     // valid channels of source 0
+    dmm_bn_t pro_bn;
     int bnb;
     const float* bnb_gamma;
     const float* bnb_beta;
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
     uint64_t* acc_full = b_empty + 8;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* x_bar = acc_empty + 2;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(x_bar + 2);
+    uint64_t* a_ready = x_bar + 2;                                       // pro: A stage transformed (4 warp arrivals)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 8);
+    float* pcoef = reinterpret_cast<float*>(tail + 512);                 // pro: [2][pro_kp] scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -124,12 +130,28 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
+        for (int s = 0; s < p.sa; ++s) mbar_init(&a_ready[s], 4);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 8);
+            mbar_init(&acc_empty[s], p.pro ? 4 : 8);        // pro: one epilogue team, the other one transforms A tiles
             mbar_init(&x_bar[s], 1);
         }
         fence_mbar_init();
+    }
+    if (p.pro) {
+        // per-channel scale / shift of the prologue BatchNorm (batch statistics of the raw input, or running statistics);
+        // CTA 0 also records mean / invstd for backward and updates the running statistics (nn.BatchNorm2d semantics)
+        const int C = p.pro_kp;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float sc = 0.f, sh = 0.f;
+            if (c < p.pro_c) {
+                const BnCoef k = bn_coef_fwd(p.pro_bn, c, blockIdx.x == 0);
+                sc = k.scale;
+                sh = k.shift;
+            }
+            pcoef[c] = sc;
+            pcoef[C + c] = sh;
+        }
     }
     if (warp == 1) {
         tmem_alloc(tmem_holder, p.tmem_cols);
@@ -221,7 +243,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                 for (int i = 0; i < MSUB; ++i) so[i] = p.sub_aoff[s][i] >> 4;
                 for (int cb = 0; cb < nblk; ++cb) {
                     c0 = clock64();
-                    mbar_wait(&a_full[ast], aph);
+                    mbar_wait(p.pro ? &a_ready[ast] : &a_full[ast], aph);
                     w_a += clock64() - c0;
                     const uint32_t a_lo = ((a_ring_u + (uint32_t)ast * p.a_stage) >> 4) | (1u << 16);
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
@@ -273,6 +295,48 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
     } else {
         // ================= epilogue: two teams of 4 warps, alternating 64-column chunks =================
         const int team = (warp - 2) >> 2;
+        if (p.pro && team == 1) {
+            // ================= prologue team: relu(bn(x)) in place on every A stage =================
+            // thread e owns the logical 16-byte chunk (8 channels) e & 7 of rows e >> 3, e >> 3 + 16, ...; the physical chunk of a
+            // 128-byte swizzled row r is (chunk ^ (r & 7)).  Zero-filled (out-of-image / beyond-C) elements may become non-zero:
+            // out-of-image pixels never reach memory (TMA store clipping, masked statistics) and channels beyond C have zero
+            // coefficients.
+            const int e = (warp - 6) * 32 + lane;
+            const int j = e & 7;
+            const int rows = (int)(p.src_tx[0] >> 7);
+            int ast = 0;
+            uint32_t aph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nblk = p.src_nblk[0];
+                for (int cb = 0; cb < nblk; ++cb) {
+                    float sc[8], sh[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        sc[i] = pcoef[cb * 64 + j * 8 + i];
+                        sh[i] = pcoef[p.pro_kp + cb * 64 + j * 8 + i];
+                    }
+                    mbar_wait(&a_full[ast], aph);
+                    uint8_t* base = a_ring + (size_t)ast * p.a_stage;
+#pragma unroll 4
+                    for (int r = e >> 3; r < rows; r += 16) {
+                        uint4* ptr = reinterpret_cast<uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
+                        uint4 v = *ptr;
+                        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float lo = fmaxf(fmaf(bf16_lo(w[i]), sc[2 * i], sh[2 * i]), 0.f);
+                            const float hi = fmaxf(fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+                            w[i] = pack_bf16x2(lo, hi);
+                        }
+                        *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[ast]);
+                    if (++ast == p.sa) { ast = 0; aph ^= 1; }
+                }
+            }
+        } else {
         const int q = warp & 3;              // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;         // accumulator row = pixel within the sub-tile
         const int px = r % p.sub_w, py = r / p.sub_w;
@@ -308,7 +372,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         if (tc.n0 + 64 * c >= p.N) break;
-                        if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
+                        if (!p.pro && ((chunk_ctr++) & 1) != (uint32_t)team) continue;
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
                         uint32_t v[4][16];
 #pragma unroll
@@ -450,6 +514,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
         }
+        }   // epilogue team
     }
 
     tc_fence_before();
@@ -564,7 +629,16 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         DMM_CHECK(d->out_sy <= 1 && d->out_sx <= 1 && d->out_py == 0 && d->out_px == 0, "igemm v2: fused BN backward reduce: no output stride");
         DMM_CHECK(d->bnb_x && d->bnb_mean && d->bnb_invstd && d->bnb_ldx % 8 == 0, "igemm v2: fused BN backward reduce: missing inputs");
     }
-    const int staging = d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : 0;
+    const bool pro = d->pro_enable != 0;
+    int pro_kp = 0;
+    if (pro) {
+        DMM_CHECK(d->out_mode == 0 && d->num_src == 1 && d->num_taps == 1 && d->tap_dx[0] == 0 && d->tap_dy[0] == 0 && d->kwidth == 64,
+                  "igemm v2: the BN-ReLU prologue needs a 1x1 convolution over one source");
+        DMM_CHECK(d->pro_bn.training ? (d->pro_bn.stats != nullptr && d->pro_bn.count > 0) : (d->pro_bn.running_mean && d->pro_bn.running_var),
+                  "igemm v2: prologue BatchNorm without statistics");
+        pro_kp = ceil_div(d->src[0].C, 64) * 64;
+    }
+    const int staging = (d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : 0) + (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
@@ -693,6 +767,12 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.stats = d->out_mode == 0 ? d->stats : nullptr;
     p.stats_ld = d->stats_ld;
     p.stats_off = d->stats_off;
+    if (pro) {
+        p.pro = 1;
+        p.pro_kp = pro_kp;
+        p.pro_c = d->src[0].C;
+        p.pro_bn = d->pro_bn;
+    }
     if (bnb) {
         dmm_view_t xv;
         xv.ptr = d->bnb_x;

@@ -61,6 +61,12 @@ struct WgradKParams {
     int stages;
     uint32_t a_chunk_bytes, b_box_bytes, stage_bytes, tmem_cols;
     long long* prof;
+    int pro;                       // BN-ReLU prologue on the A chunks (all from a_src[0], unshifted)
+    int pro_kp;                    // a_C[0] rounded up to 64
+    const float* pro_gamma;
+    const float* pro_beta;
+    const float* pro_mean;
+    const float* pro_invstd;
 };
 
 constexpr int kWgThreads = 192;
@@ -81,7 +87,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* tmem_full_bar = empty_bar + 8;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* ready_bar = tmem_full_bar + 1;                              // pro: A chunks of the stage transformed (4 warp arrivals)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(ready_bar + 8);
+    float* pcoef = reinterpret_cast<float*>(tail + 256);                  // pro: [2][pro_kp] scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -98,8 +106,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
+        for (int s = 0; s < p.stages; ++s) mbar_init(&ready_bar[s], 4);
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
+    }
+    if (p.pro) {
+        for (int c = threadIdx.x; c < p.pro_kp; c += blockDim.x) {
+            float sc = 0.f, sh = 0.f;
+            if (c < p.a_C[0]) {
+                const float mu = p.pro_mean[c];
+                sc = (p.pro_gamma ? p.pro_gamma[c] : 1.f) * p.pro_invstd[c];
+                sh = (p.pro_beta ? p.pro_beta[c] : 0.f) - mu * sc;
+            }
+            pcoef[c] = sc;
+            pcoef[p.pro_kp + c] = sh;
+        }
     }
     if (warp == 1) {
         tmem_alloc(tmem_holder, p.tmem_cols);
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             uint32_t ph = 0;
             for (int kb = 0; kb < num_k; ++kb) {
                 const long long c0 = clock64();
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(p.pro ? &ready_bar[s] : &full_bar[s], ph);
                 w_f += clock64() - c0;
                 tc_fence_after();
                 if (elect_one()) {
@@ -221,6 +242,46 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         } else {
             // ================= epilogue: TMEM -> swizzled fp32 staging -> TMA reduce-add into dw =================
             const int q = warp & 3;                       // TMEM lane quadrant = rows q*32 .. q*32+31 of the m-tile
+            if (p.pro) {
+                // the epilogue warps are idle during the main loop: they apply relu(bn(x)) in place to the A chunks of every
+                // stage (pixel rows of 128 bytes, swizzled 16-byte chunks; zero-filled out-of-image pixels meet zero B rows)
+                const int e = (warp - 2) * 32 + lane;     // 0..127
+                const int j = e & 7;
+                int s = 0;
+                uint32_t ph = 0;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    uint8_t* sa = smem + (size_t)s * p.stage_bytes;
+                    for (int i = 0; i < p.num_a; ++i) {
+                        const int ch = p.a[i].ch0 + a_off;
+                        if (ch >= p.a_C[0]) continue;     // chunk outside the view: nothing was loaded
+                        float sc[8], sh[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            sc[t] = pcoef[ch + j * 8 + t];
+                            sh[t] = pcoef[p.pro_kp + ch + j * 8 + t];
+                        }
+                        uint8_t* base = sa + i * p.a_chunk_bytes;
+#pragma unroll 4
+                        for (int r = e >> 3; r < p.kpx; r += 16) {
+                            uint4* ptr = reinterpret_cast<uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
+                            uint4 v = *ptr;
+                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float lo = fmaxf(fmaf(bf16_lo(w[t]), sc[2 * t], sh[2 * t]), 0.f);
+                                const float hi = fmaxf(fmaf(bf16_hi(w[t]), sc[2 * t + 1], sh[2 * t + 1]), 0.f);
+                                w[t] = pack_bf16x2(lo, hi);
+                            }
+                            *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready_bar[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
             const long long t_begin = clock64();
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -412,6 +473,14 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         if (rc) return rc;
         p.b_C[s] = d->b_src[s].C;
     }
+    if (d->pro_enable) {
+        DMM_CHECK(d->pro_mean && d->pro_invstd, "dmm_conv_wgrad: prologue BatchNorm without statistics");
+        for (int i = 0; i < d->num_a; ++i)
+            DMM_CHECK(d->a[i].src == 0 && d->a[i].dx == 0 && d->a[i].dy == 0, "dmm_conv_wgrad: the prologue needs unshifted A chunks of source 0");
+        p.pro = 1;
+        p.pro_kp = ceil_div(d->a_src[0].C + (d->ya - 1) * d->a_step, 64) * 64 + 64 * DMM_WG_MAX_A;
+        p.pro_gamma = d->pro_gamma; p.pro_beta = d->pro_beta; p.pro_mean = d->pro_mean; p.pro_invstd = d->pro_invstd;
+    }
     p.tiles_x = ceil_div(d->W, p.tile_w);
     p.tiles_y = ceil_div(d->H, p.tile_h);
     p.total_tiles = (long long)p.tiles_x * p.tiles_y * d->B;
@@ -447,7 +516,7 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
 
     size_t ring = (size_t)stages * p.stage_bytes;
     if (ring < 32768) ring = 32768;
-    const size_t smem = ring + 256 + 1024;
+    const size_t smem = ring + 256 + 1024 + (p.pro ? (size_t)2 * p.pro_kp * sizeof(float) : 0);
     static bool attr_set = false;
     if (!attr_set) {
         DMM_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));

@@ -31,6 +31,9 @@ from .ops import Mat, Stats, ceil_to
 FUSE_BN_BWD_REDUCE = os.environ.get("DMM_FUSE_BN_BWD_REDUCE", "1") != "0"
 # run the weight-gradient kernels on a second stream beside the data-gradient / BatchNorm-backward chain
 WGRAD_SIDE_STREAM = os.environ.get("DMM_WGRAD_SIDE_STREAM", "1") != "0"
+# dense-layer norm1 + relu1 as a PROLOGUE of conv1 (and of its weight gradient): relu(bn(x)) is applied to the operand tiles in
+# shared memory, the activated tensor is never written to HBM (tv:47-50, north-star "BN-ReLU prologues fused into the conv loads")
+FUSE_BN_PROLOGUE = os.environ.get("DMM_FUSE_BN_PROLOGUE", "1") != "0"
 
 
 class Op:
@@ -281,9 +284,10 @@ class Engine:
         lst[-1].heavy = T * ceil_to(Cg, 64) >= 512
         return lst[-1]
 
-    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B):
+    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None):
         """weight gradient: wgrad launches into a zeroed fp32 scratch matrix + unpack job into the flat gradient
-        buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x."""
+        buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x.
+        pro (_BNInfo): x is the RAW input of that BatchNorm; relu(bn(x)) is applied to the operand tiles on the fly."""
         T = len(taps)
         plan = ops.plan_conv_wgrad(x, ys, taps, M, N)
         tap_off = [tap_off[t] for t in plan["tap_order"]]
@@ -292,6 +296,10 @@ class Engine:
         nl = len(plan["launches"])
         for i, kw in enumerate(plan["launches"]):
             d = ops.make_wgrad(W=W, H=H, B=B, dw=0, ld=plan["ld"], **kw)
+            if pro is not None:
+                d.pro_enable = 1
+                d.pro_gamma, d.pro_beta = pro.gamma.data_ptr(), pro.beta.data_ptr()
+                d.pro_mean, d.pro_invstd = pro.save_mean.data_ptr(), pro.save_invstd.data_ptr()
             self._emit(lst, self.lib.dmm_conv_wgrad, d, name + ("[%d]" % i if nl > 1 else ""), kind="wgrad",
                        flops=2.0 * P * Mvalid * Nvalid * T / nl, nbytes=(P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4) / nl)
             self._fix_dw.append((d, did))
@@ -502,13 +510,21 @@ class Engine:
                 lp = "%s.denselayer%d" % (prefix, i + 1)
                 bn1 = _BNInfo(self, lp + ".norm1", Ci)
                 bn2 = _BNInfo(self, lp + ".norm2", bnk)
-                a1 = self._mat(B, Hb, Wb, Ci)
                 z1 = self._mat(B, Hb, Wb, bnk)
                 a2 = self._mat(B, Hb, Wb, bnk)
                 z1s = self._new_stats(bnk)
-                self._apply(fwd, lp + ".norm1", bn1, blk.buf, 0, Ci, blk.stats, 0, a1, 0)
-                self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [a1.view()], conv1x1[0], conv1x1[2], Ci, bnk, Ci, 1,
-                               Wb, Hb, B, z1, 0, z1s, 0)
+                if FUSE_BN_PROLOGUE:
+                    # norm1 + relu1 run inside conv1: its A tiles are the raw block-buffer channels, activated in shared memory
+                    a1 = None
+                    d1 = self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [blk.buf.view(0, Ci)], conv1x1[0], conv1x1[2],
+                                        Ci, bnk, Ci, 1, Wb, Hb, B, z1, 0, z1s, 0)
+                    d1.pro_enable = 1
+                    d1.pro_bn = self._bn_fwd(bn1, blk.stats, 0, blk.buf.P)
+                else:
+                    a1 = self._mat(B, Hb, Wb, Ci)
+                    self._apply(fwd, lp + ".norm1", bn1, blk.buf, 0, Ci, blk.stats, 0, a1, 0)
+                    self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [a1.view()], conv1x1[0], conv1x1[2], Ci, bnk, Ci, 1,
+                                   Wb, Hb, B, z1, 0, z1s, 0)
                 self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
                 self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [a2.view()], conv3x3[0], conv3x3[2], bnk, k,
                                bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
@@ -528,8 +544,12 @@ class Engine:
                     dg2 = self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
                                            k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
                     self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0, producer=dg2)
-                    self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", a1.view(), [dz1.view()], conv1x1[0],
-                                     conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B)
+                    if a1 is None:
+                        self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", blk.buf.view(0, Ci), [dz1.view()],
+                                         conv1x1[0], conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B, pro=bn1)
+                    else:
+                        self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", a1.view(), [dz1.view()], conv1x1[0],
+                                         conv1x1[2], Ci, bnk, Ci, bnk, Ci, 1, Wb, Hb, B)
                     dg1 = self._conv_dgrad(st, lp + ".conv1.dgrad", lp + ".conv1.weight", [dz1.view()], conv1x1[1], conv1x1[2],
                                            bnk, Ci, 1, Ci, Wb, Hb, B, da1)
                     self._contrib_bwd(st, lp + ".norm1.bwd", bn1, blk, Ci, da1)

@@ -43,6 +43,27 @@ typedef struct {
     int64_t sw, sh, sb;
 } dmm_view_t;
 
+/* ---- batch norm (nn.BatchNorm2d semantics, SURVEY A14) ---------------------------------------- */
+/* Forward-side description of ONE BatchNorm2d (or a channel slice of one; all pointers already
+ * offset to the slice's first channel).  training=1: batch statistics are taken from the
+ * accumulated column sums stats[slot][2][stats_ld] at stats_off (all slots summed; `count` elements
+ * per channel): normalise with mean / BIASED variance, save mean/invstd for backward, update
+ * running stats with momentum and the UNBIASED variance over count*rep elements (rep = replication
+ * factor of nn.Upsample, else 1).  training=0: running statistics. */
+typedef struct {
+    const double* stats;
+    int32_t stats_ld, stats_off;
+    double count, rep;
+    const float* gamma;
+    const float* beta;
+    float* running_mean;     /* nullable in training mode (no update) */
+    float* running_var;
+    float* save_mean;        /* nullable */
+    float* save_invstd;
+    float eps, momentum;
+    int32_t training;
+} dmm_bn_t;
+
 /* Implicit-GEMM convolution on tcgen05 (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue).
  *   out[pix(b, y*out_sy+out_py, x*out_sx+out_px), coff + n] =
  *       sum_t sum_c src[tap_src[t]](b, y + tap_dy[t], x + tap_dx[t], c) * Wp[n, k(t, c)]
@@ -89,6 +110,13 @@ typedef struct {
     const float* bnb_invstd;
     double* bnb_sums;
     int32_t bnb_sums_ld, bnb_sums_off;
+    /* Optional BN-ReLU PROLOGUE (pro_enable != 0; one source, one tap (0,0) = 1x1 convolution): src[0] holds the RAW input x and
+     * the kernel applies relu(bn(x)) to every A tile in shared memory before the MMAs read it (tv:47-50 without materialising the
+     * activated tensor).  pro_bn describes the BatchNorm over the src[0].C channels exactly like dmm_bn_relu_apply (CTA 0 also
+     * saves mean / invstd and updates the running statistics). */
+    int32_t pro_enable;
+    int32_t pad2_;
+    dmm_bn_t pro_bn;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 
@@ -128,6 +156,16 @@ typedef struct {
     int32_t splits;          /* pixel-range splits; 0 = auto */
     float* dw;
     int64_t ld;
+    /* Optional BN-ReLU PROLOGUE on the A side (pro_enable != 0; every A chunk reads a_src[0] unshifted): a_src[0] holds the RAW
+     * BatchNorm input and relu(bn(x)) is applied to the A tiles in shared memory (weight gradient of a convolution whose activated
+     * input was never materialised, see dmm_igemm_t.pro_*).  pro_bn: save_mean / save_invstd / gamma / beta of the a_src[0].C channels
+     * (training = 0 semantics: the forward pass already fixed the statistics; running_mean / running_var are NOT used). */
+    int32_t pro_enable;
+    int32_t pad_;
+    const float* pro_gamma;
+    const float* pro_beta;
+    const float* pro_mean;
+    const float* pro_invstd;
 } dmm_wgrad_t;
 int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream);
 
@@ -165,27 +203,6 @@ typedef struct {
 } dmm_unpack_job_t;
 int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream);
 int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream);
-
-/* ---- batch norm (nn.BatchNorm2d semantics, SURVEY A14) ---------------------------------------- */
-/* Forward-side description of ONE BatchNorm2d (or a channel slice of one; all pointers already
- * offset to the slice's first channel).  training=1: batch statistics are taken from the
- * accumulated column sums stats[slot][2][stats_ld] at stats_off (all slots summed; `count` elements
- * per channel): normalise with mean / BIASED variance, save mean/invstd for backward, update
- * running stats with momentum and the UNBIASED variance over count*rep elements (rep = replication
- * factor of nn.Upsample, else 1).  training=0: running statistics. */
-typedef struct {
-    const double* stats;
-    int32_t stats_ld, stats_off;
-    double count, rep;
-    const float* gamma;
-    const float* beta;
-    float* running_mean;     /* nullable in training mode (no update) */
-    float* running_var;
-    float* save_mean;        /* nullable */
-    float* save_invstd;
-    float eps, momentum;
-    int32_t training;
-} dmm_bn_t;
 
 /* y = relu(bn(x)), bf16 pixel-major [B*H*W, C] (tv:47-50,90; Dense_U_Net_lidar.py:75-76,108-115).
  * pool: 0 none; 1 = then AvgPool2d(2,2) (tv:133 moved in front of the 1x1 conv - they commute);

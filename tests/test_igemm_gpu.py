@@ -205,3 +205,49 @@ def test_fused_bn_backward_reduce_matches_separate_pass(K, Cin, Cout, H, W):
     scale1, scale2 = s1.abs().max().item() + 1e-6, s2.abs().max().item() + 1e-6
     assert (f1 - s1).abs().max().item() < 2e-4 * scale1 + 1e-3
     assert (f2 - s2).abs().max().item() < 2e-4 * scale2 + 1e-3
+
+
+def _bn_setup(x, C, seed):
+    """batch statistics of a raw (B,C,H,W) tensor in the engine's double[slots][2][C] layout + random affine."""
+    g = torch.Generator().manual_seed(seed)
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+    beta = (torch.randn(C, generator=g) * 0.3).cuda()
+    st = new_stats(C)
+    flat = x.permute(1, 0, 2, 3).reshape(C, -1).double()
+    st.buf[:C] = flat.sum(1).cuda()                      # slot 0: sums
+    st.buf[C:2 * C] = (flat * flat).sum(1).cuda()        # slot 0: sums of squares
+    mean = flat.mean(1)
+    var = flat.var(1, unbiased=False)
+    sc = gamma.cpu().double() / torch.sqrt(var + 1e-5)
+    sh = beta.cpu().double() - mean * sc
+    act = torch.relu(x.double() * sc.view(1, C, 1, 1) + sh.view(1, C, 1, 1))
+    return gamma, beta, st, mean, var, act
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(64, 128, 16, 24), (96, 128, 9, 13), (352, 128, 20, 30)])
+def test_conv1x1_bn_relu_prologue(Cin, Cout, H, W):
+    """dmm_igemm_t.pro_*: conv1x1(relu(bn(x))) with the BatchNorm-ReLU applied to the operand tiles in shared memory ==
+    nn.Conv2d(nn.ReLU(nn.BatchNorm2d(x))) of the reference (tv:47-50), incl. saved mean / invstd and running statistics."""
+    torch.manual_seed(Cin + H)
+    B = 2
+    x = bf16_round(torch.randn(B, Cin, H, W) * 1.7 + 0.4)
+    w = bf16_round(torch.randn(Cout, Cin, 1, 1) / Cin ** 0.5)
+    gamma, beta, st, mean, var, act = _bn_setup(x, Cin, 5)
+    ref = F.conv2d(bf16_round(act.float()).double(), w.double())
+    a = to_mat(x)
+    fwd, _, off = ops.conv_taps(1, 0)
+    wp, ktot, n_rows = _pack(w, Cout, Cin, 1, off, Cin, 1)
+    out = ops.new_mat(B, H, W, Cout, zero=True)
+    rm, rv = torch.zeros(Cin, device="cuda"), torch.ones(Cin, device="cuda")
+    sm, si = torch.empty(Cin, device="cuda"), torch.empty(Cin, device="cuda")
+    d = ops.make_igemm([a.view(0, Cin)], fwd, wp, ktot, n_rows, W, H, B, Cout, out.ptr(), Cout)
+    d.pro_enable = 1
+    d.pro_bn = ops.make_bn(st, 0, B * H * W, gamma, beta, rm, rv, sm, si, training=True)
+    ops.run_igemm(d)
+    torch.cuda.synchronize()
+    err = rel_l2(from_mat(out), ref)
+    assert err < TOL, "prologue conv relL2 %.3e" % err
+    n = B * H * W
+    assert torch.allclose(sm.cpu().double(), mean, atol=1e-5) and torch.allclose(si.cpu().double(), 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
+    assert torch.allclose(rm.cpu().double(), 0.1 * mean, atol=1e-5)
+    assert torch.allclose(rv.cpu().double(), 0.9 + 0.1 * var * n / (n - 1), rtol=1e-5)

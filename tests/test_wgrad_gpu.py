@@ -91,3 +91,38 @@ def test_wgrad_conv_transpose(C, H, W, OH, OW):
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
     assert err < TOL, "convT wgrad relL2 %.3e" % err
+
+
+@pytest.mark.parametrize("Cin,Cout", [(96, 128), (352, 128), (64, 128)])
+def test_wgrad_1x1_bn_relu_prologue(Cin, Cout):
+    """dmm_wgrad_t.pro_*: the weight gradient of conv1x1(relu(bn(x))) computed from the RAW x (activated in shared memory)."""
+    torch.manual_seed(Cin)
+    B, H, W = 2, 12, 20
+    x = bf16_round(torch.randn(B, Cin, H, W) * 1.5 + 0.2)
+    g = bf16_round(torch.randn(B, Cout, H, W))
+    gen = torch.Generator().manual_seed(3)
+    gamma = (torch.rand(Cin, generator=gen) + 0.5)
+    beta = torch.randn(Cin, generator=gen) * 0.3
+    mean = torch.randn(Cin, generator=gen) * 0.2 + 0.2
+    invstd = torch.rand(Cin, generator=gen) * 0.5 + 0.4
+    sc = gamma * invstd
+    act = bf16_round(torch.relu(x * sc.view(1, -1, 1, 1) + (beta - mean * sc).view(1, -1, 1, 1)))
+    w = torch.zeros(Cout, Cin, 1, 1, dtype=torch.float64, requires_grad=True)
+    F.conv2d(act.double(), w).backward(g.double())
+    ref = w.grad
+    xm = to_mat(x, ld=ops.ceil_to(Cin, 8))
+    gm = to_mat(g)
+    fwd, _, off = ops.conv_taps(1, 0)
+    plan = ops.plan_conv_wgrad(xm.view(0, Cin), [gm.view(0, Cout)], fwd, Cin, Cout)
+    dw = torch.zeros(plan["rows"] * plan["ld"], dtype=torch.float32, device="cuda")
+    dev = [t.cuda() for t in (gamma, beta, mean, invstd)]
+    for kw in plan["launches"]:
+        d = ops.make_wgrad(W=W, H=H, B=B, dw=dw, ld=plan["ld"], **kw)
+        d.pro_enable = 1
+        d.pro_gamma, d.pro_beta, d.pro_mean, d.pro_invstd = (t.data_ptr() for t in dev)
+        ops.run_wgrad(d)
+    grad = torch.full((Cout, Cin, 1, 1), float("nan"), dtype=torch.float32, device="cuda")
+    ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], Cin, Cout, grad, 1, [off[t] for t in plan["tap_order"]], Cin, 1)
+    torch.cuda.synchronize()
+    err = rel_l2(grad.cpu(), ref)
+    assert err < 2e-3, "prologue wgrad relL2 %.3e" % err      # the in-kernel fma may round a few activations differently
