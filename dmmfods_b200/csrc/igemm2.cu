@@ -21,6 +21,7 @@
 namespace dmm {
 
 constexpr int kG2Threads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps
+constexpr int kG2ThreadsPro = 448;       // + warps 10..13 = BN-ReLU prologue team (PRO instantiations)
 constexpr int kMaxSub = 4;
 constexpr int kG2MaxSmem = 232448;
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
@@ -98,8 +99,8 @@ __device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t
     return c;
 }
 
-template <int NCH, int OUT_MODE, int MSUB>
-__global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
+template <int NCH, int OUT_MODE, int MSUB, bool PRO>
+__global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
@@ -133,12 +134,12 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         for (int s = 0; s < p.sa; ++s) mbar_init(&a_ready[s], 4);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], p.pro ? 4 : 8);        // pro: one epilogue team, the other one transforms A tiles
+            mbar_init(&acc_empty[s], 8);
             mbar_init(&x_bar[s], 1);
         }
         fence_mbar_init();
     }
-    if (p.pro) {
+    if (PRO) {
         // per-channel scale / shift of the prologue BatchNorm (batch statistics of the raw input, or running statistics);
         // CTA 0 also records mean / invstd for backward and updates the running statistics (nn.BatchNorm2d semantics)
         const int C = p.pro_kp;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                 for (int i = 0; i < MSUB; ++i) so[i] = p.sub_aoff[s][i] >> 4;
                 for (int cb = 0; cb < nblk; ++cb) {
                     c0 = clock64();
-                    mbar_wait(p.pro ? &a_ready[ast] : &a_full[ast], aph);
+                    mbar_wait(PRO ? &a_ready[ast] : &a_full[ast], aph);
                     w_a += clock64() - c0;
                     const uint32_t a_lo = ((a_ring_u + (uint32_t)ast * p.a_stage) >> 4) | (1u << 16);
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
@@ -295,13 +296,13 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
     } else {
         // ================= epilogue: two teams of 4 warps, alternating 64-column chunks =================
         const int team = (warp - 2) >> 2;
-        if (p.pro && team == 1) {
+        if (PRO && team == 2) {
             // ================= prologue team: relu(bn(x)) in place on every A stage =================
             // thread e owns the logical 16-byte chunk (8 channels) e & 7 of rows e >> 3, e >> 3 + 16, ...; the physical chunk of a
             // 128-byte swizzled row r is (chunk ^ (r & 7)).  Zero-filled (out-of-image / beyond-C) elements may become non-zero:
             // out-of-image pixels never reach memory (TMA store clipping, masked statistics) and channels beyond C have zero
             // coefficients.
-            const int e = (warp - 6) * 32 + lane;
+            const int e = (warp - 10) * 32 + lane;
             const int j = e & 7;
             const int rows = (int)(p.src_tx[0] >> 7);
             int ast = 0;
@@ -316,11 +317,11 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                         sh[i] = pcoef[p.pro_kp + cb * 64 + j * 8 + i];
                     }
                     mbar_wait(&a_full[ast], aph);
-                    uint8_t* base = a_ring + (size_t)ast * p.a_stage;
+                    const uint32_t base = smem_u32(a_ring + (size_t)ast * p.a_stage);
 #pragma unroll 4
                     for (int r = e >> 3; r < rows; r += 16) {
-                        uint4* ptr = reinterpret_cast<uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
-                        uint4 v = *ptr;
+                        const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
+                        const uint4 v = lds_v4(ptr);
                         uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                             const float hi = fmaxf(fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
                             w[i] = pack_bf16x2(lo, hi);
                         }
-                        *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+                        sts_v4(ptr, make_uint4(w[0], w[1], w[2], w[3]));
                     }
                     fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
+        const uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow), xslot_u = smem_u32(xslot);
         double sacc[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         if (tc.n0 + 64 * c >= p.N) break;
-                        if (!p.pro && ((chunk_ctr++) & 1) != (uint32_t)team) continue;
+                        if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
                         uint32_t v[4][16];
 #pragma unroll
@@ -399,8 +401,8 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                                     w1.z = pack_bf16x2(__uint_as_float(v[g][12]), __uint_as_float(v[g][13]));
                                     w1.w = pack_bf16x2(__uint_as_float(v[g][14]), __uint_as_float(v[g][15]));
                                 }
-                                *reinterpret_cast<uint4*>(srow + (((2 * g) ^ (r & 7)) << 4)) = w0;
-                                *reinterpret_cast<uint4*>(srow + (((2 * g + 1) ^ (r & 7)) << 4)) = w1;
+                                sts_v4(srow_u + (((2 * g) ^ (r & 7)) << 4), w0);
+                                sts_v4(srow_u + (((2 * g + 1) ^ (r & 7)) << 4), w1);
                             }
                         }
                         fence_proxy_async();
@@ -411,13 +413,13 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                         }
                         if (do_stats) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                            const uint8_t* base = slot + ((cp & 3) << 2);
+                            const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
                             const int j = cp >> 2;
                             if (!p.bnb) {
-#pragma unroll 8
+#pragma unroll
                                 for (int i = 0; i < 32; ++i) {
-                                    const int row = rq * 32 + i;
-                                    const uint32_t u = *reinterpret_cast<const uint32_t*>(base + row * 128 + ((j ^ (row & 7)) << 4));
+                                    // row = rq*32 + i: (row & 7) == (i & 7), a compile-time pattern after unrolling
+                                    const uint32_t u = lds_u32(base + i * 128 + ((j ^ (i & 7)) << 4));
                                     const float a = bf16_lo(u), b = bf16_hi(u);
                                     s1a += a; s1b += b;
                                     s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
@@ -436,15 +438,14 @@ __global__ void __launch_bounds__(kG2Threads, 1) igemm2_kernel(const __grid_cons
                                     sc1 = (p.bnb_gamma ? __ldg(p.bnb_gamma + col + 1) : 1.f) * __ldg(p.bnb_invstd + col + 1);
                                     sh1 = (p.bnb_beta ? __ldg(p.bnb_beta + col + 1) : 0.f) - mu1 * sc1;
                                 }
-                                const uint8_t* xbase = xslot + ((cp & 3) << 2);
+                                const uint32_t xbase = xslot_u + ((cp & 3) << 2) + rq * 32 * 128;
                                 mbar_wait(&x_bar[team], x_phase);
                                 x_phase ^= 1;
-#pragma unroll 8
+#pragma unroll
                                 for (int i = 0; i < 32; ++i) {
-                                    const int row = rq * 32 + i;
-                                    const int o = row * 128 + ((j ^ (row & 7)) << 4);
-                                    const uint32_t u = *reinterpret_cast<const uint32_t*>(base + o);
-                                    const uint32_t xu = *reinterpret_cast<const uint32_t*>(xbase + o);
+                                    const int o = i * 128 + ((j ^ (i & 7)) << 4);
+                                    const uint32_t u = lds_u32(base + o);
+                                    const uint32_t xu = lds_u32(xbase + o);
                                     const float xa = bf16_lo(xu), xb = bf16_hi(xu);
                                     const float a = fmaf(xa, sc0, sh0) > 0.f ? bf16_lo(u) : 0.f;
                                     const float b = fmaf(xb, sc1, sh1) > 0.f ? bf16_hi(u) : 0.f;
@@ -794,21 +795,27 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     const int nch = ceil_div(p.n_tile, 64);
     typedef void (*KernelFn)(const Ig2Params);
     KernelFn fn = nullptr;
-    if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4> : (p.msub == 2 ? igemm2_kernel<1, 1, 2> : igemm2_kernel<1, 1, 1>);
-    else if (nch == 1) fn = p.msub == 4 ? igemm2_kernel<1, 0, 4> : (p.msub == 2 ? igemm2_kernel<1, 0, 2> : igemm2_kernel<1, 0, 1>);
-    else if (nch == 2) fn = p.msub == 2 ? igemm2_kernel<2, 0, 2> : igemm2_kernel<2, 0, 1>;
-    else if (nch == 3) fn = igemm2_kernel<3, 0, 1>;
-    else fn = igemm2_kernel<4, 0, 1>;
+#define DMM_IG2_PICK(PROFLAG)                                                                                                              \
+    do {                                                                                                                                   \
+        if (nch == 1) fn = p.msub == 4 ? igemm2_kernel<1, 0, 4, PROFLAG> : (p.msub == 2 ? igemm2_kernel<1, 0, 2, PROFLAG> : igemm2_kernel<1, 0, 1, PROFLAG>); \
+        else if (nch == 2) fn = p.msub == 2 ? igemm2_kernel<2, 0, 2, PROFLAG> : igemm2_kernel<2, 0, 1, PROFLAG>;                           \
+        else if (nch == 3) fn = igemm2_kernel<3, 0, 1, PROFLAG>;                                                                           \
+        else fn = igemm2_kernel<4, 0, 1, PROFLAG>;                                                                                         \
+    } while (0)
+    if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
+    else if (pro) DMM_IG2_PICK(true);
+    else DMM_IG2_PICK(false);
+#undef DMM_IG2_PICK
     DMM_CHECK(nch <= 2 || p.msub == 1, "igemm v2: internal msub error");
     DMM_CHECK(nch <= 1 || p.msub <= 2, "igemm v2: internal msub error");
     {
-        static KernelFn configured[16];
+        static KernelFn configured[32];
         static int nconf = 0;
         bool seen = false;
         for (int i = 0; i < nconf; ++i) seen = seen || configured[i] == fn;
         if (!seen) {
             DMM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2MaxSmem));
-            if (nconf < 16) configured[nconf++] = fn;
+            if (nconf < 32) configured[nconf++] = fn;
         }
     }
     static const int prof = env_int("DMM_IGEMM_PROF", 0);
@@ -818,7 +825,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         DMM_CUDA(cudaMemsetAsync(prof_buf, 0, 160 * 16 * sizeof(long long), stream));
         p.prof = prof_buf;
     }
-    fn<<<grid, kG2Threads, smem, stream>>>(p);
+    fn<<<grid, pro ? kG2ThreadsPro : kG2Threads, smem, stream>>>(p);
     if (prof) {
         static long long h[160 * 16];
         DMM_CUDA(cudaStreamSynchronize(stream));

@@ -70,6 +70,7 @@ struct WgradKParams {
 };
 
 constexpr int kWgThreads = 192;
+constexpr int kWgThreadsPro = 320;       // + warps 6..9: extra BN-ReLU prologue warps (they only transform A chunks)
 
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile(
@@ -79,7 +80,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
         : "memory");
 }
 
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
+__global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_constant__ WgradKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const size_t ring_bytes = (size_t)p.stages * p.stage_bytes;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int s = 0; s < p.stages; ++s) mbar_init(&ready_bar[s], 4);
+        for (int s = 0; s < p.stages; ++s) mbar_init(&ready_bar[s], 8);
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             if (p.pro) {
                 // the epilogue warps are idle during the main loop: they apply relu(bn(x)) in place to the A chunks of every
                 // stage (pixel rows of 128 bytes, swizzled 16-byte chunks; zero-filled out-of-image pixels meet zero B rows)
-                const int e = (warp - 2) * 32 + lane;     // 0..127
+                const int e = (warp - 2) * 32 + lane;     // 0..255: warps 2..9
                 const int j = e & 7;
                 int s = 0;
                 uint32_t ph = 0;
@@ -261,11 +262,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                             sc[t] = pcoef[ch + j * 8 + t];
                             sh[t] = pcoef[p.pro_kp + ch + j * 8 + t];
                         }
-                        uint8_t* base = sa + i * p.a_chunk_bytes;
+                        const uint32_t base = smem_u32(sa + i * p.a_chunk_bytes);
 #pragma unroll 4
-                        for (int r = e >> 3; r < p.kpx; r += 16) {
-                            uint4* ptr = reinterpret_cast<uint4*>(base + r * 128 + ((j ^ (r & 7)) << 4));
-                            uint4 v = *ptr;
+                        for (int r = e >> 3; r < p.kpx; r += 32) {
+                            const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
+                            const uint4 v = lds_v4(ptr);
                             uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                                 const float hi = fmaxf(fmaf(bf16_hi(w[t]), sc[2 * t + 1], sh[2 * t + 1]), 0.f);
                                 w[t] = pack_bf16x2(lo, hi);
                             }
-                            *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+                            sts_v4(ptr, make_uint4(w[0], w[1], w[2], w[3]));
                         }
                     }
                     fence_proxy_async();
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
+            if (warp >= 6) goto done;                     // prologue-only warps have no epilogue work
             const long long t_begin = clock64();
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         }
     }
 
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -532,7 +535,7 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         DMM_CUDA(cudaMemsetAsync(prof_buf, 0, prof_n * sizeof(long long), stream));
         p.prof = prof_buf;
     }
-    wgrad_kernel<<<grid, kWgThreads, smem, stream>>>(p);
+    wgrad_kernel<<<grid, p.pro ? kWgThreadsPro : kWgThreads, smem, stream>>>(p);
     DMM_LAUNCH_CHECK("wgrad_kernel");
     if (p.prof) {
         static long long h[4096 * 8];

@@ -18,12 +18,17 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "reduce4": (32, 160, 240, 512, 128, 1, 0),
     "convT4_phase11": (32, 160, 240, 128, 128, 2, 0),
     "refine1_dgrad": (32, 640, 960, 3, 64, 5, 0),
+    "b1_conv1_k160_pro": (32, 160, 240, 160, 128, 1, 2),      # out_mode 2 here = BN-ReLU prologue on a [P, 256] block buffer
+    "b2_conv1_k320_pro": (32, 80, 120, 320, 128, 1, 2),
 }
 
 def run(name, reps=5):
     B, H, W, Cin, Cout, K, om = CASES[name]
     torch.manual_seed(0)
-    ld = ops.ceil_to(Cin, 8)
+    pro = om == 2
+    if pro:
+        om = 0
+    ld = ops.ceil_to(Cin, 8) if not pro else (256 if Cin <= 256 else 512)
     a = ops.Mat((torch.randn(B * H * W, ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
     if K == 2:
         taps = [(0, dy, dx) for dy in (0, 1) for dx in (0, 1)]
@@ -40,6 +45,13 @@ def run(name, reps=5):
         st = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.ptr(), out.ld,
                            stats=ops.Stats(st, 0, out.ld), n_tile=n_tile, kwidth=kwidth)
+        if pro:
+            bst = torch.rand(ops.Stats.size(ld), dtype=torch.float64, device="cuda") * 1000 + 5000
+            g, b_ = torch.ones(ld, device="cuda"), torch.zeros(ld, device="cuda")
+            rm, rv, sm, si = (torch.zeros(ld, device="cuda") for _ in range(4))
+            d.pro_enable = 1
+            d.pro_bn = ops.make_bn(ops.Stats(bst, 0, ld), 0, B * H * W, g, b_, rm, rv, sm, si, training=True)
+            keep = (bst, g, b_, rm, rv, sm, si)
     else:
         out = torch.zeros(B, Cout, H, W, device="cuda")
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.data_ptr(), 0, out_mode=1, n_tile=n_tile)
