@@ -311,15 +311,14 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                         if (lane == 0 && n_ops >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         tmem_ld_wait();
                         __syncwarp();
-                        uint8_t* srow = slot + lane * 128;
+                        const uint32_t srow = smem_u32(slot) + lane * 128;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(srow + ((j ^ (lane & 7)) << 4)) =
-                                make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+                            sts_v4(srow + ((j ^ (lane & 7)) << 4), make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]));
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(srow + (((j + 4) ^ (lane & 7)) << 4)) =
-                                (w > 16) ? make_uint4(v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]) : make_uint4(0, 0, 0, 0);
+                            sts_v4(srow + (((j + 4) ^ (lane & 7)) << 4),
+                                   (w > 16) ? make_uint4(v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]) : make_uint4(0, 0, 0, 0));
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
