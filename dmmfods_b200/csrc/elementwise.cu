@@ -6,6 +6,7 @@
 // moves 8 channels (16 bytes) of one pixel; a block is (cx channel-chunks) x (ry pixels) = 256
 // threads so that a warp touches contiguous 16*cx-byte row segments.
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/dmmfods_b200.h"
 
 namespace dmm {
@@ -45,7 +46,15 @@ struct ColCfg {
     int cx, ry, chunks;
     dim3 grid, block;
 };
-static ColCfg col_cfg(int C, long long rows) {
+static int env_int_ew(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// bps: grid cap in blocks per SM (a multiple of the kernel's resident blocks per SM keeps the grid-stride waves full)
+static ColCfg col_cfg(int C, long long rows, int bps = kMaxBlocksPerSm) {
+    static const int bps_env = env_int_ew("DMM_EW_BPS", 0);
+    if (bps_env > 0) bps = bps_env;
     ColCfg k;
     k.chunks = (C + 7) / 8;
     k.cx = 1;
@@ -53,7 +62,7 @@ static ColCfg col_cfg(int C, long long rows) {
     k.ry = kEwThreads / k.cx;
     const int gy = (k.chunks + k.cx - 1) / k.cx;
     long long gx = (rows + k.ry - 1) / k.ry;
-    long long cap = (long long)kNumSm * kMaxBlocksPerSm / gy;
+    long long cap = (long long)kNumSm * bps / gy;
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
@@ -435,6 +444,114 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_reduce_kernel(const dm
     block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Lean reduce pass behind max_pool2d(3, 2, 1) with recorded window winners (the stem, Dense_U_Net_lidar.py:75-77): a thread owns
+// one 8-channel chunk of a 2x2 input QUAD.  The quad (qy, qx) is touched by exactly the windows (qy..qy+1, qx..qx+1), so four
+// (gradient, winner-code) loads serve four input pixels (the per-pixel kernel fetches up to four windows per pixel).  Writes
+// dz (masked, pool-routed gradient) for the apply pass and accumulates the BatchNorm sums.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_maxpool_quad_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    __shared__ float sm[2 * kEwThreads * 8];
+    __shared__ __align__(16) float cf[4][kEwThreads];
+    const int cx = blockDim.x, ry = blockDim.y;
+    const int chunk = blockIdx.y * cx + threadIdx.x;
+    const int nchunks = p.C >> 3;
+    const bool active = chunk < nchunks;
+    {
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        const int c = blockIdx.y * cx * 8 + tid;
+        if (tid < cx * 8 && c < p.C) {
+            BnCoef k = bn_coef_bwd(p.bn, c);
+            cf[0][tid] = k.scale; cf[1][tid] = k.shift; cf[2][tid] = k.mean; cf[3][tid] = k.invstd;
+        }
+    }
+    __syncthreads();
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (active) {
+        const int t8 = threadIdx.x * 8;
+        float sc[8], sh[8], mu[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = cf[0][t8 + j]; sh[j] = cf[1][t8 + j]; mu[j] = cf[2][t8 + j];
+        }
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+        const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(p.g) + chunk * 8;
+        const uint8_t* am = reinterpret_cast<const uint8_t*>(p.argmax) + chunk * 8;
+        __nv_bfloat16* dzo = reinterpret_cast<__nv_bfloat16*>(p.dz_out) + chunk * 8;
+        const int QH = (p.H + 1) >> 1, QW = (p.W + 1) >> 1;
+        const unsigned quads = (unsigned)p.B * (unsigned)QH * (unsigned)QW;
+        for (unsigned q = blockIdx.x * ry + threadIdx.y; q < quads; q += gridDim.x * ry) {
+            const int qx = (int)(q % (unsigned)QW);
+            const unsigned t = q / (unsigned)QW;
+            const int qy = (int)(t % (unsigned)QH);
+            const int b = (int)(t / (unsigned)QH);
+            // pixel i = 2*a + c of the quad is (2qy + a, 2qx + c); window w = 2*a + c is (qy + a, qx + c)
+            bool pok[4], wok[4];
+            uint4 xr[4], gr[4];
+            uint2 cd[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int a = i >> 1, c = i & 1;
+                pok[i] = (2 * qy + a < p.H) && (2 * qx + c < p.W);
+                wok[i] = (qy + a < OH) && (qx + c < OW);
+                if (pok[i]) xr[i] = ldg16(x + (((long long)b * p.H + 2 * qy + a) * p.W + 2 * qx + c) * p.ldx);
+                if (wok[i]) {
+                    const long long w = ((long long)b * OH + qy + a) * OW + qx + c;
+                    gr[i] = ldg16(g + w * p.ldg);
+                    cd[i] = __ldg(reinterpret_cast<const uint2*>(am + w * p.ldarg));
+                }
+            }
+            float gw[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (wok[i]) unpack8(gr[i], gw[i]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) gw[i][j] = 0.f;
+                    cd[i] = make_uint2(0xffffffffu, 0xffffffffu);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!pok[i]) continue;
+                const int a = i >> 1, c = i & 1;
+                float xa[8], dz[8];
+                unpack8(xr[i], xa);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] = 0.f;
+                // windows containing this pixel: rows qy (always) and qy+1 (odd pixel rows), same for columns; the winner code
+                // of pixel (iy, ix) in window (oy, ox) is (iy - 2 oy + 1) * 3 + (ix - 2 ox + 1)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int wa = w >> 1, wc = w & 1;
+                    if (wa > a || wc > c) continue;               // compile-time after unrolling
+                    const uint32_t mine = (uint32_t)((a - 2 * wa + 1) * 3 + (c - 2 * wc + 1));
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t cj = ((j < 4 ? cd[w].x : cd[w].y) >> (8 * (j & 3))) & 0xffu;
+                        if (cj == mine) dz[j] += gw[w][j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] = fmaf(xa[j], sc[j], sh[j]) > 0.f ? dz[j] : 0.f;
+                const uint4 packed = pack8(dz);
+                *reinterpret_cast<uint4*>(dzo + (((long long)b * p.H + 2 * qy + a) * p.W + 2 * qx + c) * p.lddz) = packed;
+                unpack8(packed, dz);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1[j] += dz[j];
+                    s2[j] = fmaf(dz[j], xa[j] - mu[j], s2[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
+    }
+    block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+}
+
 template <int GMODE, typename GT>
 __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_apply_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
     const int cx = blockDim.x, ry = blockDim.y;
@@ -501,13 +618,38 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_apply_kernel(const dmm
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lean same-pixel (gmode 0) variants: per-channel coefficients stay in shared memory, two rows per iteration
-// (4 independent 16-byte loads in flight per thread), <= 64 registers so that 4 blocks fit on an SM.
+// Lean same-pixel (gmode 0) variants: per-channel coefficients in registers, four rows per iteration (8 independent
+// 16-byte loads in flight per thread), two 256-thread blocks per SM and a grid of exactly one wave - measured 1.4x faster
+// than three blocks x two rows with the coefficients re-read from shared memory (scripts/bench_bn.py).
 //   reduce: s1 = sum dz, s2 = invstd * sum dz*(x - mean)
 //   apply : dx = A*dz + B*x + C with A = gamma*invstd, B = -A*invstd*c2, C = -A*c1 - B*mean
 // ---------------------------------------------------------------------------------------------
+// raw (still packed) 8-channel gradient word(s) of one row: kept packed while several rows are in flight
 template <typename GT>
-__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const dmm_bn_bwd_args_t p) {
+struct RawG8;
+template <>
+struct RawG8<__nv_bfloat16> {
+    uint4 a;
+    __device__ __forceinline__ void load(const __nv_bfloat16* g, long long idx) { a = ldg16(g + idx); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const { unpack8(a, f); }
+};
+template <>
+struct RawG8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* g, long long idx) {
+        a = __ldg(reinterpret_cast<const float4*>(g + idx));
+        b = __ldg(reinterpret_cast<const float4*>(g + idx + 4));
+    }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+constexpr int kFastRows = 4;      // rows in flight per thread of the lean kernels below
+constexpr int kFastBps = 2;       // their resident blocks per SM = their grid cap (one full wave, measured best)
+
+template <typename GT>
+__global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_reduce_fast_kernel(const dmm_bn_bwd_args_t p) {
     __shared__ float sm[2 * kEwThreads * 8];
     __shared__ __align__(16) float cf[4][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -526,45 +668,51 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_reduce_fast_kernel(const
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
-    const GT* g = reinterpret_cast<const GT*>(p.g) + chunk * 8;
-    const long long rows = (long long)p.B * p.H * p.W;
-    const long long step = (long long)gridDim.x * ry;
-    const float* csc = &cf[0][threadIdx.x * 8];
-    const float* csh = &cf[1][threadIdx.x * 8];
-    const float* cmu = &cf[2][threadIdx.x * 8];
     if (active) {
-        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += 2 * step) {
-            const long long row2 = row + step;
-            const bool has2 = row2 < rows;
-            float xa[8], xb[8], ga[8], gb[8];
-            unpack8(ldg16(x + row * p.ldx), xa);
-            load_g8<GT>(g, row * p.ldg, ga);
-            if (has2) {
-                unpack8(ldg16(x + row2 * p.ldx), xb);
-                load_g8<GT>(g, row2 * p.ldg, gb);
+        const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
+        const GT* g = reinterpret_cast<const GT*>(p.g) + chunk * 8;
+        const long long rows = (long long)p.B * p.H * p.W;
+        const long long step = (long long)gridDim.x * ry;
+        const int t8 = threadIdx.x * 8;
+        float sc[8], sh[8], mu[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = cf[0][t8 + j]; sh[j] = cf[1][t8 + j]; mu[j] = cf[2][t8 + j];
+        }
+        for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += kFastRows * step) {
+            uint4 xr[kFastRows];
+            RawG8<GT> gr[kFastRows];
+#pragma unroll
+            for (int u = 0; u < kFastRows; ++u) {
+                const long long row = row0 + u * step;
+                if (row < rows) {
+                    xr[u] = ldg16(x + row * p.ldx);
+                    gr[u].load(g, row * p.ldg);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float sc = csc[j], sh = csh[j], mu = cmu[j];
-                const float dza = fmaf(xa[j], sc, sh) > 0.f ? ga[j] : 0.f;
-                s1[j] += dza;
-                s2[j] = fmaf(dza, xa[j] - mu, s2[j]);
-                if (has2) {
-                    const float dzb = fmaf(xb[j], sc, sh) > 0.f ? gb[j] : 0.f;
-                    s1[j] += dzb;
-                    s2[j] = fmaf(dzb, xb[j] - mu, s2[j]);
+            for (int u = 0; u < kFastRows; ++u) {
+                if (row0 + u * step < rows) {
+                    float xa[8], ga[8];
+                    unpack8(xr[u], xa);
+                    gr[u].unpack(ga);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float dz = fmaf(xa[j], sc[j], sh[j]) > 0.f ? ga[j] : 0.f;
+                        s1[j] += dz;
+                        s2[j] = fmaf(dz, xa[j] - mu[j], s2[j]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
+        for (int j = 0; j < 8; ++j) s2[j] *= cf[3][t8 + j];
     }
     block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
 }
 
 template <typename GT, int OUT_MODE>
-__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const dmm_bn_bwd_args_t p) {
+__global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_apply_fast_kernel(const dmm_bn_bwd_args_t p) {
     __shared__ __align__(16) float cf[5][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -598,46 +746,55 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
     const long long rows = (long long)p.B * p.H * p.W;
     const long long step = (long long)gridDim.x * ry;
     const int t8 = threadIdx.x * 8;
-    for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += 2 * step) {
-        float xv[2][8], gv[2][8];
-        float4 pa[2], pb[2];
-        const bool has2 = row0 + step < rows;
+    float sc[8], sh[8], cA[8], cB[8], cC[8];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !has2) break;
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = cf[0][t8 + j]; sh[j] = cf[1][t8 + j]; cA[j] = cf[2][t8 + j]; cB[j] = cf[3][t8 + j]; cC[j] = cf[4][t8 + j];
+    }
+    constexpr int R = (OUT_MODE == 2 || sizeof(GT) == 4) ? 2 : kFastRows;      // fp32 streams: fewer rows, same bytes in flight
+    for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += R * step) {
+        uint4 xr[R];
+        RawG8<GT> gr[R];
+        float4 pa[R], pb[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
             const long long row = row0 + u * step;
-            unpack8(ldg16(x + row * p.ldx), xv[u]);
-            load_g8<GT>(g, row * p.ldg, gv[u]);
-            if (OUT_MODE == 2) {
-                const float* of = reinterpret_cast<const float*>(p.out) + row * p.ldo + chunk * 8;
-                pa[u] = *reinterpret_cast<const float4*>(of);
-                pb[u] = *reinterpret_cast<const float4*>(of + 4);
+            if (row < rows) {
+                xr[u] = ldg16(x + row * p.ldx);
+                gr[u].load(g, row * p.ldg);
+                if (OUT_MODE == 2) {
+                    const float* of = reinterpret_cast<const float*>(p.out) + row * p.ldo + chunk * 8;
+                    pa[u] = *reinterpret_cast<const float4*>(of);
+                    pb[u] = *reinterpret_cast<const float4*>(of + 4);
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !has2) break;
+        for (int u = 0; u < R; ++u) {
             const long long row = row0 + u * step;
-            float dx[8];
+            if (row < rows) {
+                float xa[8], ga[8], dx[8];
+                unpack8(xr[u], xa);
+                gr[u].unpack(ga);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xx = xv[u][j];
-                const float dz = fmaf(xx, cf[0][t8 + j], cf[1][t8 + j]) > 0.f ? gv[u][j] : 0.f;
-                dx[j] = fmaf(cf[2][t8 + j], dz, fmaf(cf[3][t8 + j], xx, cf[4][t8 + j]));
-            }
-            const long long o = row * p.ldo + chunk * 8;
-            if (OUT_MODE == 0) {
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8(dx);
-            } else {
-                float* of = reinterpret_cast<float*>(p.out) + o;
-                float4 a = make_float4(dx[0], dx[1], dx[2], dx[3]);
-                float4 b = make_float4(dx[4], dx[5], dx[6], dx[7]);
-                if (OUT_MODE == 2) {
-                    a.x += pa[u].x; a.y += pa[u].y; a.z += pa[u].z; a.w += pa[u].w;
-                    b.x += pb[u].x; b.y += pb[u].y; b.z += pb[u].z; b.w += pb[u].w;
+                for (int j = 0; j < 8; ++j) {
+                    const float dz = fmaf(xa[j], sc[j], sh[j]) > 0.f ? ga[j] : 0.f;
+                    dx[j] = fmaf(cA[j], dz, fmaf(cB[j], xa[j], cC[j]));
                 }
-                *reinterpret_cast<float4*>(of) = a;
-                *reinterpret_cast<float4*>(of + 4) = b;
+                const long long o = row * p.ldo + chunk * 8;
+                if (OUT_MODE == 0) {
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8(dx);
+                } else {
+                    float* of = reinterpret_cast<float*>(p.out) + o;
+                    float4 a = make_float4(dx[0], dx[1], dx[2], dx[3]);
+                    float4 b = make_float4(dx[4], dx[5], dx[6], dx[7]);
+                    if (OUT_MODE == 2) {
+                        a.x += pa[u].x; a.y += pa[u].y; a.z += pa[u].z; a.w += pa[u].w;
+                        b.x += pb[u].x; b.y += pb[u].y; b.z += pb[u].z; b.w += pb[u].w;
+                    }
+                    *reinterpret_cast<float4*>(of) = a;
+                    *reinterpret_cast<float4*>(of + 4) = b;
+                }
             }
         }
     }
@@ -646,7 +803,8 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_apply_fast_kernel(const 
 // ---------------------------------------------------------------------------------------------
 // Single-pass BN-ReLU backward "contribution" (see include/dmmfods_b200.h): sums like the reduce pass + bf16 slab A*dz.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_contrib_kernel(const dmm_bn_bwd_args_t p) {
+template <int ROWS, bool HOIST>
+__global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_contrib_kernel(const dmm_bn_bwd_args_t p) {
     __shared__ float sm[2 * kEwThreads * 8];
     __shared__ __align__(16) float cf[5][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -683,32 +841,43 @@ __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_contrib_kernel(const dmm
         const long long rows = (long long)p.B * p.H * p.W;
         const long long step = (long long)gridDim.x * ry;
         const int t8 = threadIdx.x * 8;
-        for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < rows; row += 2 * step) {
-            const long long row2 = row + step;
-            const bool has2 = row2 < rows;
-            float xa[8], xb[8], ga[8], gb[8], oa[8], ob[8];
-            unpack8(ldg16(x + row * p.ldx), xa);
-            unpack8(ldg16(g + row * p.ldg), ga);
-            if (has2) {
-                unpack8(ldg16(x + row2 * p.ldx), xb);
-                unpack8(ldg16(g + row2 * p.ldg), gb);
-            }
+        float hsc[8], hsh[8], hmu[8], hA[8];
+        if (HOIST) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float sc = cf[0][t8 + j], sh = cf[1][t8 + j], mu = cf[2][t8 + j], A = cf[4][t8 + j];
-                const float dza = fmaf(xa[j], sc, sh) > 0.f ? ga[j] : 0.f;
-                s1[j] += dza;
-                s2[j] = fmaf(dza, xa[j] - mu, s2[j]);
-                oa[j] = A * dza;
-                if (has2) {
-                    const float dzb = fmaf(xb[j], sc, sh) > 0.f ? gb[j] : 0.f;
-                    s1[j] += dzb;
-                    s2[j] = fmaf(dzb, xb[j] - mu, s2[j]);
-                    ob[j] = A * dzb;
+                hsc[j] = cf[0][t8 + j]; hsh[j] = cf[1][t8 + j]; hmu[j] = cf[2][t8 + j]; hA[j] = cf[4][t8 + j];
+            }
+        }
+        for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < rows; row0 += ROWS * step) {
+            // ROWS rows in flight; the raw 16-byte words stay packed until their row is processed
+            uint4 xr[ROWS], gr[ROWS];
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) {
+                const long long row = row0 + u * step;
+                if (row < rows) {
+                    xr[u] = ldg16(x + row * p.ldx);
+                    gr[u] = ldg16(g + row * p.ldg);
                 }
             }
-            *reinterpret_cast<uint4*>(out + row * ldo) = pack8(oa);
-            if (has2) *reinterpret_cast<uint4*>(out + row2 * ldo) = pack8(ob);
+#pragma unroll
+            for (int u = 0; u < ROWS; ++u) {
+                const long long row = row0 + u * step;
+                if (row < rows) {
+                    float xa[8], ga[8], oa[8];
+                    unpack8(xr[u], xa);
+                    unpack8(gr[u], ga);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float sc = HOIST ? hsc[j] : cf[0][t8 + j], sh = HOIST ? hsh[j] : cf[1][t8 + j];
+                        const float mu = HOIST ? hmu[j] : cf[2][t8 + j], A = HOIST ? hA[j] : cf[4][t8 + j];
+                        const float dz = fmaf(xa[j], sc, sh) > 0.f ? ga[j] : 0.f;
+                        s1[j] += dz;
+                        s2[j] = fmaf(dz, xa[j] - mu, s2[j]);
+                        oa[j] = A * dz;
+                    }
+                    *reinterpret_cast<uint4*>(out + row * ldo) = pack8(oa);
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
@@ -734,7 +903,9 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const dmm_bn_bwd_t
     k[C + c] = A * invstd * (float)(b / bn.count);
 }
 
-__global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_grad_gather_t p) {
+// R rows x S sources = 16 independent 16-byte loads in flight per thread (R chosen from the source count at launch)
+template <int R, int S>
+__global__ void __launch_bounds__(kEwThreads, kFastBps) grad_gather_kernel(const dmm_grad_gather_t p) {
     __shared__ __align__(16) float ks[3][kEwThreads];       // sum k1, sum k2, mean of the block's channels
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -756,55 +927,59 @@ __global__ void __launch_bounds__(kEwThreads, 3) grad_gather_kernel(const dmm_gr
     const int t8 = threadIdx.x * 8;
     const long long step = (long long)gridDim.x * ry;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + chunk * 8;
+    const __nv_bfloat16* xin = reinterpret_cast<const __nv_bfloat16*>(p.x) + chunk * 8;
     // element offset of this thread's chunk inside a planar source (group plane + position in the group)
     const int cg = p.gw > 0 ? (chunk * 8) / p.gw : 0, cw = p.gw > 0 ? (chunk * 8) % p.gw : 0;
-#define DMM_GSRC(S) (reinterpret_cast<const __nv_bfloat16*>(p.src[S]) + (p.plane[S] ? (long long)cg * p.plane[S] + cw : (long long)chunk * 8) + row * p.ld[S])
-    for (long long row = (long long)blockIdx.x * ry + threadIdx.y; row < p.rows; row += step) {
-        float acc[8];
+#define DMM_GSRC(S, ROW) (reinterpret_cast<const __nv_bfloat16*>(p.src[S]) + (p.plane[S] ? (long long)cg * p.plane[S] + cw : (long long)chunk * 8) + (ROW) * p.ld[S])
+    for (long long row0 = (long long)blockIdx.x * ry + threadIdx.y; row0 < p.rows; row0 += R * step) {
+        float acc[R][8];
+        uint4 xv[R];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        int s = 0;
-        for (; s + 8 <= p.nsrc; s += 8) {        // eight independent 16-byte loads in flight
-            uint4 v[8];
+        for (int r = 0; r < R; ++r) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                v[u] = ldg16(DMM_GSRC(s + u));
+            for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+            if (p.nk && row0 + r * step < p.rows) xv[r] = ldg16(xin + (row0 + r * step) * p.ldx);
+        }
+        for (int s0 = 0; s0 < p.nsrc; s0 += S) {
+            const int n = p.nsrc - s0;
+            uint4 v[R][S];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                float f[8];
-                unpack8(v[u], f);
+            for (int u = 0; u < S; ++u) {
+                if (u < n) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                    for (int r = 0; r < R; ++r)
+                        if (row0 + r * step < p.rows) v[r][u] = ldg16(DMM_GSRC(s0 + u, row0 + r * step));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < S; ++u) {
+                if (u < n) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (row0 + r * step < p.rows) {
+                            float f[8];
+                            unpack8(v[r][u], f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[r][j] += f[j];
+                        }
+                    }
+                }
             }
         }
-        for (; s + 4 <= p.nsrc; s += 4) {
-            uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                v[u] = ldg16(DMM_GSRC(s + u));
+        for (int r = 0; r < R; ++r) {
+            if (row0 + r * step < p.rows) {
+                if (p.nk) {
+                    float xf[8];
+                    unpack8(xv[r], xf);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float f[8];
-                unpack8(v[u], f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                    for (int j = 0; j < 8; ++j) acc[r][j] -= fmaf(xf[j] - ks[2][t8 + j], ks[1][t8 + j], ks[0][t8 + j]);
+                }
+                *reinterpret_cast<uint4*>(out + (row0 + r * step) * p.ldo) = pack8(acc[r]);
             }
         }
-        for (; s < p.nsrc; ++s) {
-            float f[8];
-            unpack8(ldg16(DMM_GSRC(s)), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += f[j];
-        }
-#undef DMM_GSRC_UNUSED
-        if (p.nk) {
-            float xv[8];
-            unpack8(ldg16(reinterpret_cast<const __nv_bfloat16*>(p.x) + row * p.ldx + chunk * 8), xv);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] -= fmaf(xv[j] - ks[2][t8 + j], ks[1][t8 + j], ks[0][t8 + j]);
-        }
-        *reinterpret_cast<uint4*>(out + row * p.ldo) = pack8(acc);
     }
+#undef DMM_GSRC
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1021,7 +1196,7 @@ __global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict
 // One block = one output row (b, y); thread t owns chunk t % chunks for pixels t / chunks, t / chunks + ppb, ... so the
 // inner loop has no divisions, 16-byte stores of a row are contiguous, and every up-sampled source row is read by
 // exactly two blocks.
-__global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
+__global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) {
     extern __shared__ float coef[];   // [2][Cpad]
     const int Ct = p.Cu + p.C1 + p.C2;
     const int chunks = (int)(p.ldo >> 3);
@@ -1040,11 +1215,25 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
     __syncthreads();
     const int cu = p.Cu >> 3;                        // chunks that come from the up-sampled decoder output
     const int Cx = p.C1 + p.C2;
-    const int yy = blockIdx.x % p.H, b = blockIdx.x / p.H;
     const int UH = p.H >> 1, UW = p.W >> 1;
     const long long HW = (long long)p.H * p.W;
-    // the raw network inputs of this row (fp32 NCHW planes) are staged in shared memory with coalesced loads, already activated
     float* xs = coef + 2 * Cpad;                     // [Cx][W]
+    // warps 0..6: thread t owns up-sampled chunk t % cu for pixels t / cu, t / cu + ppb, ... (no divisions in the loop);
+    // warp 7 alone writes the chunks of the raw input channels, so that no warp runs both loops (divergence)
+    const int nraw = chunks - cu;                    // raw-input chunks per pixel (1 for <= 8 raw channels)
+    const bool raw_warp = threadIdx.x >= 224;
+    const int ppb = raw_warp ? 32 / (nraw > 0 ? nraw : 1) : 224 / cu;
+    const int tl = raw_warp ? (int)threadIdx.x - 224 : (int)threadIdx.x;
+    const int nper = raw_warp ? nraw : cu;
+    const bool worker = nper > 0 && tl < ppb * nper;
+    const int ch = raw_warp ? cu + tl % (nper > 0 ? nper : 1) : tl % cu, px0 = tl / (nper > 0 ? nper : 1);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = coef[ch * 8 + j]; sh[j] = coef[Cpad + ch * 8 + j]; }
+    // persistent over image rows: the BatchNorm coefficients are finalised once per block, not once per row
+    for (int row = blockIdx.x; row < p.B * p.H; row += gridDim.x) {
+    const int yy = row % p.H, b = row / p.H;
+    // the raw network inputs of this row (fp32 NCHW planes) are staged in shared memory with coalesced loads, already activated
     for (int i = threadIdx.x; i < Cx * p.W; i += blockDim.x) {
         const int c = i / p.W, xx = i - c * p.W;
         const float v = c < p.C1 ? __ldg(p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W + xx)
@@ -1052,18 +1241,11 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
         xs[i] = fmaxf(fmaf(v, coef[p.Cu + c], coef[Cpad + p.Cu + c]), 0.f);
     }
     __syncthreads();
-    // thread t owns chunk t % chunks for pixels t / chunks, t / chunks + ppb, ...: no divisions in the loop and the 16-byte
-    // stores of the block form one contiguous stream (every chunk of every pixel of the row, in order)
-    const int ppb = blockDim.x / chunks;
-    if ((int)threadIdx.x >= ppb * chunks) return;
-    const int ch = threadIdx.x % chunks, px0 = threadIdx.x / chunks;
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + yy) * p.W * p.ldo + ch * 8;
-    if (ch < cu) {
+    if (!worker) {
+    } else if (ch < cu) {
         const __nv_bfloat16* urow = reinterpret_cast<const __nv_bfloat16*>(p.u) + ((long long)b * UH + (yy >> 1)) * UW * p.ldu + ch * 8;
-        float sc[8], sh[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = coef[ch * 8 + j]; sh[j] = coef[Cpad + ch * 8 + j]; }
-#pragma unroll 4
+#pragma unroll 8
         for (int xx = px0; xx < p.W; xx += ppb) {
             float f[8];
             unpack8(ldg16(urow + (long long)(xx >> 1) * p.ldu), f);
@@ -1079,6 +1261,8 @@ __global__ void __launch_bounds__(256) head_input_kernel(const dmm_head_t p) {
             for (int j = 0; j < 8; ++j) f[j] = (c0 + j < Cx) ? xs[(c0 + j) * p.W + xx] : 0.f;
             *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
         }
+    }
+    __syncthreads();                                 // xs is overwritten by the next row
     }
 }
 
@@ -1244,12 +1428,12 @@ __global__ void __launch_bounds__(256) head_raw_bwd_reduce_kernel(const dmm_head
 // dlogits (B, C, H, W) fp32 -> bf16 rows [B*H*W, ld]: column t*C + n = dlogits[n] at pixel (y - (kh - K/2), x - (kw - K/2)),
 // t = kh*K + kw (zero outside the image, zero beyond K*K*C).  This "im2col of the output gradient" turns both the
 // weight gradient and the data gradient of the N = num_classes KxK convolution (refine1) into plain 1x1 GEMMs.
-__global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int K,
+__global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int KH, int K,
                                                              __nv_bfloat16* __restrict__ out, int ld) {
     const int chunks = ld >> 3;
     const long long total = (long long)B * H * W * chunks;
-    const int pad = K / 2;
-    const int KC = K * K * C;
+    const int pad = K / 2, pad_h = KH / 2;
+    const int KC = KH * K * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ch = (int)(i % chunks);
         const long long pix = i / chunks;
@@ -1265,7 +1449,7 @@ __global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __rest
             if (col < KC) {
                 const int t = col / C, n = col - t * C;
                 const int kh = t / K, kw = t - kh * K;
-                const int yy = y - (kh - pad), xx = x - (kw - pad);
+                const int yy = y - (kh - pad_h), xx = x - (kw - pad);
                 if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(dl + (((long long)b * C + n) * H + yy) * W + xx);
             }
             f[j] = v;
@@ -1447,6 +1631,26 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unp
     }
 }
 
+// resident 256-thread blocks per SM of a kernel (cached): a grid-stride kernel runs best as exactly one full wave
+template <typename F>
+static int resident_bps(F fn) {
+    struct Entry { const void* f; int n; };
+    static Entry cache[64];
+    static int ncache = 0;
+    const void* key = reinterpret_cast<const void*>(fn);
+    for (int i = 0; i < ncache; ++i)
+        if (cache[i].f == key) return cache[i].n;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, kEwThreads, 0) != cudaSuccess || n < 1) n = kMaxBlocksPerSm;
+    if (ncache < 64) cache[ncache++] = {key, n};
+    return n;
+}
+#define DMM_WAVE_LAUNCH(KERNEL, C_, ROWS_, STREAM, ...)                          \
+    do {                                                                         \
+        const ColCfg kw_ = col_cfg((C_), (ROWS_), resident_bps(KERNEL));         \
+        KERNEL<<<kw_.grid, kw_.block, 0, (STREAM)>>>(__VA_ARGS__);               \
+    } while (0)
+
 static unsigned flat_grid(long long total, int threads) {
     long long g = (total + threads - 1) / threads;
     const long long cap = (long long)kNumSm * 16;
@@ -1473,11 +1677,11 @@ extern "C" int dmm_bn_relu_apply(const dmm_bn_apply_t* d, void* stream_) {
     if (d->pool == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
     if (OH <= 0 || OW <= 0) return 0;
     DMM_CHECK(d->pool == 0 || (long long)d->B * d->H * d->W < (1ll << 31), "dmm_bn_relu_apply: too many pixels for a pooled mode");
-    ColCfg k = col_cfg(d->C, (long long)d->B * OH * OW);
-    if (d->pool == 0 && d->ystats == nullptr) bn_apply_fast_kernel<<<k.grid, k.block, 0, stream>>>(*d);
-    else if (d->pool == 0) bn_relu_apply_kernel<0><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
-    else if (d->pool == 1) bn_relu_apply_kernel<1><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
-    else bn_relu_apply_kernel<2><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);
+    const long long orows = (long long)d->B * OH * OW;
+    if (d->pool == 0 && d->ystats == nullptr) DMM_WAVE_LAUNCH(bn_apply_fast_kernel, d->C, orows, stream, *d);
+    else if (d->pool == 0) DMM_WAVE_LAUNCH(bn_relu_apply_kernel<0>, d->C, orows, stream, *d, OH, OW);
+    else if (d->pool == 1) DMM_WAVE_LAUNCH(bn_relu_apply_kernel<1>, d->C, orows, stream, *d, OH, OW);
+    else DMM_WAVE_LAUNCH(bn_relu_apply_kernel<2>, d->C, orows, stream, *d, OH, OW);
     DMM_LAUNCH_CHECK("bn_relu_apply_kernel");
     return 0;
 }
@@ -1495,8 +1699,9 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
     int OH = d->H, OW = d->W;
     if (d->gmode == 1) { OH = d->H / 2; OW = d->W / 2; }
     if (d->gmode == 2) { OH = (d->H - 1) / 2 + 1; OW = (d->W - 1) / 2 + 1; }
-    ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W);
+    const long long irows = (long long)d->B * d->H * d->W;
     if (d->gmode == 0 && d->dz_out == nullptr) {      // lean same-pixel kernels
+        const ColCfg k = col_cfg(d->C, irows, kFastBps);
         if (PASS == 0) {
             if (d->g_is_f32) bn_bwd_reduce_fast_kernel<float><<<k.grid, k.block, 0, stream>>>(*d);
             else bn_bwd_reduce_fast_kernel<__nv_bfloat16><<<k.grid, k.block, 0, stream>>>(*d);
@@ -1517,7 +1722,7 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
     if (d->gmode == 1 && !d->g_is_f32 && d->dz_out == nullptr && d->H % 2 == 0 && d->W % 2 == 0) {      // lean pooled kernels
         ColCfg kp = col_cfg(d->C, (long long)d->B * OH * OW);
         unsigned gx = (unsigned)(d->B * OH);
-        const unsigned cap = (unsigned)(kNumSm * kMaxBlocksPerSm) / kp.grid.y;
+        const unsigned cap = (unsigned)(kNumSm * 3) / kp.grid.y;      // launch bounds (256, 3): one full wave
         if (gx > cap) gx = cap > 0 ? cap : 1;
         kp.grid.x = gx;
         if (PASS == 0) bn_bwd_pool_fast_kernel<0, 0><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
@@ -1527,10 +1732,16 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
         DMM_LAUNCH_CHECK("bn_bwd pooled kernel");
         return 0;
     }
+    if (PASS == 0 && d->gmode == 2 && !d->g_is_f32 && d->argmax && d->dz_out) {      // lean max-pool reduce (the stem)
+        const long long quads = (long long)d->B * ((d->H + 1) / 2) * ((d->W + 1) / 2);
+        DMM_WAVE_LAUNCH(bn_bwd_maxpool_quad_kernel, d->C, quads, stream, *d, OH, OW);
+        DMM_LAUNCH_CHECK("bn_bwd_maxpool_quad_kernel");
+        return 0;
+    }
 #define DMM_BWD_LAUNCH(GM, GT)                                                                      \
     do {                                                                                            \
-        if (PASS == 0) bn_relu_bwd_reduce_kernel<GM, GT><<<k.grid, k.block, 0, stream>>>(*d, OH, OW); \
-        else bn_relu_bwd_apply_kernel<GM, GT><<<k.grid, k.block, 0, stream>>>(*d, OH, OW);           \
+        if (PASS == 0) DMM_WAVE_LAUNCH((bn_relu_bwd_reduce_kernel<GM, GT>), d->C, irows, stream, *d, OH, OW); \
+        else DMM_WAVE_LAUNCH((bn_relu_bwd_apply_kernel<GM, GT>), d->C, irows, stream, *d, OH, OW);           \
     } while (0)
     if (d->g_is_f32) {
         if (d->gmode == 0) DMM_BWD_LAUNCH(0, float);
@@ -1561,8 +1772,8 @@ extern "C" int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream)
     DMM_CHECK(d->gmode == 0 && !d->g_is_f32, "dmm_bn_relu_bwd_contrib: same-pixel bf16 gradients only");
     DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd, "dmm_bn_relu_bwd_contrib: missing BN state");
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
-    ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W);
-    bn_bwd_contrib_kernel<<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
+    ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W, kFastBps);
+    bn_bwd_contrib_kernel<kFastRows, true><<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
     DMM_LAUNCH_CHECK("bn_bwd_contrib_kernel");
     return 0;
 }
@@ -1585,8 +1796,9 @@ extern "C" int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream) {
         DMM_CHECK(d->plane[s] == 0 || (d->gw > 0 && d->gw % 8 == 0 && d->plane[s] % 8 == 0), "dmm_grad_gather: planar source %d", s);
     }
     if (d->rows <= 0) return 0;
-    ColCfg k = col_cfg(d->C, d->rows);
-    grad_gather_kernel<<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
+    static const int gather_bps = env_int_ew("DMM_GATHER_BPS", kFastBps);
+    ColCfg k = col_cfg(d->C, d->rows, gather_bps);
+    grad_gather_kernel<2, 8><<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);      // (4 rows x 4 sources measured slower)
     DMM_LAUNCH_CHECK("grad_gather_kernel");
     return 0;
 }
@@ -1627,6 +1839,8 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
     const int chunks = (int)(d->ldo / 8);
     DMM_CHECK(chunks <= 256, "dmm_head_input: ldo %lld too large", (long long)d->ldo);
+    DMM_CHECK(d->Cu >= 8 && d->Cu <= 224 * 8 && chunks - d->Cu / 8 <= 32 && chunks * 8 >= d->Cu + d->C1 + d->C2,
+              "dmm_head_input: unsupported channel split (Cu=%d, raw=%d, ldo=%lld)", d->Cu, d->C1 + d->C2, (long long)d->ldo);
     const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * d->W) * sizeof(float);
     DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: row of %d raw channels x %d pixels does not fit in shared memory", d->C1 + d->C2, d->W);
     static bool head_attr = false;
@@ -1634,7 +1848,11 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
         DMM_CUDA(cudaFuncSetAttribute(head_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         head_attr = true;
     }
-    head_input_kernel<<<(unsigned)(d->B * d->H), 256, smem, (cudaStream_t)stream>>>(*d);
+    int head_bps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&head_bps, head_input_kernel, 256, smem) != cudaSuccess || head_bps < 1) head_bps = 4;
+    static const int head_bps_env = env_int_ew("DMM_HEAD_BPS", 0);
+    const long long hrows = (long long)d->B * d->H, hcap = (long long)kNumSm * (head_bps_env > 0 ? head_bps_env : head_bps);
+    head_input_kernel<<<(unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;
 }
@@ -1781,8 +1999,20 @@ extern "C" int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, in
               "dmm_dlogits_im2col: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const long long total = (long long)B * H * W * (ld / 8);
-    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, K,
+    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, K, K,
                                                                                   reinterpret_cast<__nv_bfloat16*>(out), (int)ld);
     DMM_LAUNCH_CHECK("dlogits_im2col_kernel");
+    return 0;
+}
+
+extern "C" int dmm_dlogits_unfold_w(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
+                                    int64_t ld, void* stream) {
+    DMM_CHECK(dlogits && out && C > 0 && K >= 1 && (K & 1) && ld % 8 == 0 && ld >= (int64_t)K * C,
+              "dmm_dlogits_unfold_w: bad arguments");
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const long long total = (long long)B * H * W * (ld / 8);
+    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, 1, K,
+                                                                                  reinterpret_cast<__nv_bfloat16*>(out), (int)ld);
+    DMM_LAUNCH_CHECK("dlogits_unfold_w");
     return 0;
 }

@@ -263,7 +263,7 @@ class Engine:
         self._fix_w.append((d, wid))
         return d
 
-    def _conv_dgrad(self, lst, name, wname, srcs, taps, tap_off, Cg, Cin, sn, sc, W, H, B, out):
+    def _conv_dgrad(self, lst, name, wname, srcs, taps, tap_off, Cg, Cin, sn, sc, W, H, B, out, cdiv=0, sc2=0, heavy=None):
         """data gradient: igemm over the output-gradient views `srcs` (Cg channels) -> out [P, >=Cin]."""
         T = len(taps)
         # a narrow (<= 16 channels) single gradient source: four taps share one 64-wide K block of the packed weights
@@ -273,7 +273,7 @@ class Engine:
         n_rows = ceil_to(Cin, n_tile)
         wid = self._req_wpk(n_rows, T * Kp)
         self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cin, n_rows=n_rows, C=Cg, T=T, tap_off=tap_off,
-                                    sn=sn, sc=sc, kwidth=kwidth))
+                                    sn=sn, sc=sc, kwidth=kwidth, cdiv=cdiv, sc2=sc2))
         d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cin, out.ptr(), out.ld, n_tile=n_tile, kwidth=kwidth)
         P = B * H * W
         self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_dgrad", flops=2.0 * P * Cin * Cg * T,
@@ -281,10 +281,10 @@ class Engine:
         self._fix_w.append((d, wid))
         # "heavy": enough MMA work per output chunk that a longer epilogue stays hidden (KxK data gradients); the 1x1 data
         # gradients of the dense layers are epilogue/HBM-bound and lose more than the separate reduce pass costs
-        lst[-1].heavy = T * ceil_to(Cg, 64) >= 512
+        lst[-1].heavy = (T * ceil_to(Cg, 64) >= 512) if heavy is None else heavy
         return lst[-1]
 
-    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None):
+    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None, n_off=0):
         """weight gradient: wgrad launches into a zeroed fp32 scratch matrix + unpack job into the flat gradient
         buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x.
         pro (_BNInfo): x is the RAW input of that BatchNorm; relu(bn(x)) is applied to the operand tiles on the fly."""
@@ -304,7 +304,7 @@ class Engine:
                        flops=2.0 * P * Mvalid * Nvalid * T / nl, nbytes=(P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4) / nl)
             self._fix_dw.append((d, did))
         self._unpack_jobs.append(dict(wname=wname, did=did, grad=self.grad[wname], dt=plan["dt"], dm=plan["dm"], dn=plan["dn"], M=Mvalid,
-                                      N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst)))
+                                      N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst), dw_off=n_off * plan["dn"]))
         self._stage_params.setdefault(id(lst), []).append(wname)
 
     def _conv_wgrad_tail(self, lst, name, wname, xtail, c_off, r, y, taps, tap_off, N, Nvalid, sn, sc, W, H, B):
@@ -763,9 +763,15 @@ class Engine:
                        25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
         if self.need_backward:
             st = []
-            dl = self._mat(B, H, W, 16)      # d(logits) as a pixel-major bf16 matrix (channels >= num_classes are zero)
+            # d(logits) as a pixel-major bf16 matrix.  With 5 * num_classes <= 16 the five HORIZONTAL shifts of every class
+            # share the 16 columns (column kw*ncls + n = dlogits[n](y, x - (kw - 2))): the data gradient of refine1 is then a
+            # 5-tap vertical convolution (5 instead of 25 MMAs per tile); columns 2*ncls.. hold the unshifted gradient.
+            dl = self._mat(B, H, W, 16)
+            unfold = 5 * self.ncls <= 16
 
-            def run_dl(_a, stream, lib=self.lib, dl=dl):
+            def run_dl(_a, stream, lib=self.lib, dl=dl, unfold=unfold):
+                if unfold:
+                    return lib.dmm_dlogits_unfold_w(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, 5, dl.ptr(), dl.ld, stream)
                 return lib.dmm_nchw_to_nhwc_bf16(C.c_void_p(self.dlogits.data_ptr()), B, self.ncls, H, W, dl.ptr(), dl.ld, stream)
             self._emit(st, run_dl, None, hp + ".dlogits_nhwc", kind="nchw_to_nhwc", nbytes=B * H * W * (self.ncls * 4 + 16 * 2))
             da1h = self._tmpmat("head_da1", B, H, W, nf2)
@@ -774,9 +780,16 @@ class Engine:
             # refine1 (5x5, 64 -> num_classes): weight gradient = activation x 25 shifted views of d(logits) (one halo patch,
             # five wide MMAs per k-step); data gradient = a 25-tap convolution over the 16-channel d(logits) matrix
             self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)], conv5[0], conv5[2],
-                             nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B)
-            dgh = self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1], conv5[2],
-                                   self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
+                             nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B, n_off=2 * self.ncls if unfold else 0)
+            if unfold:
+                # packed weight column (tap kh, channel c = kw*ncls + n) <- w[n, ci, kh, kw]
+                dgh = self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, 16)],
+                                       [(0, 2 - kh, 0) for kh in range(5)], [5 * kh for kh in range(5)], 5 * self.ncls, nf2, 25, 1,
+                                       W, H, B, da1h, cdiv=self.ncls, sc2=nf2 * 25,
+                                       heavy=os.environ.get("DMM_HEAD_DGRAD_FUSED", "1") != "0")
+            else:
+                dgh = self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, self.ncls)], conv5[1],
+                                       conv5[2], self.ncls, nf2, 25, nf2 * 25, W, H, B, da1h)
             self._bn_bwd(st, hp + ".norm1.bwd", bn1, r0, 0, nf2, da1h.ptr(), da1h.ld, dr0.ptr(), dr0.ld, 0, producer=dgh)
             if Cu % 64 == 0 and 0 < cx <= 16:
                 # the 128 decoder channels fill one 128-row m-tile exactly; the few raw input channels go through the tail path
@@ -852,7 +865,7 @@ class Engine:
             d.dw = base + 4 * offs[did]
         uj = np.zeros(len(self._unpack_jobs), dtype=_UNPACK_DT)
         for i, j in enumerate(self._unpack_jobs):
-            uj[i]["dw"] = base + 4 * offs[j["did"]]
+            uj[i]["dw"] = base + 4 * (offs[j["did"]] + j.get("dw_off", 0))
             uj[i]["grad"] = j["grad"].data_ptr()
             uj[i]["dt"], uj[i]["dm"], uj[i]["dn"] = j["dt"], j["dm"], j["dn"]
             uj[i]["M"], uj[i]["N"], uj[i]["T"] = j["M"], j["N"], j["T"]

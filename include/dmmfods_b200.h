@@ -352,6 +352,11 @@ int dmm_nchw_to_nhwc_bf16(const float* x, int32_t B, int32_t C, int32_t H, int32
  * convolution (refine1, Dense_U_Net_lidar.py:130-131) into plain 1x1 GEMMs over K*K*C columns. */
 int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
                        int64_t ld, void* stream);
+/* Horizontal-only variant: column kw*C + n = dlogits[n](y, x - (kw - K/2)).  With it the data gradient of the KxK head
+ * convolution is a K-tap VERTICAL convolution over K*C (<= 16) channels instead of K*K taps over C channels, and the
+ * weight gradient needs K instead of K*K shifted views. */
+int dmm_dlogits_unfold_w(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
+                         int64_t ld, void* stream);
 /* fp32 rows [P, C] (pitch lds) -> bf16 rows (pitch ldd): slices of the fp32 dense-block gradient buffer. */
 int dmm_rows_f32_to_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t P, int32_t C,
                          void* stream);

@@ -18,6 +18,7 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "reduce4": (32, 160, 240, 512, 128, 1, 0),
     "convT4_phase11": (32, 160, 240, 128, 128, 2, 0),
     "refine1_dgrad": (32, 640, 960, 3, 64, 5, 0),
+    "refine1_dgrad_v": (32, 640, 960, 16, 64, -5, 0),          # K < 0: |K| vertical taps over the horizontally unfolded d(logits)
     "b1_conv1_k160_pro": (32, 160, 240, 160, 128, 1, 2),      # out_mode 2 here = BN-ReLU prologue on a [P, 256] block buffer
     "b2_conv1_k320_pro": (32, 80, 120, 320, 128, 1, 2),
 }
@@ -30,7 +31,9 @@ def run(name, reps=5):
         om = 0
     ld = ops.ceil_to(Cin, 8) if not pro else (256 if Cin <= 256 else 512)
     a = ops.Mat((torch.randn(B * H * W, ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
-    if K == 2:
+    if K < 0:
+        taps = [(0, -K // 2 - kh, 0) for kh in range(-K)]
+    elif K == 2:
         taps = [(0, dy, dx) for dy in (0, 1) for dx in (0, 1)]
     else:
         taps = ops.conv_taps(K, (K - 1) // 2)[0]

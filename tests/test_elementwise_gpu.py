@@ -312,11 +312,12 @@ def test_adam_flat_matches_torch_adam():
     assert torch.allclose(p.cpu(), ref_p.detach(), rtol=1e-5, atol=1e-6)
 
 
-def test_maxpool_backward_with_recorded_argmax():
+@pytest.mark.parametrize("H,W,gf32", [(18, 22, True), (18, 22, False), (17, 21, False), (9, 12, False)])
+def test_maxpool_backward_with_recorded_argmax(H, W, gf32):
     """stem path of the engine: forward records each window's winner, backward routes through the codes and the reduce
-    pass stores dz so that the apply pass runs with gmode 0."""
+    pass stores dz so that the apply pass runs with gmode 0 (bf16 gradients take the 2x2-quad kernel)."""
     torch.manual_seed(51)
-    B, C, H, W = 2, 64, 18, 22
+    B, C = 2, 64
     gamma, beta, rm, rv, sm, si = _bn_setup(C, 3)
     x = bf16_round(torch.randn(B, C, H, W) * 1.5 + 0.2)
     x[:, :, 4:8, 4:8] = x[:, :, 4:5, 4:5]                      # exact ties inside windows
@@ -325,6 +326,8 @@ def test_maxpool_backward_with_recorded_argmax():
     bd = beta.cpu().double().requires_grad_(True)
     a = F.max_pool2d(F.relu(F.batch_norm(xd, None, None, gd, bd, training=True, eps=1e-5)), 3, 2, 1)
     g = torch.randn_like(a).float()
+    if not gf32:
+        g = bf16_round(g)
     a.backward(g.double())
     OH, OW = a.shape[2], a.shape[3]
     xm = to_mat(x)
@@ -339,13 +342,15 @@ def test_maxpool_backward_with_recorded_argmax():
     torch.cuda.synchronize()
     assert rel_l2(from_mat(y), a.detach()) < TOL_BF16
     gt = g.permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda()
+    if not gf32:
+        gt = gt.to(torch.bfloat16)
     sums = new_stats(C)
     dgam = torch.zeros(C, device="cuda")
     dbet = torch.zeros(C, device="cuda")
     bnb = ops.make_bn_bwd(sums, 0, B * H * W, gamma, beta, sm, si, dgam, dbet)
     dz = ops.new_mat(B, H, W, C)
     out = ops.new_mat(B, H, W, C)
-    d1 = ops.make_bn_bwd_args(xm, 0, C, gt.data_ptr(), C, bnb, out.ptr(), C, 0, gmode=2, g_is_f32=True)
+    d1 = ops.make_bn_bwd_args(xm, 0, C, gt.data_ptr(), C, bnb, out.ptr(), C, 0, gmode=2, g_is_f32=gf32)
     d1.argmax, d1.ldarg = amax.data_ptr(), C
     d1.dz_out, d1.lddz = dz.ptr().value, C
     d2 = ops.make_bn_bwd_args(xm, 0, C, dz.ptr(), C, bnb, out.ptr(), C, 0, gmode=0)
@@ -380,3 +385,87 @@ def test_dlogits_im2col():
         ref = dp[:, :, 2 * pad - kh:2 * pad - kh + H, 2 * pad - kw:2 * pad - kw + W]      # dl(y - (kh-pad), x - (kw-pad))
         assert torch.equal(got[:, t * C:(t + 1) * C], ref), t
     assert float(got[:, K * K * C:].abs().max()) == 0.0
+
+
+def test_dlogits_unfold_w():
+    """column kw*C + n = dlogits[n](y, x - (kw - K/2)): the operand that turns refine1's data gradient into a 5-tap vertical
+    convolution (Dense_U_Net_lidar.py:130-131 backward)."""
+    torch.manual_seed(53)
+    B, C, H, W, K = 2, 3, 7, 13, 5
+    dl = torch.randn(B, C, H, W)
+    ld = 16
+    out = ops.new_mat(B, H, W, ld)
+    import ctypes
+    from dmmfods_b200 import _lib
+    _lib.check(_lib.load().dmm_dlogits_unfold_w(ctypes.c_void_p(dl.cuda().data_ptr()), B, C, H, W, K, out.ptr(), ld, ops._stream()),
+               "dlogits_unfold_w")
+    torch.cuda.synchronize()
+    got = from_mat(out)
+    pad = K // 2
+    dp = F.pad(bf16_round(dl).double(), (pad, pad, 0, 0))
+    for kw in range(K):
+        ref = dp[:, :, :, 2 * pad - kw:2 * pad - kw + W]
+        assert torch.equal(got[:, kw * C:(kw + 1) * C], ref), kw
+    assert float(got[:, K * C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_dense_block_deferred_bn_backward(planar):
+    """dense-block backward algebra: every consumer i of a block buffer writes the slab A_i*dz_i and its sums
+    (dmm_bn_relu_bwd_contrib), dmm_bn_bwd_finalize turns the sums into the per-channel correction vectors, and
+    dmm_grad_gather forms sum_i slab_i - sum_i (k1_i + k2_i (x - mean)) for a channel range.  Must equal autograd through
+    sum_i <g_i, relu(bn_i(x[:, :C_i]))> (tv:47-50,96-104 backward) on the same bf16-rounded inputs."""
+    import ctypes as C
+    from dmmfods_b200 import _lib
+    lib = _lib.load()
+    B, H, W, Cbuf, gw = 2, 9, 11, 96, 32
+    consumers = [64, 96, 96]
+    c0, Cg = 32, 32
+    torch.manual_seed(5)
+    x = bf16_round(torch.randn(B, Cbuf, H, W) * 1.3 - 0.1)
+    xd = x.double().requires_grad_(True)
+    xm = to_mat(x)
+    P = B * H * W
+    v = x.double().permute(1, 0, 2, 3).reshape(Cbuf, -1)
+    mean = v.mean(1).float().cuda()
+    invstd = (1.0 / torch.sqrt(v.var(1, unbiased=False) + 1e-5)).float().cuda()
+    keep, loss = [], 0.0
+    g = _lib.GradGather()
+    refs = []
+    for i, Ci in enumerate(consumers):
+        gamma, beta, _, _, _, _ = _bn_setup(Ci, 40 + i)
+        gd = gamma.cpu().double().requires_grad_(True)
+        bd = beta.cpu().double().requires_grad_(True)
+        gi = bf16_round(torch.randn(B, Ci, H, W))
+        loss = loss + (F.relu(F.batch_norm(xd[:, :Ci], None, None, gd, bd, training=True, eps=1e-5)) * gi.double()).sum()
+        gm = to_mat(gi)
+        sums = new_stats(Ci)
+        dgam, dbet = torch.zeros(Ci, device="cuda"), torch.zeros(Ci, device="cuda")
+        bnb = ops.make_bn_bwd(sums, 0, P, gamma, beta, mean, invstd, dgam, dbet)
+        slab = torch.zeros(P * Ci, dtype=torch.bfloat16, device="cuda")
+        d = ops.make_bn_bwd_args(xm, 0, Ci, gm.ptr(), gm.ld, bnb, slab.data_ptr(), Ci, 0)
+        if planar:
+            d.out_gw, d.out_plane = gw, P * gw
+        _lib.check(lib.dmm_bn_relu_bwd_contrib(C.byref(d), None), "contrib")
+        kvec = torch.zeros(2 * Ci, device="cuda")
+        _lib.check(lib.dmm_bn_bwd_finalize(C.byref(bnb), Ci, C.c_void_p(kvec.data_ptr()), None), "finalize")
+        if planar:
+            g.src[i], g.ld[i], g.plane[i] = slab.data_ptr() + 2 * (c0 // gw) * P * gw, gw, P * gw
+        else:
+            g.src[i], g.ld[i], g.plane[i] = slab.data_ptr() + 2 * c0, Ci, 0
+        g.k1[i], g.k2[i] = kvec.data_ptr() + 4 * c0, kvec.data_ptr() + 4 * (Ci + c0)
+        keep += [gamma, beta, gm, sums, dgam, dbet, slab, kvec, bnb]
+        refs.append((dgam, dbet, gd, bd))
+    loss.backward()
+    g.gw = gw if planar else 0
+    g.nsrc = g.nk = len(consumers)
+    g.mean = mean.data_ptr() + 4 * c0
+    g.x, g.ldx = xm.ptr(c0).value, xm.ld
+    out = ops.new_mat(B, H, W, Cg, zero=True)
+    g.rows, g.C, g.out, g.ldo = P, Cg, out.ptr().value, out.ld
+    _lib.check(lib.dmm_grad_gather(C.byref(g), None), "gather")
+    torch.cuda.synchronize()
+    err = rel_l2(from_mat(out), xd.grad[:, c0:c0 + Cg])
+    assert err < 1e-2, "deferred BN backward relL2 %.3e" % err          # three bf16 slabs summed
+    for dgam, dbet, gd, bd in refs:
+        assert rel_l2(dgam.cpu(), gd.grad) < 1e-4 and rel_l2(dbet.cpu(), bd.grad) < 1e-4
