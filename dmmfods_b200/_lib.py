@@ -41,7 +41,7 @@ class Igemm(C.Structure):
                 ("stats_ld", c_int32), ("stats_off", c_int32),
                 ("bnb_x", c_void_p), ("bnb_ldx", c_int64), ("bnb_gamma", c_void_p), ("bnb_beta", c_void_p),
                 ("bnb_mean", c_void_p), ("bnb_invstd", c_void_p), ("bnb_sums", c_void_p), ("bnb_sums_ld", c_int32),
-                ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("pad2_", c_int32), ("pro_bn", Bn)]
+                ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("fold_kw", c_int32), ("pro_bn", Bn)]
 
 
 WG_MAX_A = 8

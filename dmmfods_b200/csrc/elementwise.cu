@@ -1612,7 +1612,8 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pac
         float v = 0.f;
         if (n < j.n_valid && c < j.C) {
             const int cdiv = j.cdiv > 0 ? j.cdiv : 1;
-            v = j.w[(long long)n * j.sn + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]];
+            const long long nidx = j.ndiv > 1 ? (long long)(n / j.ndiv) * j.sn + (long long)(n % j.ndiv) * j.sn2 : (long long)n * j.sn;
+            v = j.w[nidx + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]];
         }
         dst[i] = __float2bfloat16_rn(v);
     }

@@ -25,6 +25,7 @@ constexpr int kG2ThreadsPro = 448;       // + warps 10..13 = BN-ReLU prologue te
 constexpr int kMaxSub = 4;
 constexpr int kG2MaxSmem = 232448;
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
+constexpr uint32_t kFoldPitch = 80;      // out_mode 2: fp32 staging row of 16 accumulator columns, padded to 20 words (bank spread)
 
 struct Ig2Params {
     CUtensorMap a_maps[DMM_MAX_SRC];
@@ -51,6 +52,10 @@ struct Ig2Params {
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
     int Wv, Hv;
+    int x_step, x_org;             // tile column origin = tx * x_step + x_org (out_mode 2: tiles overlap by fold_kw - 1 columns)
+    int nsx;                       // sub-tiles per tile row
+    int fold_kw, fold_c;           // out_mode 2: kernel width folded into N, classes (<= 4)
+    int tw_log, sw_log, sh_log;    // out_mode 2: log2 of TW, sub_w, sub_h
     long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
     float* out32;
     int OH, OW, out_sy, out_sx, out_py, out_px;
@@ -93,7 +98,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t
     t /= p.tiles_x;
     const int ty = (int)(t % p.tiles_y);
     c.b = (int)(t / p.tiles_y);
-    c.x0 = tx * p.TW;
+    c.x0 = tx * p.x_step + p.x_org;
     c.y0 = ty * p.TH;
     c.n0 = nt * p.n_tile;
     return c;
@@ -106,7 +111,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * kStageSlot : 0);          // bnb: one x tile per epilogue team
+    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
     uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
@@ -366,6 +371,52 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             mbar_wait(&acc_full[as], accph);
             w_full += clock64() - c0;
             tc_fence_after();
+            if (OUT_MODE == 2) {
+                // kernel columns folded into N: stage the fp32 accumulators of the whole tile, then every output pixel sums its
+                // fold_kw horizontal neighbours (column kw*C + n of the pixel kw - fold_kw/2 to its right)
+                const uint32_t stg_u = smem_u32(stg);
+                asm volatile("bar.sync 3, 256;" ::: "memory");       // the previous tile has been read out
+                for (int sub = team; sub < MSUB; sub += 2) {
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * MSUB + sub) * p.n_tile;
+                    uint32_t v[16];
+                    tmem_ld16(trow, v);
+                    tmem_ld_wait();
+                    const uint32_t dst = stg_u + (uint32_t)(sub * 128 + r) * kFoldPitch;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) sts_v4(dst + 16 * g, make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                // thread e owns tile column e % TW (TW, sub_w, sub_h are powers of two: shifts only) and walks down the rows
+                const int e = (warp - 2) * 32 + lane;
+                const int K = p.fold_kw, C = p.fold_c, TWo = p.TW - (K - 1);
+                const int xo = e & (p.TW - 1);
+                const int x = tc.x0 + (K >> 1) + xo;
+                const long long plane = (long long)p.OH * p.OW;
+                if (xo < TWo && x < p.W) {
+                    for (int yy = e >> p.tw_log; yy < p.TH; yy += 256 >> p.tw_log) {
+                        const int y = tc.y0 + yy;
+                        if (y >= p.H) break;
+                        const int base = (((yy >> p.sh_log) * p.nsx) << 7) + ((yy & (p.sub_h - 1)) << p.sw_log);
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int kw = 0; kw < K; ++kw) {
+                            const int xt = xo + kw;
+                            const uint32_t src = stg_u + (uint32_t)(base + ((xt >> p.sw_log) << 7) + (xt & (p.sub_w - 1))) * kFoldPitch +
+                                                 (uint32_t)(kw * C) * 4u;
+#pragma unroll
+                            for (int n = 0; n < 4; ++n)
+                                if (n < C) acc[n] += __uint_as_float(lds_u32(src + 4u * n));
+                        }
+                        float* o = p.out32 + (long long)tc.b * C * plane + (long long)y * p.OW + x;
+#pragma unroll
+                        for (int n = 0; n < 4; ++n)
+                            if (n < C) o[n * plane] = acc[n];
+                    }
+                }
+                continue;
+            }
             for (int sub = 0; sub < MSUB; ++sub) {
                 const int x = tc.x0 + p.sub_x[sub] + px, y = tc.y0 + p.sub_y[sub] + py;
                 const bool valid = (x < p.Wv) && (y < p.Hv);
@@ -545,6 +596,15 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     const int tpk = d->kwidth == 16 ? 4 : 1;       // kwidth 16: sources of <= 16 channels, weights packed [n][tap*16 + c]
     DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
     DMM_CHECK(d->out_mode == 0 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
+    const bool fold = d->out_mode == 2;
+    if (fold) {
+        DMM_CHECK(d->fold_kw >= 1 && (d->fold_kw & 1) && d->N % d->fold_kw == 0 && d->kwidth == 64 && d->num_src == 1,
+                  "igemm v2: out_mode 2 needs an odd fold_kw dividing N, one source, kwidth 64");
+        DMM_CHECK(d->out_sy <= 1 && d->out_sx <= 1 && d->out_py == 0 && d->out_px == 0 && (d->OH <= 0 || d->OH == d->H) && (d->OW <= 0 || d->OW == d->W),
+                  "igemm v2: out_mode 2: no output stride / phase");
+        for (int t = 0; t < d->num_taps; ++t) DMM_CHECK(d->tap_dx[t] == 0, "igemm v2: out_mode 2: taps must be kernel rows (dx == 0)");
+        DMM_CHECK(d->tile_w > d->fold_kw - 1, "igemm v2: out_mode 2: tile_w %d too narrow", d->tile_w);
+    }
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -639,7 +699,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
                   "igemm v2: prologue BatchNorm without statistics");
         pro_kp = ceil_div(d->src[0].C, 64) * 64;
     }
-    const int staging = (d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : 0) + (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
+    const int staging = (d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0)) +
+                        (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
@@ -683,7 +744,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             if (max_taps == 1 && b_stage_c <= 16384 && rest / b_stage_c >= 6) c.sb = 6;
             int sa = (avail - c.sb * b_stage_c) / (int)c.a_stage;
             c.sa = sa > 4 ? 4 : sa;
-            c.tiles = (long long)ceil_div(d->W, c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
+            c.tiles = (long long)ceil_div(d->W, fold ? c.TW - (d->fold_kw - 1) : c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
             // crude per-tile time (cycles): L2 -> smem bytes at 32 B/cycle/SM vs MMA time + stage hand-overs
             const double l2 = (double)nkb_total * pw * ph * 128.0 / 32.0;
             double wbytes = 0, waits = 0;
@@ -705,7 +766,19 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.sa = best.sa; p.sb = best.sb;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
-    p.tiles_x = ceil_div(d->W, p.TW);
+    p.x_step = fold ? p.TW - (d->fold_kw - 1) : p.TW;
+    p.x_org = fold ? -(d->fold_kw / 2) : 0;
+    p.nsx = best.nsx;
+    p.fold_kw = fold ? d->fold_kw : 0;
+    p.fold_c = fold ? d->N / d->fold_kw : 0;
+    if (fold) {
+        DMM_CHECK(p.fold_c <= 4 && best.nsx == 1, "igemm v2: out_mode 2 supports at most 4 classes (got %d)", p.fold_c);
+        auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+        p.tw_log = ilog2(p.TW); p.sw_log = ilog2(p.sub_w); p.sh_log = ilog2(p.sub_h);
+        DMM_CHECK((1 << p.tw_log) == p.TW && (1 << p.sw_log) == p.sub_w && (1 << p.sh_log) == p.sub_h && p.TW <= 256,
+                  "igemm v2: out_mode 2 needs power-of-two tiles");
+    }
+    p.tiles_x = ceil_div(d->W, p.x_step);
     p.tiles_y = ceil_div(d->H, p.TH);
     p.tiles_n = tiles_n;
     p.total_tiles = best.tiles;
@@ -802,7 +875,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         else if (nch == 3) fn = igemm2_kernel<3, 0, 1, PROFLAG>;                                                                           \
         else fn = igemm2_kernel<4, 0, 1, PROFLAG>;                                                                                         \
     } while (0)
-    if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
+    if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, false> : igemm2_kernel<1, 2, 1, false>);
+    else if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
     else if (pro) DMM_IG2_PICK(true);
     else DMM_IG2_PICK(false);
 #undef DMM_IG2_PICK

@@ -241,25 +241,31 @@ class Engine:
         lst.append(Op(fn, arg, name, gbuf, kind, flops, nbytes))
 
     def _conv_fwd(self, lst, name, wname, srcs, taps, tap_off, Cin, Cout, sn, sc, W, H, B, out, coff, stats, stats_off,
-                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None):
-        """emit pack job + igemm launch for a forward convolution (or one ConvTranspose phase)."""
+                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None, fold_kw=0, tile_w=None):
+        """emit pack job + igemm launch for a forward convolution (or one ConvTranspose phase).
+        fold_kw (out_mode 2): `taps` / `tap_off` are the kernel ROWS; the kernel columns are folded into the GEMM's N (packed
+        weight row kw*Cout + n)."""
         T = len(taps)
         Kp = ceil_to(Cin, ops.KWIDTH)
-        n_tile = ops.pick_n_tile(Cout)
-        n_rows = ceil_to(Cout, n_tile)
+        N = Cout * fold_kw if fold_kw else Cout
+        n_tile = ops.pick_n_tile(N)
+        n_rows = ceil_to(N, n_tile)
         if not self.training:
             stats = None
         wid = self._req_wpk(n_rows, T * Kp)
-        self._pack_jobs.append(dict(w=self.p[wname], wid=wid, n_valid=Cout, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off,
-                                    sn=sn, sc=sc))
-        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, Cout,
+        job = dict(w=self.p[wname], wid=wid, n_valid=N, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off, sn=sn, sc=sc)
+        if fold_kw:
+            job.update(ndiv=Cout, sn=1, sn2=sn)        # row kw*Cout + n <- w[n, :, kh, kw]
+        self._pack_jobs.append(job)
+        d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, N,
                            out_ptr if out_ptr is not None else out.ptr(), 0 if out is None else out.ld, coff=coff,
                            out_mode=out_mode, stats=stats, stats_off=stats_off, out_stride=out_stride,
-                           out_phase=out_phase, out_hw=out_hw, n_tile=n_tile)
+                           out_phase=out_phase, out_hw=out_hw, n_tile=n_tile, fold_kw=fold_kw, tile_w=tile_w)
         P = B * H * W
-        osz = 4 if out_mode == 1 else 2
-        self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_fprop", flops=2.0 * P * Cout * Cin * T,
-                   nbytes=P * (Cin * 2 + Cout * osz) + Cout * Cin * T * 2)
+        osz = 4 if out_mode else 2
+        kk = fold_kw if fold_kw else 1
+        self._emit(lst, self.lib.dmm_conv_igemm, d, name, kind="igemm_fprop", flops=2.0 * P * Cout * Cin * T * kk,
+                   nbytes=P * (Cin * 2 + Cout * osz) + Cout * Cin * T * kk * 2)
         self._fix_w.append((d, wid))
         return d
 
@@ -759,8 +765,14 @@ class Engine:
         a1h = self._mat(B, H, W, nf2)
         self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
         conv5 = ops.conv_taps(5, 2)
-        self._conv_fwd(fwd, hp + ".refine1", hp + ".refine1.weight", [a1h.view()], conv5[0], conv5[2], nf2, self.ncls, nf2 * 25,
-                       25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
+        if 5 * self.ncls <= 16 and os.environ.get("DMM_HEAD_FOLD", "1") != "0":
+            # kernel columns folded into N: 5 (kernel rows) instead of 25 MMAs per pixel tile, horizontal sum in the epilogue
+            self._conv_fwd(fwd, hp + ".refine1", hp + ".refine1.weight", [a1h.view()], [(0, kh - 2, 0) for kh in range(5)],
+                           [5 * kh for kh in range(5)], nf2, self.ncls, nf2 * 25, 25, W, H, B, None, 0, None, 0, out_mode=2,
+                           out_ptr=self.logits.data_ptr(), fold_kw=5, tile_w=32 if W >= 28 else (16 if W >= 12 else 8))
+        else:
+            self._conv_fwd(fwd, hp + ".refine1", hp + ".refine1.weight", [a1h.view()], conv5[0], conv5[2], nf2, self.ncls, nf2 * 25,
+                           25, W, H, B, None, 0, None, 0, out_mode=1, out_ptr=self.logits.data_ptr())
         if self.need_backward:
             st = []
             # d(logits) as a pixel-major bf16 matrix.  With 5 * num_classes <= 16 the five HORIZONTAL shifts of every class
@@ -844,6 +856,7 @@ class Engine:
             pj[i]["tap_off"][:j["T"]] = j["tap_off"]
             pj[i]["sn"], pj[i]["sc"] = j["sn"], j["sc"]
             pj[i]["sc2"], pj[i]["cdiv"] = j.get("sc2", 0), j.get("cdiv", 0)
+            pj[i]["sn2"], pj[i]["ndiv"] = j.get("sn2", 0), j.get("ndiv", 0)
         self._pack_tab = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
         self._n_pack = len(self._pack_jobs)
         self._param_ptrs = [j["w"].data_ptr() for j in self._pack_jobs]
@@ -1049,7 +1062,7 @@ class Engine:
 
 _PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32), ("n_rows", np.int32), ("C", np.int32),
                      ("kwidth", np.int32), ("T", np.int32), ("tap_off", np.int32, (32,)), ("sn", np.int64),
-                     ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("pad_", np.int32)], align=True)
+                     ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("ndiv", np.int32), ("sn2", np.int64)], align=True)
 _UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("dt", np.int64), ("dm", np.int64), ("dn", np.int64),
                        ("M", np.int32), ("N", np.int32), ("T", np.int32), ("accumulate", np.int32),
                        ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64)], align=True)

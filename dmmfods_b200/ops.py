@@ -180,8 +180,9 @@ def convt_wgrad_taps():
 # ------------------------------------------------------------------------------------------------
 def make_igemm(srcs, taps, weights, ktot, n_rows, W, H, B, N, out_ptr, ldo, coff=0, out_mode=0, stats=None,
                stats_off=0, out_stride=(1, 1), out_phase=(0, 0), out_hw=None, n_tile=None, tile_w=None,
-               kwidth=KWIDTH):
+               kwidth=KWIDTH, fold_kw=0):
     d = Igemm()
+    d.fold_kw = fold_kw
     assert 1 <= len(srcs) <= MAX_SRC and 1 <= len(taps) <= MAX_TAPS
     for i, v in enumerate(srcs):
         d.src[i] = v

@@ -74,6 +74,10 @@ typedef struct {
  * 5x5 (:130-131), 7x7/s2 via im2col (:73-74,157-158), the 4 sub-pixel phases of
  * nn.ConvTranspose2d(C,C,3,stride=2,padding=1) (:117-118) and the data-gradients of all of them.
  * out_mode 0: bf16 NHWC rows of pitch ldo.   out_mode 1: fp32 NCHW (B, n_valid, OH, OW).
+ * out_mode 2: fp32 NCHW (B, N / fold_kw, H, W) of a fold_kw-wide convolution with few output channels whose KERNEL COLUMNS are
+ *   folded into the GEMM's N: the taps are the kernel ROWS only (dx == 0), weight row kw*C + n holds w[n, :, kh, kw]
+ *   (C = N / fold_kw classes, N <= 16), and the epilogue forms out[n](y, x) = sum_kw acc[(y, x + kw - fold_kw/2)][kw*C + n]
+ *   from tiles that overlap by fold_kw - 1 columns.  K*K -> K MMAs per tile for the 5x5, 64 -> 3 head convolution (:130-131).
  * stats (nullable): double[DMM_STATS_SLOTS][2][stats_ld], column sums / sums of squares of the
  * bf16-rounded outputs are atomically added at [.., stats_off + n]. */
 typedef struct {
@@ -115,7 +119,7 @@ typedef struct {
      * activated tensor).  pro_bn describes the BatchNorm over the src[0].C channels exactly like dmm_bn_relu_apply (CTA 0 also
      * saves mean / invstd and updates the running statistics). */
     int32_t pro_enable;
-    int32_t pad2_;
+    int32_t fold_kw;         /* out_mode 2: kernel width folded into N (odd); else 0 */
     dmm_bn_t pro_bn;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
@@ -188,10 +192,11 @@ typedef struct {
     void* dst;
     int32_t n_valid, n_rows, C, kwidth, T;
     int32_t tap_off[DMM_MAX_TAPS];
-    int64_t sn, sc;          /* source element of (n, c, t): w[n*sn + (c / cdiv)*sc + (c % cdiv)*sc2 + tap_off[t]] */
+    int64_t sn, sc;          /* source element of (n, c, t): w[nidx + (c / cdiv)*sc + (c % cdiv)*sc2 + tap_off[t]] */
     int64_t sc2;
     int32_t cdiv;            /* 0 or 1: plain channel index */
-    int32_t pad_;
+    int32_t ndiv;            /* 0 or 1: nidx = n*sn; else nidx = (n / ndiv)*sn + (n % ndiv)*sn2 (kernel columns folded into n) */
+    int64_t sn2;
 } dmm_pack_job_t;
 typedef struct {
     const float* dw;

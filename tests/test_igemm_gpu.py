@@ -93,6 +93,29 @@ def test_conv5x5_logits_fp32_nchw():
     assert err < 1e-5, "5x5 fp32 logits relL2 %.3e" % err    # fp32 accumulate of bf16 products, fp32 store
 
 
+@pytest.mark.parametrize("H,W,tile_w", [(16, 24, 16), (40, 70, 32), (9, 13, 8), (33, 64, 32), (20, 28, 32)])
+def test_conv5x5_logits_folded_kernel_columns(H, W, tile_w):
+    """out_mode 2: the five kernel columns ride in the GEMM's N (weight row kw*C + n), five kernel-row taps, the epilogue sums
+    the horizontal neighbours; tiles overlap by four columns.  Same result as the 25-tap launch (Dense_U_Net_lidar.py:130-131)."""
+    torch.manual_seed(4)
+    B, Cin, Cout = 2, 64, 3
+    x = bf16_round(torch.randn(B, Cin, H, W))
+    w = bf16_round(torch.randn(Cout, Cin, 5, 5) / 40.0)
+    ref = F.conv2d(x.double(), w.double(), padding=2)
+    a = to_mat(x)
+    wp = torch.zeros(16, 5 * Cin, dtype=torch.bfloat16)
+    wp[:15] = w.permute(3, 0, 2, 1).reshape(15, 5 * Cin).to(torch.bfloat16)      # (kw, n) x (kh, ci)
+    wp = wp.cuda()
+    out = torch.full((B, Cout, H, W), float("nan"), dtype=torch.float32, device="cuda")
+    taps = [(0, kh - 2, 0) for kh in range(5)]
+    d = ops.make_igemm([a.view()], taps, wp, 5 * Cin, 16, W, H, B, 15, out.data_ptr(), 0, out_mode=2, fold_kw=5, tile_w=tile_w)
+    ops.run_igemm(d)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all()), "folded 5x5: output pixels left unwritten"
+    err = rel_l2(out.cpu(), ref)
+    assert err < 1e-5, "folded 5x5 fp32 logits relL2 %.3e" % err
+
+
 @pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (256, 5, 7, 10, 14), (128, 5, 7, 9, 13), (64, 4, 4, 8, 7)])
 def test_conv_transpose_phases(C, H, W, OH, OW):
     """nn.ConvTranspose2d(C, C, 3, stride=2, padding=1)(x, output_size=(OH, OW)) as 4 sub-pixel GEMMs."""
