@@ -1627,7 +1627,8 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unp
         const int m = (int)(r % j.M);
         const int t = (int)(r / j.M);
         const float v = j.dw[(long long)t * j.dt + (long long)m * j.dm + (long long)n * j.dn];
-        float* gp = j.grad + (long long)n * j.sn + (long long)m * j.sc + j.tap_off[t];
+        const long long nidx = j.ndiv > 1 ? (long long)(n % j.ndiv) * j.sn + (long long)(n / j.ndiv) * j.sn2 : (long long)n * j.sn;
+        float* gp = j.grad + nidx + (long long)m * j.sc + j.tap_off[t];
         *gp = j.accumulate ? *gp + v : v;
     }
 }
@@ -2006,11 +2007,54 @@ extern "C" int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, in
     return 0;
 }
 
+namespace dmm {
+// one thread per pixel: K*C (<= 16) gathered values -> one 32-byte row; neighbouring threads read neighbouring x (coalesced,
+// the K shifted reads of a plane row hit L1)
+__global__ void __launch_bounds__(256) dlogits_unfold_w16_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int K,
+                                                                 __nv_bfloat16* __restrict__ out) {
+    const long long total = (long long)B * H * W;
+    const long long HW = (long long)H * W;
+    const int pad = K / 2;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(pix % W);
+        const long long t = pix / W;                     // b * H + y
+        const long long b = t / H;
+        const float* row = dl + b * C * HW + (t - b * H) * W;      // class 0, this image row
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+#pragma unroll
+        for (int kw = 0; kw < 5; ++kw) {
+            if (kw < K) {
+                const int xx = x - (kw - pad);
+                if (xx >= 0 && xx < W) {
+#pragma unroll
+                    for (int n = 0; n < 3; ++n)
+                        if (n < C && kw * C + n < 16) f[kw * C + n] = __ldg(row + n * HW + xx);
+                }
+            }
+        }
+        float lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { lo[j] = f[j]; hi[j] = f[8 + j]; }
+        uint4* o = reinterpret_cast<uint4*>(out + pix * 16);
+        o[0] = pack8(lo);
+        o[1] = pack8(hi);
+    }
+}
+}  // namespace dmm
+
 extern "C" int dmm_dlogits_unfold_w(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
                                     int64_t ld, void* stream) {
     DMM_CHECK(dlogits && out && C > 0 && K >= 1 && (K & 1) && ld % 8 == 0 && ld >= (int64_t)K * C,
               "dmm_dlogits_unfold_w: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
+    if (ld == 16 && K <= 5 && C <= 3) {
+        dlogits_unfold_w16_kernel<<<flat_grid((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+            dlogits, B, C, H, W, K, reinterpret_cast<__nv_bfloat16*>(out));
+        DMM_LAUNCH_CHECK("dlogits_unfold_w16_kernel");
+        return 0;
+    }
     const long long total = (long long)B * H * W * (ld / 8);
     dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, 1, K,
                                                                                   reinterpret_cast<__nv_bfloat16*>(out), (int)ld);

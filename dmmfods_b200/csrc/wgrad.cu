@@ -427,14 +427,22 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         for (int g = 0; g < d->num_b; ++g)
             p.b_goff[g] = (uint32_t)((d->b[g].dy - mindy) * pw + (d->b[g].dx - mindx)) * row_bytes;
         b_part = p.fam_bytes;
-        // merge runs of groups one pixel apart in x (same dy) that are n_tile columns apart in dw
+        // merge runs of groups one pixel apart in x (same dy) - or one patch row apart in y (same dx) - that are n_tile columns
+        // apart in dw: one MMA of N = count * n_tile whose atom stride (LBO) is one pixel / one patch row
         int nsg = 0;
         for (int g = 0; g < d->num_b;) {
             int c = 1;
             while (g + c < d->num_b && (c + 1) * d->n_tile <= 256 && d->b[g + c].dy == d->b[g].dy && d->b[g + c].dx == d->b[g].dx + c &&
                    d->b[g + c].out0 == d->b[g].out0 + c * d->n_tile)
                 ++c;
-            p.sg_first[nsg] = g; p.sg_count[nsg] = c; p.sg_lbo[nsg] = row_bytes;
+            uint32_t lbo = row_bytes;
+            if (c == 1) {
+                while (g + c < d->num_b && (c + 1) * d->n_tile <= 256 && d->b[g + c].dx == d->b[g].dx && d->b[g + c].dy == d->b[g].dy + c &&
+                       d->b[g + c].out0 == d->b[g].out0 + c * d->n_tile)
+                    ++c;
+                if (c > 1) lbo = (uint32_t)pw * row_bytes;
+            }
+            p.sg_first[nsg] = g; p.sg_count[nsg] = c; p.sg_lbo[nsg] = lbo;
             ++nsg;
             g += c;
         }

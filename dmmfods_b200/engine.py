@@ -290,7 +290,7 @@ class Engine:
         lst[-1].heavy = (T * ceil_to(Cg, 64) >= 512) if heavy is None else heavy
         return lst[-1]
 
-    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None, n_off=0):
+    def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None, n_off=0, ndiv=0, sn2=0):
         """weight gradient: wgrad launches into a zeroed fp32 scratch matrix + unpack job into the flat gradient
         buffer.  x: View with M channels, ys: Views with N channels, taps: (ysrc, dy, dx) applied to x.
         pro (_BNInfo): x is the RAW input of that BatchNorm; relu(bn(x)) is applied to the operand tiles on the fly."""
@@ -310,7 +310,7 @@ class Engine:
                        flops=2.0 * P * Mvalid * Nvalid * T / nl, nbytes=(P * (M * 2 + N * 2 * len(ys)) + T * M * N * 4) / nl)
             self._fix_dw.append((d, did))
         self._unpack_jobs.append(dict(wname=wname, did=did, grad=self.grad[wname], dt=plan["dt"], dm=plan["dm"], dn=plan["dn"], M=Mvalid,
-                                      N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst), dw_off=n_off * plan["dn"]))
+                                      N=Nvalid, T=T, tap_off=tap_off, sn=sn, sc=sc, stage=id(lst), dw_off=n_off * plan["dn"], ndiv=ndiv, sn2=sn2))
         self._stage_params.setdefault(id(lst), []).append(wname)
 
     def _conv_wgrad_tail(self, lst, name, wname, xtail, c_off, r, y, taps, tap_off, N, Nvalid, sn, sc, W, H, B):
@@ -791,8 +791,15 @@ class Engine:
             da0 = self._tmpmat("head_da0", B, H, W, ld0)
             # refine1 (5x5, 64 -> num_classes): weight gradient = activation x 25 shifted views of d(logits) (one halo patch,
             # five wide MMAs per k-step); data gradient = a 25-tap convolution over the 16-channel d(logits) matrix
-            self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)], conv5[0], conv5[2],
-                             nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B, n_off=2 * self.ncls if unfold else 0)
+            if unfold:
+                # dW[n, ci, kh, kw] = sum_p a1h(p + (kh - 2, 0))[ci] * dl(p)[kw*ncls + n]: five kernel-row taps, the kernel columns
+                # ride in the 16 gradient columns (one N = 80 MMA per k-step instead of five)
+                self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)],
+                                 [(0, kh - 2, 0) for kh in range(5)], [5 * kh for kh in range(5)], nf2, 16, nf2, 5 * self.ncls,
+                                 nf2 * 25, 25, W, H, B, ndiv=self.ncls, sn2=1)
+            else:
+                self._conv_wgrad(st, hp + ".refine1.wgrad", hp + ".refine1.weight", a1h.view(), [dl.view(0, 16)], conv5[0], conv5[2],
+                                 nf2, 16, nf2, self.ncls, nf2 * 25, 25, W, H, B)
             if unfold:
                 # packed weight column (tap kh, channel c = kw*ncls + n) <- w[n, ci, kh, kw]
                 dgh = self._conv_dgrad(st, hp + ".refine1.dgrad", hp + ".refine1.weight", [dl.view(0, 16)],
@@ -885,6 +892,7 @@ class Engine:
             uj[i]["accumulate"] = 0
             uj[i]["tap_off"][:j["T"]] = j["tap_off"]
             uj[i]["sn"], uj[i]["sc"] = j["sn"], j["sc"]
+            uj[i]["sn2"], uj[i]["ndiv"] = j.get("sn2", 0), j.get("ndiv", 0)
         self._unpack_tab = torch.from_numpy(uj.view(np.uint8).copy()).to(dev)
         self._n_unpack = len(self._unpack_jobs)
         self.bwd = []
@@ -1065,4 +1073,5 @@ _PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32)
                      ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("ndiv", np.int32), ("sn2", np.int64)], align=True)
 _UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("dt", np.int64), ("dm", np.int64), ("dn", np.int64),
                        ("M", np.int32), ("N", np.int32), ("T", np.int32), ("accumulate", np.int32),
-                       ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64)], align=True)
+                       ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64), ("sn2", np.int64), ("ndiv", np.int32),
+                       ("pad_", np.int32)], align=True)

@@ -205,6 +205,9 @@ typedef struct {
     int32_t M, N, T, accumulate;
     int32_t tap_off[DMM_MAX_TAPS];
     int64_t sn, sc;
+    int64_t sn2;             /* ndiv > 1: the n-part of the address is (n % ndiv)*sn + (n / ndiv)*sn2 (kernel columns folded into n) */
+    int32_t ndiv;
+    int32_t pad_;
 } dmm_unpack_job_t;
 int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream);
 int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream);

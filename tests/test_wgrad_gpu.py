@@ -64,6 +64,36 @@ def test_wgrad_5x5_three_classes():
     _conv_wgrad_case(2, 64, 3, 12, 16, 5, seed=24)
 
 
+@pytest.mark.parametrize("H,W", [(12, 16), (33, 41), (64, 96)])
+def test_wgrad_5x5_three_classes_unfolded_columns(H, W):
+    """refine1 through the horizontally unfolded d(logits) (dmm_dlogits_unfold_w): five kernel-row taps merged into ONE
+    N = 80 MMA per k-step (vertical family, atom stride = one patch row); gradient column kw*C + n -> dW[n, :, kh, kw]."""
+    import ctypes
+    from dmmfods_b200 import _lib
+    torch.manual_seed(29)
+    B, Cin, Cout, K = 2, 64, 3, 5
+    x = bf16_round(torch.randn(B, Cin, H, W))
+    g = torch.randn(B, Cout, H, W)
+    w = torch.zeros(Cout, Cin, K, K, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, padding=2).backward(bf16_round(g).double())
+    xm = to_mat(x)
+    gl = ops.new_mat(B, H, W, 16)
+    _lib.check(_lib.load().dmm_dlogits_unfold_w(ctypes.c_void_p(g.cuda().data_ptr()), B, Cout, H, W, K, gl.ptr(), 16, ops._stream()),
+               "unfold")
+    taps = [(0, kh - 2, 0) for kh in range(K)]
+    plan, dw = _run_plan(xm.view(0, Cin), [gl.view(0, 16)], taps, Cin, 16, W, H, B)
+    assert len(plan["launches"]) == 1
+    grad = torch.full((Cout, Cin, K, K), float("nan"), dtype=torch.float32, device="cuda")
+    dwv = dw.view(-1)
+    for i, t in enumerate(plan["tap_order"]):            # (tap, m, n) -> dW[n % C, m, kh, n // C]
+        kh = t
+        blk = torch.stack([dwv[i * plan["dt"] + torch.arange(Cin, device="cuda") * plan["dm"] + n * plan["dn"]] for n in range(K * Cout)], 1)
+        grad[:, :, kh, :] = blk.view(Cin, K, Cout).permute(2, 0, 1)
+    torch.cuda.synchronize()
+    err = rel_l2(grad.cpu(), w.grad)
+    assert err < TOL, "unfolded 5x5 wgrad relL2 %.3e" % err
+
+
 def test_wgrad_many_tiles_split():
     _conv_wgrad_case(4, 256, 128, 64, 96, 1, seed=25, splits=0)
     _conv_wgrad_case(4, 128, 32, 32, 48, 3, seed=26, splits=7)
