@@ -20,8 +20,8 @@
 
 namespace dmm {
 
-constexpr int kG2Threads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps
-constexpr int kG2ThreadsPro = 448;       // + warps 10..13 = BN-ReLU prologue team (PRO instantiations)
+constexpr int kG2Threads = 352;          // warp 0 weight TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps, warp 10 patch TMA
+constexpr int kG2ThreadsPro = 480;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA (PRO instantiations)
 constexpr int kMaxSub = 4;
 constexpr int kG2MaxSmem = 232448;
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 
     if (warp == 0) {
         // ================= TMA producer =================
+        // ================= weight (B) TMA producer; the halo patches (A) have their own producer warp so that the next
+        // patch is requested the moment its stage frees up instead of after the current block's weight stages =================
         if (lane == 0) {
-            int ast = 0, bst = 0;
-            uint32_t aph = 0, bph = 0;
+            int bst = 0;
+            uint32_t bph = 0;
             long long w_a = 0, w_b = 0;
             const long long t_begin = clock64();
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -188,13 +190,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
                     if (t0 == t1) continue;
                     for (int cb = 0; cb < nblk; ++cb) {
-                        long long c0 = clock64();
-                        mbar_wait(&a_empty[ast], aph ^ 1);
-                        w_a += clock64() - c0;
-                        mbar_arrive_expect_tx(&a_full[ast], p.src_tx[s]);
-                        tma_load_4d(a_ring + (size_t)ast * p.a_stage, &p.a_maps[s], &a_full[ast], cb * 64, tc.x0 + p.src_ox[s],
-                                    tc.y0 + p.src_oy[s], tc.b);
-                        if (++ast == p.sa) { ast = 0; aph ^= 1; }
+                        long long c0;
                         for (int t = t0; t < t1; t += p.tps) {
                             const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
                             c0 = clock64();
@@ -214,6 +210,26 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 p.prof[blockIdx.x * 16 + 0] = clock64() - t_begin;
                 p.prof[blockIdx.x * 16 + 1] = w_a;
                 p.prof[blockIdx.x * 16 + 2] = w_b;
+            }
+        }
+    } else if (warp == (PRO ? 14 : 10)) {
+        // ================= halo-patch (A) TMA producer =================
+        if (lane == 0) {
+            int ast = 0;
+            uint32_t aph = 0;
+            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                for (int s = 0; s < p.num_src; ++s) {
+                    if (p.src_tap0[s] == p.src_tap0[s + 1]) continue;
+                    const int nblk = p.src_nblk[s];
+                    for (int cb = 0; cb < nblk; ++cb) {
+                        mbar_wait(&a_empty[ast], aph ^ 1);
+                        mbar_arrive_expect_tx(&a_full[ast], p.src_tx[s]);
+                        tma_load_4d(a_ring + (size_t)ast * p.a_stage, &p.a_maps[s], &a_full[ast], cb * 64, tc.x0 + p.src_ox[s],
+                                    tc.y0 + p.src_oy[s], tc.b);
+                        if (++ast == p.sa) { ast = 0; aph ^= 1; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
