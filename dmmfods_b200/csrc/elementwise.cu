@@ -1123,16 +1123,24 @@ __global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restri
         }
         koff[k] = o;
     }
-    for (int i = threadIdx.x; i < C * 7 * PW; i += blockDim.x) {
-        const int px = i % PW;
-        const int r = i / PW;
-        const int kh = r % 7, ci = r / 7;
-        const int iy = iy0 + kh, ix = ix0 + px;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-            v = ci < C1 ? __ldg(x1 + (((long long)b * C1 + ci) * H + iy) * W + ix)
-                        : __ldg(x2 + (((long long)b * C2 + (ci - C1)) * H + iy) * W + ix);
-        patch[i] = v;
+    // one warp per patch row (channel, kernel row): five independent coalesced loads per lane, no divisions in the loop
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < C * 7; r += (int)(blockDim.x >> 5)) {
+            const int ci = r / 7, kh = r - ci * 7;
+            const int iy = iy0 + kh;
+            const bool yok = iy >= 0 && iy < H;
+            const float* src = ci < C1 ? x1 + (((long long)b * C1 + ci) * H + iy) * W : x2 + (((long long)b * C2 + (ci - C1)) * H + iy) * W;
+            float v[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int px = lane + 32 * u, ix = ix0 + px;
+                v[u] = (yok && px < PW && ix >= 0 && ix < W) ? __ldg(src + ix) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if (lane + 32 * u < PW) patch[r * PW + lane + 32 * u] = v[u];
+        }
     }
     __syncthreads();
     const int chunks = kpad >> 3;
@@ -1234,6 +1242,35 @@ __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) 
     for (int row = blockIdx.x; row < p.B * p.H; row += gridDim.x) {
     const int yy = row % p.H, b = row / p.H;
     // the raw network inputs of this row (fp32 NCHW planes) are staged in shared memory with coalesced loads, already activated
+    if (Cx <= 8 && (p.W & 3) == 0) {
+        // one float4 per plane and thread, all planes in flight at once (a scalar loop pays one memory round trip per element)
+        const int W4 = p.W >> 2;
+        for (int x4 = threadIdx.x; x4 < W4; x4 += blockDim.x) {
+            for (int c0 = 0; c0 < Cx; c0 += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + k;
+                    if (c < Cx) {
+                        const float* src = c < p.C1 ? p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W
+                                                    : p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + (long long)yy * p.W;
+                        v[k] = __ldg(reinterpret_cast<const float4*>(src) + x4);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + k;
+                    if (c < Cx) {
+                        const float sc_ = coef[p.Cu + c], sh_ = coef[Cpad + p.Cu + c];
+                        float4 o;
+                        o.x = fmaxf(fmaf(v[k].x, sc_, sh_), 0.f); o.y = fmaxf(fmaf(v[k].y, sc_, sh_), 0.f);
+                        o.z = fmaxf(fmaf(v[k].z, sc_, sh_), 0.f); o.w = fmaxf(fmaf(v[k].w, sc_, sh_), 0.f);
+                        *reinterpret_cast<float4*>(xs + c * p.W + 4 * x4) = o;
+                    }
+                }
+            }
+        }
+    } else
     for (int i = threadIdx.x; i < Cx * p.W; i += blockDim.x) {
         const int c = i / p.W, xx = i - c * p.W;
         const float v = c < p.C1 ? __ldg(p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W + xx)

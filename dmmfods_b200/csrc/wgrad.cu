@@ -517,6 +517,8 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
     const long long items = (long long)d->ya * d->yb;
     if (splits <= 0) {
         splits = num_sms / items;                         // one wave: every CTA is resident at once
+        static const int split_div = wg_env_int("DMM_WGRAD_SPLIT_DIV", 1);
+        if (split_div > 1) splits = splits / split_div > 0 ? splits / split_div : 1;
         const long long min_k = 8;                        // amortise prologue + reduce epilogue
         if (splits > p.total_tiles / min_k) splits = p.total_tiles / min_k;
     }

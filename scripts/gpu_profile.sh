@@ -15,4 +15,6 @@ python scripts/bench_wgrad.py b1_conv2 > gpurun_out/plain_wg.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 3 -c 1 -o gpurun_out/${TAG}_wgrad_b1conv2 python scripts/bench_wgrad.py b1_conv2 > gpurun_out/ncu_wg.log 2>&1
 $B > gpurun_out/plain_bench2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:bn_bwd_contrib -s 5 -c 1 -o gpurun_out/${TAG}_bn_bwd_contrib $B > gpurun_out/ncu_bn.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:head_input_kernel -c 1 -o gpurun_out/${TAG}_head_input $B > gpurun_out/ncu_head.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:grad_gather -s 3 -c 1 -o gpurun_out/${TAG}_grad_gather $B > gpurun_out/ncu_gather.log 2>&1
 ls -la gpurun_out/*.ncu-rep
