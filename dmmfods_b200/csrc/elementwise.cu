@@ -914,10 +914,18 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) grad_gather_kernel(const
         const int tid = threadIdx.y * cx + threadIdx.x;
         const int c = blockIdx.y * cx * 8 + tid;
         if (tid < cx * 8 && c < p.C) {
+            // eight consumers per batch: sixteen independent loads in flight (a plain loop is one memory round trip per consumer)
             float a = 0.f, b = 0.f;
-            for (int j = 0; j < p.nk; ++j) {
-                a += __ldg(p.k1[j] + c);
-                b += __ldg(p.k2[j] + c);
+            for (int j0 = 0; j0 < p.nk; j0 += 8) {
+                float va[8], vb[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = j0 + u < p.nk;
+                    va[u] = ok ? __ldg(p.k1[j0 + u] + c) : 0.f;
+                    vb[u] = ok ? __ldg(p.k2[j0 + u] + c) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a += va[u]; b += vb[u]; }
             }
             ks[0][tid] = a; ks[1][tid] = b; ks[2][tid] = p.nk ? __ldg(p.mean + c) : 0.f;
         }
@@ -1225,7 +1233,7 @@ __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) 
     const int Cx = p.C1 + p.C2;
     const int UH = p.H >> 1, UW = p.W >> 1;
     const long long HW = (long long)p.H * p.W;
-    float* xs = coef + 2 * Cpad;                     // [Cx][W]
+    float* xs = coef + 2 * Cpad;                     // [Cx][2 rows][W]
     // warps 0..6: thread t owns up-sampled chunk t % cu for pixels t / cu, t / cu + ppb, ... (no divisions in the loop);
     // warp 7 alone writes the chunks of the raw input channels, so that no warp runs both loops (divergence)
     const int nraw = chunks - cu;                    // raw-input chunks per pixel (1 for <= 8 raw channels)
@@ -1238,22 +1246,25 @@ __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) 
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = coef[ch * 8 + j]; sh[j] = coef[Cpad + ch * 8 + j]; }
-    // persistent over image rows: the BatchNorm coefficients are finalised once per block, not once per row
-    for (int row = blockIdx.x; row < p.B * p.H; row += gridDim.x) {
-    const int yy = row % p.H, b = row / p.H;
-    // the raw network inputs of this row (fp32 NCHW planes) are staged in shared memory with coalesced loads, already activated
+    // persistent over PAIRS of image rows (one row of the up-sampled source): the BatchNorm coefficients are finalised once
+    // per block, and one load + one activation of a source chunk feeds its 2x2 output pixels (four 16-byte stores)
+    for (int ur = blockIdx.x; ur < p.B * UH; ur += gridDim.x) {
+    const int uy = ur % UH, b = ur / UH;
+    // the raw network inputs of the two rows (fp32 NCHW planes) are staged in shared memory, already activated: xs[c][r][W]
     if (Cx <= 8 && (p.W & 3) == 0) {
-        // one float4 per plane and thread, all planes in flight at once (a scalar loop pays one memory round trip per element)
+        // one float4 per plane and thread, four planes in flight at once (a scalar loop pays one memory round trip per element)
         const int W4 = p.W >> 2;
-        for (int x4 = threadIdx.x; x4 < W4; x4 += blockDim.x) {
+        for (int i = threadIdx.x; i < 2 * W4; i += blockDim.x) {
+            const int r = i >= W4 ? 1 : 0, x4 = i - r * W4;
+            const long long rowoff = (long long)(2 * uy + r) * p.W;
             for (int c0 = 0; c0 < Cx; c0 += 4) {
                 float4 v[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int c = c0 + k;
                     if (c < Cx) {
-                        const float* src = c < p.C1 ? p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W
-                                                    : p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + (long long)yy * p.W;
+                        const float* src = c < p.C1 ? p.x1 + ((long long)b * p.C1 + c) * HW + rowoff
+                                                    : p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + rowoff;
                         v[k] = __ldg(reinterpret_cast<const float4*>(src) + x4);
                     }
                 }
@@ -1265,41 +1276,51 @@ __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) 
                         float4 o;
                         o.x = fmaxf(fmaf(v[k].x, sc_, sh_), 0.f); o.y = fmaxf(fmaf(v[k].y, sc_, sh_), 0.f);
                         o.z = fmaxf(fmaf(v[k].z, sc_, sh_), 0.f); o.w = fmaxf(fmaf(v[k].w, sc_, sh_), 0.f);
-                        *reinterpret_cast<float4*>(xs + c * p.W + 4 * x4) = o;
+                        *reinterpret_cast<float4*>(xs + (c * 2 + r) * p.W + 4 * x4) = o;
                     }
                 }
             }
         }
-    } else
-    for (int i = threadIdx.x; i < Cx * p.W; i += blockDim.x) {
-        const int c = i / p.W, xx = i - c * p.W;
-        const float v = c < p.C1 ? __ldg(p.x1 + ((long long)b * p.C1 + c) * HW + (long long)yy * p.W + xx)
-                                 : __ldg(p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + (long long)yy * p.W + xx);
-        xs[i] = fmaxf(fmaf(v, coef[p.Cu + c], coef[Cpad + p.Cu + c]), 0.f);
+    } else {
+        for (int i = threadIdx.x; i < Cx * 2 * p.W; i += blockDim.x) {
+            const int cr = i / p.W, xx = i - cr * p.W;
+            const int c = cr >> 1, r = cr & 1;
+            const long long off = (long long)(2 * uy + r) * p.W + xx;
+            const float v = c < p.C1 ? __ldg(p.x1 + ((long long)b * p.C1 + c) * HW + off)
+                                     : __ldg(p.x2 + ((long long)b * p.C2 + (c - p.C1)) * HW + off);
+            xs[i] = fmaxf(fmaf(v, coef[p.Cu + c], coef[Cpad + p.Cu + c]), 0.f);
+        }
     }
     __syncthreads();
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + yy) * p.W * p.ldo + ch * 8;
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + ((long long)b * p.H + 2 * uy) * p.W * p.ldo + ch * 8;
+    const long long rstep = (long long)p.W * p.ldo;          // next output row
     if (!worker) {
     } else if (ch < cu) {
-        const __nv_bfloat16* urow = reinterpret_cast<const __nv_bfloat16*>(p.u) + ((long long)b * UH + (yy >> 1)) * UW * p.ldu + ch * 8;
+        const __nv_bfloat16* urow = reinterpret_cast<const __nv_bfloat16*>(p.u) + ((long long)b * UH + uy) * UW * p.ldu + ch * 8;
 #pragma unroll 8
-        for (int xx = px0; xx < p.W; xx += ppb) {
+        for (int ux = px0; ux < UW; ux += ppb) {
             float f[8];
-            unpack8(ldg16(urow + (long long)(xx >> 1) * p.ldu), f);
+            unpack8(ldg16(urow + (long long)ux * p.ldu), f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-            *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
+            const uint4 v = pack8(f);
+            __nv_bfloat16* o = orow + (long long)(2 * ux) * p.ldo;
+            *reinterpret_cast<uint4*>(o) = v;
+            *reinterpret_cast<uint4*>(o + p.ldo) = v;
+            *reinterpret_cast<uint4*>(o + rstep) = v;
+            *reinterpret_cast<uint4*>(o + rstep + p.ldo) = v;
         }
     } else {
         const int c0 = ch * 8 - p.Cu;                // first raw-input channel of this chunk
-        for (int xx = px0; xx < p.W; xx += ppb) {
+        for (int i = px0; i < 2 * p.W; i += ppb) {
+            const int r = i >= p.W ? 1 : 0, xx = i - r * p.W;
             float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (c0 + j < Cx) ? xs[(c0 + j) * p.W + xx] : 0.f;
-            *reinterpret_cast<uint4*>(orow + (long long)xx * p.ldo) = pack8(f);
+            for (int j = 0; j < 8; ++j) f[j] = (c0 + j < Cx) ? xs[((c0 + j) * 2 + r) * p.W + xx] : 0.f;
+            *reinterpret_cast<uint4*>(orow + r * rstep + (long long)xx * p.ldo) = pack8(f);
         }
     }
-    __syncthreads();                                 // xs is overwritten by the next row
+    __syncthreads();                                 // xs is overwritten by the next row pair
     }
 }
 
@@ -1880,8 +1901,8 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     DMM_CHECK(chunks <= 256, "dmm_head_input: ldo %lld too large", (long long)d->ldo);
     DMM_CHECK(d->Cu >= 8 && d->Cu <= 224 * 8 && chunks - d->Cu / 8 <= 32 && chunks * 8 >= d->Cu + d->C1 + d->C2,
               "dmm_head_input: unsupported channel split (Cu=%d, raw=%d, ldo=%lld)", d->Cu, d->C1 + d->C2, (long long)d->ldo);
-    const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * d->W) * sizeof(float);
-    DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: row of %d raw channels x %d pixels does not fit in shared memory", d->C1 + d->C2, d->W);
+    const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * 2 * d->W) * sizeof(float);
+    DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: two rows of %d raw channels x %d pixels do not fit in shared memory", d->C1 + d->C2, d->W);
     static bool head_attr = false;
     if (!head_attr) {
         DMM_CUDA(cudaFuncSetAttribute(head_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1890,7 +1911,7 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     int head_bps = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&head_bps, head_input_kernel, 256, smem) != cudaSuccess || head_bps < 1) head_bps = 4;
     static const int head_bps_env = env_int_ew("DMM_HEAD_BPS", 0);
-    const long long hrows = (long long)d->B * d->H, hcap = (long long)kNumSm * (head_bps_env > 0 ? head_bps_env : head_bps);
+    const long long hrows = (long long)d->B * (d->H / 2), hcap = (long long)kNumSm * (head_bps_env > 0 ? head_bps_env : head_bps);
     head_input_kernel<<<(unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream>>>(*d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;

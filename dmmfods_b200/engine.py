@@ -736,7 +736,9 @@ class Engine:
         nf2 = Cu // 2
         bn1 = _BNInfo(self, hp + ".norm1", nf2)
         xst = self._new_stats(8 if cx <= 8 else ceil_to(cx, 8))
-        ld0 = ceil_to(Ct, 8)
+        # row pitch of the head activations: a multiple of 16 channels keeps every pixel row 32-byte (sector) aligned, so neither
+        # the 16-byte stores of head_input nor the 128-byte TMA-store rows of refine0's data gradient leave partial sectors
+        ld0 = ceil_to(Ct, int(os.environ.get("DMM_HEAD_LD_ALIGN", "16")))
         a0 = self._mat(B, H, W, ld0)
 
         def run_xstats(_a, stream, lib=self.lib):
@@ -814,7 +816,7 @@ class Engine:
                 # the 128 decoder channels fill one 128-row m-tile exactly; the few raw input channels go through the tail path
                 self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Cu), [dr0.view()], conv3x3[0],
                                  conv3x3[2], Cu, nf2, Cu, nf2, Ct * 9, 9, W, H, B)
-                self._conv_wgrad_tail(st, hp + ".refine0.wgrad[tail]", hp + ".refine0.weight", a0.view(Cu, ld0 - Cu), Cu, cx,
+                self._conv_wgrad_tail(st, hp + ".refine0.wgrad[tail]", hp + ".refine0.weight", a0.view(Cu, min(16, ld0 - Cu)), Cu, cx,
                                       dr0.view(), conv3x3[0], conv3x3[2], nf2, nf2, Ct * 9, 9, W, H, B)
             else:
                 self._conv_wgrad(st, hp + ".refine0.wgrad", hp + ".refine0.weight", a0.view(0, Ct), [dr0.view()], conv3x3[0],
