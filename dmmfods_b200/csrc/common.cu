@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Host-side plumbing shared by all kernels: thread-local error string, CUDA error mapping and
 // TMA tensor-map encoding (cuTensorMapEncodeTiled resolved at run time through
 // cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda and can be
@@ -137,3 +138,10 @@ extern "C" int dmm_sizeof(int which) {
         default: return -1;
     }
 }
+
+namespace dmm {
+bool pdl_enabled() {
+    static const bool on = getenv("DMM_PDL") && atoi(getenv("DMM_PDL")) != 0;      // off by default: measured 0.7 % slower (85.0 vs 84.4 ms)
+    return on;
+}
+}  // namespace dmm

@@ -1,6 +1,7 @@
 // Common device/host helpers for the dmmfods_b200 sm_100a kernels.
 // PTX wrappers: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld).
 #pragma once
+#include <string.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -302,6 +303,27 @@ __device__ __forceinline__ BnCoef bn_coef_fwd(const dmm_bn_t& bn, int c, bool wr
     return k;
 }
 
+
+// Programmatic dependent launch: every kernel of the step begins with pdl_prologue() and is launched through launch_k() with
+// programmatic stream serialization, so the next kernel's blocks are scheduled (and its launch latency paid) while the tail of
+// the current one drains; griddepcontrol.wait (a no-op without the attribute) keeps the full memory dependency.  Measured on
+// the training step inside its CUDA graph: 85.0-85.6 ms with, 84.3-84.6 ms without - hence OFF unless DMM_PDL=1.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl_enabled()) { cfg.attrs = attr; cfg.numAttrs = 1; }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #endif  // __CUDACC__
 

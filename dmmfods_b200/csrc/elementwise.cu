@@ -101,6 +101,7 @@ __device__ __forceinline__ void block_col_reduce_atomic(float (&a)[8], float (&b
 // ---------------------------------------------------------------------------------------------
 template <int POOL>
 __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_apply_t p, int OH, int OW) {
+    pdl_prologue();
     __shared__ float sm[2 * kEwThreads * 8];
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_apply_kernel(const dmm_bn_
 // flight per thread, coefficients in registers.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads, 4) bn_apply_fast_kernel(const dmm_bn_apply_t p) {
+    pdl_prologue();
     __shared__ float cf[2][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -396,6 +398,7 @@ __device__ __forceinline__ void bn_relu_dz(const dmm_bn_bwd_args_t& p, const __n
 
 template <int GMODE, typename GT>
 __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_reduce_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    pdl_prologue();
     __shared__ float sm[2 * kEwThreads * 8];
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_reduce_kernel(const dm
 // dz (masked, pool-routed gradient) for the apply pass and accumulates the BatchNorm sums.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_maxpool_quad_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    pdl_prologue();
     __shared__ float sm[2 * kEwThreads * 8];
     __shared__ __align__(16) float cf[4][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -554,6 +558,7 @@ __global__ void __launch_bounds__(kEwThreads, 2) bn_bwd_maxpool_quad_kernel(cons
 
 template <int GMODE, typename GT>
 __global__ void __launch_bounds__(kEwThreads) bn_relu_bwd_apply_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    pdl_prologue();
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
     const int nchunks = p.C >> 3;
@@ -650,6 +655,7 @@ constexpr int kFastBps = 2;       // their resident blocks per SM = their grid c
 
 template <typename GT>
 __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_reduce_fast_kernel(const dmm_bn_bwd_args_t p) {
+    pdl_prologue();
     __shared__ float sm[2 * kEwThreads * 8];
     __shared__ __align__(16) float cf[4][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -713,6 +719,7 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_reduce_fast_kerne
 
 template <typename GT, int OUT_MODE>
 __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_apply_fast_kernel(const dmm_bn_bwd_args_t p) {
+    pdl_prologue();
     __shared__ __align__(16) float cf[5][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -805,6 +812,7 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_apply_fast_kernel
 // ---------------------------------------------------------------------------------------------
 template <int ROWS, bool HOIST>
 __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_contrib_kernel(const dmm_bn_bwd_args_t p) {
+    pdl_prologue();
     __shared__ float sm[2 * kEwThreads * 8];
     __shared__ __align__(16) float cf[5][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -886,6 +894,7 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_contrib_kernel(co
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const dmm_bn_bwd_t bn, int C, float* __restrict__ k) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double a = 0.0, b = 0.0;
@@ -906,6 +915,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const dmm_bn_bwd_t
 // R rows x S sources = 16 independent 16-byte loads in flight per thread (R chosen from the source count at launch)
 template <int R, int S>
 __global__ void __launch_bounds__(kEwThreads, kFastBps) grad_gather_kernel(const dmm_grad_gather_t p) {
+    pdl_prologue();
     __shared__ __align__(16) float ks[3][kEwThreads];       // sum k1, sum k2, mean of the block's channels
     const int cx = blockDim.x, ry = blockDim.y;
     const int chunk = blockIdx.y * cx + threadIdx.x;
@@ -997,6 +1007,7 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) grad_gather_kernel(const
 // ---------------------------------------------------------------------------------------------
 template <int PASS, int OUT_MODE>
 __global__ void __launch_bounds__(kEwThreads, 3) bn_bwd_pool_fast_kernel(const dmm_bn_bwd_args_t p, int OH, int OW) {
+    pdl_prologue();
     __shared__ float sm[PASS == 0 ? 2 * kEwThreads * 8 : 1];
     __shared__ __align__(16) float cf[5][kEwThreads];
     const int cx = blockDim.x, ry = blockDim.y;
@@ -1110,6 +1121,7 @@ constexpr int kIm2colPx = 64;
 __global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restrict__ x1, int C1,
                                                            const float* __restrict__ x2, int C2, int B, int H, int W,
                                                            int OH, int OW, __nv_bfloat16* __restrict__ out, int kpad) {
+    pdl_prologue();
     extern __shared__ float im_sm[];                 // [C][7][PW] patch, then int koff[kpad]
     const int C = C1 + C2;
     const int PW = 2 * kIm2colPx + 5;
@@ -1171,6 +1183,7 @@ __global__ void __launch_bounds__(256) im2col_7x7s2_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict__ x, int C, long long HW,
                                                          double* stats, int ld, int off, int splits) {
+    pdl_prologue();
     __shared__ double sm[2][8];
     const int plane = blockIdx.x / splits;   // b*C + c
     const int sp = blockIdx.x - plane * splits;
@@ -1213,6 +1226,7 @@ __global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict
 // inner loop has no divisions, 16-byte stores of a row are contiguous, and every up-sampled source row is read by
 // exactly two blocks.
 __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) {
+    pdl_prologue();
     extern __shared__ float coef[];   // [2][Cpad]
     const int Ct = p.Cu + p.C1 + p.C2;
     const int chunks = (int)(p.ldo >> 3);
@@ -1329,6 +1343,7 @@ __global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) 
 // One thread per (UP-SAMPLED-SOURCE pixel, chunk) so that the 4 children are reduced in registers.
 template <int PASS>
 __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_t p) {
+    pdl_prologue();
     extern __shared__ float sm[];   // PASS 0: [2][Cpad] block partial sums ; coefficient tables
     const int Ct = p.Cu + p.C1 + p.C2;
     const int chunks = (Ct + 7) >> 3;
@@ -1430,6 +1445,7 @@ __global__ void __launch_bounds__(256) head_input_bwd_kernel(const dmm_head_bwd_
 // (sum dz, sum dz*xhat) of the C1+C2 (<= 8) RAW input channels of the head BatchNorm: one thread per pixel, the
 // fp32 planes are read coalesced, the 8 gradient columns [Cu, Cu+8) with one 16-byte load.
 __global__ void __launch_bounds__(256) head_raw_bwd_reduce_kernel(const dmm_head_bwd_t p) {
+    pdl_prologue();
     __shared__ float red[2][8][8];
     const int Cx = p.C1 + p.C2;
     float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
@@ -1488,6 +1504,7 @@ __global__ void __launch_bounds__(256) head_raw_bwd_reduce_kernel(const dmm_head
 // weight gradient and the data gradient of the N = num_classes KxK convolution (refine1) into plain 1x1 GEMMs.
 __global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int KH, int K,
                                                              __nv_bfloat16* __restrict__ out, int ld) {
+    pdl_prologue();
     const int chunks = ld >> 3;
     const long long total = (long long)B * H * W * chunks;
     const int pad = K / 2, pad_h = KH / 2;
@@ -1519,6 +1536,7 @@ __global__ void __launch_bounds__(256) dlogits_im2col_kernel(const float* __rest
 // fp32 NCHW -> bf16 pixel-major rows (channels >= C zero-filled up to ldo)
 __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restrict__ x, int B, int C, long long HW,
                                                            __nv_bfloat16* __restrict__ out, int ldo) {
+    pdl_prologue();
     const int chunks = ldo >> 3;
     const long long total = (long long)B * HW * chunks;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1541,6 +1559,7 @@ __global__ void __launch_bounds__(256) nchw_to_rows_kernel(const float* __restri
 __global__ void __launch_bounds__(256) rows_f32_to_bf16_kernel(const float* __restrict__ src, long long lds,
                                                                __nv_bfloat16* __restrict__ dst, long long ldd,
                                                                long long P, int C) {
+    pdl_prologue();
     const int chunks = C >> 3;
     const long long total = P * chunks;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1558,6 +1577,7 @@ __global__ void __launch_bounds__(256) rows_f32_to_bf16_kernel(const float* __re
 __global__ void __launch_bounds__(256) bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ t,
                                                          long long n4, int C, long long HW4, float* __restrict__ loss,
                                                          float* __restrict__ grad, double* class_sums) {
+    pdl_prologue();
     // vectors of 4 never straddle a (b, c) plane because HW % 4 == 0 (checked on the host)
     __shared__ double sm[8][8];
     float cs[8];
@@ -1612,6 +1632,7 @@ struct PackArgs {
 };
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst,
                                                            const PackArgs a) {
+    pdl_prologue();
     const long long total = (long long)a.n_rows * a.ktot;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i / a.ktot);
@@ -1627,6 +1648,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dw, long long dt, long long dm,
                                                            long long dn, int M, int N, float* __restrict__ grad,
                                                            const PackArgs a, int accumulate) {
+    pdl_prologue();
     const long long total = (long long)a.T * M * N;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int n = (int)(i % N);
@@ -1642,6 +1664,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n, float lr,
                                                    float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt) {
+    pdl_prologue();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float gi = g[i];
         const float pi = p[i];
@@ -1657,6 +1680,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 // batched forms: one launch for all weight tensors of the network (job tables live in device memory)
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pack_job_t* __restrict__ jobs) {
+    pdl_prologue();
     const dmm_pack_job_t& j = jobs[blockIdx.y];
     const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
     const long long ktot = (long long)Kp * j.T;
@@ -1677,6 +1701,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pac
     }
 }
 __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unpack_job_t* __restrict__ jobs) {
+    pdl_prologue();
     const dmm_unpack_job_t& j = jobs[blockIdx.y];
     const long long total = (long long)j.T * j.M * j.N;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1708,7 +1733,7 @@ static int resident_bps(F fn) {
 #define DMM_WAVE_LAUNCH(KERNEL, C_, ROWS_, STREAM, ...)                          \
     do {                                                                         \
         const ColCfg kw_ = col_cfg((C_), (ROWS_), resident_bps(KERNEL));         \
-        KERNEL<<<kw_.grid, kw_.block, 0, (STREAM)>>>(__VA_ARGS__);               \
+        launch_k(KERNEL, kw_.grid, kw_.block, 0, (STREAM), __VA_ARGS__);               \
     } while (0)
 
 static unsigned flat_grid(long long total, int threads) {
@@ -1763,14 +1788,14 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
     if (d->gmode == 0 && d->dz_out == nullptr) {      // lean same-pixel kernels
         const ColCfg k = col_cfg(d->C, irows, kFastBps);
         if (PASS == 0) {
-            if (d->g_is_f32) bn_bwd_reduce_fast_kernel<float><<<k.grid, k.block, 0, stream>>>(*d);
-            else bn_bwd_reduce_fast_kernel<__nv_bfloat16><<<k.grid, k.block, 0, stream>>>(*d);
+            if (d->g_is_f32) launch_k(bn_bwd_reduce_fast_kernel<float>, k.grid, k.block, 0, stream, *d);
+            else launch_k(bn_bwd_reduce_fast_kernel<__nv_bfloat16>, k.grid, k.block, 0, stream, *d);
         } else {
 #define DMM_APPLY_FAST(GT)                                                                              \
     do {                                                                                                \
-        if (d->out_mode == 0) bn_bwd_apply_fast_kernel<GT, 0><<<k.grid, k.block, 0, stream>>>(*d);      \
-        else if (d->out_mode == 1) bn_bwd_apply_fast_kernel<GT, 1><<<k.grid, k.block, 0, stream>>>(*d); \
-        else bn_bwd_apply_fast_kernel<GT, 2><<<k.grid, k.block, 0, stream>>>(*d);                       \
+        if (d->out_mode == 0) launch_k(bn_bwd_apply_fast_kernel<GT, 0>, k.grid, k.block, 0, stream, *d);      \
+        else if (d->out_mode == 1) launch_k(bn_bwd_apply_fast_kernel<GT, 1>, k.grid, k.block, 0, stream, *d); \
+        else launch_k(bn_bwd_apply_fast_kernel<GT, 2>, k.grid, k.block, 0, stream, *d);                       \
     } while (0)
             if (d->g_is_f32) DMM_APPLY_FAST(float);
             else DMM_APPLY_FAST(__nv_bfloat16);
@@ -1785,10 +1810,10 @@ static int launch_bn_bwd(const dmm_bn_bwd_args_t* d, cudaStream_t stream) {
         const unsigned cap = (unsigned)(kNumSm * 3) / kp.grid.y;      // launch bounds (256, 3): one full wave
         if (gx > cap) gx = cap > 0 ? cap : 1;
         kp.grid.x = gx;
-        if (PASS == 0) bn_bwd_pool_fast_kernel<0, 0><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
-        else if (d->out_mode == 0) bn_bwd_pool_fast_kernel<1, 0><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
-        else if (d->out_mode == 1) bn_bwd_pool_fast_kernel<1, 1><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
-        else bn_bwd_pool_fast_kernel<1, 2><<<kp.grid, kp.block, 0, stream>>>(*d, OH, OW);
+        if (PASS == 0) launch_k(bn_bwd_pool_fast_kernel<0, 0>, kp.grid, kp.block, 0, stream, *d, OH, OW);
+        else if (d->out_mode == 0) launch_k(bn_bwd_pool_fast_kernel<1, 0>, kp.grid, kp.block, 0, stream, *d, OH, OW);
+        else if (d->out_mode == 1) launch_k(bn_bwd_pool_fast_kernel<1, 1>, kp.grid, kp.block, 0, stream, *d, OH, OW);
+        else launch_k(bn_bwd_pool_fast_kernel<1, 2>, kp.grid, kp.block, 0, stream, *d, OH, OW);
         DMM_LAUNCH_CHECK("bn_bwd pooled kernel");
         return 0;
     }
@@ -1833,7 +1858,7 @@ extern "C" int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream)
     DMM_CHECK(d->bn.sums && d->bn.save_mean && d->bn.save_invstd, "dmm_bn_relu_bwd_contrib: missing BN state");
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
     ColCfg k = col_cfg(d->C, (long long)d->B * d->H * d->W, kFastBps);
-    bn_bwd_contrib_kernel<kFastRows, true><<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);
+    launch_k(bn_bwd_contrib_kernel<kFastRows, true>, k.grid, k.block, 0, (cudaStream_t)stream, *d);
     DMM_LAUNCH_CHECK("bn_bwd_contrib_kernel");
     return 0;
 }
@@ -1841,7 +1866,7 @@ extern "C" int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream)
 extern "C" int dmm_bn_bwd_finalize(const dmm_bn_bwd_t* bn, int32_t C, float* k, void* stream) {
     DMM_CHECK(bn && k && bn->sums && bn->save_invstd && bn->count > 0, "dmm_bn_bwd_finalize: missing inputs");
     if (C <= 0) return 0;
-    bn_bwd_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*bn, C, k);
+    launch_k(bn_bwd_finalize_kernel, (unsigned)((C + 255) / 256), 256, 0, (cudaStream_t)stream, *bn, C, k);
     DMM_LAUNCH_CHECK("bn_bwd_finalize_kernel");
     return 0;
 }
@@ -1858,7 +1883,7 @@ extern "C" int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream) {
     if (d->rows <= 0) return 0;
     static const int gather_bps = env_int_ew("DMM_GATHER_BPS", kFastBps);
     ColCfg k = col_cfg(d->C, d->rows, gather_bps);
-    grad_gather_kernel<2, 8><<<k.grid, k.block, 0, (cudaStream_t)stream>>>(*d);      // (4 rows x 4 sources measured slower)
+    launch_k(grad_gather_kernel<2, 8>, k.grid, k.block, 0, (cudaStream_t)stream, *d);      // (4 rows x 4 sources measured slower)
     DMM_LAUNCH_CHECK("grad_gather_kernel");
     return 0;
 }
@@ -1872,7 +1897,7 @@ extern "C" int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, in
     const int segs = (OW + kIm2colPx - 1) / kIm2colPx;
     const size_t smem = (size_t)(C1 + C2) * 7 * (2 * kIm2colPx + 5) * sizeof(float) + (size_t)kpad * sizeof(int);
     DMM_CHECK(smem <= 48 * 1024, "dmm_im2col_7x7s2: %d input channels need %zu bytes of shared memory", C1 + C2, smem);
-    im2col_7x7s2_kernel<<<(unsigned)((long long)B * OH * segs), 256, smem, (cudaStream_t)stream>>>(
+    launch_k(im2col_7x7s2_kernel, (unsigned)((long long)B * OH * segs), 256, smem, (cudaStream_t)stream, 
         x1, C1, x2, C2, B, H, W, OH, OW, reinterpret_cast<__nv_bfloat16*>(out), kpad);
     DMM_LAUNCH_CHECK("im2col_7x7s2_kernel");
     return 0;
@@ -1884,7 +1909,7 @@ extern "C" int dmm_nchw_stats(const float* x, int32_t B, int32_t C, int64_t HW, 
     if (B <= 0 || HW <= 0) return 0;
     int splits = (int)((HW + 65535) / 65536);
     if (splits < 1) splits = 1;
-    nchw_stats_kernel<<<(unsigned)(B * C * splits), 256, 0, (cudaStream_t)stream>>>(x, C, HW, stats, stats_ld, stats_off, splits);
+    launch_k(nchw_stats_kernel, (unsigned)(B * C * splits), 256, 0, (cudaStream_t)stream, x, C, HW, stats, stats_ld, stats_off, splits);
     DMM_LAUNCH_CHECK("nchw_stats_kernel");
     return 0;
 }
@@ -1912,7 +1937,7 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&head_bps, head_input_kernel, 256, smem) != cudaSuccess || head_bps < 1) head_bps = 4;
     static const int head_bps_env = env_int_ew("DMM_HEAD_BPS", 0);
     const long long hrows = (long long)d->B * (d->H / 2), hcap = (long long)kNumSm * (head_bps_env > 0 ? head_bps_env : head_bps);
-    head_input_kernel<<<(unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream>>>(*d);
+    launch_k(head_input_kernel, (unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream, *d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;
 }
@@ -1936,9 +1961,9 @@ static int launch_head_bwd(const dmm_head_bwd_t* d, cudaStream_t stream) {
     long long gx = (rows + ry - 1) / ry;
     if (gx > 148 * 8) gx = 148 * 8;
     const size_t smem = (size_t)6 * chunks * 8 * sizeof(float);
-    head_input_bwd_kernel<PASS><<<dim3((unsigned)gx), dim3((unsigned)nch, (unsigned)ry), smem, stream>>>(*d);
+    launch_k(head_input_bwd_kernel<PASS>, dim3((unsigned)gx), dim3((unsigned)nch, (unsigned)ry), smem, stream, *d);
     if (PASS == 0)
-        head_raw_bwd_reduce_kernel<<<flat_grid((long long)d->B * d->H * d->W, 256), 256, 0, stream>>>(*d);
+        launch_k(head_raw_bwd_reduce_kernel, flat_grid((long long)d->B * d->H * d->W, 256), 256, 0, stream, *d);
     DMM_LAUNCH_CHECK("head_input_bwd_kernel");
     return 0;
 }
@@ -1954,7 +1979,7 @@ extern "C" int dmm_nchw_to_nhwc_bf16(const float* x, int32_t B, int32_t C, int32
     DMM_CHECK(x && out && C > 0 && ldo % 8 == 0 && ldo >= C, "dmm_nchw_to_nhwc_bf16: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const long long total = (long long)B * H * W * (ldo / 8);
-    nchw_to_rows_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(nchw_to_rows_kernel, flat_grid(total, 256), 256, 0, (cudaStream_t)stream, 
         x, B, C, (long long)H * W, reinterpret_cast<__nv_bfloat16*>(out), (int)ldo);
     DMM_LAUNCH_CHECK("nchw_to_rows_kernel");
     return 0;
@@ -1966,7 +1991,7 @@ extern "C" int dmm_rows_f32_to_bf16(const float* src, int64_t lds, void* dst, in
     DMM_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
               "dmm_rows_f32_to_bf16: pointers must be 16-byte aligned");
     if (P <= 0) return 0;
-    rows_f32_to_bf16_kernel<<<flat_grid(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(rows_f32_to_bf16_kernel, flat_grid(P * (C / 8), 256), 256, 0, (cudaStream_t)stream, 
         src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, P, C);
     DMM_LAUNCH_CHECK("rows_f32_to_bf16_kernel");
     return 0;
@@ -1979,7 +2004,7 @@ extern "C" int dmm_bce_logits(const float* logits, const float* target, int64_t 
               (long long)HW);
     DMM_CHECK(class_sums == nullptr || (C >= 1 && C <= 8), "dmm_bce_logits: per-class sums support at most 8 classes");
     if (n <= 0) return 0;
-    bce_logits_kernel<<<flat_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(logits, target, n / 4, C, HW / 4, loss, grad,
+    launch_k(bce_logits_kernel, flat_grid(n / 4, 256), 256, 0, (cudaStream_t)stream, logits, target, n / 4, C, HW / 4, loss, grad,
                                                                               class_sums);
     DMM_LAUNCH_CHECK("bce_logits_kernel");
     return 0;
@@ -2007,7 +2032,7 @@ extern "C" int dmm_pack_weights(const float* w, void* dst, int32_t n_valid, int3
     PackArgs a;
     int rc = fill_pack_args(a, n_valid, n_rows, C, kwidth, T, tap_off, sn, sc);
     if (rc) return rc;
-    pack_weights_kernel<<<flat_grid((long long)n_rows * a.ktot, 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(pack_weights_kernel, flat_grid((long long)n_rows * a.ktot, 256), 256, 0, (cudaStream_t)stream, 
         w, reinterpret_cast<__nv_bfloat16*>(dst), a);
     DMM_LAUNCH_CHECK("pack_weights_kernel");
     return 0;
@@ -2019,7 +2044,7 @@ extern "C" int dmm_unpack_wgrad(const float* dw, int64_t dt, int64_t dm, int64_t
     PackArgs a;
     int rc = fill_pack_args(a, N, N, M, 1, T, tap_off, sn, sc);
     if (rc) return rc;
-    unpack_wgrad_kernel<<<flat_grid((long long)T * M * N, 256), 256, 0, (cudaStream_t)stream>>>(dw, dt, dm, dn, M, N, grad, a,
+    launch_k(unpack_wgrad_kernel, flat_grid((long long)T * M * N, 256), 256, 0, (cudaStream_t)stream, dw, dt, dm, dn, M, N, grad, a,
                                                                                                 accumulate);
     DMM_LAUNCH_CHECK("unpack_wgrad_kernel");
     return 0;
@@ -2031,7 +2056,7 @@ extern "C" int dmm_adam_flat(float* param, const float* grad, float* exp_avg, fl
     if (n <= 0) return 0;
     const float bc1 = 1.f - powf(beta1, (float)step);
     const float bc2 = 1.f - powf(beta2, (float)step);
-    adam_kernel<<<flat_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+    launch_k(adam_kernel, flat_grid(n, 256), 256, 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                     weight_decay, bc1, sqrtf(bc2));
     DMM_LAUNCH_CHECK("adam_kernel");
     return 0;
@@ -2040,7 +2065,7 @@ extern "C" int dmm_adam_flat(float* param, const float* grad, float* exp_avg, fl
 extern "C" int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream) {
     DMM_CHECK(njobs >= 0 && (njobs == 0 || jobs_device), "dmm_pack_weights_batched: bad arguments");
     if (njobs == 0) return 0;
-    pack_weights_batched_kernel<<<dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream>>>(jobs_device);
+    launch_k(pack_weights_batched_kernel, dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream, jobs_device);
     DMM_LAUNCH_CHECK("pack_weights_batched_kernel");
     return 0;
 }
@@ -2048,7 +2073,7 @@ extern "C" int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32
 extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream) {
     DMM_CHECK(njobs >= 0 && (njobs == 0 || jobs_device), "dmm_unpack_wgrad_batched: bad arguments");
     if (njobs == 0) return 0;
-    unpack_wgrad_batched_kernel<<<dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream>>>(jobs_device);
+    launch_k(unpack_wgrad_batched_kernel, dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream, jobs_device);
     DMM_LAUNCH_CHECK("unpack_wgrad_batched_kernel");
     return 0;
 }
@@ -2059,7 +2084,7 @@ extern "C" int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, in
               "dmm_dlogits_im2col: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const long long total = (long long)B * H * W * (ld / 8);
-    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, K, K,
+    launch_k(dlogits_im2col_kernel, flat_grid(total, 256), 256, 0, (cudaStream_t)stream, dlogits, B, C, H, W, K, K,
                                                                                   reinterpret_cast<__nv_bfloat16*>(out), (int)ld);
     DMM_LAUNCH_CHECK("dlogits_im2col_kernel");
     return 0;
@@ -2070,6 +2095,7 @@ namespace dmm {
 // the K shifted reads of a plane row hit L1)
 __global__ void __launch_bounds__(256) dlogits_unfold_w16_kernel(const float* __restrict__ dl, int B, int C, int H, int W, int K,
                                                                  __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     const long long total = (long long)B * H * W;
     const long long HW = (long long)H * W;
     const int pad = K / 2;
@@ -2108,13 +2134,13 @@ extern "C" int dmm_dlogits_unfold_w(const float* dlogits, int32_t B, int32_t C, 
               "dmm_dlogits_unfold_w: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     if (ld == 16 && K <= 5 && C <= 3) {
-        dlogits_unfold_w16_kernel<<<flat_grid((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream>>>(
+        launch_k(dlogits_unfold_w16_kernel, flat_grid((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream, 
             dlogits, B, C, H, W, K, reinterpret_cast<__nv_bfloat16*>(out));
         DMM_LAUNCH_CHECK("dlogits_unfold_w16_kernel");
         return 0;
     }
     const long long total = (long long)B * H * W * (ld / 8);
-    dlogits_im2col_kernel<<<flat_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(dlogits, B, C, H, W, 1, K,
+    launch_k(dlogits_im2col_kernel, flat_grid(total, 256), 256, 0, (cudaStream_t)stream, dlogits, B, C, H, W, 1, K,
                                                                                   reinterpret_cast<__nv_bfloat16*>(out), (int)ld);
     DMM_LAUNCH_CHECK("dlogits_unfold_w");
     return 0;

@@ -45,6 +45,7 @@ constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 template <int OUT_MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
+    pdl_prologue();
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment (SWIZZLE_128B atoms)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -355,8 +356,8 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
         attr_set = true;
     }
     DMM_CHECK(smem <= (size_t)kMaxSmem, "dmm_conv_igemm: %zu bytes of shared memory requested", smem);
-    if (d->out_mode == 0) igemm_kernel<0><<<grid, kThreads, smem, stream>>>(p);
-    else igemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    if (d->out_mode == 0) launch_k(igemm_kernel<0>, grid, kThreads, smem, stream, p);
+    else launch_k(igemm_kernel<1>, grid, kThreads, smem, stream, p);
     DMM_LAUNCH_CHECK("igemm_kernel");
     return 0;
 }

@@ -144,6 +144,18 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         }
         fence_mbar_init();
     }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, p.tmem_cols);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
+        if (OUT_MODE == 0) tma_prefetch_desc(&p.o_map);
+        if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
+    }
+    // everything above is independent of earlier kernels: wait for them (programmatic dependent launch) only here
+    pdl_prologue();
     if (PRO) {
         // per-channel scale / shift of the prologue BatchNorm (batch statistics of the raw input, or running statistics);
         // CTA 0 also records mean / invstd for backward and updates the running statistics (nn.BatchNorm2d semantics)
@@ -158,16 +170,6 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             pcoef[c] = sc;
             pcoef[C + c] = sh;
         }
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_holder, p.tmem_cols);
-        tmem_relinquish();
-    }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.b_map);
-        if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
-        if (OUT_MODE == 0) tma_prefetch_desc(&p.o_map);
-        if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
     }
     tc_fence_before();
     __syncthreads();
@@ -915,7 +917,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         DMM_CUDA(cudaMemsetAsync(prof_buf, 0, 160 * 16 * sizeof(long long), stream));
         p.prof = prof_buf;
     }
-    fn<<<grid, pro ? kG2ThreadsPro : kG2Threads, smem, stream>>>(p);
+    launch_k(fn, grid, pro ? kG2ThreadsPro : kG2Threads, smem, stream, p);
     if (prof) {
         static long long h[160 * 16];
         DMM_CUDA(cudaStreamSynchronize(stream));

@@ -111,6 +111,17 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
+    if (warp == 1) {
+        tmem_alloc(tmem_holder, p.tmem_cols);
+        tmem_relinquish();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_maps[p.a[0].map]);
+        tma_prefetch_desc(&p.b_maps[p.b[0].map]);
+        tma_prefetch_desc(&p.dw_map);
+    }
+    // everything above is independent of earlier kernels: wait for them (programmatic dependent launch) only here
+    pdl_prologue();
     if (p.pro) {
         for (int c = threadIdx.x; c < p.pro_kp; c += blockDim.x) {
             float sc = 0.f, sh = 0.f;
@@ -122,15 +133,6 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
             pcoef[c] = sc;
             pcoef[p.pro_kp + c] = sh;
         }
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_holder, p.tmem_cols);
-        tmem_relinquish();
-    }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.a_maps[p.a[0].map]);
-        tma_prefetch_desc(&p.b_maps[p.b[0].map]);
-        tma_prefetch_desc(&p.dw_map);
     }
     tc_fence_before();
     __syncthreads();
@@ -544,7 +546,7 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         DMM_CUDA(cudaMemsetAsync(prof_buf, 0, prof_n * sizeof(long long), stream));
         p.prof = prof_buf;
     }
-    wgrad_kernel<<<grid, p.pro ? kWgThreadsPro : kWgThreads, smem, stream>>>(p);
+    launch_k(wgrad_kernel, grid, p.pro ? kWgThreadsPro : kWgThreads, smem, stream, p);
     DMM_LAUNCH_CHECK("wgrad_kernel");
     if (p.prof) {
         static long long h[4096 * 8];

@@ -476,7 +476,7 @@ class Engine:
         # ---------------- stem (features.conv0/norm0/relu0/pool0) ----------------
         def stem(prefix, x1, c1, x2, c2, blk):
             cin = c1 + c2
-            kpad = ceil_to(cin * 49, 8)
+            kpad = ceil_to(cin * 49, int(os.environ.get("DMM_COL_ALIGN", "16")))       # 32-byte aligned rows: whole-sector stores
             col = self._mat(B, H2, W2, kpad)
 
             def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
