@@ -4,9 +4,11 @@ with backward) + fused flat Adam - the per-iteration work of Dense_U_Net_lidar_A
 uses plain nn.BatchNorm2d), gradients are SUMMED over ranks (the reference back-propagates the sum over all samples,
 Agent.py:264).
 """
+import ctypes as C
+
 import torch
 
-from . import ops
+from . import _lib, ops
 from .engine import Engine
 
 
@@ -204,3 +206,68 @@ class Trainer:
         n = len(eng.fwd) + len(eng.bwd) + 1 + len([s for s in eng.segments if s[2]]) + 1 + 1   # + pack, unpacks, bce, adam
         n += sum(1 for op in eng.fwd if op.kind == "nchw_stats" and eng.c2)                     # second input tensor
         return n
+
+
+class Evaluator:
+    """Validation / inference side of the hot path (SURVEY 8(f) N1 + N4): the body of `Dense_U_Net_lidar_Agent.validate`
+    (Agent.py:337-352) - eval-mode forward (running-statistics BatchNorm, no backward buffers), per-class BCE loss sums,
+    whole-image IoU per instance and class, class-wise accuracy - as one replayable CUDA graph over static buffers.
+
+        ev = Evaluator(model, B, H, W)
+        out = ev.step(image, lidar, ht_map)      # dict: loss_per_class, iou_per_instance_per_class (nan = empty union),
+                                                 #       iou_nans, acc_per_class   (CUDA tensors, no host sync)
+        maps = ev.heat_maps()                    # sigmoid(logits) of the last step (notebook visual check)
+    """
+
+    def __init__(self, model, B, H, W, iou_threshold=0.7, use_graph=True):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("dmmfods_b200.Evaluator: the model must live on a CUDA device (no CPU path)")
+        self.model = model
+        self.eng = model.engine(B, H, W, training=False, need_backward=False)
+        self.threshold = float(iou_threshold)
+        self.use_graph = bool(use_graph)
+        self.graph = None
+        ncls = self.eng.ncls
+        self.B, self.H, self.W, self.ncls = B, H, W, ncls
+        self._target = torch.zeros(B, ncls, H, W, dtype=torch.float32, device=dev)
+        self._counts = torch.zeros(B * ncls, 3, dtype=torch.int64, device=dev)
+
+    def _run(self):
+        eng = self.eng
+        eng.forward(eng.in1, eng.in2)
+        eng.loss(self._target)
+        self._counts.zero_()
+        _lib.check(_lib.load().dmm_step_metrics(C.c_void_p(eng.logits.data_ptr()), C.c_void_p(self._target.data_ptr()),
+                                                self.B * self.ncls, self.H * self.W, self.threshold,
+                                                C.c_void_p(self._counts.data_ptr()), ops._stream()), "dmm_step_metrics")
+
+    def step(self, x1, x2, target):
+        eng = self.eng
+        eng.check_param_pointers()
+        if x1 is not eng.in1:
+            eng.in1.copy_(x1, non_blocking=True)
+        if eng.c2 and x2 is not eng.in2:
+            eng.in2.copy_(x2, non_blocking=True)
+        self._target.copy_(target, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._run()
+                torch.cuda.current_stream().wait_stream(s)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._run()
+            self.graph.replay()
+        else:
+            self._run()
+        c = self._counts.view(self.B, self.ncls, 3)
+        iou = c[:, :, 0].float() / c[:, :, 1].float()                      # nan where the union is empty (helper:311-343)
+        acc = c[:, :, 2].sum(0).double() / float(self.B * self.H * self.W)    # (TP + TN) / all, per class (helper:369-401)
+        return dict(loss_per_class=eng.class_sums, iou_per_instance_per_class=iou, iou_nans=torch.isnan(iou).sum(0),
+                    acc_per_class=acc, logits=eng.logits)
+
+    def heat_maps(self):
+        return torch.sigmoid(self.eng.logits)

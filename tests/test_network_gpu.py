@@ -133,6 +133,36 @@ def test_eval_mode_forward_matches_golden():
     assert e < 2e-2
 
 
+def test_evaluator_matches_reference_validation_body():
+    """Evaluator.step = the body of Agent.validate (Agent.py:337-352): eval-mode logits vs the reference golden, per-class BCE
+    sums vs torch on the same logits, IoU / accuracy vs the numpy oracle of helper:311-401 on the same logits (exact counts)."""
+    import numpy as np
+    from dmmfods_b200.trainer import Evaluator
+    from oracle import lidar_heatmap_oracle as lo
+    g, mc, sd, x1, x2, tgt = load_tiny("mid")
+    for k in g.files:
+        if k.startswith("new/"):
+            sd[k[4:]] = torch.from_numpy(g[k])
+    model = Dense_U_Net_lidar(_cfg_from(mc))
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    B, _, H, W = x1.shape
+    ev = Evaluator(model, B, H, W, iou_threshold=0.0)          # logits are thresholded raw (Agent.py:343), 0.0 splits them
+    for _ in range(2):                                          # second call replays the captured graph
+        out = ev.step(x1.cuda(), x2.cuda(), tgt.cuda())
+    torch.cuda.synchronize()
+    logits = out["logits"].cpu()
+    assert rel_l2(logits, torch.from_numpy(g["eval_logits64"])) < 2e-2
+    ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.double(), tgt.double(), reduction="none").sum((0, 2, 3))
+    assert rel_l2(out["loss_per_class"].cpu(), ref_loss) < 1e-5
+    iou_ref = lo.iou_whole_img_batch(logits.numpy(), tgt.numpy(), 0.0)
+    assert np.array_equal(out["iou_per_instance_per_class"].cpu().numpy(), iou_ref, equal_nan=True)
+    assert np.array_equal(out["iou_nans"].cpu().numpy(), np.isnan(iou_ref).sum(0))
+    acc_ref = lo.accuracy(tgt.numpy(), logits.numpy(), 0.0)
+    assert np.allclose(out["acc_per_class"].cpu().numpy(), acc_ref, rtol=0, atol=1e-12)
+    assert torch.equal(ev.heat_maps().cpu(), torch.sigmoid(out["logits"]).cpu())
+
+
 @pytest.mark.parametrize("c2,cb,B,H,W", [(1, 2, 1, 128, 128), (1, 4, 3, 64, 128), (0, 1, 2, 96, 64)])
 def test_train_step_matches_oracle_other_shapes(c2, cb, B, H, W):
     """fresh seeded weights/inputs and other fusion points / block depths: CUDA path vs the CPU oracle (bf16-emulated)
