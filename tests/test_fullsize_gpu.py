@@ -1,0 +1,110 @@
+"""Parity at the FULL resolution of BASELINE config 3 (mid-fusion DenseNet-121, 640x960 RGB + LiDAR image):
+(a) one training step (forward + BCE + backward) of the CUDA path against the CPU oracle on the same seeded inputs at
+    batch 1 (the oracle needs a few seconds there), and
+(b) a size-independent property that covers the batch dimension: a batch made of k copies of a sample has the SAME
+    BatchNorm batch statistics, so every copy reproduces the same logits and the (sum-reduced) loss and all gradients
+    scale by k (Agent.py:247-264: the loss is summed over samples).
+Tolerances are written in the tests: the bf16 yard-stick of this 121-layer network at random initialisation is measured
+in place (bf16-emulated oracle vs exact fp32 oracle: logits 1.5e-1, gradients 6.7e-2)."""
+import pytest
+import torch
+
+from dmmfods_b200 import config as cfgmod
+from dmmfods_b200 import synthetic
+from dmmfods_b200.model import Dense_U_Net_lidar, FusedBCEWithLogits
+from gpu_util import rel_l2
+from oracle import dense_unet_oracle as du
+
+pytestmark = pytest.mark.gpu
+H, W = 640, 960
+MC = {"growth_rate": 32, "block_config": (6, 12, 24, 16), "num_init_features": 64, "bn_size": 4,
+      "stream_1_in_channels": 3, "stream_2_in_channels": 1, "concat_before_block_num": 3,
+      "num_layers_before_blocks": 4, "drop_rate": 0, "num_classes": 3, "memory_efficient": False}
+
+
+def _model_and_state():
+    c = cfgmod.get_config("/nonexistent")
+    for k, v in MC.items():
+        setattr(c.model, k, v)
+    torch.manual_seed(123)
+    model = Dense_U_Net_lidar(c)
+    gen = torch.Generator().manual_seed(7)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=gen) + 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=gen) * 0.2
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    return model, sd
+
+
+def _step(model, x1, x2, tgt):
+    model.zero_grad(set_to_none=True)
+    logits = model(x1.cuda(), x2.cuda())
+    loss = FusedBCEWithLogits()(logits, tgt.cuda())
+    loss.backward(torch.ones_like(loss))
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    return logits.detach().clone(), loss.detach().double().sum().item(), grads
+
+
+def _global(grads, ref, scale=1.0):
+    num = sum(((grads[k].double().cpu() - scale * ref[k].double().cpu()) ** 2).sum().item() for k in ref)
+    den = sum(((scale * ref[k].double()) ** 2).sum().item() for k in ref)
+    return (num / den) ** 0.5
+
+
+@pytest.fixture(scope="module")
+def full_res():
+    model, sd = _model_and_state()
+    x1 = torch.from_numpy(synthetic.rgb_image(1, H, W, seed=11))
+    x2 = torch.from_numpy(synthetic.lidar_image(1, H, W, seed=12))
+    tgt = torch.from_numpy(synthetic.target_maps(1, H, W, seed=13))
+    model = model.cuda().train()
+    return model, sd, x1, x2, tgt
+
+
+def test_full_resolution_train_step_matches_oracle(full_res):
+    """vs the bf16-EMULATED fp32 oracle (same rounding points: the check of the implementation) and vs the exact fp32 oracle,
+    whose distance to the emulated one is the bf16 yard-stick of this 121-layer network at random initialisation."""
+    model, sd, x1, x2, tgt = full_res
+    model.load_state_dict(sd, strict=True)
+    logits, loss_sum, grads = _step(model, x1, x2, tgt)
+    emu = du.oracle_train_step(sd, MC, x1, x2, tgt, dtype=torch.float32, emulate_bf16=True)
+    ref = du.oracle_train_step(sd, MC, x1, x2, tgt, dtype=torch.float32)
+    yard_logits = rel_l2(emu["logits"], ref["logits"])
+    yard_grad = _global(emu["grads"], ref["grads"])
+    e_logits, e_logits_exact = rel_l2(logits.cpu(), emu["logits"]), rel_l2(logits.cpu(), ref["logits"])
+    ref_loss = ref["loss"].double().sum().item()
+    e_loss = abs(loss_sum - ref_loss) / abs(ref_loss)
+    e_grad, e_grad_exact = _global(grads, emu["grads"]), _global(grads, ref["grads"])
+    print("\n[640x960 DenseNet-121 mid-fusion, B=1] logits relL2 %.3e vs bf16-emulated oracle, %.3e vs exact fp32 (yard-stick "
+          "emulated vs exact %.3e); loss rel %.3e; grad global relL2 %.3e vs emulated, %.3e vs exact (yard-stick %.3e)"
+          % (e_logits, e_logits_exact, yard_logits, e_loss, e_grad, e_grad_exact, yard_grad))
+    assert e_loss < 2e-3
+    assert e_logits < max(4e-2, 0.5 * yard_logits)
+    assert e_logits_exact < 1.5 * yard_logits + 2e-2
+    assert e_grad < 1.5e-1
+    assert e_grad_exact < 1.5 * yard_grad + 2e-2
+
+
+def test_batch_replication_property_at_full_resolution(full_res):
+    """k copies of one sample share its BatchNorm statistics: inside the replicated batch every copy must produce the SAME
+    logits (same tiles, same arithmetic per image: 1e-5), and against the single-sample run the copies, the summed loss / k
+    and the gradients / k agree up to the distance between two bf16 realisations of this network (different accumulation
+    orders flip bf16 roundings that 121 layers amplify; the CUDA path sits 7e-2 from the bf16-emulated oracle)."""
+    model, sd, x1, x2, tgt = full_res
+    model.load_state_dict(sd, strict=True)
+    l1, s1, g1 = _step(model, x1, x2, tgt)
+    model.load_state_dict(sd, strict=True)                      # same running statistics as before the first step
+    k = 2
+    lk, sk, gk = _step(model, x1.repeat(k, 1, 1, 1), x2.repeat(k, 1, 1, 1), tgt.repeat(k, 1, 1, 1))
+    e_copy = rel_l2(lk[1:2].cpu(), lk[0:1].cpu())
+    e_single = rel_l2(lk[0:1].cpu(), l1.cpu())
+    e_loss = abs(sk - k * s1) / abs(k * s1)
+    e_grad = _global(gk, g1, scale=float(k))
+    print("\n[replication x%d at 640x960] copy-vs-copy logits relL2 %.3e; copy vs single run %.3e; loss rel %.3e; gradient relL2 %.3e"
+          % (k, e_copy, e_single, e_loss, e_grad))
+    assert e_copy < 1e-5
+    assert e_single < 1e-1
+    assert e_loss < 1e-3
+    assert e_grad < 1.5e-1
