@@ -131,6 +131,7 @@ SIGNATURES = {
     "dmm_head_input_bwd_reduce": (C.c_int, [C.POINTER(HeadBwd), c_void_p]),
     "dmm_head_input_bwd_apply": (C.c_int, [C.POINTER(HeadBwd), c_void_p]),
     "dmm_nchw_to_nhwc_bf16": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "dmm_unfold_w7s2": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dmm_dlogits_im2col": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dmm_dlogits_unfold_w": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dmm_rows_f32_to_bf16": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),

@@ -2078,6 +2078,95 @@ extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int
     return 0;
 }
 
+namespace dmm {
+// stem: horizontal unfold of the 7x7 / stride-2 convolution.  out[(b, iy, ox)][kw*C + c] = x[c](iy, 2*ox + kw - 3); one thread
+// per (image row, output column); the 7 shifted reads of neighbouring threads overlap (L1), the row is written as 16-byte words
+// One block per image row (persistent): the C input planes of the row are staged in shared memory with coalesced float4 loads,
+// then thread (pixel, 8-column chunk) gathers its 8 values from shared memory and writes one 16-byte word; consecutive threads
+// write consecutive words.  CT: compile-time channel count (0 = generic) keeps the column -> (kw, c) split division-free.
+template <int CT>
+__global__ void __launch_bounds__(256) unfold_w7s2_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
+                                                          int B, int H, int W, int OW, __nv_bfloat16* __restrict__ out, int ld) {
+    pdl_prologue();
+    extern __shared__ float urow[];                       // [C][W + 8]: 3 zero columns left, >= 3 right (padding of the conv)
+    const int C = CT > 0 ? CT : C1 + C2;
+    const int chunks = ld >> 3;
+    const int pitch = W + 8;
+    const long long HW = (long long)H * W;
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+        const int b = row / H, iy = row - b * H;
+        if ((W & 3) == 0 && C <= 4) {
+            // float4 loads, all planes of the row in flight at once; margins zeroed separately
+            for (int x4 = threadIdx.x; x4 < (W >> 2); x4 += blockDim.x) {
+                float4 v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C)
+                        v[c] = __ldg(reinterpret_cast<const float4*>(c < C1 ? x1 + ((long long)b * C1 + c) * HW + (long long)iy * W
+                                                                            : x2 + ((long long)b * C2 + (c - C1)) * HW + (long long)iy * W) + x4);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < C) {
+                        float* d = urow + c * pitch + 3 + 4 * x4;
+                        d[0] = v[c].x; d[1] = v[c].y; d[2] = v[c].z; d[3] = v[c].w;
+                    }
+            }
+            for (int i = threadIdx.x; i < C * 8; i += blockDim.x) {
+                const int c = i >> 3, m = i & 7;
+                urow[c * pitch + (m < 3 ? m : W + m)] = 0.f;          // columns 0..2 and W+3..W+7
+            }
+        } else {
+            for (int i = threadIdx.x; i < C * pitch; i += blockDim.x) {
+                const int c = i / pitch, xx = i - c * pitch - 3;
+                float v = 0.f;
+                if (xx >= 0 && xx < W)
+                    v = c < C1 ? __ldg(x1 + ((long long)b * C1 + c) * HW + (long long)iy * W + xx)
+                               : __ldg(x2 + ((long long)b * C2 + (c - C1)) * HW + (long long)iy * W + xx);
+                urow[i] = v;
+            }
+        }
+        __syncthreads();
+        __nv_bfloat16* orow = out + (long long)row * OW * ld;
+        for (int i = threadIdx.x; i < OW * chunks; i += blockDim.x) {
+            const int ox = i / chunks, ch = i - ox * chunks;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = ch * 8 + j;
+                float v = 0.f;
+                if (col < 7 * C) {
+                    const int kw = col / C, c = col - kw * C;
+                    v = urow[c * pitch + 2 * ox + kw];     // = x[c](iy, 2 ox + kw - 3) with the 3-column left margin
+                }
+                f[j] = v;
+            }
+            *reinterpret_cast<uint4*>(orow + (long long)i * 8) = pack8(f);
+        }
+        __syncthreads();
+    }
+}
+}  // namespace dmm
+
+extern "C" int dmm_unfold_w7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H, int32_t W, void* out,
+                               int64_t ld, void* stream) {
+    DMM_CHECK(x1 && out && C1 > 0 && C2 >= 0 && (C2 == 0 || x2), "dmm_unfold_w7s2: bad inputs");
+    DMM_CHECK(ld % 8 == 0 && ld >= 7 * (C1 + C2), "dmm_unfold_w7s2: ld=%lld too small / not a multiple of 8", (long long)ld);
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const int OW = (W + 6 - 7) / 2 + 1;
+    const int Cc = C1 + C2;
+    const size_t usmem = (size_t)Cc * (W + 8) * sizeof(float);
+    DMM_CHECK(usmem <= 48 * 1024, "dmm_unfold_w7s2: a row of %d channels x %d pixels does not fit in shared memory", Cc, W);
+    const long long urows = (long long)B * H, ucap = (long long)kNumSm * 8;
+    const unsigned ugrid = (unsigned)(urows < ucap ? urows : ucap);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (Cc == 1) launch_k(unfold_w7s2_kernel<1>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
+    else if (Cc == 3) launch_k(unfold_w7s2_kernel<3>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
+    else if (Cc == 4) launch_k(unfold_w7s2_kernel<4>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
+    else launch_k(unfold_w7s2_kernel<0>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
+    DMM_LAUNCH_CHECK("unfold_w7s2_kernel");
+    return 0;
+}
+
 extern "C" int dmm_dlogits_im2col(const float* dlogits, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, void* out,
                                   int64_t ld, void* stream) {
     DMM_CHECK(dlogits && out && C > 0 && K >= 1 && (K & 1) && ld % 8 == 0 && ld >= (int64_t)K * K * C,

@@ -241,7 +241,7 @@ class Engine:
         lst.append(Op(fn, arg, name, gbuf, kind, flops, nbytes))
 
     def _conv_fwd(self, lst, name, wname, srcs, taps, tap_off, Cin, Cout, sn, sc, W, H, B, out, coff, stats, stats_off,
-                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None, fold_kw=0, tile_w=None):
+                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None, fold_kw=0, tile_w=None, cdiv=0, sc2=0):
         """emit pack job + igemm launch for a forward convolution (or one ConvTranspose phase).
         fold_kw (out_mode 2): `taps` / `tap_off` are the kernel ROWS; the kernel columns are folded into the GEMM's N (packed
         weight row kw*Cout + n)."""
@@ -253,7 +253,7 @@ class Engine:
         if not self.training:
             stats = None
         wid = self._req_wpk(n_rows, T * Kp)
-        job = dict(w=self.p[wname], wid=wid, n_valid=N, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off, sn=sn, sc=sc)
+        job = dict(w=self.p[wname], wid=wid, n_valid=N, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off, sn=sn, sc=sc, cdiv=cdiv, sc2=sc2)
         if fold_kw:
             job.update(ndiv=Cout, sn=1, sn2=sn)        # row kw*Cout + n <- w[n, :, kh, kw]
         self._pack_jobs.append(job)
@@ -476,19 +476,36 @@ class Engine:
         # ---------------- stem (features.conv0/norm0/relu0/pool0) ----------------
         def stem(prefix, x1, c1, x2, c2, blk):
             cin = c1 + c2
-            kpad = ceil_to(cin * 49, int(os.environ.get("DMM_COL_ALIGN", "16")))       # 32-byte aligned rows: whole-sector stores
-            col = self._mat(B, H2, W2, kpad)
-
-            def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
-                return lib.dmm_im2col_7x7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
-                                            B, H, W, col.ptr(), col.ld, stream)
-            self._emit(fwd, run_im2col, None, prefix + ".im2col", kind="im2col",
-                       nbytes=B * H * W * cin * 4 + B * H2 * W2 * kpad * 2)
             z0 = self._mat(B, H2, W2, self.nif)
             z0s = self._new_stats(self.nif)
             self.named[prefix + ".conv0"] = z0
-            self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
-                           cin * 49, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0)
+            # (a single-channel stream keeps the small im2col matrix: its 7 narrow tap loads make the weight gradient slower)
+            unfold = 7 * cin <= 64 and cin >= int(os.environ.get("DMM_STEM_UNFOLD_MIN_C", "2"))
+            if unfold:
+                # horizontal unfold only: xw[(b, iy, ox)][kw*cin + c] = x[c](iy, 2 ox + kw - 3) for ALL input rows; conv0 is then
+                # a 7-tap vertical convolution over the even-row / odd-row views of xw (input row 2 oy + kh - 3 = 2 (oy + dy) + p)
+                cw = ceil_to(7 * cin, 16)
+                xw = self._mat(B, H, W2, cw)
+
+                def run_unfold(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, xw=xw, lib=self.lib):
+                    return lib.dmm_unfold_w7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
+                                               B, H, W, xw.ptr(), xw.ld, stream)
+                self._emit(fwd, run_unfold, None, prefix + ".im2col", kind="im2col", nbytes=B * H * W * cin * 4 + B * H * W2 * cw * 2)
+                phases = [xw.row_phase_view(0), xw.row_phase_view(1)]
+                vtaps = [((kh - 3) % 2, (kh - 3 - (kh - 3) % 2) // 2, 0) for kh in range(7)]        # (phase, dy, 0)
+                self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", phases, vtaps, [7 * kh for kh in range(7)],
+                               7 * cin, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0, cdiv=cin, sc2=49)
+            else:
+                kpad = ceil_to(cin * 49, int(os.environ.get("DMM_COL_ALIGN", "16")))   # 32-byte aligned rows: whole-sector stores
+                col = self._mat(B, H2, W2, kpad)
+
+                def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
+                    return lib.dmm_im2col_7x7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
+                                                B, H, W, col.ptr(), col.ld, stream)
+                self._emit(fwd, run_im2col, None, prefix + ".im2col", kind="im2col",
+                           nbytes=B * H * W * cin * 4 + B * H2 * W2 * kpad * 2)
+                self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
+                               cin * 49, self.nif, cin * 49, 1, W2, H2, B, z0, 0, z0s, 0)
             bn0 = _BNInfo(self, prefix + ".norm0", self.nif)
             amax = torch.empty((B * blk.H * blk.W, self.nif), dtype=torch.uint8, device=self._alloc_dev)
             self._keep.append(amax)
@@ -504,8 +521,15 @@ class Engine:
                 self._bn_bwd(st, prefix + ".norm0.bwd", bn0, z0, 0, self.nif, g0.ptr(), g0.ld, dz0.ptr(), dz0.ld, 0,
                              gmode=2, dz_tmp=dzr)
                 st[-2].arg.argmax, st[-2].arg.ldarg = amax.data_ptr(), self.nif
-                self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
-                                 [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
+                if unfold:
+                    # dW[n, c, kh, kw] = sum_p dz0(p)[n] * xw_phase(p + dy)[kw*cin + c]: roles of "x" and "y" swapped so that the
+                    # two row-phase views are the tap sources; gradient column kw*cin + c -> w[n, c, kh, kw]
+                    self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", dz0.view(), phases,
+                                     [(p_, -dy_, 0) for (p_, dy_, _) in vtaps], [7 * kh for kh in range(7)], self.nif, cw,
+                                     self.nif, 7 * cin, 49 if cin > 1 else 1, cin * 49, W2, H2, B, ndiv=cin if cin > 1 else 0, sn2=1)
+                else:
+                    self._conv_wgrad(st, prefix + ".conv0.wgrad", prefix + ".conv0.weight", col.view(0, kpad), [dz0.view()],
+                                     [(0, 0, 0)], [0], kpad, self.nif, cin * 49, self.nif, cin * 49, 1, W2, H2, B)
                 self._bwd_stages.append(st)
 
         # ---------------- dense block ----------------

@@ -64,6 +64,15 @@ class Mat:
         v.sw, v.sh, v.sb = self.ld, self.ld * self.W, self.ld * self.W * self.H
         return v
 
+    def row_phase_view(self, py, c0=0, C_=None):
+        """view of the image rows 2i+py (all columns) - even / odd input rows of a stride-2 convolution."""
+        C_ = self.ld - c0 if C_ is None else C_
+        v = View()
+        v.ptr = self.t.data_ptr() + 2 * (py * self.W * self.ld + c0)
+        v.C, v.W, v.H, v.B = C_, self.W, (self.H - py + 1) // 2, self.B
+        v.sw, v.sh, v.sb = self.ld, 2 * self.ld * self.W, self.ld * self.W * self.H
+        return v
+
     def phase_view(self, py, px, c0=0, C_=None):
         """view of the pixels (2i+py, 2j+px) - sub-pixel phase of a stride-2 transposed conv output."""
         C_ = self.ld - c0 if C_ is None else C_

@@ -312,6 +312,12 @@ int dmm_grad_gather(const dmm_grad_gather_t* d, void* stream);
  * :228-229). */
 int dmm_im2col_7x7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H,
                      int32_t W, void* out, int32_t kpad, void* stream);
+/* Stem without the im2col matrix: horizontal unfold only.  out[(b, iy, ox)][kw*C + c] = x[c](iy, 2*ox + kw - 3) as bf16 rows of
+ * pitch ld (>= 7*C, zero padded), C = C1 + C2, OW = (W - 1) / 2 + 1, ALL H input rows.  conv0 (7x7, stride 2, padding 3,
+ * Dense_U_Net_lidar.py:73-74) is then a 7-tap VERTICAL convolution over the even-row / odd-row views of that tensor
+ * (dmm_conv_igemm with two strided sources), 2.5x less data than the [P/4, 49*C] im2col matrix. */
+int dmm_unfold_w7s2(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H, int32_t W, void* out,
+                    int64_t ld, void* stream);
 /* per-plane sums of an fp32 NCHW tensor (B, C, H*W) -> stats (raw network inputs feeding the head BN). */
 int dmm_nchw_stats(const float* x, int32_t B, int32_t C, int64_t HW, double* stats, int32_t stats_ld,
                    int32_t stats_off, void* stream);

@@ -1,0 +1,5 @@
+#!/bin/bash
+export PYTHONPATH=/root/repo
+timeout 900 python -m pytest tests/test_elementwise_gpu.py tests/test_network_gpu.py -x -q > gpurun_out/exp17_test.log 2>&1
+DMM_STEM_UNFOLD=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-step --dump-ops gpurun_out/ops_v36_0.json > gpurun_out/bench_v36_0.log 2>&1
+DMM_STEM_UNFOLD=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-step --dump-ops gpurun_out/ops_v36_1.json > gpurun_out/bench_v36_1.log 2>&1

@@ -387,6 +387,31 @@ def test_dlogits_im2col():
     assert float(got[:, K * K * C:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("C1,C2,H,W,ld", [(3, 0, 10, 24, 32), (3, 1, 7, 13, 32), (1, 0, 9, 18, 16)])
+def test_stem_unfold_w7s2(C1, C2, H, W, ld):
+    """out[(b, iy, ox)][kw*C + c] = x[c](iy, 2 ox + kw - 3): the operand that makes conv0 (7x7, stride 2, padding 3,
+    Dense_U_Net_lidar.py:73-74) a 7-tap vertical convolution over even / odd input rows."""
+    import ctypes
+    from dmmfods_b200 import _lib
+    torch.manual_seed(61)
+    B, Cc = 2, C1 + C2
+    x1 = torch.randn(B, C1, H, W)
+    x2 = torch.randn(B, C2, H, W) if C2 else None
+    OW = (W - 1) // 2 + 1
+    out = torch.full((B * H * OW, ld), float("nan"), dtype=torch.bfloat16, device="cuda")
+    x1c, x2c = x1.cuda(), (x2.cuda() if C2 else None)
+    _lib.check(_lib.load().dmm_unfold_w7s2(ctypes.c_void_p(x1c.data_ptr()), C1, ctypes.c_void_p(x2c.data_ptr()) if C2 else None, C2,
+                                           B, H, W, ctypes.c_void_p(out.data_ptr()), ld, ops._stream()), "unfold_w7s2")
+    torch.cuda.synchronize()
+    x = torch.cat([x1, x2], 1) if C2 else x1
+    xp = F.pad(bf16_round(x), (3, 3 + 2, 0, 0))
+    got = out.float().cpu().view(B, H, OW, ld)
+    for kw in range(7):
+        ref = xp[:, :, :, kw:kw + 2 * OW:2].permute(0, 2, 3, 1)              # (B, H, OW, C)
+        assert torch.equal(got[..., kw * Cc:(kw + 1) * Cc], ref), kw
+    assert float(got[..., 7 * Cc:].abs().max()) == 0.0
+
+
 def test_dlogits_unfold_w():
     """column kw*C + n = dlogits[n](y, x - (kw - K/2)): the operand that turns refine1's data gradient into a 5-tap vertical
     convolution (Dense_U_Net_lidar.py:130-131 backward)."""
