@@ -2086,7 +2086,9 @@ namespace dmm {
 // write consecutive words.  CT: compile-time channel count (0 = generic) keeps the column -> (kw, c) split division-free.
 template <int CT>
 __global__ void __launch_bounds__(256) unfold_w7s2_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2,
-                                                          int B, int H, int W, int OW, __nv_bfloat16* __restrict__ out, int ld) {
+                                                          int B, int H, int W, int OW, __nv_bfloat16* __restrict__ out, int ld,
+                                                          int K, int stride, int flip) {
+    // out[(b, iy, ox)][kw*C + c] = x[c](iy, stride*ox + kw' - K/2), kw' = flip ? K-1-kw : kw   (K <= 7)
     pdl_prologue();
     extern __shared__ float urow[];                       // [C][W + 8]: 3 zero columns left, >= 3 right (padding of the conv)
     const int C = CT > 0 ? CT : C1 + C2;
@@ -2134,9 +2136,10 @@ __global__ void __launch_bounds__(256) unfold_w7s2_kernel(const float* __restric
             for (int j = 0; j < 8; ++j) {
                 const int col = ch * 8 + j;
                 float v = 0.f;
-                if (col < 7 * C) {
+                if (col < K * C) {
                     const int kw = col / C, c = col - kw * C;
-                    v = urow[c * pitch + 2 * ox + kw];     // = x[c](iy, 2 ox + kw - 3) with the 3-column left margin
+                    const int kk = flip ? K - 1 - kw : kw;
+                    v = urow[c * pitch + stride * ox + kk + (3 - (K >> 1))];      // 3-column left margin
                 }
                 f[j] = v;
             }
@@ -2159,10 +2162,10 @@ extern "C" int dmm_unfold_w7s2(const float* x1, int32_t C1, const float* x2, int
     const long long urows = (long long)B * H, ucap = (long long)kNumSm * 8;
     const unsigned ugrid = (unsigned)(urows < ucap ? urows : ucap);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    if (Cc == 1) launch_k(unfold_w7s2_kernel<1>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
-    else if (Cc == 3) launch_k(unfold_w7s2_kernel<3>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
-    else if (Cc == 4) launch_k(unfold_w7s2_kernel<4>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
-    else launch_k(unfold_w7s2_kernel<0>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld);
+    if (Cc == 1) launch_k(unfold_w7s2_kernel<1>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld, 7, 2, 0);
+    else if (Cc == 3) launch_k(unfold_w7s2_kernel<3>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld, 7, 2, 0);
+    else if (Cc == 4) launch_k(unfold_w7s2_kernel<4>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld, 7, 2, 0);
+    else launch_k(unfold_w7s2_kernel<0>, ugrid, 256, usmem, (cudaStream_t)stream, x1, C1, x2, C2, B, H, W, OW, o, (int)ld, 7, 2, 0);
     DMM_LAUNCH_CHECK("unfold_w7s2_kernel");
     return 0;
 }
@@ -2222,6 +2225,18 @@ extern "C" int dmm_dlogits_unfold_w(const float* dlogits, int32_t B, int32_t C, 
     DMM_CHECK(dlogits && out && C > 0 && K >= 1 && (K & 1) && ld % 8 == 0 && ld >= (int64_t)K * C,
               "dmm_dlogits_unfold_w: bad arguments");
     if (B <= 0 || H <= 0 || W <= 0) return 0;
+    if (K <= 7 && (size_t)C * (W + 8) * sizeof(float) <= 48 * 1024) {
+        // row-staged gather (same kernel as the stem unfold, stride 1, columns in flipped order: x - (kw - K/2))
+        const size_t usmem = (size_t)C * (W + 8) * sizeof(float);
+        const long long urows = (long long)B * H, ucap = (long long)kNumSm * 8;
+        const unsigned ugrid = (unsigned)(urows < ucap ? urows : ucap);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+        const float* nul = nullptr;
+        if (C == 3) launch_k(unfold_w7s2_kernel<3>, ugrid, 256, usmem, (cudaStream_t)stream, dlogits, C, nul, 0, B, H, W, W, o, (int)ld, K, 1, 1);
+        else launch_k(unfold_w7s2_kernel<0>, ugrid, 256, usmem, (cudaStream_t)stream, dlogits, C, nul, 0, B, H, W, W, o, (int)ld, K, 1, 1);
+        DMM_LAUNCH_CHECK("unfold kernel (dlogits)");
+        return 0;
+    }
     if (ld == 16 && K <= 5 && C <= 3) {
         launch_k(dlogits_unfold_w16_kernel, flat_grid((long long)B * H * W, 256), 256, 0, (cudaStream_t)stream, 
             dlogits, B, C, H, W, K, reinterpret_cast<__nv_bfloat16*>(out));

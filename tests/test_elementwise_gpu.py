@@ -412,13 +412,13 @@ def test_stem_unfold_w7s2(C1, C2, H, W, ld):
     assert float(got[..., 7 * Cc:].abs().max()) == 0.0
 
 
-def test_dlogits_unfold_w():
+@pytest.mark.parametrize("W,ld", [(13, 16), (16, 16), (24, 24)])
+def test_dlogits_unfold_w(W, ld):
     """column kw*C + n = dlogits[n](y, x - (kw - K/2)): the operand that turns refine1's data gradient into a 5-tap vertical
     convolution (Dense_U_Net_lidar.py:130-131 backward)."""
     torch.manual_seed(53)
-    B, C, H, W, K = 2, 3, 7, 13, 5
+    B, C, H, K = 2, 3, 7, 5
     dl = torch.randn(B, C, H, W)
-    ld = 16
     out = ops.new_mat(B, H, W, ld)
     import ctypes
     from dmmfods_b200 import _lib
