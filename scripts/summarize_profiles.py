@@ -60,7 +60,7 @@ if os.path.isfile(lc):
 oj = os.path.join(ROOT, "gpurun_out", tag + "_ops.json")
 if launches and os.path.isfile(oj):
     ops = json.load(open(oj))
-    ours = ("igemm", "wgrad_kernel", "bn_", "head_", "im2col", "nchw_", "rows_f32", "grad_gather", "dlogits_")
+    ours = ("igemm", "wgrad_kernel", "bn_", "head_", "im2col", "nchw_", "rows_f32", "grad_gather", "dlogits_", "unfold_")
     skip = ("pack_weights", "unpack_wgrad", "bce_logits", "adam", "at::")
     seq = [d for d in launches.values() if d["name"].startswith(ours) and not d["name"].startswith(skip)]
     # an op = one launch, except the head input statistics (two nchw_stats launches for two input tensors)
