@@ -64,6 +64,7 @@ struct Ig2Params {
     int pro;                       // BN-ReLU prologue on the A tiles of source 0 (1x1 convolutions)
     int pro_kp;                    // padded channel count of source 0 (multiple of 64)
     int pro_c;                     // valid channels of source 0
+    int pro_pw;                    // > 0: K x K prologue - patch width in pixels; out-of-image patch pixels are forced to zero
     dmm_bn_t pro_bn;
     int bnb;
     const float* bnb_gamma;
@@ -332,6 +333,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             uint32_t aph = 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nblk = p.src_nblk[0];
+                const TileCoord tcp = decode_tile(p, tile);
+                const int px_org = tcp.x0 + p.src_ox[0], py_org = tcp.y0 + p.src_oy[0];
                 for (int cb = 0; cb < nblk; ++cb) {
                     float sc[8], sh[8];
 #pragma unroll
@@ -341,6 +344,31 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     }
                     mbar_wait(&a_full[ast], aph);
                     const uint32_t base = smem_u32(a_ring + (size_t)ast * p.a_stage);
+                    if (p.pro_pw > 0) {
+                        // K x K: the zero padding applies to the ACTIVATED tensor, so patch pixels outside the image (TMA
+                        // zero-filled raw values) must stay zero instead of becoming relu(shift)
+                        int pr = 0, pc = e >> 3;
+                        while (pc >= p.pro_pw) { pc -= p.pro_pw; ++pr; }
+                        for (int r = e >> 3; r < rows; r += 16) {
+                            const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
+                            const int yy = py_org + pr, xx = px_org + pc;
+                            uint4 o = make_uint4(0, 0, 0, 0);
+                            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+                                const uint4 v = lds_v4(ptr);
+                                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const float lo = fmaxf(fmaf(bf16_lo(w[i]), sc[2 * i], sh[2 * i]), 0.f);
+                                    const float hi = fmaxf(fmaf(bf16_hi(w[i]), sc[2 * i + 1], sh[2 * i + 1]), 0.f);
+                                    w[i] = pack_bf16x2(lo, hi);
+                                }
+                                o = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
+                            sts_v4(ptr, o);
+                            pc += 16;
+                            while (pc >= p.pro_pw) { pc -= p.pro_pw; ++pr; }
+                        }
+                    } else {
 #pragma unroll 4
                     for (int r = e >> 3; r < rows; r += 16) {
                         const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
@@ -353,6 +381,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             w[i] = pack_bf16x2(lo, hi);
                         }
                         sts_v4(ptr, make_uint4(w[0], w[1], w[2], w[3]));
+                    }
                     }
                     fence_proxy_async();                  // generic-proxy writes -> visible to the tensor core (async proxy)
                     __syncwarp();
@@ -711,8 +740,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     const bool pro = d->pro_enable != 0;
     int pro_kp = 0;
     if (pro) {
-        DMM_CHECK(d->out_mode == 0 && d->num_src == 1 && d->num_taps == 1 && d->tap_dx[0] == 0 && d->tap_dy[0] == 0 && d->kwidth == 64,
-                  "igemm v2: the BN-ReLU prologue needs a 1x1 convolution over one source");
+        DMM_CHECK(d->out_mode == 0 && d->num_src == 1 && d->kwidth == 64 && d->out_sy <= 1 && d->out_sx <= 1,
+                  "igemm v2: the BN-ReLU prologue needs one source, kwidth 64 and a stride-1 output");
         DMM_CHECK(d->pro_bn.training ? (d->pro_bn.stats != nullptr && d->pro_bn.count > 0) : (d->pro_bn.running_mean && d->pro_bn.running_var),
                   "igemm v2: prologue BatchNorm without statistics");
         pro_kp = ceil_div(d->src[0].C, 64) * 64;
@@ -863,6 +892,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         p.pro = 1;
         p.pro_kp = pro_kp;
         p.pro_c = d->src[0].C;
+        p.pro_pw = (hx > 0 || hy > 0) ? p.TW + (maxdx[0] - mindx[0]) : 0;
         p.pro_bn = d->pro_bn;
     }
     if (bnb) {

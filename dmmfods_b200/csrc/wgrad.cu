@@ -63,6 +63,8 @@ struct WgradKParams {
     long long* prof;
     int pro;                       // BN-ReLU prologue on the A chunks (all from a_src[0], unshifted)
     int pro_kp;                    // a_C[0] rounded up to 64
+    int pro_mask;                  // B groups are shifted (K x K): A rows outside the image must be zero (padding of the activation)
+    int W, H, tw_log;              // image size and log2(tile_w) for that test
     const float* pro_gamma;
     const float* pro_beta;
     const float* pro_mean;
@@ -253,6 +255,12 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                 int s = 0;
                 uint32_t ph = 0;
                 for (int kb = 0; kb < num_k; ++kb) {
+                    int mx0 = 0, my0 = 0;
+                    if (p.pro_mask) {
+                        long long t = tile_lo + kb;
+                        mx0 = (int)(t % p.tiles_x) * p.tile_w;
+                        my0 = (int)((t / p.tiles_x) % p.tiles_y) * p.tile_h;
+                    }
                     mbar_wait(&full_bar[s], ph);
                     uint8_t* sa = smem + (size_t)s * p.stage_bytes;
                     for (int i = 0; i < p.num_a; ++i) {
@@ -268,6 +276,13 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
 #pragma unroll 4
                         for (int r = e >> 3; r < p.kpx; r += 32) {
                             const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
+                            if (p.pro_mask) {
+                                const int yy = my0 + p.a[i].dy + (r >> p.tw_log), xx = mx0 + p.a[i].dx + (r & (p.tile_w - 1));
+                                if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) {
+                                    sts_v4(ptr, make_uint4(0, 0, 0, 0));
+                                    continue;
+                                }
+                            }
                             const uint4 v = lds_v4(ptr);
                             uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -492,6 +507,14 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         p.pro = 1;
         p.pro_kp = ceil_div(d->a_src[0].C + (d->ya - 1) * d->a_step, 64) * 64 + 64 * DMM_WG_MAX_A;
         p.pro_gamma = d->pro_gamma; p.pro_beta = d->pro_beta; p.pro_mean = d->pro_mean; p.pro_invstd = d->pro_invstd;
+        // shifted B groups pair an out-of-image A row with an in-image B row: such A rows must be the zero padding of the activation
+        bool shifted = false;
+        for (int g = 0; g < d->num_b; ++g) shifted = shifted || d->b[g].dx != 0 || d->b[g].dy != 0;
+        p.pro_mask = shifted ? 1 : 0;
+        p.W = d->W; p.H = d->H;
+        p.tw_log = 0;
+        while ((1 << p.tw_log) < p.tile_w) ++p.tw_log;
+        DMM_CHECK((1 << p.tw_log) == p.tile_w, "dmm_conv_wgrad: tile_w must be a power of two");
     }
     p.tiles_x = ceil_div(d->W, p.tile_w);
     p.tiles_y = ceil_div(d->H, p.tile_h);

@@ -34,6 +34,10 @@ WGRAD_SIDE_STREAM = os.environ.get("DMM_WGRAD_SIDE_STREAM", "1") != "0"
 # dense-layer norm1 + relu1 as a PROLOGUE of conv1 (and of its weight gradient): relu(bn(x)) is applied to the operand tiles in
 # shared memory, the activated tensor is never written to HBM (tv:47-50, north-star "BN-ReLU prologues fused into the conv loads")
 FUSE_BN_PROLOGUE = os.environ.get("DMM_FUSE_BN_PROLOGUE", "1") != "0"
+# the same for norm2 + relu2 in front of the 3x3 growth convolution (halo patches activated in shared memory, out-of-image
+# pixels kept at zero) and its weight gradient.  OFF by default: measured +0.85 ms per step (the 3x3 kernels are shared-memory
+# bound, the extra in-place pass costs conv2 fprop +1.5 ms and its weight gradient +1.75 ms against 2.4 ms of saved BN-ReLU)
+FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE_KXK", "0") != "0"
 
 
 class Op:
@@ -541,7 +545,6 @@ class Engine:
                 bn1 = _BNInfo(self, lp + ".norm1", Ci)
                 bn2 = _BNInfo(self, lp + ".norm2", bnk)
                 z1 = self._mat(B, Hb, Wb, bnk)
-                a2 = self._mat(B, Hb, Wb, bnk)
                 z1s = self._new_stats(bnk)
                 if FUSE_BN_PROLOGUE:
                     # norm1 + relu1 run inside conv1: its A tiles are the raw block-buffer channels, activated in shared memory
@@ -555,9 +558,17 @@ class Engine:
                     self._apply(fwd, lp + ".norm1", bn1, blk.buf, 0, Ci, blk.stats, 0, a1, 0)
                     self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [a1.view()], conv1x1[0], conv1x1[2], Ci, bnk, Ci, 1,
                                    Wb, Hb, B, z1, 0, z1s, 0)
-                self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
-                self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [a2.view()], conv3x3[0], conv3x3[2], bnk, k,
-                               bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
+                if FUSE_BN_PROLOGUE_KXK:
+                    a2 = None
+                    d2 = self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [z1.view()], conv3x3[0], conv3x3[2], bnk, k,
+                                        bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
+                    d2.pro_enable = 1
+                    d2.pro_bn = self._bn_fwd(bn2, z1s, 0, z1.P)
+                else:
+                    a2 = self._mat(B, Hb, Wb, bnk)
+                    self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
+                    self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [a2.view()], conv3x3[0], conv3x3[2], bnk, k,
+                                   bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
                 if self.need_backward:
                     st = []
                     kk = ceil_to(k, 8)
@@ -569,8 +580,9 @@ class Engine:
                     da1_full = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
                     da1 = Mat(da1_full.t.view(-1)[:B * Hb * Wb * Ci].view(B * Hb * Wb, Ci), B, Hb, Wb)
                     self._gather(st, lp + ".gout", blk, Ci, k, go)
-                    self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", a2.view(), [go.view(0, k)], conv3x3[0],
-                                     conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B)
+                    self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", (z1 if a2 is None else a2).view(),
+                                     [go.view(0, k)], conv3x3[0], conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B,
+                                     pro=bn2 if a2 is None else None)
                     dg2 = self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
                                            k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
                     self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0, producer=dg2)

@@ -114,10 +114,11 @@ typedef struct {
     const float* bnb_invstd;
     double* bnb_sums;
     int32_t bnb_sums_ld, bnb_sums_off;
-    /* Optional BN-ReLU PROLOGUE (pro_enable != 0; one source, one tap (0,0) = 1x1 convolution): src[0] holds the RAW input x and
-     * the kernel applies relu(bn(x)) to every A tile in shared memory before the MMAs read it (tv:47-50 without materialising the
-     * activated tensor).  pro_bn describes the BatchNorm over the src[0].C channels exactly like dmm_bn_relu_apply (CTA 0 also
-     * saves mean / invstd and updates the running statistics). */
+    /* Optional BN-ReLU PROLOGUE (pro_enable != 0; one source, stride-1 output): src[0] holds the RAW input x and the kernel
+     * applies relu(bn(x)) to every A tile / halo patch in shared memory before the MMAs read it (tv:47-50 without materialising
+     * the activated tensor).  With K x K taps the patch pixels outside the image stay zero (the convolution pads the ACTIVATED
+     * tensor).  pro_bn describes the BatchNorm over the src[0].C channels exactly like dmm_bn_relu_apply (CTA 0 also saves
+     * mean / invstd and updates the running statistics). */
     int32_t pro_enable;
     int32_t fold_kw;         /* out_mode 2: kernel width folded into N (odd); else 0 */
     dmm_bn_t pro_bn;
@@ -163,7 +164,8 @@ typedef struct {
     /* Optional BN-ReLU PROLOGUE on the A side (pro_enable != 0; every A chunk reads a_src[0] unshifted): a_src[0] holds the RAW
      * BatchNorm input and relu(bn(x)) is applied to the A tiles in shared memory (weight gradient of a convolution whose activated
      * input was never materialised, see dmm_igemm_t.pro_*).  pro_bn: save_mean / save_invstd / gamma / beta of the a_src[0].C channels
-     * (training = 0 semantics: the forward pass already fixed the statistics; running_mean / running_var are NOT used). */
+     * (training = 0 semantics: the forward pass already fixed the statistics; running_mean / running_var are NOT used).
+     * When the B groups are shifted (K x K), A rows outside the image are written as zeros (the padding of the activation). */
     int32_t pro_enable;
     int32_t pad_;
     const float* pro_gamma;

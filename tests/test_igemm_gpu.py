@@ -274,3 +274,29 @@ def test_conv1x1_bn_relu_prologue(Cin, Cout, H, W):
     assert torch.allclose(sm.cpu().double(), mean, atol=1e-5) and torch.allclose(si.cpu().double(), 1 / torch.sqrt(var + 1e-5), rtol=1e-5)
     assert torch.allclose(rm.cpu().double(), 0.1 * mean, atol=1e-5)
     assert torch.allclose(rv.cpu().double(), 0.9 + 0.1 * var * n / (n - 1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 32, 12, 20), (128, 32, 17, 9), (64, 48, 33, 40)])
+def test_conv3x3_bn_relu_prologue(Cin, Cout, H, W):
+    """K x K prologue: conv3x3(relu(bn(x)), padding=1) from the RAW x - the halo patch is activated in shared memory and the
+    patch pixels outside the image stay zero (the reference pads the ACTIVATED tensor, tv:51-53 / norm2-relu2-conv2)."""
+    torch.manual_seed(Cin + W)
+    B = 2
+    x = bf16_round(torch.randn(B, Cin, H, W) * 1.7 + 0.4)
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5)
+    gamma, beta, st, mean, var, act = _bn_setup(x, Cin, 6)
+    ref = F.conv2d(bf16_round(act.float()).double(), w.double(), padding=1)
+    a = to_mat(x)
+    fwd, _, off = ops.conv_taps(3, 1)
+    wp, ktot, n_rows = _pack(w, Cout, Cin, 9, off, Cin * 9, 9)
+    out = ops.new_mat(B, H, W, Cout, zero=True)
+    rm, rv = torch.zeros(Cin, device="cuda"), torch.ones(Cin, device="cuda")
+    sm, si = torch.empty(Cin, device="cuda"), torch.empty(Cin, device="cuda")
+    d = ops.make_igemm([a.view(0, Cin)], fwd, wp, ktot, n_rows, W, H, B, Cout, out.ptr(), Cout)
+    d.pro_enable = 1
+    d.pro_bn = ops.make_bn(st, 0, B * H * W, gamma, beta, rm, rv, sm, si, training=True)
+    ops.run_igemm(d)
+    torch.cuda.synchronize()
+    err = rel_l2(from_mat(out), ref)
+    assert err < TOL, "3x3 prologue conv relL2 %.3e" % err
+    assert torch.allclose(sm.cpu().double(), mean, atol=1e-5)

@@ -156,3 +156,38 @@ def test_wgrad_1x1_bn_relu_prologue(Cin, Cout):
     torch.cuda.synchronize()
     err = rel_l2(grad.cpu(), ref)
     assert err < 2e-3, "prologue wgrad relL2 %.3e" % err      # the in-kernel fma may round a few activations differently
+
+
+@pytest.mark.parametrize("H,W", [(12, 20), (17, 9), (33, 40)])
+def test_wgrad_3x3_bn_relu_prologue(H, W):
+    """weight gradient of conv3x3(relu(bn(x)), padding 1) from the RAW x (family mode: the gradient patch is shifted, so activation
+    rows outside the image must be written as zeros - partial tiles at the right / bottom edges)."""
+    torch.manual_seed(H + W)
+    B, Cin, Cout = 2, 128, 32
+    x = bf16_round(torch.randn(B, Cin, H, W) * 1.5 + 0.2)
+    g = bf16_round(torch.randn(B, Cout, H, W))
+    gen = torch.Generator().manual_seed(4)
+    gamma = (torch.rand(Cin, generator=gen) + 0.5)
+    beta = torch.randn(Cin, generator=gen) * 0.3 + 0.2       # mostly positive shifts: relu(shift) != 0 outside the image
+    mean = torch.randn(Cin, generator=gen) * 0.2 + 0.2
+    invstd = torch.rand(Cin, generator=gen) * 0.5 + 0.4
+    sc = gamma * invstd
+    act = bf16_round(torch.relu(x * sc.view(1, -1, 1, 1) + (beta - mean * sc).view(1, -1, 1, 1)))
+    w = torch.zeros(Cout, Cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(act.double(), w, padding=1).backward(g.double())
+    xm = to_mat(x)
+    gm = to_mat(g)
+    fwd, _, off = ops.conv_taps(3, 1)
+    plan = ops.plan_conv_wgrad(xm.view(0, Cin), [gm.view(0, Cout)], fwd, Cin, Cout)
+    dw = torch.zeros(plan["rows"] * plan["ld"], dtype=torch.float32, device="cuda")
+    dev = [t.cuda() for t in (gamma, beta, mean, invstd)]
+    for kw in plan["launches"]:
+        d = ops.make_wgrad(W=W, H=H, B=B, dw=dw, ld=plan["ld"], **kw)
+        d.pro_enable = 1
+        d.pro_gamma, d.pro_beta, d.pro_mean, d.pro_invstd = (t.data_ptr() for t in dev)
+        ops.run_wgrad(d)
+    grad = torch.full((Cout, Cin, 3, 3), float("nan"), dtype=torch.float32, device="cuda")
+    ops.unpack_wgrad(dw, plan["dt"], plan["dm"], plan["dn"], Cin, Cout, grad, 9, [off[t] for t in plan["tap_order"]], Cin * 9, 9)
+    torch.cuda.synchronize()
+    err = rel_l2(grad.cpu(), w.grad)
+    assert err < 2e-3, "3x3 prologue wgrad relL2 %.3e" % err
