@@ -269,7 +269,7 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
               "dmm_conv_igemm: bad tile_w %d", d->tile_w);
     DMM_CHECK(d->n_tile >= 16 && d->n_tile <= 256 && d->n_tile % 16 == 0, "dmm_conv_igemm: bad n_tile %d", d->n_tile);
     DMM_CHECK(d->N >= 1 && d->out != nullptr && d->weights != nullptr, "dmm_conv_igemm: bad output/weights");
-    DMM_CHECK(d->out_mode >= 0 && d->out_mode <= 2, "dmm_conv_igemm: bad out_mode %d", d->out_mode);
+    DMM_CHECK(d->out_mode >= 0 && d->out_mode <= 3, "dmm_conv_igemm: bad out_mode %d", d->out_mode);
     if (d->B <= 0 || d->H <= 0 || d->W <= 0) return 0;
     {
         // v2 (persistent, halo patches in shared memory) handles every kwidth-64 launch; DMM_IGEMM_V1=1 keeps v1
@@ -283,9 +283,9 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
             if (used) { ++tapped; packed16 = d->src[s].C <= 16; }
         }
         packed16 = packed16 && tapped == 1;
-        if ((d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode == 2)) return igemm2_launch(d, stream);
+        if ((d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode >= 2)) return igemm2_launch(d, stream);
     }
-    DMM_CHECK(d->out_mode != 2, "dmm_conv_igemm: out_mode 2 needs kwidth 64");
+    DMM_CHECK(d->out_mode < 2, "dmm_conv_igemm: out_mode 2 / 3 need kwidth 64");
 
     IgemmKParams p;
     memset(&p, 0, sizeof(p));

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
+    uint8_t* xstg = stg + ((OUT_MODE == 0 || OUT_MODE == 3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
     uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.b_map);
         if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
-        if (OUT_MODE == 0) tma_prefetch_desc(&p.o_map);
+        if (OUT_MODE == 0 || OUT_MODE == 3) tma_prefetch_desc(&p.o_map);
         if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
     }
     // everything above is independent of earlier kernels: wait for them (programmatic dependent launch) only here
@@ -393,9 +393,17 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         const int q = warp & 3;              // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;         // accumulator row = pixel within the sub-tile
         const int px = r % p.sub_w, py = r / p.sub_w;
-        const bool do_stats = (OUT_MODE == 0) && (p.stats != nullptr);
+        const bool do_stats = (OUT_MODE == 0 || OUT_MODE == 3) && (p.stats != nullptr);
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
         uint8_t* slot = stg + team * kStageSlot;
+        if (OUT_MODE == 3) {
+            // compact staging: 4 image rows x (32 - 2) valid pixels = 120 rows; rows 120..127 stay zero for the statistics loop
+            if (r >= 120) {
+#pragma unroll
+                for (int c16 = 0; c16 < 8; ++c16) sts_v4(smem_u32(slot) + r * 128 + c16 * 16, make_uint4(0, 0, 0, 0));
+            }
+            epi_bar(team);
+        }
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
@@ -468,7 +476,68 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 const int x = tc.x0 + p.sub_x[sub] + px, y = tc.y0 + p.sub_y[sub] + py;
                 const bool valid = (x < p.Wv) && (y < p.Hv);
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * MSUB + sub) * p.n_tile;
-                if (OUT_MODE == 0) {
+                if (OUT_MODE == 3) {
+                    // 3 kernel columns folded into N = 3 * C (C = 32): lane = pixel of one 32-pixel image row (sub_w == 32), output
+                    // pixel px = column block 0 of lane px-1 + block 1 of lane px + block 2 of lane px+1 (warp shuffles); lanes 0 and
+                    // 31 are the halo.  bf16 result -> compact staging rows (4 x 30) -> TMA store + statistics like out_mode 0.
+                    if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
+                    float o[32];
+                    {
+                        uint32_t v[2][16];
+                        tmem_ld16(trow + 32, v[0]);
+                        tmem_ld16(trow + 48, v[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i >> 4][i & 15]);
+                        tmem_ld16(trow, v[0]);
+                        tmem_ld16(trow + 16, v[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] += __shfl_up_sync(0xffffffffu, __uint_as_float(v[i >> 4][i & 15]), 1);
+                        tmem_ld16(trow + 64, v[0]);
+                        tmem_ld16(trow + 80, v[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i >> 4][i & 15]), 1);
+                    }
+                    if (r == 0) bulk_wait_read0();
+                    epi_bar(team);
+                    if (lane >= 1 && lane <= 30) {
+                        const int rc = q * 30 + lane - 1;                       // compact staging row
+                        const uint32_t srow3 = slot_u + rc * 128;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 w = make_uint4(0, 0, 0, 0);
+                            if (valid && x >= 0) {
+                                w.x = pack_bf16x2(o[8 * g + 0], o[8 * g + 1]);
+                                w.y = pack_bf16x2(o[8 * g + 2], o[8 * g + 3]);
+                                w.z = pack_bf16x2(o[8 * g + 4], o[8 * g + 5]);
+                                w.w = pack_bf16x2(o[8 * g + 6], o[8 * g + 7]);
+                            }
+                            sts_v4(srow3 + ((g ^ (rc & 7)) << 4), w);
+                        }
+                    }
+                    fence_proxy_async();
+                    epi_bar(team);
+                    if (r == 0) {
+                        tma_store_4d(&p.o_map, slot, 0, tc.x0 + p.sub_x[sub] + 1, tc.y0 + p.sub_y[sub], tc.b);
+                        bulk_commit();
+                    }
+                    if (do_stats) {
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                        const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
+                        const int j = cp >> 2;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t u = lds_u32(base + i * 128 + ((j ^ (i & 7)) << 4));
+                            const float a = bf16_lo(u), b = bf16_hi(u);
+                            s1a += a; s1b += b;
+                            s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
+                        }
+                        sacc[0][0] += (double)s1a; sacc[0][1] += (double)s1b;
+                        sacc[0][2] += (double)s2a; sacc[0][3] += (double)s2b;
+                    }
+                } else if (OUT_MODE == 0) {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         if (tc.n0 + 64 * c >= p.N) break;
@@ -580,10 +649,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int col = tc.n0 + c * 64 + 2 * cp;
-                    if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
+                    if (c * 64 + 2 * cp < (OUT_MODE == 3 ? p.fold_c : p.n_tile) && col < (OUT_MODE == 3 ? p.fold_c : p.N)) {
                         atomicAdd(st + col, sacc[c][0]);
                         atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                        if (col + 1 < p.N) {
+                        if (col + 1 < (OUT_MODE == 3 ? p.fold_c : p.N)) {
                             atomicAdd(st + col + 1, sacc[c][1]);
                             atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                         }
@@ -598,17 +667,17 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int col = last_n0 + c * 64 + 2 * cp;
-                if (c * 64 + 2 * cp < p.n_tile && col < p.N) {
+                if (c * 64 + 2 * cp < (OUT_MODE == 3 ? p.fold_c : p.n_tile) && col < (OUT_MODE == 3 ? p.fold_c : p.N)) {
                     atomicAdd(st + col, sacc[c][0]);
                     atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                    if (col + 1 < p.N) {
+                    if (col + 1 < (OUT_MODE == 3 ? p.fold_c : p.N)) {
                         atomicAdd(st + col + 1, sacc[c][1]);
                         atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                     }
                 }
             }
         }
-        if (OUT_MODE == 0 && r == 0) bulk_wait_all();
+        if ((OUT_MODE == 0 || OUT_MODE == 3) && r == 0) bulk_wait_all();
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
@@ -642,8 +711,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     DMM_CHECK(d->kwidth == 64 || d->kwidth == 16, "igemm v2: kwidth must be 64 or 16");
     const int tpk = d->kwidth == 16 ? 4 : 1;       // kwidth 16: sources of <= 16 channels, weights packed [n][tap*16 + c]
     DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
-    DMM_CHECK(d->out_mode == 0 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
-    const bool fold = d->out_mode == 2;
+    DMM_CHECK(d->out_mode == 0 || d->out_mode == 3 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
+    const bool fold = d->out_mode == 2 || d->out_mode == 3;
+    if (d->out_mode == 3)
+        DMM_CHECK(d->fold_kw == 3 && d->N == 96 && d->n_tile == 96 && d->tile_w == 32 && d->bnb_sums == nullptr && !d->pro_enable,
+                  "igemm v2: out_mode 3 is the 3x3, 32-output-channel growth convolution with its kernel columns folded into N = 96");
     if (fold) {
         DMM_CHECK(d->fold_kw >= 1 && (d->fold_kw & 1) && d->N % d->fold_kw == 0 && d->kwidth == 64 && d->num_src == 1,
                   "igemm v2: out_mode 2 needs an odd fold_kw dividing N, one source, kwidth 64");
@@ -746,7 +818,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
                   "igemm v2: prologue BatchNorm without statistics");
         pro_kp = ceil_div(d->src[0].C, 64) * 64;
     }
-    const int staging = (d->out_mode == 0 ? (bnb ? 4 : 2) * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0)) +
+    const int staging = ((d->out_mode == 0 || d->out_mode == 3) ? (bnb ? 4 : 2) * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0)) +
                         (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
@@ -819,7 +891,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.fold_kw = fold ? d->fold_kw : 0;
     p.fold_c = fold ? d->N / d->fold_kw : 0;
     if (fold) {
-        DMM_CHECK(p.fold_c <= 4 && best.nsx == 1, "igemm v2: out_mode 2 supports at most 4 classes (got %d)", p.fold_c);
+        DMM_CHECK((d->out_mode == 3 || p.fold_c <= 4) && best.nsx == 1, "igemm v2: out_mode 2 supports at most 4 classes (got %d)", p.fold_c);
+        DMM_CHECK(d->out_mode != 3 || (p.sub_w == 32 && p.sub_h == 4), "igemm v2: out_mode 3 needs 32 x 4 sub-tiles");
         auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
         p.tw_log = ilog2(p.TW); p.sw_log = ilog2(p.sub_w); p.sh_log = ilog2(p.sub_h);
         DMM_CHECK((1 << p.tw_log) == p.TW && (1 << p.sw_log) == p.sub_w && (1 << p.sh_log) == p.sub_h && p.TW <= 256,
@@ -871,21 +944,21 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.Wv = d->W < OWv ? d->W : OWv;
     p.Hv = d->H < OHv ? d->H : OHv;
     p.OH = OH; p.OW = OW; p.out_sy = osy; p.out_sx = osx; p.out_py = d->out_py; p.out_px = d->out_px;
-    if (d->out_mode == 0) {
+    if (d->out_mode == 0 || d->out_mode == 3) {
         DMM_CHECK(d->ldo % 8 == 0 && d->coff % 8 == 0, "igemm v2: output pitch %lld / channel offset %d must be multiples of 8",
                   (long long)d->ldo, d->coff);
         dmm_view_t ov;
         ov.ptr = reinterpret_cast<const uint16_t*>(d->out) + ((long long)d->out_py * OW + d->out_px) * d->ldo + d->coff;
-        ov.C = d->N; ov.W = OWv; ov.H = OHv; ov.B = d->B;
+        ov.C = d->out_mode == 3 ? d->N / d->fold_kw : d->N; ov.W = OWv; ov.H = OHv; ov.B = d->B;
         ov.sw = (long long)osx * d->ldo;
         ov.sh = (long long)osy * OW * d->ldo;
         ov.sb = (long long)OH * OW * d->ldo;
-        int rc = view_to_tmap(&p.o_map, ov, 64, p.sub_w, p.sub_h, 128);
+        int rc = view_to_tmap(&p.o_map, ov, 64, d->out_mode == 3 ? p.sub_w - 2 : p.sub_w, p.sub_h, 128);
         if (rc) return rc;
     } else {
         p.out32 = reinterpret_cast<float*>(d->out);
     }
-    p.stats = d->out_mode == 0 ? d->stats : nullptr;
+    p.stats = (d->out_mode == 0 || d->out_mode == 3) ? d->stats : nullptr;
     p.stats_ld = d->stats_ld;
     p.stats_off = d->stats_off;
     if (pro) {
@@ -923,7 +996,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         else if (nch == 3) fn = igemm2_kernel<3, 0, 1, PROFLAG>;                                                                           \
         else fn = igemm2_kernel<4, 0, 1, PROFLAG>;                                                                                         \
     } while (0)
-    if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, false> : igemm2_kernel<1, 2, 1, false>);
+    if (d->out_mode == 3) fn = p.msub == 2 ? igemm2_kernel<1, 3, 2, false> : igemm2_kernel<1, 3, 1, false>;
+    else if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, false> : igemm2_kernel<1, 2, 1, false>);
     else if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
     else if (pro) DMM_IG2_PICK(true);
     else DMM_IG2_PICK(false);

@@ -36,13 +36,15 @@ def split_batch(batch):
 class BatchFileRing:
     """iterate over batch files as (image, lidar, heat_maps) pinned float32 tensors, `depth` batches read ahead.
 
-    Every slot of the ring owns its pinned buffers; a yielded triple stays valid until `depth` further batches have been
-    yielded (enough for one step in flight + one prefetch)."""
+    Every slot of the ring owns its pinned buffers; a yielded triple stays valid until TWO further batches have been taken
+    from the iterator (one step in flight + one prefetch).  The reader thread fills a slot BEFORE it blocks on the queue of
+    `depth - 1` finished batches, so depth + 2 slots are needed: the slot it overwrites for batch n held batch n - depth - 2,
+    and at that moment at least n - (depth - 1) batches have been taken."""
 
     def __init__(self, root, files, depth=3, pin=None, epochs=1):
         self.root, self.files, self.depth, self.epochs = root, list(files), max(2, int(depth)), epochs
         self.pin = torch.cuda.is_available() if pin is None else bool(pin)
-        self._slots = [None] * (self.depth + 1)
+        self._slots = [None] * (self.depth + 2)
 
     def __len__(self):
         return len(self.files) * self.epochs
