@@ -78,6 +78,8 @@ typedef struct {
  *   folded into the GEMM's N: the taps are the kernel ROWS only (dx == 0), weight row kw*C + n holds w[n, :, kh, kw]
  *   (C = N / fold_kw classes, N <= 16), and the epilogue forms out[n](y, x) = sum_kw acc[(y, x + kw - fold_kw/2)][kw*C + n]
  *   from tiles that overlap by fold_kw - 1 columns.  K*K -> K MMAs per tile for the 5x5, 64 -> 3 head convolution (:130-131).
+ * out_mode 3: the same fold for the 3x3, 128 -> 32 growth convolutions (tv:51-53): fold_kw = 3, N = n_tile = 96 (weight row
+ *   kw*32 + n), tile_w = 32; output = bf16 NHWC slice (ldo, coff) + stats of the 32 real output channels like out_mode 0.
  * stats (nullable): double[DMM_STATS_SLOTS][2][stats_ld], column sums / sums of squares of the
  * bf16-rounded outputs are atomically added at [.., stats_off + n]. */
 typedef struct {
@@ -120,7 +122,7 @@ typedef struct {
      * tensor).  pro_bn describes the BatchNorm over the src[0].C channels exactly like dmm_bn_relu_apply (CTA 0 also saves
      * mean / invstd and updates the running statistics). */
     int32_t pro_enable;
-    int32_t fold_kw;         /* out_mode 2: kernel width folded into N (odd); else 0 */
+    int32_t fold_kw;         /* out_mode 2 / 3: kernel width folded into N (odd); else 0 */
     dmm_bn_t pro_bn;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);

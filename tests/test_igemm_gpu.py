@@ -335,4 +335,5 @@ def test_conv3x3_growth_folded_kernel_columns(H, W, coff, extra):
     assert torch.allclose(s2[coff:coff + Cout].cpu(), (g * g).sum(1), rtol=1e-4, atol=1e-6)
     other = torch.ones(ldo, dtype=torch.bool)
     other[coff:coff + Cout] = False
-    assert float(s1.cpu()[other].abs().max()) == 0.0 and float(s2.cpu()[other].abs().max()) == 0.0, "statistics outside the slice"
+    if bool(other.any()):
+        assert float(s1.cpu()[other].abs().max()) == 0.0 and float(s2.cpu()[other].abs().max()) == 0.0, "statistics outside the slice"
