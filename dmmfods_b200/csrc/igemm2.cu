@@ -107,12 +107,15 @@ __device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t
 
 template <int NCH, int OUT_MODE, int MSUB, bool PRO>
 __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
+    // OUT_MODE 3 / 4 (internal): 3 kernel columns folded into N = 3 * FC for FC = 32 / 64 output channels (C-ABI out_mode 3)
+    constexpr bool FOLD3 = OUT_MODE == 3 || OUT_MODE == 4;
+    constexpr int FC = OUT_MODE == 4 ? 64 : 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + ((OUT_MODE == 0 || OUT_MODE == 3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
+    uint8_t* xstg = stg + ((OUT_MODE == 0 || FOLD3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
     uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.b_map);
         if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
-        if (OUT_MODE == 0 || OUT_MODE == 3) tma_prefetch_desc(&p.o_map);
+        if (OUT_MODE == 0 || FOLD3) tma_prefetch_desc(&p.o_map);
         if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
     }
     // everything above is independent of earlier kernels: wait for them (programmatic dependent launch) only here
@@ -393,10 +396,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         const int q = warp & 3;              // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;         // accumulator row = pixel within the sub-tile
         const int px = r % p.sub_w, py = r / p.sub_w;
-        const bool do_stats = (OUT_MODE == 0 || OUT_MODE == 3) && (p.stats != nullptr);
+        const bool do_stats = (OUT_MODE == 0 || FOLD3) && (p.stats != nullptr);
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
         uint8_t* slot = stg + team * kStageSlot;
-        if (OUT_MODE == 3) {
+        if (FOLD3) {
             // compact staging: 4 image rows x (32 - 2) valid pixels = 120 rows; rows 120..127 stay zero for the statistics loop
             if (r >= 120) {
 #pragma unroll
@@ -476,29 +479,35 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 const int x = tc.x0 + p.sub_x[sub] + px, y = tc.y0 + p.sub_y[sub] + py;
                 const bool valid = (x < p.Wv) && (y < p.Hv);
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (as * MSUB + sub) * p.n_tile;
-                if (OUT_MODE == 3) {
-                    // 3 kernel columns folded into N = 3 * C (C = 32): lane = pixel of one 32-pixel image row (sub_w == 32), output
-                    // pixel px = column block 0 of lane px-1 + block 1 of lane px + block 2 of lane px+1 (warp shuffles); lanes 0 and
-                    // 31 are the halo.  bf16 result -> compact staging rows (4 x 30) -> TMA store + statistics like out_mode 0.
+                if (FOLD3) {
+                    // 3 kernel columns folded into N = 3 * FC: lane = pixel of one 32-pixel image row (sub_w == 32), output pixel
+                    // px = column block 0 of lane px-1 + block 1 of lane px + block 2 of lane px+1 (warp shuffles); lanes 0 and 31
+                    // are the halo.  bf16 result -> compact staging rows (4 x 30) -> TMA store + statistics like out_mode 0.
                     if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
-                    float o[32];
+                    float o[FC];
                     {
-                        uint32_t v[2][16];
-                        tmem_ld16(trow + 32, v[0]);
-                        tmem_ld16(trow + 48, v[1]);
-                        tmem_ld_wait();
+                        uint32_t v[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i >> 4][i & 15]);
-                        tmem_ld16(trow, v[0]);
-                        tmem_ld16(trow + 16, v[1]);
-                        tmem_ld_wait();
+                        for (int g = 0; g < FC / 16; ++g) {
+                            tmem_ld16(trow + FC + 16 * g, v);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] += __shfl_up_sync(0xffffffffu, __uint_as_float(v[i >> 4][i & 15]), 1);
-                        tmem_ld16(trow + 64, v[0]);
-                        tmem_ld16(trow + 80, v[1]);
-                        tmem_ld_wait();
+                            for (int i = 0; i < 16; ++i) o[16 * g + i] = __uint_as_float(v[i]);
+                        }
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i >> 4][i & 15]), 1);
+                        for (int g = 0; g < FC / 16; ++g) {
+                            tmem_ld16(trow + 16 * g, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[16 * g + i] += __shfl_up_sync(0xffffffffu, __uint_as_float(v[i]), 1);
+                        }
+#pragma unroll
+                        for (int g = 0; g < FC / 16; ++g) {
+                            tmem_ld16(trow + 2 * FC + 16 * g, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[16 * g + i] += __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), 1);
+                        }
                     }
                     if (r == 0) bulk_wait_read0();
                     epi_bar(team);
@@ -506,7 +515,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         const int rc = q * 30 + lane - 1;                       // compact staging row
                         const uint32_t srow3 = slot_u + rc * 128;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
+                        for (int g = 0; g < FC / 8; ++g) {
                             uint4 w = make_uint4(0, 0, 0, 0);
                             if (valid && x >= 0) {
                                 w.x = pack_bf16x2(o[8 * g + 0], o[8 * g + 1]);
@@ -649,10 +658,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int col = tc.n0 + c * 64 + 2 * cp;
-                    if (c * 64 + 2 * cp < (OUT_MODE == 3 ? p.fold_c : p.n_tile) && col < (OUT_MODE == 3 ? p.fold_c : p.N)) {
+                    if (c * 64 + 2 * cp < (FOLD3 ? p.fold_c : p.n_tile) && col < (FOLD3 ? p.fold_c : p.N)) {
                         atomicAdd(st + col, sacc[c][0]);
                         atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                        if (col + 1 < (OUT_MODE == 3 ? p.fold_c : p.N)) {
+                        if (col + 1 < (FOLD3 ? p.fold_c : p.N)) {
                             atomicAdd(st + col + 1, sacc[c][1]);
                             atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                         }
@@ -667,17 +676,17 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int col = last_n0 + c * 64 + 2 * cp;
-                if (c * 64 + 2 * cp < (OUT_MODE == 3 ? p.fold_c : p.n_tile) && col < (OUT_MODE == 3 ? p.fold_c : p.N)) {
+                if (c * 64 + 2 * cp < (FOLD3 ? p.fold_c : p.n_tile) && col < (FOLD3 ? p.fold_c : p.N)) {
                     atomicAdd(st + col, sacc[c][0]);
                     atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                    if (col + 1 < (OUT_MODE == 3 ? p.fold_c : p.N)) {
+                    if (col + 1 < (FOLD3 ? p.fold_c : p.N)) {
                         atomicAdd(st + col + 1, sacc[c][1]);
                         atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
                     }
                 }
             }
         }
-        if ((OUT_MODE == 0 || OUT_MODE == 3) && r == 0) bulk_wait_all();
+        if ((OUT_MODE == 0 || FOLD3) && r == 0) bulk_wait_all();
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
@@ -714,8 +723,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     DMM_CHECK(d->out_mode == 0 || d->out_mode == 3 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
     const bool fold = d->out_mode == 2 || d->out_mode == 3;
     if (d->out_mode == 3)
-        DMM_CHECK(d->fold_kw == 3 && d->N == 96 && d->n_tile == 96 && d->tile_w == 32 && d->bnb_sums == nullptr && !d->pro_enable,
-                  "igemm v2: out_mode 3 is the 3x3, 32-output-channel growth convolution with its kernel columns folded into N = 96");
+        DMM_CHECK(d->fold_kw == 3 && (d->N == 96 || d->N == 192) && d->n_tile == d->N && d->tile_w == 32 && d->bnb_sums == nullptr && !d->pro_enable,
+                  "igemm v2: out_mode 3 is a 3x3 convolution with 32 or 64 output channels whose kernel columns are folded into N = 96 / 192");
     if (fold) {
         DMM_CHECK(d->fold_kw >= 1 && (d->fold_kw & 1) && d->N % d->fold_kw == 0 && d->kwidth == 64 && d->num_src == 1,
                   "igemm v2: out_mode 2 needs an odd fold_kw dividing N, one source, kwidth 64");
@@ -996,7 +1005,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         else if (nch == 3) fn = igemm2_kernel<3, 0, 1, PROFLAG>;                                                                           \
         else fn = igemm2_kernel<4, 0, 1, PROFLAG>;                                                                                         \
     } while (0)
-    if (d->out_mode == 3) fn = p.msub == 2 ? igemm2_kernel<1, 3, 2, false> : igemm2_kernel<1, 3, 1, false>;
+    if (d->out_mode == 3 && d->N == 192) fn = igemm2_kernel<1, 4, 1, false>;
+    else if (d->out_mode == 3) fn = p.msub == 2 ? igemm2_kernel<1, 3, 2, false> : igemm2_kernel<1, 3, 1, false>;
     else if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, false> : igemm2_kernel<1, 2, 1, false>);
     else if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
     else if (pro) DMM_IG2_PICK(true);

@@ -805,8 +805,13 @@ class Engine:
         r0s = self._new_stats(nf2)
         self.named["head.a0"] = a0
         self.named["head.refine0"] = r0
-        self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
-                       W, H, B, r0, 0, r0s, 0)
+        if nf2 == 64 and os.environ.get("DMM_HEAD_FOLD0", "0") != "0":
+            # kernel columns folded into N = 192 (igemm out_mode 3): 3 taps at 96 cycles per MMA instead of 9 taps of N = 64
+            self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], [(0, kh - 1, 0) for kh in range(3)],
+                           [3 * kh for kh in range(3)], Ct, nf2, Ct * 9, 9, W, H, B, r0, 0, r0s, 0, out_mode=3, fold_kw=3, tile_w=32)
+        else:
+            self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
+                           W, H, B, r0, 0, r0s, 0)
         a1h = self._mat(B, H, W, nf2)
         self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
         conv5 = ops.conv_taps(5, 2)

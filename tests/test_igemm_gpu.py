@@ -302,24 +302,28 @@ def test_conv3x3_bn_relu_prologue(Cin, Cout, H, W):
     assert torch.allclose(sm.cpu().double(), mean, atol=1e-5)
 
 
-@pytest.mark.parametrize("H,W,coff,extra", [(12, 30, 0, 0), (16, 40, 64, 32), (9, 13, 32, 0), (33, 64, 0, 32), (5, 91, 32, 32)])
-def test_conv3x3_growth_folded_kernel_columns(H, W, coff, extra):
+@pytest.mark.parametrize("H,W,coff,extra,Cin,Cout", [(12, 30, 0, 0, 128, 32), (16, 40, 64, 32, 128, 32), (9, 13, 32, 0, 128, 32),
+                                                     (33, 64, 0, 32, 128, 32), (5, 91, 32, 32, 128, 32)])
+def test_conv3x3_growth_folded_kernel_columns(H, W, coff, extra, Cin, Cout):
     """out_mode 3: conv2 of a dense layer (3x3, 128 -> 32) with the three kernel columns folded into N = 96 (weight row
     kw*32 + n), three kernel-row taps, neighbours summed with warp shuffles; bf16 slice of a block buffer + BN statistics
     exactly like the 9-tap launch (tv:51-53)."""
     torch.manual_seed(H * W)
-    B, Cin, Cout = 2, 128, 32
+    B = 2
     x = bf16_round(torch.randn(B, Cin, H, W))
     w = bf16_round(torch.randn(Cout, Cin, 3, 3) / (Cin * 9) ** 0.5)
     ref = F.conv2d(x.double(), w.double(), padding=1)
     a = to_mat(x)
-    wp = w.permute(3, 0, 2, 1).reshape(3 * Cout, 3 * Cin).to(torch.bfloat16).contiguous().cuda()       # (kw, n) x (kh, ci)
+    Kp = ops.ceil_to(Cin, 64)
+    wp = torch.zeros(3 * Cout, 3, Kp, dtype=torch.bfloat16)
+    wp[:, :, :Cin] = w.permute(3, 0, 2, 1).reshape(3 * Cout, 3, Cin).to(torch.bfloat16)                # (kw, n) x (kh, ci)
+    wp = wp.reshape(3 * Cout, 3 * Kp).contiguous().cuda()
     ldo = coff + Cout + extra
     out = ops.new_mat(B, H, W, ldo, zero=True)
     st = new_stats(ldo)
     taps = [(0, kh - 1, 0) for kh in range(3)]
-    d = ops.make_igemm([a.view()], taps, wp, 3 * Cin, 96, W, H, B, 96, out.ptr(), ldo, coff=coff, out_mode=3, stats=st,
-                       stats_off=coff, n_tile=96, fold_kw=3, tile_w=32)
+    d = ops.make_igemm([a.view(0, Cin)], taps, wp, 3 * Kp, 3 * Cout, W, H, B, 3 * Cout, out.ptr(), ldo, coff=coff, out_mode=3,
+                       stats=st, stats_off=coff, n_tile=3 * Cout, fold_kw=3, tile_w=32)
     ops.run_igemm(d)
     torch.cuda.synchronize()
     got = from_mat(out, coff, Cout)
