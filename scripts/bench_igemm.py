@@ -18,6 +18,8 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "reduce4": (32, 160, 240, 512, 128, 1, 0),
     "convT4_phase11": (32, 160, 240, 128, 128, 2, 0),
     "refine1_dgrad": (32, 640, 960, 3, 64, 5, 0),
+    "b1_conv2_fold": (32, 160, 240, 128, 96, -3, 4),           # out_mode 4 here = C-ABI out_mode 3 (3 kernel columns folded, bf16 + stats)
+    "refine0_fold": (32, 640, 960, 136, 192, -3, 4),
     "refine1_fold": (32, 640, 960, 64, 15, -5, 3),             # out_mode 3 here = folded kernel columns (out_mode 2 of the C-ABI)
     "refine1_dgrad_v": (32, 640, 960, 16, 64, -5, 0),          # K < 0: |K| vertical taps over the horizontally unfolded d(logits)
     "b1_conv1_k160_pro": (32, 160, 240, 160, 128, 1, 2),      # out_mode 2 here = BN-ReLU prologue on a [P, 256] block buffer
@@ -56,6 +58,11 @@ def run(name, reps=5):
             d.pro_enable = 1
             d.pro_bn = ops.make_bn(ops.Stats(bst, 0, ld), 0, B * H * W, g, b_, rm, rv, sm, si, training=True)
             keep = (bst, g, b_, rm, rv, sm, si)
+    elif om == 4:
+        out = ops.new_mat(B, H, W, Cout // 3)
+        st = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
+        d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.ptr(), out.ld, out_mode=3,
+                           stats=ops.Stats(st, 0, out.ld), n_tile=Cout, fold_kw=3, tile_w=32)
     elif om == 3:
         out = torch.zeros(B, Cout // 5, H, W, device="cuda")
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.data_ptr(), 0, out_mode=2, n_tile=n_tile,
