@@ -806,7 +806,9 @@ class Engine:
         self.named["head.a0"] = a0
         self.named["head.refine0"] = r0
         if nf2 == 64 and os.environ.get("DMM_HEAD_FOLD0", "0") != "0":
-            # kernel columns folded into N = 192 (igemm out_mode 3): 3 taps at 96 cycles per MMA instead of 9 taps of N = 64
+            # kernel columns folded into N = 192 (igemm out_mode 3): 3 taps at 96 cycles per MMA instead of 9 taps of N = 64.
+            # Parity-tested but OFF: only one 128-pixel sub-tile fits in TMEM at N = 192, so every tile re-streams all weights
+            # and the launch is L2-bound at the same 3.9 ms as the 9-tap form (measured)
             self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], [(0, kh - 1, 0) for kh in range(3)],
                            [3 * kh for kh in range(3)], Ct, nf2, Ct * 9, 9, W, H, B, r0, 0, r0s, 0, out_mode=3, fold_kw=3, tile_w=32)
         else:

@@ -303,8 +303,8 @@ def test_conv3x3_bn_relu_prologue(Cin, Cout, H, W):
 
 
 @pytest.mark.parametrize("H,W,coff,extra,Cin,Cout", [(12, 30, 0, 0, 128, 32), (16, 40, 64, 32, 128, 32), (9, 13, 32, 0, 128, 32),
-                                                     (33, 64, 0, 32, 128, 32), (5, 91, 32, 32, 128, 32)]
-                         + ([(18, 61, 0, 0, 136, 64), (7, 30, 64, 0, 64, 64)] if __import__("os").environ.get("DMM_TEST_FOLD64") else []))
+                                                     (33, 64, 0, 32, 128, 32), (5, 91, 32, 32, 128, 32), (18, 61, 0, 0, 136, 64),
+                                                     (7, 30, 64, 0, 64, 64)])
 def test_conv3x3_growth_folded_kernel_columns(H, W, coff, extra, Cin, Cout):
     """out_mode 3: conv2 of a dense layer (3x3, 128 -> 32) with the three kernel columns folded into N = 96 (weight row
     kw*32 + n), three kernel-row taps, neighbours summed with warp shuffles; bf16 slice of a block buffer + BN statistics
