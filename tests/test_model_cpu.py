@@ -157,3 +157,19 @@ def test_engine_rejects_sizes_the_reference_rejects():
         Engine(params, m.model_cfg(), 1, 72, 96, plan_only=True)     # 72/4 = 18 -> 9 is odd at block 2
     with pytest.raises(ValueError):
         Engine(params, m.model_cfg(), 1, 63, 96, plan_only=True)
+
+
+def test_row_phase_views_cover_all_rows():
+    """ops.Mat.row_phase_view: the even / odd image-row views used by the stem's 7-tap vertical convolution (input row
+    2*oy + kh - 3 = 2*(oy + dy) + p) - pure host geometry, checked on a CPU tensor."""
+    import torch
+    from dmmfods_b200 import ops
+    B, H, W, ld = 2, 7, 5, 16
+    t = torch.arange(B * H * W * ld, dtype=torch.float32).to(torch.bfloat16).view(B * H * W, ld)
+    m = ops.Mat(t, B, H, W)
+    ev, od = m.row_phase_view(0), m.row_phase_view(1)
+    assert (ev.H, od.H) == ((H + 1) // 2, H // 2) and ev.W == od.W == W and ev.C == od.C == ld
+    assert ev.sw == ld and ev.sh == 2 * W * ld and ev.sb == H * W * ld
+    assert od.ptr - ev.ptr == 2 * W * ld                      # one image row further, in bytes of bf16
+    taps = [((kh - 3) % 2, (kh - 3 - (kh - 3) % 2) // 2) for kh in range(7)]
+    assert [2 * dy + p for p, dy in taps] == [kh - 3 for kh in range(7)]
