@@ -81,7 +81,7 @@ def test_full_resolution_train_step_matches_oracle(full_res):
           "emulated vs exact %.3e); loss rel %.3e; grad global relL2 %.3e vs emulated, %.3e vs exact (yard-stick %.3e)"
           % (e_logits, e_logits_exact, yard_logits, e_loss, e_grad, e_grad_exact, yard_grad))
     assert e_loss < 2e-3
-    assert e_logits < max(4e-2, 0.5 * yard_logits)
+    assert e_logits < max(4e-2, 0.75 * yard_logits)         # measured 0.49 x; two uncorrelated realisations would sit at 1.41 x
     assert e_logits_exact < 1.5 * yard_logits + 2e-2
     assert e_grad < 1.5e-1
     assert e_grad_exact < 1.5 * yard_grad + 2e-2
