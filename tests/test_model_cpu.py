@@ -173,3 +173,31 @@ def test_row_phase_views_cover_all_rows():
     assert od.ptr - ev.ptr == 2 * W * ld                      # one image row further, in bytes of bf16
     taps = [((kh - 3) % 2, (kh - 3 - (kh - 3) % 2) // 2) for kh in range(7)]
     assert [2 * dy + p for p, dy in taps] == [kh - 3 for kh in range(7)]
+
+
+def test_default_plan_uses_the_folded_and_unfolded_formulations():
+    """structure of the DenseNet-121 mid-fusion plan built without a GPU: the formulations DESIGN.md describes are the ones the
+    engine emits by default (growth convolutions with folded kernel columns, 5-tap head convolution with fp32 NCHW output,
+    stem unfold for the RGB stream / im2col for the LiDAR stream, conv1 with the BN-ReLU prologue, KxK prologue off)."""
+    from dmmfods_b200.engine import Engine
+    m = Dense_U_Net_lidar(_cfg(1, 3))
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    eng = Engine(params, m.model_cfg(), 2, 64, 96, plan_only=True)
+    fwd = {op.name: op for op in eng.fwd}
+    conv2 = [op for n, op in fwd.items() if n.endswith(".conv2")]
+    assert len(conv2) == 2 * (6 + 12) + 24 + 16
+    assert all(op.arg.out_mode == 3 and op.arg.fold_kw == 3 and op.arg.N == 96 and op.arg.num_taps == 3 and not op.arg.pro_enable
+               for op in conv2)
+    conv1 = [op for n, op in fwd.items() if n.endswith(".conv1")]
+    assert len(conv1) == len(conv2) and all(op.arg.pro_enable == 1 and op.arg.num_taps == 1 for op in conv1)
+    r1 = fwd["dec_out_to_heat_maps.refine1"].arg
+    assert (r1.out_mode, r1.fold_kw, r1.N, r1.num_taps) == (2, 5, 15, 5)
+    r0 = fwd["dec_out_to_heat_maps.refine0"].arg
+    assert (r0.out_mode, r0.num_taps, r0.N) == (0, 9, 64)
+    s1, s2 = fwd["features.conv0"].arg, fwd["stream_2_features.conv0"].arg
+    assert (s1.num_src, s1.num_taps) == (2, 7) and (s2.num_src, s2.num_taps) == (1, 1)
+    # backward: refine1's data gradient is the 5-tap vertical form, its weight gradient one launch over 5 taps
+    bwd = {op.name: op for op in eng.bwd}
+    assert bwd["dec_out_to_heat_maps.refine1.dgrad"].arg.num_taps == 5
+    assert bwd["dec_out_to_heat_maps.refine1.wgrad"].arg.num_b == 5
+    assert any(n.endswith(".norm2") for n in fwd)                      # norm2 is still a separate BN-ReLU pass (KxK prologue off)
