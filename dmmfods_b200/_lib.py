@@ -94,7 +94,7 @@ class HeadBwd(C.Structure):
                 ("lddu", c_int64)]
 
 
-GATHER_MAX = 40
+GATHER_MAX = 56
 
 
 class GradGather(C.Structure):

@@ -33,13 +33,33 @@ def split_batch(batch):
     return batch[:, :3, :, :], batch[:, 3, :, :].unsqueeze(1), batch[:, 4:, :, :]
 
 
+def mark_async_read(tensors, event):
+    """tag host tensors with the CUDA event recorded after an asynchronous (non_blocking) device copy that reads them."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            t._dmm_read_event = event
+
+
+def wait_async_reads(t):
+    """block until the asynchronous device copies that were reading host tensor `t` (mark_async_read) have completed."""
+    ev = getattr(t, "_dmm_read_event", None)
+    if ev is not None:
+        ev.synchronize()
+        t._dmm_read_event = None
+
+
 class BatchFileRing:
     """iterate over batch files as (image, lidar, heat_maps) pinned float32 tensors, `depth` batches read ahead.
 
     Every slot of the ring owns its pinned buffers; a yielded triple stays valid until TWO further batches have been taken
     from the iterator (one step in flight + one prefetch).  The reader thread fills a slot BEFORE it blocks on the queue of
     `depth - 1` finished batches, so depth + 2 slots are needed: the slot it overwrites for batch n held batch n - depth - 2,
-    and at that moment at least n - (depth - 1) batches have been taken."""
+    and at that moment at least n - (depth - 1) batches have been taken.
+
+    Slot reuse is additionally tied to COPY COMPLETION: a consumer that reads a yielded tensor asynchronously (the
+    non-blocking host -> device copies of `Trainer.prefetch` / `Trainer.step`) tags it with the CUDA event recorded after
+    the copy (`mark_async_read`), and the reader thread waits for that event before it overwrites the slot - a host that
+    runs ahead of the GPU (CUDA-graph steps, page-cached files) can therefore never corrupt an in-flight batch."""
 
     def __init__(self, root, files, depth=3, pin=None, epochs=1):
         self.root, self.files, self.depth, self.epochs = root, list(files), max(2, int(depth)), epochs
@@ -57,6 +77,7 @@ class BatchFileRing:
             bufs = tuple(torch.empty(p.shape, dtype=torch.float32, pin_memory=self.pin) for p in parts)
             self._slots[slot] = bufs
         for b, p in zip(bufs, parts):
+            wait_async_reads(b)
             b.copy_(p)
         return bufs
 

@@ -410,12 +410,19 @@ class Engine:
 
     def _gather(self, lst, name, blk, c0, C_, dst):
         """gradient of channels [c0, c0+C_) of a block buffer = sum of the slabs of every consumer of those channels (all of
-        them run earlier in the backward program) minus the deferred BatchNorm corrections.  Sources are resolved in _finalize."""
-        d = _lib.GradGather()
-        d.rows, d.C = blk.buf.P, C_
-        d.out, d.ldo = dst.ptr().value, dst.ld
-        self._emit(lst, self.lib.dmm_grad_gather, d, name, kind="grad_gather", nbytes=0.0)
-        self._gathers.append((lst[-1], blk, c0, C_))
+        them run earlier in the backward program) minus the deferred BatchNorm corrections.  Sources are resolved in _finalize
+        (one dmm_grad_gather launch, or a chain of launches that accumulate into dst when a block has more than
+        DMM_GATHER_MAX consumers)."""
+        descs = []
+
+        def run_gather(_a, stream, descs=descs, lib=self.lib):
+            for d in descs:
+                rc = lib.dmm_grad_gather(C.byref(d), stream)
+                if rc:
+                    return rc
+            return 0
+        self._emit(lst, run_gather, None, name, kind="grad_gather", nbytes=0.0)
+        self._gathers.append((lst[-1], blk, c0, C_, dst, descs))
 
     def _cast(self, lst, name, src, c0, C_, dst):
         def run(_arg, stream, src=src, c0=c0, C_=C_, dst=dst, lib=self.lib):
@@ -971,36 +978,56 @@ class Engine:
                     lo = hi = 0
                 self.segments.append((seg_ops, job_lo, job_i - job_lo, lo, hi))
                 seg_ops, seg_names, job_lo = [], [], job_i
-        for op, blk, c0, C_ in self._gathers:
-            d = op.arg
+        self.gather_launches = 0
+        for op, blk, c0, C_, dst, descs in self._gathers:
             srcs = [c for c in blk.contribs if c["C"] >= c0 + C_]
-            if not srcs or len(srcs) > _lib.GATHER_MAX:
-                raise RuntimeError("dmmfods_b200: %d gradient sources for channels [%d, %d) of a block buffer (%s)"
-                                   % (len(srcs), c0, c0 + C_, op.name))
-            nk = 0
+            if not srcs:
+                raise RuntimeError("dmmfods_b200: no gradient source for channels [%d, %d) of a block buffer (%s)"
+                                   % (c0, c0 + C_, op.name))
             gws = {c.get("gw", 0) for c in srcs} - {0}
             if len(gws) > 1 or any(c0 % g_ for g_ in gws):
                 raise RuntimeError("dmmfods_b200: inconsistent planar slab groups for %s" % op.name)
-            d.gw = gws.pop() if gws else 0
-            for i, c in enumerate(srcs):
-                if c.get("gw", 0):        # planar: group c0 / gw starts at that plane; the kernel adds further groups itself
-                    plane = blk.buf.P * c["gw"]
-                    d.src[i] = c["mat"].t.data_ptr() + 2 * (c0 // c["gw"]) * plane
-                    d.ld[i] = c["gw"]
-                    d.plane[i] = plane
-                else:
-                    d.src[i] = c["mat"].ptr(c0).value
-                    d.ld[i] = c["mat"].ld
-                    d.plane[i] = 0
-                if c["k"] is not None:
-                    d.k1[nk] = c["k"].data_ptr() + 4 * c0
-                    d.k2[nk] = c["k"].data_ptr() + 4 * (c["C"] + c0)
-                    d.mean = c["mean"].data_ptr() + 4 * c0
-                    nk += 1
-            d.nsrc, d.nk = len(srcs), nk
-            if nk:
-                d.x, d.ldx = blk.buf.ptr(c0).value, blk.buf.ld
-            op.bytes = float(blk.buf.P * C_ * 2 * (len(srcs) + 1 + (1 if nk else 0)))
+            gw = gws.pop() if gws else 0
+            # more consumers than one launch takes: chain, every further launch re-reads dst as its first source
+            groups, i, first = [], 0, True
+            while i < len(srcs):
+                n = _lib.GATHER_MAX if first else _lib.GATHER_MAX - 1
+                groups.append(srcs[i:i + n])
+                i += n
+                first = False
+            any_k = False
+            for gi, grp in enumerate(groups):
+                d = _lib.GradGather()
+                d.rows, d.C = blk.buf.P, C_
+                d.out, d.ldo = dst.ptr().value, dst.ld
+                d.gw = gw
+                ns = nk = 0
+                if gi > 0:
+                    d.src[0], d.ld[0], d.plane[0] = dst.ptr().value, dst.ld, 0
+                    ns = 1
+                for c in grp:
+                    if c.get("gw", 0):    # planar: group c0 / gw starts at that plane; the kernel adds further groups itself
+                        plane = blk.buf.P * c["gw"]
+                        d.src[ns] = c["mat"].t.data_ptr() + 2 * (c0 // c["gw"]) * plane
+                        d.ld[ns] = c["gw"]
+                        d.plane[ns] = plane
+                    else:
+                        d.src[ns] = c["mat"].ptr(c0).value
+                        d.ld[ns] = c["mat"].ld
+                        d.plane[ns] = 0
+                    ns += 1
+                    if c["k"] is not None:
+                        d.k1[nk] = c["k"].data_ptr() + 4 * c0
+                        d.k2[nk] = c["k"].data_ptr() + 4 * (c["C"] + c0)
+                        d.mean = c["mean"].data_ptr() + 4 * c0
+                        nk += 1
+                d.nsrc, d.nk = ns, nk
+                if nk:
+                    d.x, d.ldx = blk.buf.ptr(c0).value, blk.buf.ld
+                    any_k = True
+                descs.append(d)
+            self.gather_launches += len(descs)
+            op.bytes = float(blk.buf.P * C_ * 2 * (len(srcs) + 1 + (1 if any_k else 0) + 2 * (len(descs) - 1)))
         seen = set()
         for op in self.bwd:
             if op.gbuf is not None:

@@ -133,7 +133,8 @@ def compute_IoU_whole_img_batch(ground_truth_map_batch, estimated_heat_map_batch
     per-sample Python loop."""
     B, Cc = ground_truth_map_batch.shape[:2]
     c = _metric_counts(ground_truth_map_batch, estimated_heat_map_batch, threshold).view(B, Cc, 3)
-    return c[:, :, 0].float() / c[:, :, 1].float()
+    # the reference allocates its result with torch.zeros(...) on the HOST and the agent feeds it to np.nanmean (Agent.py:251-252)
+    return (c[:, :, 0].float() / c[:, :, 1].float()).cpu()
 
 
 def compute_accuracy(ground_truth, prediction, threshold=0.7):

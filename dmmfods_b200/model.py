@@ -56,7 +56,13 @@ class _Transition(nn.Sequential):
 
 
 class _NetFn(torch.autograd.Function):
-    """autograd bridge: forward = engine forward program, backward = engine backward program."""
+    """autograd bridge: forward = engine forward program, backward = engine backward program.
+
+    The parameter gradients handed to autograd are VIEWS of the engine's flat fp32 gradient buffer (no per-tensor copies: 510
+    tensors on DenseNet-121).  autograd's AccumulateGrad adopts such a view as `p.grad` when `p.grad` is None (the state
+    after `optimizer.zero_grad()`), which is what the reference loop does every step (Agent.py:263).  If gradients are being
+    ACCUMULATED over several backward passes (`p.grad` already set), aliased `p.grad`s are detached from the buffer first and
+    copies are returned, so `p.grad += g` keeps its meaning."""
 
     @staticmethod
     def forward(ctx, model, eng, x1, x2, *params):
@@ -64,6 +70,8 @@ class _NetFn(torch.autograd.Function):
         ctx.model = model
         out = eng.forward(x1, x2)
         ctx.version = eng.fwd_count
+        # the logits buffer is engine-owned and rewritten by the next forward: hand out a copy (236 MB at 32x3x640x960:
+        # ~0.07 ms of an ~80 ms step) so that a caller may keep predictions of earlier steps, as with the reference module
         return out.clone()
 
     @staticmethod
@@ -72,8 +80,22 @@ class _NetFn(torch.autograd.Function):
         if ctx.version != eng.fwd_count:
             raise RuntimeError("dmmfods_b200: backward() called after another forward() of the same shape "
                                "(activations are kept in static buffers: one outstanding graph per shape)")
+        plist = ctx.model._param_list
+        lo = eng.gflat.data_ptr()
+        hi = lo + eng.gflat.numel() * 4
+        accumulate = False
+        for p in plist:
+            g = p.grad
+            if g is not None:
+                accumulate = True
+                if lo <= g.data_ptr() < hi:
+                    p.grad = g.clone()          # un-alias before the engine rewrites its buffer
         grads = eng.backward(dlogits.contiguous())
-        outs = tuple(grads[n].clone() for n in ctx.model._param_order)
+        names = ctx.model._param_order
+        if accumulate:
+            outs = tuple(grads[n].clone() for n in names)
+        else:
+            outs = tuple(grads[n].view(grads[n].shape) for n in names)     # fresh view objects: adoptable by AccumulateGrad
         return (None, None, None, None) + outs
 
 
@@ -190,6 +212,7 @@ class Dense_U_Net_lidar(nn.Module):
         self.num_params = sum(p.numel() for p in self.parameters())
         self._engines = {}
         self._param_order = None
+        self._param_list = None
 
     # ------------------------------------------------------------------------------------------------
     def model_cfg(self):
@@ -220,6 +243,7 @@ class Dense_U_Net_lidar(nn.Module):
             self._engines[key] = (eng, sig)
             ent = self._engines[key]
         self._param_order = [k for k, _ in self.named_parameters()]
+        self._param_list = [p for _, p in self.named_parameters()]
         return ent[0]
 
     def forward(self, stream_1_data, stream_2_data):
@@ -246,6 +270,7 @@ class Dense_U_Net_lidar(nn.Module):
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_engines"] = {}
+        d["_param_list"] = None
         return d
 
     def __deepcopy__(self, memo):
@@ -254,7 +279,7 @@ class Dense_U_Net_lidar(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            setattr(new, k, {} if k == "_engines" else copy.deepcopy(v, memo))
+            setattr(new, k, {} if k == "_engines" else (None if k == "_param_list" else copy.deepcopy(v, memo)))
         return new
 
 

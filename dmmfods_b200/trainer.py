@@ -5,10 +5,12 @@ uses plain nn.BatchNorm2d), gradients are SUMMED over ranks (the reference back-
 Agent.py:264).
 """
 import ctypes as C
+import os
 
 import torch
 
 from . import _lib, ops
+from .data import mark_async_read
 from .engine import Engine
 
 
@@ -45,10 +47,46 @@ class BucketReducer:
         self.pending = []
 
 
+class StepLR:
+    """torch.optim.lr_scheduler.StepLR semantics for the flat fused Adam (Agent.py:63-67, stepped once per epoch at
+    Agent.py:297-298): lr = base_lr * gamma ** (epoch // step_size)."""
+
+    def __init__(self, trainer, step_size, gamma=0.1):
+        self.trainer, self.step_size, self.gamma = trainer, int(step_size), float(gamma)
+        self.base_lr = trainer.lr
+        self.last_epoch = 0
+
+    def step(self):
+        self.last_epoch += 1
+        self.trainer.lr = self.base_lr * self.gamma ** (self.last_epoch // self.step_size)
+
+    def get_last_lr(self):
+        return [self.trainer.lr]
+
+    def state_dict(self):
+        return {"step_size": self.step_size, "gamma": self.gamma, "base_lr": self.base_lr, "last_epoch": self.last_epoch}
+
+    def load_state_dict(self, sd):
+        self.step_size, self.gamma = int(sd["step_size"]), float(sd["gamma"])
+        self.base_lr, self.last_epoch = float(sd["base_lr"]), int(sd["last_epoch"])
+        self.trainer.lr = self.base_lr * self.gamma ** (self.last_epoch // self.step_size)
+
+
 class Trainer:
-    def __init__(self, model, B, H, W, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, distributed=None,
-                 bucket_bytes=32 << 20, use_graph=False):
+    """forward + loss + backward + (all-reduce) + Adam over static buffers.
+
+        tr = Trainer(model, B, H, W, lr=..., use_graph=True)
+        loss_per_class = tr.step(image, lidar, ht_map)          # CUDA or pinned host tensors
+
+    The returned per-class loss sums are the ENGINE'S STATIC buffer (float64 CUDA tensor): the next step() overwrites it;
+    `.clone()` it (or copy it to the host) to keep the value."""
+
+    def __init__(self, model, B, H, W, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False,
+                 distributed=None, bucket_bytes=32 << 20, use_graph=False, graph_nccl=None):
         import torch.distributed as dist
+        if amsgrad:
+            raise NotImplementedError("dmmfods_b200.Trainer: amsgrad=True is not supported by the fused flat Adam "
+                                      "(the reference default is False, helper:151)")
         self.model = model.train()
         self.dist = dist if (distributed if distributed is not None else (dist.is_available() and dist.is_initialized()
                                                                           and dist.get_world_size() > 1)) else None
@@ -77,12 +115,14 @@ class Trainer:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.steps = 0
         self.reducer = BucketReducer(self.dist, dev) if self.dist is not None else None
-        # single GPU: one CUDA graph for forward + loss + backward.  Data parallel: one graph for forward + loss and one per
-        # backward segment, the bucket all-reduces are issued between them (NCCL calls stay outside the graphs)
+        # one CUDA graph for forward + loss + backward; data parallel: the bucket all-reduces (NCCL, side stream) are captured
+        # INSIDE that graph (graph_nccl, default), or - DMM_GRAPH_NCCL=0 / capture failure - one graph for forward + loss and
+        # one per backward segment with the all-reduces issued between them
         self.use_graph = bool(use_graph)
+        self.graph_nccl = (os.environ.get("DMM_GRAPH_NCCL", "1") != "0") if graph_nccl is None else bool(graph_nccl)
         self.graph = None
         self.seg_graphs = None
-        self._static_target = None
+        self._static_target = torch.empty((B, self.eng.ncls, H, W), dtype=torch.float32, device=dev)
         self._copy_stream, self._stage, self._staged, self._stage_ready, self._stage_free = None, None, None, None, None
 
     # ------------------------------------------------------------------------------------------------
@@ -110,6 +150,8 @@ class Trainer:
                 dst.copy_(src, non_blocking=True)
             self._stage_ready = torch.cuda.Event()
             self._stage_ready.record(cs)
+        # the pinned sources must not be refilled before this copy has run (BatchFileRing waits for the event)
+        mark_async_read((x1, x2, target), self._stage_ready)
         self._staged = (x1, x2, target)
 
     def _take_staged(self, x1, x2, target):
@@ -121,38 +163,40 @@ class Trainer:
         self._staged = None
         return self._stage
 
-    def step(self, x1, x2, target, prefetch_next=None):
-        """one optimisation step; x1/x2/target: CUDA tensors or pinned host tensors (copied asynchronously).
-        prefetch_next: optional (x1, x2, target) of the following step (see prefetch()).
-        Returns the per-class loss sums (float64 CUDA tensor of num_classes entries, Agent.py:248)."""
+    def _load_inputs(self, x1, x2, target):
+        """bring this step's inputs into the engine-owned static buffers (in1, in2, target)."""
         eng = self.eng
         staged = self._take_staged(x1, x2, target)
         if staged is not None:
             # hand-over: device-to-device into the engine-owned buffers, then the staging buffers are free again and the
             # next prefetch overlaps with this step's kernels
-            if self._static_target is None:
-                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
             eng.in1.copy_(staged[0], non_blocking=True)
             if eng.c2:
                 eng.in2.copy_(staged[1], non_blocking=True)
             self._static_target.copy_(staged[2], non_blocking=True)
             self._stage_free = torch.cuda.Event()
             self._stage_free.record()
-            x1, x2, target = eng.in1, eng.in2, self._static_target
-        if not target.is_cuda:
-            if self._static_target is None:
-                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
-            self._static_target.copy_(target, non_blocking=True)
-            target = self._static_target
+            return
+        host = []
+        for dst, src in ((eng.in1, x1), (eng.in2 if eng.c2 else None, x2), (self._static_target, target)):
+            if dst is None or src is dst:
+                continue
+            dst.copy_(src, non_blocking=True)
+            if not src.is_cuda:
+                host.append(src)
+        if host:
+            ev = torch.cuda.Event()
+            ev.record()
+            mark_async_read(host, ev)
+
+    def step(self, x1, x2, target, prefetch_next=None):
+        """one optimisation step; x1/x2/target: CUDA tensors or pinned host tensors (copied asynchronously).
+        prefetch_next: optional (x1, x2, target) of the following step (see prefetch()).
+        Returns the per-class loss sums (float64 CUDA tensor of num_classes entries, Agent.py:248) - the engine's static
+        buffer, overwritten by the next step."""
+        eng = self.eng
+        self._load_inputs(x1, x2, target)
         if self.use_graph:
-            if self._static_target is None:
-                self._static_target = torch.empty(target.shape, dtype=torch.float32, device=self.pflat.device)
-            if target is not self._static_target:
-                self._static_target.copy_(target, non_blocking=True)
-            if x1 is not eng.in1:
-                eng.in1.copy_(x1, non_blocking=True)
-            if eng.c2 and x2 is not eng.in2:
-                eng.in2.copy_(x2, non_blocking=True)
             if self.graph is None:
                 self._capture()
             self.graph.replay()
@@ -163,8 +207,8 @@ class Trainer:
                         self.reducer(i, flat)
                 self.reducer.finish()
         else:
-            eng.forward(x1, x2)
-            self._fwd_loss_bwd(target)
+            eng.forward(eng.in1, eng.in2)
+            self._fwd_loss_bwd(self._static_target)
         if prefetch_next is not None:
             self.prefetch(*prefetch_next)
         self.steps += 1
@@ -172,32 +216,54 @@ class Trainer:
                       self.weight_decay, self.steps)
         return eng.class_sums
 
+    def _bn_state(self):
+        return [v for k, v in self.eng.p.items() if "running_" in k or k.endswith("num_batches_tracked")]
+
     def _capture(self):
-        """CUDA graph of forward + loss + backward over the engine's static buffers (launch-bound otherwise)."""
+        """CUDA graph of forward + loss + backward over the engine's static buffers (launch-bound otherwise).
+        The warm-up pass torch's capture rules require is a real forward + backward: the BatchNorm running statistics and
+        num_batches_tracked it updates are restored afterwards, so the first replayed step is the ONLY momentum update of this
+        batch (state_dict parity with the un-graphed path and with the reference)."""
         eng = self.eng
-        # warm-up on a side stream as torch's capture rules require, then capture
+        state = self._bn_state()
+        saved = [t.clone() for t in state]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             eng.forward(eng.in1, eng.in2)
             self._fwd_loss_bwd(self._static_target)
         torch.cuda.current_stream().wait_stream(s)
+        for t, v in zip(state, saved):
+            t.copy_(v)
         g = torch.cuda.CUDAGraph()
         if self.dist is None:
             with torch.cuda.graph(g):
                 eng.forward(eng.in1, eng.in2)
                 self._fwd_loss_bwd(self._static_target)
-        else:
-            with torch.cuda.graph(g):
-                eng.forward(eng.in1, eng.in2)
-                eng.loss(self._static_target)
-                eng.backward_begin()
-            self.seg_graphs = []
-            for i in range(len(eng.segments)):
-                gi = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gi, pool=g.pool()):
-                    flat = eng.backward_segment(i)
-                self.seg_graphs.append((gi, flat))
+            self.graph = g
+            return
+        if self.graph_nccl:
+            try:
+                with torch.cuda.graph(g):
+                    eng.forward(eng.in1, eng.in2)
+                    self._fwd_loss_bwd(self._static_target)
+                self.graph = g
+                return
+            except Exception as e:      # noqa: BLE001  (NCCL build without capture support: say so, use the segmented form)
+                import sys
+                sys.stderr.write("dmmfods_b200.Trainer: capturing the NCCL all-reduces failed (%s); using per-segment graphs\n" % e)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            eng.forward(eng.in1, eng.in2)
+            eng.loss(self._static_target)
+            eng.backward_begin()
+        self.seg_graphs = []
+        for i in range(len(eng.segments)):
+            gi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gi, pool=g.pool()):
+                flat = eng.backward_segment(i)
+            self.seg_graphs.append((gi, flat))
         self.graph = g
 
     def launches_per_step(self):
@@ -205,6 +271,7 @@ class Trainer:
         eng = self.eng
         n = len(eng.fwd) + len(eng.bwd) + 1 + len([s for s in eng.segments if s[2]]) + 1 + 1   # + pack, unpacks, bce, adam
         n += sum(1 for op in eng.fwd if op.kind == "nchw_stats" and eng.c2)                     # second input tensor
+        n += eng.gather_launches - sum(1 for op in eng.bwd if op.kind == "grad_gather")          # chained gathers
         return n
 
 

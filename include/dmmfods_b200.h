@@ -287,7 +287,7 @@ int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
  *                             of the block buffer from the slabs of all its consumers (those with a fully corrected dx pass no k). */
 int dmm_bn_relu_bwd_contrib(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_bwd_finalize(const dmm_bn_bwd_t* bn, int32_t C, float* k, void* stream);
-#define DMM_GATHER_MAX 40
+#define DMM_GATHER_MAX 56
 typedef struct {
     const void* src[DMM_GATHER_MAX];     /* bf16 rows, already offset to the first channel of the range */
     int64_t ld[DMM_GATHER_MAX];

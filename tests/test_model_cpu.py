@@ -201,3 +201,39 @@ def test_default_plan_uses_the_folded_and_unfolded_formulations():
     assert bwd["dec_out_to_heat_maps.refine1.dgrad"].arg.num_taps == 5
     assert bwd["dec_out_to_heat_maps.refine1.wgrad"].arg.num_b == 5
     assert any(n.endswith(".norm2") for n in fwd)                      # norm2 is still a separate BN-ReLU pass (KxK prologue off)
+
+
+@pytest.mark.parametrize("factory", ["densenet121_u_lidar", "densenet161_u_lidar", "densenet169_u_lidar", "densenet201_u_lidar"])
+def test_training_plans_of_all_four_factories(factory):
+    """every exported factory (Dense_U_Net_lidar.py:335-388) yields a TRAINING engine plan: densenet201's 48-layer block has
+    50 consumers of its first channels, more than one dmm_grad_gather launch took in round 1 (DMM_GATHER_MAX)."""
+    from dmmfods_b200 import _lib as L, model as M
+    from dmmfods_b200.engine import Engine
+    m = getattr(M, factory)(pretrained=False, config=_cfg(1, 3))
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    eng = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True)
+    assert sorted(eng.param_names) == sorted(k for k, _ in m.named_parameters())
+    gathers = [g for g in eng._gathers]
+    assert gathers and all(1 <= len(g[5]) for g in gathers)
+    most = max(sum(d.nsrc for d in g[5]) - (len(g[5]) - 1) for g in gathers)
+    assert most == max(m.block_config) + 2
+    assert all(d.nsrc <= L.GATHER_MAX and d.nk <= L.GATHER_MAX for g in gathers for d in g[5])
+
+
+def test_gather_chain_beyond_gather_max(monkeypatch):
+    """more consumers than DMM_GATHER_MAX: the gather is emitted as a chain of launches that re-read their own output."""
+    from dmmfods_b200 import _lib as L
+    from dmmfods_b200.engine import Engine
+    monkeypatch.setattr(L, "GATHER_MAX", 8)
+    c = _cfg(1, 3, growth_rate=16, block_config=(2, 12, 2, 2), num_init_features=32, bn_size=2)
+    m = Dense_U_Net_lidar(c)
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    eng = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True)
+    chained = [g for g in eng._gathers if len(g[5]) > 1]
+    assert chained
+    for g in chained:
+        descs, dst = g[5], g[4]
+        assert all(d.nsrc <= 8 for d in descs)
+        assert all(d.src[0] == dst.ptr().value and d.plane[0] == 0 for d in descs[1:])      # accumulator first
+        assert sum(d.nsrc for d in descs) - (len(descs) - 1) == len([c_ for c_ in g[1].contribs if c_["C"] >= g[2] + g[3]])
+    assert eng.gather_launches > len(eng._gathers)
