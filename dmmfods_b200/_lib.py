@@ -118,6 +118,8 @@ SIGNATURES = {
                                    C.POINTER(c_int32), c_int64, c_int64, c_int32, c_void_p]),
     "dmm_pack_weights_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_unpack_wgrad_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
+    "dmm_pack_weights_work": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "dmm_unpack_wgrad_work": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "dmm_bn_relu_apply": (C.c_int, [C.POINTER(BnApply), c_void_p]),
     "dmm_bn_relu_bwd_reduce": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),
     "dmm_bn_relu_bwd_apply": (C.c_int, [C.POINTER(BnBwdArgs), c_void_p]),

@@ -45,6 +45,18 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// L2 promotion of the bf16 tensor maps (DMM_TMA_L2_PROMO = 0 / 64 / 128 / 256, default 256): with 256 B a 128-byte box row of a
+// narrow channel slice of a wide block buffer pulls a second, unused 128 bytes from DRAM (ncu: 2x reads on 64-channel slices).
+static CUtensorMapL2promotion l2_promotion() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DMM_TMA_L2_PROMO");
+        v = (e && *e) ? atoi(e) : 256;
+    }
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                  : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
     EncodeTiledFn enc = get_encode();
@@ -74,7 +86,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     DMM_CHECK((int)(box[0] * 2) <= (swizzle_bytes ? swizzle_bytes : 512), "tensor map inner box %u elements exceeds the swizzle span",
               box[0]);
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DMM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu.. box %u,%u..)", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);

@@ -1678,42 +1678,71 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
-// batched forms: one launch for all weight tensors of the network (job tables live in device memory)
-__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pack_job_t* __restrict__ jobs) {
-    pdl_prologue();
-    const dmm_pack_job_t& j = jobs[blockIdx.y];
+// batched forms: one launch for all weight tensors of the network (job tables live in device memory).
+// `work` (optional): int32 pairs (job, chunk) - one block per `chunk_elems` consecutive elements of a job, so that the 9.4 M
+// element ConvTranspose tensors and the 64-element BatchNorm-sized jobs load the SMs evenly (without it: 32 blocks per job).
+__device__ __forceinline__ void pack_job_range(const dmm_pack_job_t& j, long long i0, long long i1, long long stride) {
     const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
     const long long ktot = (long long)Kp * j.T;
-    const long long total = (long long)j.n_rows * ktot;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cdiv = j.cdiv > 0 ? j.cdiv : 1;
+    for (long long i = i0; i < i1; i += stride) {
         const int n = (int)(i / ktot);
-        const long long k = i - (long long)n * ktot;
-        const int t = (int)(k / Kp);
-        const int c = (int)(k - (long long)t * Kp);
+        const int k = (int)(i - (long long)n * ktot);
+        const int t = k / Kp;
+        const int c = k - t * Kp;
         float v = 0.f;
         if (n < j.n_valid && c < j.C) {
-            const int cdiv = j.cdiv > 0 ? j.cdiv : 1;
             const long long nidx = j.ndiv > 1 ? (long long)(n / j.ndiv) * j.sn + (long long)(n % j.ndiv) * j.sn2 : (long long)n * j.sn;
-            v = j.w[nidx + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]];
+            v = __ldg(j.w + nidx + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]);
         }
         dst[i] = __float2bfloat16_rn(v);
     }
 }
-__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unpack_job_t* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const dmm_pack_job_t* __restrict__ jobs) {
     pdl_prologue();
-    const dmm_unpack_job_t& j = jobs[blockIdx.y];
-    const long long total = (long long)j.T * j.M * j.N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const dmm_pack_job_t& j = jobs[blockIdx.y];
+    const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
+    const long long total = (long long)j.n_rows * Kp * j.T;
+    pack_job_range(j, (long long)blockIdx.x * blockDim.x + threadIdx.x, total, (long long)gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(256) pack_weights_work_kernel(const dmm_pack_job_t* __restrict__ jobs, const int2* __restrict__ work,
+                                                                int chunk_elems) {
+    pdl_prologue();
+    const int2 w = work[blockIdx.x];
+    const dmm_pack_job_t& j = jobs[w.x];
+    const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
+    const long long total = (long long)j.n_rows * Kp * j.T;
+    const long long i0 = (long long)w.y * chunk_elems;
+    const long long i1 = i0 + chunk_elems < total ? i0 + chunk_elems : total;
+    pack_job_range(j, i0 + threadIdx.x, i1, blockDim.x);
+}
+__device__ __forceinline__ void unpack_job_range(const dmm_unpack_job_t& j, long long i0, long long i1, long long stride) {
+    for (long long i = i0; i < i1; i += stride) {
         const int n = (int)(i % j.N);
-        const long long r = i / j.N;
-        const int m = (int)(r % j.M);
-        const int t = (int)(r / j.M);
+        const int r = (int)(i / j.N);
+        const int m = r % j.M;
+        const int t = r / j.M;
         const float v = j.dw[(long long)t * j.dt + (long long)m * j.dm + (long long)n * j.dn];
         const long long nidx = j.ndiv > 1 ? (long long)(n % j.ndiv) * j.sn + (long long)(n / j.ndiv) * j.sn2 : (long long)n * j.sn;
         float* gp = j.grad + nidx + (long long)m * j.sc + j.tap_off[t];
         *gp = j.accumulate ? *gp + v : v;
     }
+}
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const dmm_unpack_job_t* __restrict__ jobs) {
+    pdl_prologue();
+    const dmm_unpack_job_t& j = jobs[blockIdx.y];
+    unpack_job_range(j, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)j.T * j.M * j.N, (long long)gridDim.x * blockDim.x);
+}
+__global__ void __launch_bounds__(256) unpack_wgrad_work_kernel(const dmm_unpack_job_t* __restrict__ jobs, const int2* __restrict__ work,
+                                                                int chunk_elems) {
+    pdl_prologue();
+    const int2 w = work[blockIdx.x];
+    const dmm_unpack_job_t& j = jobs[w.x];
+    const long long total = (long long)j.T * j.M * j.N;
+    const long long i0 = (long long)w.y * chunk_elems;
+    const long long i1 = i0 + chunk_elems < total ? i0 + chunk_elems : total;
+    unpack_job_range(j, i0 + threadIdx.x, i1, blockDim.x);
 }
 
 // resident 256-thread blocks per SM of a kernel (cached): a grid-stride kernel runs best as exactly one full wave
@@ -2075,6 +2104,26 @@ extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int
     if (njobs == 0) return 0;
     launch_k(unpack_wgrad_batched_kernel, dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream, jobs_device);
     DMM_LAUNCH_CHECK("unpack_wgrad_batched_kernel");
+    return 0;
+}
+
+extern "C" int dmm_pack_weights_work(const dmm_pack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
+                                     void* stream) {
+    DMM_CHECK(nwork >= 0 && (nwork == 0 || (jobs_device && work_device)) && chunk_elems >= 256, "dmm_pack_weights_work: bad arguments");
+    if (nwork == 0) return 0;
+    launch_k(pack_weights_work_kernel, dim3((unsigned)nwork, 1, 1), 256, 0, (cudaStream_t)stream, jobs_device,
+             reinterpret_cast<const int2*>(work_device), chunk_elems);
+    DMM_LAUNCH_CHECK("pack_weights_work_kernel");
+    return 0;
+}
+
+extern "C" int dmm_unpack_wgrad_work(const dmm_unpack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
+                                      void* stream) {
+    DMM_CHECK(nwork >= 0 && (nwork == 0 || (jobs_device && work_device)) && chunk_elems >= 256, "dmm_unpack_wgrad_work: bad arguments");
+    if (nwork == 0) return 0;
+    launch_k(unpack_wgrad_work_kernel, dim3((unsigned)nwork, 1, 1), 256, 0, (cudaStream_t)stream, jobs_device,
+             reinterpret_cast<const int2*>(work_device), chunk_elems);
+    DMM_LAUNCH_CHECK("unpack_wgrad_work_kernel");
     return 0;
 }
 

@@ -40,6 +40,18 @@ FUSE_BN_PROLOGUE = os.environ.get("DMM_FUSE_BN_PROLOGUE", "1") != "0"
 FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE_KXK", "0") != "0"
 
 
+# weight pack / gradient unpack as load-balanced (job, chunk) launches (DMM_BALANCED_PACK=0: 32 blocks per job as in round 1)
+BALANCED_PACK = os.environ.get("DMM_BALANCED_PACK", "1") != "0"
+WORK_CHUNK = 8192
+
+
+def _work_table(sizes, dev):
+    """int32 [n, 2] device table of (job, chunk) pairs covering `sizes[job]` elements in chunks of WORK_CHUNK."""
+    rows = [(j, c) for j, n in enumerate(sizes) for c in range((int(n) + WORK_CHUNK - 1) // WORK_CHUNK)]
+    t = torch.tensor(rows, dtype=torch.int32).view(-1, 2) if rows else torch.zeros((0, 2), dtype=torch.int32)
+    return t.to(dev)
+
+
 class Op:
     """one C-ABI launch.  kind / flops / bytes: kernel family and ALGORITHMIC work of the launch (each distinct
     input element read once + each output written once; 2*M*N*K of the reference operator) for roofline reports."""
@@ -925,6 +937,8 @@ class Engine:
             pj[i]["sn2"], pj[i]["ndiv"] = j.get("sn2", 0), j.get("ndiv", 0)
         self._pack_tab = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
         self._n_pack = len(self._pack_jobs)
+        # load-balanced launch: one block per WORK_CHUNK consecutive packed elements of a job
+        self._pack_work = _work_table([j["n_rows"] * j["T"] * ceil_to(j["C"], j.get("kwidth", ops.KWIDTH)) for j in self._pack_jobs], dev)
         self._param_ptrs = [j["w"].data_ptr() for j in self._pack_jobs]
         self._pack_src = [j["w"] for j in self._pack_jobs]
         # backward program = stages in reverse forward order, cut into SEGMENTS whose parameter gradients form one
@@ -954,8 +968,10 @@ class Engine:
             uj[i]["sn2"], uj[i]["ndiv"] = j.get("sn2", 0), j.get("ndiv", 0)
         self._unpack_tab = torch.from_numpy(uj.view(np.uint8).copy()).to(dev)
         self._n_unpack = len(self._unpack_jobs)
+        self._unpack_sizes = [j["T"] * j["M"] * j["N"] for j in self._unpack_jobs]
         self.bwd = []
         self.segments = []       # (ops, first unpack job, number of unpack jobs, flat_lo, flat_hi)
+        self._seg_work = []      # per segment: (job, chunk) work table of its unpack jobs (indices relative to job_lo)
         seg_ops, seg_names, job_lo, job_i = [], [], 0, 0
         done = set()
         for si, st in enumerate(stages):
@@ -977,6 +993,7 @@ class Engine:
                 else:
                     lo = hi = 0
                 self.segments.append((seg_ops, job_lo, job_i - job_lo, lo, hi))
+                self._seg_work.append(_work_table(self._unpack_sizes[job_lo:job_i], dev))
                 seg_ops, seg_names, job_lo = [], [], job_i
         self.gather_launches = 0
         for op, blk, c0, C_, dst, descs in self._gathers:
@@ -1098,8 +1115,12 @@ class Engine:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.training:
             self._stats.zero_used()
-        _lib.check(self.lib.dmm_pack_weights_batched(C.c_void_p(self._pack_tab.data_ptr()), self._n_pack, stream),
-                   "dmm_pack_weights_batched")
+        if BALANCED_PACK:
+            _lib.check(self.lib.dmm_pack_weights_work(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
+                                                      self._pack_work.shape[0], WORK_CHUNK, stream), "dmm_pack_weights_work")
+        else:
+            _lib.check(self.lib.dmm_pack_weights_batched(C.c_void_p(self._pack_tab.data_ptr()), self._n_pack, stream),
+                       "dmm_pack_weights_batched")
         self._run(self.fwd)
         if self.training and self.nbt:
             torch._foreach_add_(self.nbt, 1)
@@ -1134,9 +1155,13 @@ class Engine:
         self._run(seg_ops)
         self._join_side(torch.cuda.current_stream())
         if njobs:
-            tab = self._unpack_tab.data_ptr()
-            _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab + job_lo * _UNPACK_DT.itemsize), njobs, stream),
-                       "dmm_unpack_wgrad_batched")
+            tab = self._unpack_tab.data_ptr() + job_lo * _UNPACK_DT.itemsize
+            if BALANCED_PACK:
+                work = self._seg_work[i]
+                _lib.check(self.lib.dmm_unpack_wgrad_work(C.c_void_p(tab), C.c_void_p(work.data_ptr()), work.shape[0], WORK_CHUNK,
+                                                          stream), "dmm_unpack_wgrad_work")
+            else:
+                _lib.check(self.lib.dmm_unpack_wgrad_batched(C.c_void_p(tab), njobs, stream), "dmm_unpack_wgrad_batched")
         return self.gflat[lo:hi] if hi > lo else None
 
     def loss(self, target, loss_out=None):

@@ -215,6 +215,13 @@ typedef struct {
 } dmm_unpack_job_t;
 int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream);
 int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream);
+/* Load-balanced forms: `work_device` = int32 pairs (job index, chunk index) in device memory, one thread block per pair
+ * handles elements [chunk*chunk_elems, (chunk+1)*chunk_elems) of that job (the tensors of one network span 64 ... 9.4 M
+ * elements; 32 blocks per job left the largest job alone on the GPU for 0.9 ms). */
+int dmm_pack_weights_work(const dmm_pack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
+                          void* stream);
+int dmm_unpack_wgrad_work(const dmm_unpack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
+                          void* stream);
 
 /* y = relu(bn(x)), bf16 pixel-major [B*H*W, C] (tv:47-50,90; Dense_U_Net_lidar.py:75-76,108-115).
  * pool: 0 none; 1 = then AvgPool2d(2,2) (tv:133 moved in front of the 1x1 conv - they commute);

@@ -24,6 +24,15 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "refine1_dgrad_v": (32, 640, 960, 16, 64, -5, 0),          # K < 0: |K| vertical taps over the horizontally unfolded d(logits)
     "b1_conv1_k160_pro": (32, 160, 240, 160, 128, 1, 2),      # out_mode 2 here = BN-ReLU prologue on a [P, 256] block buffer
     "b2_conv1_k320_pro": (32, 80, 120, 320, 128, 1, 2),
+    "b1_conv1_k64_pro": (32, 160, 240, 64, 128, 1, 2),
+    "b3_conv1_k640_pro": (32, 40, 60, 640, 128, 1, 2),
+    "b3_conv1_k992_pro": (32, 40, 60, 992, 128, 1, 2),
+    "b4_conv1_k768_pro": (32, 20, 30, 768, 128, 1, 2),
+    "b1_conv1_dgrad_n160": (32, 160, 240, 128, 160, 1, 0),      # conv1 data gradient: K = 128 -> N = Ci
+    "b2_conv1_dgrad_n320": (32, 80, 120, 128, 320, 1, 0),
+    "b3_conv1_dgrad_n640": (32, 40, 60, 128, 640, 1, 0),
+    "b3_conv1_dgrad_n992": (32, 40, 60, 128, 992, 1, 0),
+    "b4_conv1_dgrad_n768": (32, 20, 30, 128, 768, 1, 0),
 }
 
 def run(name, reps=5):
@@ -32,7 +41,7 @@ def run(name, reps=5):
     pro = om == 2
     if pro:
         om = 0
-    ld = ops.ceil_to(Cin, 8) if not pro else (256 if Cin <= 256 else 512)
+    ld = ops.ceil_to(Cin, 8) if not pro else (256 if Cin <= 256 else (512 if Cin <= 512 else 1024))
     a = ops.Mat((torch.randn(B * H * W, ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
     if K < 0:
         taps = [(0, -K // 2 - kh, 0) for kh in range(-K)]

@@ -179,7 +179,57 @@ def dn121_probe():
     print("dn121_mid_probe.npz num_params", model.num_params)
 
 
+def fullsize_yardstick(H=640, W=960):
+    """BASELINE config 3 at FULL resolution, batch 1, the exact state / inputs of tests/test_fullsize_gpu.py (seed-123 init,
+    BatchNorm affine parameters randomised with generator 7, input seeds 11 / 12 / 13), executed by the UNMODIFIED reference:
+    fp64 run (golden loss sums, a logits crop, gradient norms) and the reference's OWN error levels against it when it runs
+    in fp32 and under torch.autocast('cpu', bfloat16) - the bf16 yard-stick SURVEY 8(c)(5) prescribes."""
+    import copy
+    model_mod, _ = ref_shim.ref_modules()
+    cfg = ref_shim.ref_config(stream_2_in_channels=1, concat_before_block_num=3)
+    torch.manual_seed(123)
+    model = model_mod.densenet121_u_lidar(pretrained=False, config=cfg)
+    g = torch.Generator().manual_seed(7)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=g) + 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=g) * 0.2
+    x1 = torch.from_numpy(synthetic.rgb_image(1, H, W, seed=11))
+    x2 = torch.from_numpy(synthetic.lidar_image(1, H, W, seed=12))
+    tgt = torch.from_numpy(synthetic.target_maps(1, H, W, seed=13))
+    rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm()).item()
+    out = {"shape": np.array([1, H, W]), "seeds": np.array([11, 12, 13]),
+           "param_checksum": np.array([sum(v.double().sum().item() for v in model.state_dict().values() if v.is_floating_point())])}
+    m64 = copy.deepcopy(model)
+    logits64, loss64 = _train_step(m64, x1, x2, tgt, torch.float64)
+    out["loss64_per_class"] = loss64.sum(dim=(0, 2, 3)).numpy()
+    out["logits64_crop"] = logits64[:, :, 300:340, 400:480].float().numpy()
+    out["logits64_norm"] = np.array([logits64.norm().item()])
+    out["grad64_names"] = np.array([k for k, _ in m64.named_parameters()])
+    out["grad64_norm"] = np.array([p.grad.norm().item() for _, p in m64.named_parameters()])
+    out["grad64_refine1"] = dict(m64.named_parameters())["dec_out_to_heat_maps.refine1.weight"].grad.float().numpy()
+    out["grad64_conv0"] = dict(m64.named_parameters())["features.conv0.weight"].grad.float().numpy()
+    m32 = copy.deepcopy(model)
+    logits32, _ = _train_step(m32, x1, x2, tgt, torch.float32)
+    out["ref_fp32_err"] = np.array([rel(logits32, logits64), _gerr(list(m32.parameters()), list(m64.parameters()))])
+    del m32
+    mbf = copy.deepcopy(model)
+    mbf.train()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        lg = mbf(x1, x2)
+    ls = torch.nn.BCEWithLogitsLoss(reduction="none")(lg.float(), tgt)
+    ls.backward(torch.ones_like(ls))
+    out["ref_bf16_autocast_err"] = np.array([rel(lg.detach().float(), logits64), _gerr(list(mbf.parameters()), list(m64.parameters()))])
+    out["ref_bf16_autocast_loss_rel"] = np.array([abs(ls.double().sum().item() - loss64.sum().item()) / loss64.sum().item()])
+    np.savez_compressed(os.path.join(OUT, "fullsize_yardstick.npz"), **out)
+    print("fullsize_yardstick.npz: ref fp32 err", out["ref_fp32_err"], "ref bf16-autocast err", out["ref_bf16_autocast_err"],
+          "loss rel", out["ref_bf16_autocast_loss_rel"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "fullsize":
+        fullsize_yardstick()
+        sys.exit(0)
     lidar_heatmap()
     for f in ("no", "early", "mid"):
         tiny_unet(f)

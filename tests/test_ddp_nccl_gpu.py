@@ -1,0 +1,119 @@
+"""-m gpu, 2 ranks over NCCL (skipped with fewer than 2 GPUs): on-hardware correctness of the data-parallel path
+("allreduce-SUM of per-rank grads == the gradient of the concatenated batch with per-shard BN statistics").
+
+Every rank trains on its own shard; checked on both ranks:
+  * the flat gradient buffer after backward + bucketed all-reduce equals the SUM over ranks of the gradients each rank
+    computes alone on its shard (fp32 round-off: the weight-gradient split-K reduce-adds are unordered),
+  * eager launches, per-segment graphs and the single step graph with the NCCL all-reduces captured inside leave the
+    SAME parameters, and the parameters of the two ranks stay bit-identical (same reduced gradient, same Adam),
+  * BatchNorm running statistics stay per rank (plain nn.BatchNorm2d in the reference) and differ between the ranks.
+"""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+B, H, W = 2, 64, 96
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dmmfods_b200 import synthetic
+        from dmmfods_b200.trainer import Trainer
+        from test_trainer_gpu import _model
+
+        def shard(i):
+            s = 1000 * rank + i
+            return tuple(torch.from_numpy(f(B, H, W, seed=s + o)).cuda() for f, o in
+                         ((synthetic.rgb_image, 1), (synthetic.lidar_image, 2), (synthetic.target_maps, 3)))
+
+        # ---- gradient equality ----
+        model = _model().cuda()
+        tr = Trainer(model, B, H, W, lr=1e-3, distributed=True, use_graph=False, bucket_bytes=64 << 10)
+        eng = tr.eng
+        x1, x2, tg = shard(0)
+        bn0 = {k: v.clone() for k, v in model.state_dict().items() if "running_" in k}
+        eng.forward(x1, x2)
+        eng.loss(tg)
+        eng.backward()                               # no reducer: this rank's own gradient
+        local = eng.gflat.clone()
+        for k, v in bn0.items():                     # undo the running-statistics update of the extra forward
+            model.state_dict()[k].copy_(v)
+        eng.forward(x1, x2)
+        eng.loss(tg)
+        eng.backward(on_bucket=tr.reducer)
+        tr.reducer.finish()
+        torch.cuda.synchronize()
+        reduced = eng.gflat.clone()
+        allg = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(allg, local)
+        want = sum(a.double() for a in allg)
+        err = ((reduced.double() - want).norm() / want.norm()).item()
+        nb = len([s for s in eng.segments if s[4] > s[3]])
+        assert err < 1e-5, "all-reduced gradient vs sum of per-rank gradients: relL2 %.3e" % err
+        assert nb >= 2, "expected several gradient buckets, got %d" % nb
+        assert sum(n for _, n in tr.reducer.ranges) == eng.gflat.numel()
+
+        # ---- three execution forms leave the same parameters; ranks stay in lock-step ----
+        finals = {}
+        for label, kw in (("eager", dict(use_graph=False)), ("segment_graphs", dict(use_graph=True, graph_nccl=False)),
+                          ("one_graph", dict(use_graph=True, graph_nccl=True))):
+            m = _model().cuda()
+            t = Trainer(m, B, H, W, lr=1e-3, distributed=True, bucket_bytes=64 << 10, **kw)
+            for i in range(3):
+                t.step(*shard(i))
+            torch.cuda.synchronize()
+            if label == "one_graph":
+                assert t.seg_graphs is None and t.graph is not None, "the NCCL all-reduces were not captured in the step graph"
+            finals[label] = t.pflat.clone()
+            other = [torch.empty_like(t.pflat) for _ in range(world)]
+            dist.all_gather(other, t.pflat)
+            assert torch.equal(other[0], other[1]), "%s: parameters of the two ranks diverged" % label
+            rm = torch.cat([v.flatten() for k, v in m.state_dict().items() if k.endswith("running_mean")])
+            rms = [torch.empty_like(rm) for _ in range(world)]
+            dist.all_gather(rms, rm)
+            assert not torch.equal(rms[0], rms[1]), "BatchNorm statistics must stay per rank"
+            nbt = [int(v) for k, v in m.state_dict().items() if k.endswith("num_batches_tracked")]
+            assert set(nbt) == {3}, "%s: num_batches_tracked %s after 3 steps" % (label, sorted(set(nbt)))
+        ref = finals["eager"].double()
+        errs = {k: ((v.double() - ref).norm() / ref.norm()).item() for k, v in finals.items()}
+        assert all(e < 1e-4 for e in errs.values()), errs
+        out.put((rank, "ok", err, errs))
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        out.put((rank, "fail: %r\n%s" % (e, traceback.format_exc()), 0, {}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_nccl_gradient_sum_and_graph_forms():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=500) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] == "ok" for r in res), res
+    print("\n[2-rank NCCL] reduced-vs-sum relL2 %.3e; parameters vs eager after 3 steps: %s" % (res[0][2], res[0][3]))
