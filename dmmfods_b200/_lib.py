@@ -140,6 +140,8 @@ SIGNATURES = {
     "dmm_bce_logits": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
     "dmm_lidar_splat": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dmm_lidar_splat_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dmm_heatmap_boxes_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dmm_lidar_pool": (C.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "dmm_heatmap_boxes": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dmm_pool_kxk": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

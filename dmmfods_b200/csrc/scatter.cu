@@ -164,6 +164,139 @@ __global__ void __launch_bounds__(256) pool_kxk_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Batched single-pass forms for the per-step on-GPU pre-processing of BASELINE config 4 (compulsory traffic
+// 4*H*W + 12*N bytes per LiDAR frame, 12*H*W + 20*N_box per heat-map frame): one launch for all frames of the batch, every
+// output pixel is written exactly once and nothing else touches HBM (the per-frame entry points above need a scratch image:
+// fill + atomicMax + resolve = 12*H*W resp. 36*H*W bytes).
+//   LiDAR: a CTA owns a kSplatTH x kSplatTW pixel tile whose "last writer" indices live in SHARED memory; it scans the frame's
+//          points (L2-resident after the first CTA), paints the overlap of every point's k x k square with atomicMax on shared
+//          memory, then writes the tile (value of the winning point, optionally range-transformed for the network input).
+//   boxes: a CTA first culls the frame's boxes against its tile (order preserved), then every pixel scans the surviving boxes
+//          from the LAST to the first and takes the first hit of its class - "later boxes overwrite earlier ones" without atomics.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSplatTW = 256, kSplatTH = 64;      // 64 KB of int32 per tile
+
+__global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __restrict__ pts, const int32_t* __restrict__ offs, int H, int W,
+                                                               int shift, int mode, float* __restrict__ img) {
+    extern __shared__ int32_t tile[];
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * kSplatTW, ty0 = blockIdx.y * kSplatTH;
+    const int tw = min(kSplatTW, W - tx0), th = min(kSplatTH, H - ty0);
+    for (int i = threadIdx.x; i < kSplatTW * kSplatTH; i += blockDim.x) tile[i] = -1;
+    __syncthreads();
+    const int p0 = offs[b], n = offs[b + 1] - p0;
+    const float* fp = pts + 3ll * p0;
+    const float fs = (float)shift;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = __ldg(fp + 3 * i + 0), y = __ldg(fp + 3 * i + 1);
+        // identical arithmetic to lidar_mark_kernel (helper:503-511)
+        int min_y = py_int(__fsub_rn(y, fs));
+        if (min_y < 0) min_y = 0;
+        int max_y = py_int(__fadd_rn(__fadd_rn(y, fs), 1.f));
+        if (max_y > H - 1) max_y = H - 1;
+        int min_x = py_int(__fsub_rn(x, fs));
+        if (min_x < 0) min_x = 0;
+        int max_x = py_int(__fadd_rn(__fadd_rn(x, fs), 1.f));
+        if (max_x > W - 1) max_x = W - 1;
+        int y0, y1, x0, x1;
+        py_slice(min_y, max_y, H, y0, y1);
+        py_slice(min_x, max_x, W, x0, x1);
+        y0 = max(y0, ty0); y1 = min(y1, ty0 + th);
+        x0 = max(x0, tx0); x1 = min(x1, tx0 + tw);
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) atomicMax(&tile[(yy - ty0) * kSplatTW + (xx - tx0)], i);
+    }
+    __syncthreads();
+    float* out = img + (long long)b * H * W;
+    for (int i = threadIdx.x; i < kSplatTW * th; i += blockDim.x) {
+        const int ry = i / kSplatTW, rx = i - ry * kSplatTW;
+        if (rx >= tw) continue;
+        const int32_t w = tile[i];
+        float v = w < 0 ? -1.0f : __ldg(fp + 3ll * w + 2);
+        if (mode == 1) {                   // network input: the range transform of pool_lidar_tensor at full resolution, negatives -> 0
+            v = lidar_value_transform(v);
+            v = v < 0.f ? 0.f : v;
+        }
+        out[(long long)(ty0 + ry) * W + tx0 + rx] = v;
+    }
+}
+
+constexpr int kBoxTW = 128, kBoxTH = 16, kBoxMax = 512;
+
+__global__ void __launch_bounds__(256) heatmap_tile_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ offs, int H, int W,
+                                                           float* __restrict__ maps) {
+    __shared__ int32_t sb[kBoxMax][6];        // culled boxes of this tile in paint order: cls, x, y, w, h, (unused)
+    __shared__ int32_t flags[kBoxMax];
+    __shared__ int nsel;
+    const int b = blockIdx.z;
+    const int tx0 = blockIdx.x * kBoxTW, ty0 = blockIdx.y * kBoxTH;
+    const int tx1 = min(tx0 + kBoxTW, W), ty1 = min(ty0 + kBoxTH, H);
+    const int p0 = offs[b], n = offs[b + 1] - p0;
+    const int32_t* fb = boxes + 5ll * p0;
+    float* out = maps + (long long)b * 3 * H * W;
+    // the boxes are processed in chunks of kBoxMax (paint order); a later chunk overwrites what an earlier one painted
+    for (int c0 = 0; c0 < n || c0 == 0; c0 += kBoxMax) {
+        const int cn = min(kBoxMax, n - c0);
+        for (int i = threadIdx.x; i < kBoxMax; i += blockDim.x) {
+            int f = 0;
+            if (i < cn) {
+                const int32_t* q = fb + 5ll * (c0 + i);
+                const int type = q[0], x = q[1], y = q[2], w = q[3], h = q[4];
+                const int x0 = max(x, 0), y0 = max(y, 0), x1 = min(x + w, W), y1 = min(y + h, H);
+                f = (type == 1 || type == 2 || type == 4) && x1 > x0 && y1 > y0 && x0 < tx1 && x1 > tx0 && y0 < ty1 && y1 > ty0;
+            }
+            flags[i] = f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {               // order-preserving compaction (<= 512 flags, once per tile)
+            int m = 0;
+            for (int i = 0; i < cn; ++i)
+                if (flags[i]) {
+                    const int32_t* q = fb + 5ll * (c0 + i);
+                    sb[m][0] = q[0] == 1 ? 0 : (q[0] == 2 ? 1 : 2);
+                    sb[m][1] = q[1]; sb[m][2] = q[2]; sb[m][3] = q[3]; sb[m][4] = q[4];
+                    ++m;
+                }
+            nsel = m;
+        }
+        __syncthreads();
+        const int m = nsel;
+        for (int i = threadIdx.x; i < kBoxTW * kBoxTH; i += blockDim.x) {
+            const int ry = i / kBoxTW, rx = i - ry * kBoxTW;
+            const int px = tx0 + rx, py = ty0 + ry;
+            if (px >= W || py >= H) continue;
+            float v[3] = {0.f, 0.f, 0.f};
+            bool hit[3] = {false, false, false};
+            for (int j = m - 1; j >= 0; --j) {
+                const int cls = sb[j][0];
+                if (hit[cls]) continue;
+                const int x = sb[j][1], y = sb[j][2], w = sb[j][3], h = sb[j][4];
+                // the reference paints maps[c, y:y+h, x:x+w] for in-bounds boxes; clipped like heatmap_mark_kernel
+                if (px < max(x, 0) || px >= min(x + w, W) || py < max(y, 0) || py >= min(y + h, H)) continue;
+                hit[cls] = true;
+                float val = 1.f;
+                if (cls == 1) {            // pedestrian silhouette (helper:238-250), same rule order as heatmap_resolve_kernel
+                    const int c = px - x, r = py - y;
+                    const int hf = h / 5, wf = w / 4;
+                    if (r < hf && c < wf) val = 0.3f;
+                    if (r < hf && c >= 3 * wf) val = 0.3f;
+                    if (r >= 3 * hf && c < wf) val = 0.5f;
+                    if (r >= 3 * hf && c >= 3 * wf) val = 0.5f;
+                    if (r >= 3 * hf && c >= wf && c < 3 * wf) val = 0.75f;
+                }
+                v[cls] = val;
+            }
+            const long long o = (long long)py * W + px;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (c0 == 0 || hit[c]) out[(long long)c * H * W + o] = v[c];
+        }
+        __syncthreads();
+        if (n == 0) break;
+    }
+}
+
 static unsigned grid_for(long long total) {
     long long g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -189,6 +322,30 @@ extern "C" int dmm_lidar_splat(const float* points, int32_t n_points, int32_t H,
     }
     lidar_resolve_kernel<<<grid_for(n), 256, 0, stream>>>(points, scratch, n, img);
     DMM_LAUNCH_CHECK("lidar_splat kernels");
+    return 0;
+}
+
+extern "C" int dmm_lidar_splat_batched(const float* points, const int32_t* offsets, int32_t B, int32_t H, int32_t W, int32_t kernel_size,
+                                       int32_t mode, float* img, void* stream) {
+    DMM_CHECK(img && offsets && B > 0 && H > 0 && W > 0 && kernel_size >= 1 && (mode == 0 || mode == 1), "dmm_lidar_splat_batched: bad arguments");
+    static bool configured = false;
+    const size_t smem = (size_t)kSplatTW * kSplatTH * sizeof(int32_t);
+    if (!configured) {
+        DMM_CUDA(cudaFuncSetAttribute(lidar_splat_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)((W + kSplatTW - 1) / kSplatTW), (unsigned)((H + kSplatTH - 1) / kSplatTH), (unsigned)B);
+    lidar_splat_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(points, offsets, H, W, (kernel_size - 1) / 2, mode, img);
+    DMM_LAUNCH_CHECK("lidar_splat_tile_kernel");
+    return 0;
+}
+
+extern "C" int dmm_heatmap_boxes_batched(const int32_t* boxes, const int32_t* offsets, int32_t B, int32_t H, int32_t W, float* maps,
+                                         void* stream) {
+    DMM_CHECK(maps && offsets && B > 0 && H > 0 && W > 0, "dmm_heatmap_boxes_batched: bad arguments");
+    dim3 grid((unsigned)((W + kBoxTW - 1) / kBoxTW), (unsigned)((H + kBoxTH - 1) / kBoxTH), (unsigned)B);
+    heatmap_tile_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, offsets, H, W, maps);
+    DMM_LAUNCH_CHECK("heatmap_tile_kernel");
     return 0;
 }
 

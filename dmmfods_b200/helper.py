@@ -87,6 +87,70 @@ def create_ground_truth_maps(ground_truth, width_img=1920, height_img=1280):
     return maps
 
 
+class BatchPreprocessor:
+    """Per-step on-GPU pre-processing of a whole batch (BASELINE config 4): the LiDAR point lists of B frames -> (B,1,H,W)
+    network input (helper:493-515 splat + the range transform of helper:472-481 at full resolution) and the label boxes of
+    B frames -> (B,3,H,W) heat-map targets (helper:276-305), ONE single-pass launch each (dmm_lidar_splat_batched,
+    dmm_heatmap_boxes_batched).  Static device buffers of fixed capacity + device-resident frame offsets: the two launches can
+    sit inside a captured CUDA graph while the number of points / boxes changes from step to step.
+
+        pre = BatchPreprocessor(B, H, W, max_points=40000, max_boxes=256)
+        pre.load(points_per_frame, labels_per_frame)     # host -> static device buffers (async copies)
+        pre.run(lidar_out, target_out)                   # two kernel launches on the current stream
+    """
+
+    def __init__(self, B, H, W, max_points=40000, max_boxes=256, kernel_size=5, transform=True):
+        dev = _dev()
+        self.B, self.H, self.W, self.kernel_size, self.mode = B, H, W, int(kernel_size), 1 if transform else 0
+        self.max_points, self.max_boxes = int(max_points), int(max_boxes)
+        self.points = torch.zeros((B * self.max_points, 3), dtype=torch.float32, device=dev)
+        self.boxes = torch.zeros((B * self.max_boxes, 5), dtype=torch.int32, device=dev)
+        self.p_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.b_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self._h_points = torch.zeros((B * self.max_points, 3), dtype=torch.float32).pin_memory()
+        self._h_boxes = torch.zeros((B * self.max_boxes, 5), dtype=torch.int32).pin_memory()
+        self._h_poff = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self._h_boff = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.h2d_bytes = 0
+
+    def load(self, points_per_frame, labels_per_frame):
+        """points_per_frame: B arrays (N_b,3) float32; labels_per_frame: B label dicts (helper:625-640) or int32 (N_b,5) arrays."""
+        assert len(points_per_frame) == self.B and len(labels_per_frame) == self.B
+        np_, nb_ = 0, 0
+        hp, hb = self._h_points.numpy(), self._h_boxes.numpy()
+        for i in range(self.B):
+            pts = np.asarray(points_per_frame[i], dtype=np.float32).reshape(-1, 3)
+            lab = labels_per_frame[i]
+            bx = boxes_from_ground_truth(lab, self.W, self.H) if isinstance(lab, dict) else np.asarray(lab, dtype=np.int32).reshape(-1, 5)
+            if pts.shape[0] > self.max_points or bx.shape[0] > self.max_boxes:
+                raise ValueError("frame %d: %d points / %d boxes exceed the static capacity (%d / %d)"
+                                 % (i, pts.shape[0], bx.shape[0], self.max_points, self.max_boxes))
+            self._h_poff[i], self._h_boff[i] = np_, nb_
+            hp[np_:np_ + pts.shape[0]] = pts
+            hb[nb_:nb_ + bx.shape[0]] = bx
+            np_ += pts.shape[0]
+            nb_ += bx.shape[0]
+        self._h_poff[self.B], self._h_boff[self.B] = np_, nb_
+        self.points[:np_].copy_(self._h_points[:np_], non_blocking=True)
+        self.boxes[:nb_].copy_(self._h_boxes[:nb_], non_blocking=True)
+        self.p_off.copy_(self._h_poff, non_blocking=True)
+        self.b_off.copy_(self._h_boff, non_blocking=True)
+        self.h2d_bytes = np_ * 12 + nb_ * 20 + 8 * (self.B + 1)
+        return np_, nb_
+
+    def run(self, lidar_out, target_out):
+        """lidar_out: (B,1,H,W) float32 CUDA tensor, target_out: (B,3,H,W); either may be None."""
+        lib = _lib.load()
+        if lidar_out is not None:
+            assert lidar_out.is_contiguous() and tuple(lidar_out.shape) == (self.B, 1, self.H, self.W)
+            _lib.check(lib.dmm_lidar_splat_batched(_ptr(self.points), _ptr(self.p_off), self.B, self.H, self.W, self.kernel_size,
+                                                   self.mode, _ptr(lidar_out), _stream()), "dmm_lidar_splat_batched")
+        if target_out is not None:
+            assert target_out.is_contiguous() and tuple(target_out.shape) == (self.B, 3, self.H, self.W)
+            _lib.check(lib.dmm_heatmap_boxes_batched(_ptr(self.boxes), _ptr(self.b_off), self.B, self.H, self.W, _ptr(target_out),
+                                                     _stream()), "dmm_heatmap_boxes_batched")
+
+
 def _pool(img_tensor, k, is_max):
     dev = _dev()
     x = img_tensor.to(device=dev, dtype=torch.float32).contiguous()

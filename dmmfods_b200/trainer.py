@@ -82,7 +82,7 @@ class Trainer:
     `.clone()` it (or copy it to the host) to keep the value."""
 
     def __init__(self, model, B, H, W, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False,
-                 distributed=None, bucket_bytes=32 << 20, use_graph=False, graph_nccl=None):
+                 distributed=None, bucket_bytes=32 << 20, use_graph=False, graph_nccl=None, preprocess=None):
         import torch.distributed as dist
         if amsgrad:
             raise NotImplementedError("dmmfods_b200.Trainer: amsgrad=True is not supported by the fused flat Adam "
@@ -122,10 +122,20 @@ class Trainer:
         self.graph_nccl = (os.environ.get("DMM_GRAPH_NCCL", "1") != "0") if graph_nccl is None else bool(graph_nccl)
         self.graph = None
         self.seg_graphs = None
+        # preprocess(lidar_buffer, target_buffer): optional on-GPU pre-processing launched at the head of every step (inside the
+        # step graph): fills the engine's LiDAR input and the heat-map targets from raw point lists / label boxes
+        # (helper.BatchPreprocessor.run - BASELINE config 4); step() is then called with x2 = target = None
+        self.preprocess = preprocess
         self._static_target = torch.empty((B, self.eng.ncls, H, W), dtype=torch.float32, device=dev)
         self._copy_stream, self._stage, self._staged, self._stage_ready, self._stage_free = None, None, None, None, None
 
     # ------------------------------------------------------------------------------------------------
+    def _forward(self):
+        eng = self.eng
+        if self.preprocess is not None:
+            self.preprocess(eng.in2 if eng.c2 else None, self._static_target)
+        eng.forward(eng.in1, eng.in2)
+
     def _fwd_loss_bwd(self, target):
         eng = self.eng
         eng.loss(target)
@@ -141,13 +151,14 @@ class Trainer:
         dev = self.pflat.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in (x1, x2, target)]
+            self._stage = [None if t is None else torch.empty(t.shape, dtype=torch.float32, device=dev) for t in (x1, x2, target)]
         cs = self._copy_stream
         if self._stage_free is not None:
             cs.wait_event(self._stage_free)          # the previous hand-over has finished reading the staging buffers
         with torch.cuda.stream(cs):
             for dst, src in zip(self._stage, (x1, x2, target)):
-                dst.copy_(src, non_blocking=True)
+                if src is not None:
+                    dst.copy_(src, non_blocking=True)
             self._stage_ready = torch.cuda.Event()
             self._stage_ready.record(cs)
         # the pinned sources must not be refilled before this copy has run (BatchFileRing waits for the event)
@@ -171,15 +182,16 @@ class Trainer:
             # hand-over: device-to-device into the engine-owned buffers, then the staging buffers are free again and the
             # next prefetch overlaps with this step's kernels
             eng.in1.copy_(staged[0], non_blocking=True)
-            if eng.c2:
+            if eng.c2 and staged[1] is not None:
                 eng.in2.copy_(staged[1], non_blocking=True)
-            self._static_target.copy_(staged[2], non_blocking=True)
+            if staged[2] is not None:
+                self._static_target.copy_(staged[2], non_blocking=True)
             self._stage_free = torch.cuda.Event()
             self._stage_free.record()
             return
         host = []
         for dst, src in ((eng.in1, x1), (eng.in2 if eng.c2 else None, x2), (self._static_target, target)):
-            if dst is None or src is dst:
+            if dst is None or src is dst or src is None:
                 continue
             dst.copy_(src, non_blocking=True)
             if not src.is_cuda:
@@ -207,7 +219,7 @@ class Trainer:
                         self.reducer(i, flat)
                 self.reducer.finish()
         else:
-            eng.forward(eng.in1, eng.in2)
+            self._forward()
             self._fwd_loss_bwd(self._static_target)
         if prefetch_next is not None:
             self.prefetch(*prefetch_next)
@@ -230,7 +242,7 @@ class Trainer:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            eng.forward(eng.in1, eng.in2)
+            self._forward()
             self._fwd_loss_bwd(self._static_target)
         torch.cuda.current_stream().wait_stream(s)
         for t, v in zip(state, saved):
@@ -238,14 +250,14 @@ class Trainer:
         g = torch.cuda.CUDAGraph()
         if self.dist is None:
             with torch.cuda.graph(g):
-                eng.forward(eng.in1, eng.in2)
+                self._forward()
                 self._fwd_loss_bwd(self._static_target)
             self.graph = g
             return
         if self.graph_nccl:
             try:
                 with torch.cuda.graph(g):
-                    eng.forward(eng.in1, eng.in2)
+                    self._forward()
                     self._fwd_loss_bwd(self._static_target)
                 self.graph = g
                 return
@@ -255,7 +267,7 @@ class Trainer:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            eng.forward(eng.in1, eng.in2)
+            self._forward()
             eng.loss(self._static_target)
             eng.backward_begin()
         self.seg_graphs = []

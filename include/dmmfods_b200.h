@@ -405,6 +405,15 @@ int dmm_lidar_pool(const float* img, int32_t H, int32_t W, float* out, void* str
  * scratch: int32[3*H*W]. */
 int dmm_heatmap_boxes(const int32_t* boxes, int32_t n_boxes, int32_t H, int32_t W, int32_t* scratch,
                       float* maps, void* stream);
+/* Batched single-pass forms (BASELINE config 4: per-step on-GPU pre-processing of a whole batch in ONE launch each, every
+ * output pixel written once, no scratch image): frame b owns rows offsets[b] .. offsets[b+1] of `points` (float32 [.,3]) /
+ * `boxes` (int32 [.,5]); offsets: int32[B+1] in DEVICE memory.  img: (B,1,H,W); mode 0 = the raw image of
+ * lidar_array_to_image_like_tensor (-1 background), mode 1 = network input: the range transform of pool_lidar_tensor
+ * (helper:472-481) applied at full resolution, negatives -> 0.  maps: (B,3,H,W).  Bit-identical to the per-frame calls. */
+int dmm_lidar_splat_batched(const float* points, const int32_t* offsets, int32_t B, int32_t H, int32_t W, int32_t kernel_size,
+                            int32_t mode, float* img, void* stream);
+int dmm_heatmap_boxes_batched(const int32_t* boxes, const int32_t* offsets, int32_t B, int32_t H, int32_t W, float* maps,
+                              void* stream);
 /* helper:438-444 maxpool_tensor / helper:430-436 avgpool_tensor: (C,H,W) -> (C,H/k,W/k). */
 int dmm_pool_kxk(const float* img, int32_t C, int32_t H, int32_t W, int32_t k, int32_t is_max,
                  float* out, void* stream);

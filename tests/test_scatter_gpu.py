@@ -108,3 +108,51 @@ def test_step_metrics_match_oracle(seed, shape):
     last = shape[0] - 1
     iou1 = helper.compute_IoU_whole_img_per_class(torch.from_numpy(gt[last]), torch.from_numpy(pred[last]), 0.5).cpu().numpy()
     assert np.array_equal(np.nan_to_num(iou1), np.nan_to_num(orc.iou_whole_img_batch(gt[last:], pred[last:], 0.5)[0]))
+
+
+def test_batched_single_pass_forms_equal_the_per_frame_reference():
+    """BASELINE config 4 pre-processing: dmm_lidar_splat_batched / dmm_heatmap_boxes_batched (one launch per batch, every pixel
+    written once) against the golden full-resolution frame of the unmodified reference and against the numpy oracle on
+    ragged frames: an empty frame, a frame whose boxes exceed one shared-memory chunk (> 512), out-of-range points."""
+    H, W = 1280, 1920
+    pts0, boxes0 = GOLD["full_points"], GOLD["full_boxes"]
+    frames_p = [pts0, np.zeros((0, 3), np.float32), synthetic.lidar_points(12000, H, W, seed=5, out_of_range=0.05), pts0[:7]]
+    many = synthetic.boxes(700, H, W, seed=9)
+    frames_b = [_labels(boxes0), {}, many, synthetic.boxes(3, H, W, seed=10)]
+    pre = helper.BatchPreprocessor(4, H, W, max_points=40000, max_boxes=800, transform=False)
+    pre.load(frames_p, frames_b)
+    img = torch.full((4, 1, H, W), 123.0, device="cuda")
+    maps = torch.full((4, 3, H, W), 123.0, device="cuda")
+    pre.run(img, maps)
+    a, m = img.cpu().numpy(), maps.cpu().numpy()
+    # frame 0 = the golden frame of the unmodified reference
+    assert np.array_equal(a[0][:, 600:700, 900:1100], GOLD["full_img_crop"])
+    assert a[0].astype(np.float64).sum() == GOLD["full_img_sum"][0] and (a[0].astype(np.float64) ** 2).sum() == GOLD["full_img_sum"][1]
+    assert m[0].astype(np.float64).sum() == GOLD["full_maps_sum"][0]
+    assert np.array_equal(helper.maxpool_tensor(maps[0]).cpu().numpy(), GOLD["full_maps_pooled"])
+    for b in range(4):
+        assert np.array_equal(a[b], orc.lidar_array_to_image(frames_p[b], (1, H, W), 5)), "lidar frame %d" % b
+        assert np.array_equal(m[b], orc.create_ground_truth_maps(frames_b[b], W, H)), "heat-map frame %d" % b
+    # mode 1: the range transform of pool_lidar_tensor at full resolution (network input), negatives -> 0
+    pre_t = helper.BatchPreprocessor(4, H, W, max_points=40000, max_boxes=800, transform=True)
+    pre_t.load(frames_p, frames_b)
+    pre_t.run(img, None)
+    want = np.stack([np.maximum(orc.lidar_value_transform(orc.lidar_array_to_image(p, (1, H, W), 5)), 0.0) for p in frames_p])
+    assert np.array_equal(img.cpu().numpy(), want.astype(np.float32))
+    with pytest.raises(ValueError):
+        pre.load([np.zeros((50000, 3), np.float32)] * 4, frames_b)
+
+
+def test_batched_forms_small_odd_shapes():
+    for seed, (H, W) in enumerate([(40, 50), (65, 257), (130, 300)]):
+        B = 3
+        fp = [synthetic.lidar_points(400 + 100 * i, H, W, seed=seed * 10 + i, out_of_range=0.1) for i in range(B)]
+        fb = [synthetic.boxes(10 + 5 * i, H, W, seed=seed * 10 + i) for i in range(B)]
+        pre = helper.BatchPreprocessor(B, H, W, max_points=1000, max_boxes=64, transform=False)
+        pre.load(fp, fb)
+        img = torch.empty((B, 1, H, W), device="cuda")
+        maps = torch.empty((B, 3, H, W), device="cuda")
+        pre.run(img, maps)
+        for b in range(B):
+            assert np.array_equal(img[b].cpu().numpy(), orc.lidar_array_to_image(fp[b], (1, H, W), 5))
+            assert np.array_equal(maps[b].cpu().numpy(), orc.create_ground_truth_maps(fb[b], W, H))
