@@ -188,7 +188,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def kernel_breakdown(eng, x1, x2, tgt, dump=None, pre=None):
+def kernel_breakdown(eng, x1, x2, tgt, dump=None, pre=None, backward=True):
     """one instrumented step: CUDA events around every launch, grouped by kernel family.  The stream is first held busy by
     a device-side spin so that the host enqueues the whole program ahead of the GPU: the event pairs then bracket kernels
     that run back to back (un-held, the small launches of blocks 3/4 are host-bound and their brackets include the gap)."""
@@ -218,7 +218,8 @@ def kernel_breakdown(eng, x1, x2, tgt, dump=None, pre=None):
             pre()
         eng.forward(x1, x2)
         eng.loss(tgt)
-        eng.backward()
+        if backward:
+            eng.backward()
         torch.cuda.synchronize()
     finally:
         eng._run = orig_run
@@ -335,7 +336,7 @@ def run_cfg5(args, wl):
         if best is None or row["images_per_s"] > best["images_per_s"]:
             best = row
         if B == wl["sweep"][-1] or B == 32:
-            fam = kernel_breakdown(ev.eng, x1, x2, tg) if B == 32 else None
+            fam = kernel_breakdown(ev.eng, x1, x2, tg, backward=False) if B == 32 else None
             if fam is not None:
                 roof, kernels, _ = roofline_from({k: v for k, v in fam.items()}, peaks)
         del ev, x1, x2, tg

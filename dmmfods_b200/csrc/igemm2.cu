@@ -49,6 +49,7 @@ struct Ig2Params {
     int n_tile, N;
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
+    int nslot;                                      // out_mode 0: staging slots per epilogue team (1..3)
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
     int Wv, Hv;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + ((OUT_MODE == 0 || FOLD3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
+    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * p.nslot * kStageSlot : (FOLD3 ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0)));   // bnb: one x tile per team
     uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
@@ -398,7 +399,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         const int px = r % p.sub_w, py = r / p.sub_w;
         const bool do_stats = (OUT_MODE == 0 || FOLD3) && (p.stats != nullptr);
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
-        uint8_t* slot = stg + team * kStageSlot;
+        // out_mode 0: `nslot` staging slots per team, used round-robin: the TMA store of a chunk drains (behind whatever loads are
+        // queued in the SM's TMA unit) while the next chunks are staged; FOLD3 keeps one slot per team
+        uint8_t* slot = stg + team * (OUT_MODE == 0 ? p.nslot : 1) * kStageSlot;
+        uint32_t slot_i = 0;
         if (FOLD3) {
             // compact staging: 4 image rows x (32 - 2) valid pixels = 120 rows; rows 120..127 stay zero for the statistics loop
             if (r >= 120) {
@@ -410,7 +414,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
-        const uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow), xslot_u = smem_u32(xslot);
+        uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow);
+        const uint32_t slot0_u = slot_u, xslot_u = smem_u32(xslot);
         double sacc[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -556,7 +561,14 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
-                        if (r == 0) bulk_wait_read0();       // the team's previous TMA store has finished reading the slot
+                        // round-robin slot; its previous TMA store (nslot chunks ago) must have finished reading it
+                        slot_u = slot0_u + slot_i * kStageSlot;
+                        srow_u = slot_u + r * 128;
+                        if (r == 0) {
+                            if (p.nslot == 1) bulk_wait_read0();
+                            else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                        }
                         tmem_ld_wait();
                         epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
                         if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
@@ -584,9 +596,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         fence_proxy_async();
                         epi_bar(team);
                         if (r == 0) {
-                            tma_store_4d(&p.o_map, slot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
+                            tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
+                        if (++slot_i == (uint32_t)p.nslot) slot_i = 0;
                         if (do_stats) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
@@ -827,13 +840,20 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
                   "igemm v2: prologue BatchNorm without statistics");
         pro_kp = ceil_div(d->src[0].C, 64) * 64;
     }
-    const int staging = ((d->out_mode == 0 || d->out_mode == 3) ? (bnb ? 4 : 2) * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0)) +
+    int max_taps = 1;
+    for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
+    // staging slots per epilogue team (out_mode 0): the 1x1 convolutions are output-heavy and their TMA stores queue behind the
+    // prefetched operand loads of the SM's TMA unit - three slots let the epilogue run ahead of the drain (DMM_IGEMM_NSLOT)
+    static const int nslot_env = env_int("DMM_IGEMM_NSLOT", 0);
+    int nslot = nslot_env > 0 ? nslot_env : ((max_taps == 1 && !bnb) ? 3 : 1);
+    if (nslot > 3) nslot = 3;
+    if (d->out_mode != 0) nslot = 1;
+    const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 2 : 0)) * (int)kStageSlot
+                                          : (d->out_mode == 3 ? 2 * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0))) +
                         (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
     const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
-    int max_taps = 1;
-    for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
     const int mma_hw = d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4;   // cycles per MMA (measured law)
     Tiling best;
     best.msub = 0;
@@ -869,7 +889,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             const int b_stage_c = ceil_div(c.tps, tpk) * (int)b_tap;
             c.sb = rest / b_stage_c;
             if (c.sb > 4) c.sb = 4;
-            if (max_taps == 1 && b_stage_c <= 16384 && rest / b_stage_c >= 6) c.sb = 6;
+            static const int sb1 = env_int("DMM_IGEMM_SB1", 3);      // 1x1: one weight block per stage, few stages suffice
+            if (max_taps == 1) { if (c.sb > sb1) c.sb = sb1; if (c.sb < 2) c.sb = 2; }
             int sa = (avail - c.sb * b_stage_c) / (int)c.a_stage;
             c.sa = sa > 4 ? 4 : sa;
             c.tiles = (long long)ceil_div(d->W, fold ? c.TW - (d->fold_kw - 1) : c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
@@ -892,6 +913,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.msub = best.msub; p.sub_w = best.sub_w; p.sub_h = best.sub_h;
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
+    p.nslot = nslot;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
     p.x_step = fold ? p.TW - (d->fold_kw - 1) : p.TW;

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(256) pool_kxk_kernel(const float* __restrict__
 //          from the LAST to the first and takes the first hit of its class - "later boxes overwrite earlier ones" without atomics.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSplatTW = 256, kSplatTH = 64;      // 64 KB of int32 per tile
+constexpr int kSplatChunk = 2048;
 
 __global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __restrict__ pts, const int32_t* __restrict__ offs, int H, int W,
                                                                int shift, int mode, float* __restrict__ img) {
@@ -188,24 +189,39 @@ __global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __re
     const int p0 = offs[b], n = offs[b + 1] - p0;
     const float* fp = pts + 3ll * p0;
     const float fs = (float)shift;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const float x = __ldg(fp + 3 * i + 0), y = __ldg(fp + 3 * i + 1);
-        // identical arithmetic to lidar_mark_kernel (helper:503-511)
-        int min_y = py_int(__fsub_rn(y, fs));
-        if (min_y < 0) min_y = 0;
-        int max_y = py_int(__fadd_rn(__fadd_rn(y, fs), 1.f));
-        if (max_y > H - 1) max_y = H - 1;
-        int min_x = py_int(__fsub_rn(x, fs));
-        if (min_x < 0) min_x = 0;
-        int max_x = py_int(__fadd_rn(__fadd_rn(x, fs), 1.f));
-        if (max_x > W - 1) max_x = W - 1;
-        int y0, y1, x0, x1;
-        py_slice(min_y, max_y, H, y0, y1);
-        py_slice(min_x, max_x, W, x0, x1);
-        y0 = max(y0, ty0); y1 = min(y1, ty0 + th);
-        x0 = max(x0, tx0); x1 = min(x1, tx0 + tw);
-        for (int yy = y0; yy < y1; ++yy)
-            for (int xx = x0; xx < x1; ++xx) atomicMax(&tile[(yy - ty0) * kSplatTW + (xx - tx0)], i);
+    // the frame's points stream through shared memory in chunks of kSplatChunk (coalesced loads, every CTA of the frame reads
+    // the same L2-resident list); each thread then tests kSplatChunk / 256 points against the tile
+    __shared__ float sxy[2][kSplatChunk];
+    for (int c0 = 0; c0 < n; c0 += kSplatChunk) {
+        const int cn = min(kSplatChunk, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            sxy[0][i] = __ldg(fp + 3ll * (c0 + i) + 0);
+            sxy[1][i] = __ldg(fp + 3ll * (c0 + i) + 1);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
+            const float x = sxy[0][i], y = sxy[1][i];
+            // identical arithmetic to lidar_mark_kernel (helper:503-511)
+            int min_y = py_int(__fsub_rn(y, fs));
+            if (min_y < 0) min_y = 0;
+            int max_y = py_int(__fadd_rn(__fadd_rn(y, fs), 1.f));
+            if (max_y > H - 1) max_y = H - 1;
+            int y0, y1;
+            py_slice(min_y, max_y, H, y0, y1);
+            y0 = max(y0, ty0); y1 = min(y1, ty0 + th);
+            if (y0 >= y1) continue;
+            int min_x = py_int(__fsub_rn(x, fs));
+            if (min_x < 0) min_x = 0;
+            int max_x = py_int(__fadd_rn(__fadd_rn(x, fs), 1.f));
+            if (max_x > W - 1) max_x = W - 1;
+            int x0, x1;
+            py_slice(min_x, max_x, W, x0, x1);
+            x0 = max(x0, tx0); x1 = min(x1, tx0 + tw);
+            const int idx = c0 + i;
+            for (int yy = y0; yy < y1; ++yy)
+                for (int xx = x0; xx < x1; ++xx) atomicMax(&tile[(yy - ty0) * kSplatTW + (xx - tx0)], idx);
+        }
     }
     __syncthreads();
     float* out = img + (long long)b * H * W;

@@ -120,7 +120,7 @@ def test_trainer_steps_equal_the_reference_loop_body(use_graph, prefetch):
         sums.append(cs.clone().cpu())
     torch.cuda.synchronize()
     for a, b in zip(sums, ref_sums):
-        assert _rel(a, b) < 1e-6, (a, b)
+        assert _rel(a, b) < 2e-5, (a, b)         # the reference loop sums the fp32 loss tensor in fp32, the engine in fp64
     _compare_states(model.state_dict(), want, init, "Trainer(use_graph=%s, prefetch=%s)" % (use_graph, prefetch))
     # the module's parameters ARE views of the trainer's flat buffer (an optimizer or checkpoint sees the trained values)
     p0 = next(model.parameters())
