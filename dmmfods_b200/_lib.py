@@ -41,7 +41,8 @@ class Igemm(C.Structure):
                 ("stats_ld", c_int32), ("stats_off", c_int32),
                 ("bnb_x", c_void_p), ("bnb_ldx", c_int64), ("bnb_gamma", c_void_p), ("bnb_beta", c_void_p),
                 ("bnb_mean", c_void_p), ("bnb_invstd", c_void_p), ("bnb_sums", c_void_p), ("bnb_sums_ld", c_int32),
-                ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("fold_kw", c_int32), ("pro_bn", Bn)]
+                ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("fold_kw", c_int32), ("pro_bn", Bn),
+                ("dtype", c_int32), ("pad_", c_int32)]
 
 
 WG_MAX_A = 8
@@ -139,6 +140,10 @@ SIGNATURES = {
     "dmm_rows_f32_to_bf16": (C.c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     "dmm_bce_logits": (C.c_int, [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "dmm_bn_relu_apply_f32": (C.c_int, [C.POINTER(BnApply), c_void_p]),
+    "dmm_head_input_f32": (C.c_int, [C.POINTER(Head), c_void_p]),
+    "dmm_im2col_7x7s2_f32": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "dmm_pack_weights_work_f32": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "dmm_lidar_splat": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dmm_lidar_splat_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dmm_heatmap_boxes_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

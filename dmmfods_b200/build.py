@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libdmmfods_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["common.cu", "igemm.cu", "igemm2.cu", "wgrad.cu", "elementwise.cu", "scatter.cu"]
+SOURCES = ["common.cu", "igemm.cu", "igemm2.cu", "wgrad.cu", "elementwise.cu", "scatter.cu", "strict.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 

@@ -57,8 +57,9 @@ static CUtensorMapL2promotion l2_promotion() {
                   : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int make_tmap_elem(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
+    DMM_CHECK(elem_bytes == 2 || elem_bytes == 4, "tensor map element size %d", elem_bytes);
     EncodeTiledFn enc = get_encode();
     DMM_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     DMM_CHECK(rank >= 2 && rank <= 5, "tensor map rank %d", rank);
@@ -75,7 +76,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
                   (unsigned long long)dims[i], box[i]);
     }
     for (int i = 0; i + 1 < rank; ++i) {
-        gstr[i] = strides_elems[i] * 2ull;
+        gstr[i] = strides_elems[i] * (unsigned long long)elem_bytes;
         DMM_CHECK(gstr[i] % 16 == 0 && gstr[i] > 0, "tensor map stride %d = %llu bytes is not a positive multiple of 16", i,
                   (unsigned long long)gstr[i]);
     }
@@ -83,14 +84,19 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
     else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
     else if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
-    DMM_CHECK((int)(box[0] * 2) <= (swizzle_bytes ? swizzle_bytes : 512), "tensor map inner box %u elements exceeds the swizzle span",
+    DMM_CHECK((int)(box[0] * elem_bytes) <= (swizzle_bytes ? swizzle_bytes : 512), "tensor map inner box %u elements exceeds the swizzle span",
               box[0]);
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, l2_promotion(),
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DMM_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu.. box %u,%u..)", (int)r,
               rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return 0;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes) {
+    return make_tmap_elem(out, 2, base, rank, dims, strides_elems, box, swizzle_bytes);
 }
 
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems, uint32_t box_cols,

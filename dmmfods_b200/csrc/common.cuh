@@ -39,6 +39,10 @@ int check_cuda(cudaError_t e, const char* what);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
 
+// same for 2-byte (bf16) or 4-byte (fp32) elements
+int make_tmap_elem(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes);
+
 // fp32 2-D tensor map (row-major [rows][row_stride]) for TMA reduce-add epilogues; swizzle_bytes in {0, 128}.
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_elems, uint32_t box_cols,
                      uint32_t box_rows, int swizzle_bytes);
@@ -171,6 +175,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp32 operands read as tf32 (K = 8 per instruction) / fp32 accumulate.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -210,6 +224,17 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major
     d |= 1u << 10;                       // B format: BF16
     d |= (uint32_t)(a_mn_major & 1) << 15;
     d |= (uint32_t)(b_mn_major & 1) << 16;
+    d |= (uint32_t)(N >> 3) << 17;
+    d |= (uint32_t)(M >> 4) << 24;
+    return d;
+}
+
+// Instruction descriptor for kind::tf32 (A/B format 2 = TF32, K-major), fp32 D.
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                        // D format: F32
+    d |= 2u << 7;                        // A format: TF32
+    d |= 2u << 10;                       // B format: TF32
     d |= (uint32_t)(N >> 3) << 17;
     d |= (uint32_t)(M >> 4) << 24;
     return d;

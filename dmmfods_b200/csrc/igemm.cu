@@ -42,7 +42,9 @@ struct IgemmKParams {
 constexpr int kThreads = 192;
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 
-template <int OUT_MODE>
+// TF32: fp32 storage (activations, packed weights, output), tcgen05.mma kind::tf32 (K = 8 per instruction, fp32 accumulate) -
+// the strict-tolerance arithmetic mode (dmm_igemm_t.dtype == 1); kwidth = 32 fp32 channels = one 128-byte swizzle row.
+template <int OUT_MODE, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmKParams p) {
     pdl_prologue();
@@ -116,10 +118,10 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
-        const uint32_t layout = (p.kwidth == 64) ? 2u : 6u;           // SW128 : SW32
-        const uint32_t sbo = (p.kwidth == 64) ? 1024u : 256u;         // 8 rows x row bytes
-        const int full_ksteps = p.kwidth / 16;
+        const uint32_t idesc = TF32 ? make_idesc_tf32(128, p.n_tile) : make_idesc_bf16(128, p.n_tile, 0, 0);
+        const uint32_t layout = (TF32 || p.kwidth == 64) ? 2u : 6u;   // SW128 : SW32
+        const uint32_t sbo = (TF32 || p.kwidth == 64) ? 1024u : 256u; // 8 rows x row bytes
+        const int full_ksteps = TF32 ? p.kwidth / 8 : p.kwidth / 16;
         int kb = 0;
         for (int tp = 0; tp < p.num_taps; ++tp) {
             const int src = p.tap_src[tp];
@@ -136,7 +138,8 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t ad = make_smem_desc(sa + k * 32, 16, sbo, layout);
                         const uint64_t bd = make_smem_desc(sb + k * 32, 16, sbo, layout);
-                        umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (TF32) umma_tf32(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        else umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);
                     if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -166,7 +169,19 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
-            if (OUT_MODE == 0) {
+            if (OUT_MODE == 0 && TF32) {
+                if (valid) {
+                    float* orow = reinterpret_cast<float*>(p.out) + pix * p.ldo + p.coff + nb;
+                    if (nb + 16 <= p.N && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0)) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) reinterpret_cast<float4*>(orow)[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < p.N) orow[j] = v[j];
+                    }
+                }
+            } else if (OUT_MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = bf16_round(v[j]);
                 if (valid) {
@@ -245,14 +260,17 @@ static uint32_t tmem_cols_for(int n) {
 
 int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream);
 
-int view_to_tmap(CUtensorMap* out, const dmm_view_t& v, int box_c, int box_w, int box_h, int swizzle) {
+int view_to_tmap_elem(CUtensorMap* out, const dmm_view_t& v, int box_c, int box_w, int box_h, int swizzle, int elem_bytes) {
     uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.B};
     uint64_t strides[3] = {(uint64_t)v.sw, (uint64_t)v.sh, (uint64_t)v.sb};
     // degenerate dims: the driver still wants valid (16-B multiple) strides
     if (v.H == 1 && strides[1] == 0) strides[1] = (uint64_t)v.W * v.sw;
     if (v.B == 1 && strides[2] == 0) strides[2] = strides[1] * (uint64_t)v.H;
     uint32_t box[4] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_h, 1u};
-    return make_tmap_bf16(out, v.ptr, 4, dims, strides, box, swizzle);
+    return make_tmap_elem(out, elem_bytes, v.ptr, 4, dims, strides, box, swizzle);
+}
+int view_to_tmap(CUtensorMap* out, const dmm_view_t& v, int box_c, int box_w, int box_h, int swizzle) {
+    return view_to_tmap_elem(out, v, box_c, box_w, box_h, swizzle, 2);
 }
 
 }  // namespace dmm
@@ -262,7 +280,8 @@ using namespace dmm;
 extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DMM_CHECK(d != nullptr, "dmm_conv_igemm: null descriptor");
-    DMM_CHECK(d->kwidth == 64 || d->kwidth == 16, "dmm_conv_igemm: kwidth must be 64 or 16 (got %d)", d->kwidth);
+    DMM_CHECK(d->dtype == 0 || d->dtype == 1, "dmm_conv_igemm: dtype must be 0 (bf16) or 1 (fp32 storage, tf32 MMA)");
+    DMM_CHECK(d->dtype == 1 ? d->kwidth == 32 : (d->kwidth == 64 || d->kwidth == 16), "dmm_conv_igemm: kwidth must be 64 or 16 (32 in the fp32 mode), got %d", d->kwidth);
     DMM_CHECK(d->num_src >= 1 && d->num_src <= DMM_MAX_SRC, "dmm_conv_igemm: bad num_src %d", d->num_src);
     DMM_CHECK(d->num_taps >= 1 && d->num_taps <= DMM_MAX_TAPS, "dmm_conv_igemm: bad num_taps %d", d->num_taps);
     DMM_CHECK(d->tile_w == 128 || d->tile_w == 64 || d->tile_w == 32 || d->tile_w == 16 || d->tile_w == 8,
@@ -283,24 +302,29 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
             if (used) { ++tapped; packed16 = d->src[s].C <= 16; }
         }
         packed16 = packed16 && tapped == 1;
-        if ((d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode >= 2)) return igemm2_launch(d, stream);
+        if (d->dtype != 1 && (d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode >= 2)) return igemm2_launch(d, stream);
     }
     DMM_CHECK(d->out_mode < 2, "dmm_conv_igemm: out_mode 2 / 3 need kwidth 64");
+    const bool tf32 = d->dtype == 1;
+    const int esz = tf32 ? 4 : 2;
+    const int kstep = tf32 ? 8 : 16;
+    if (tf32) DMM_CHECK(d->kwidth == 32 && !d->pro_enable && d->bnb_sums == nullptr && d->fold_kw == 0,
+                        "dmm_conv_igemm: the fp32 / tf32 mode needs kwidth 32 and no fused prologue / BN-backward epilogue");
 
     IgemmKParams p;
     memset(&p, 0, sizeof(p));
     p.kwidth = d->kwidth;
     p.tile_w = d->tile_w;
     p.tile_h = 128 / d->tile_w;
-    const int swz = d->kwidth == 64 ? 128 : 32;
+    const int swz = (tf32 || d->kwidth == 64) ? 128 : 32;
     long long ktot = 0;
     for (int s = 0; s < d->num_src; ++s) {
         const dmm_view_t& v = d->src[s];
         DMM_CHECK(v.ptr != nullptr && v.C >= 1, "dmm_conv_igemm: source %d empty", s);
         p.src_nblk[s] = ceil_div(v.C, d->kwidth);
         const int rem = v.C - (p.src_nblk[s] - 1) * d->kwidth;
-        p.src_lastk[s] = ceil_div(rem, 16);
-        int rc = view_to_tmap(&p.a_maps[s], v, d->kwidth, p.tile_w, p.tile_h, swz);
+        p.src_lastk[s] = ceil_div(rem, kstep);
+        int rc = view_to_tmap_elem(&p.a_maps[s], v, d->kwidth, p.tile_w, p.tile_h, swz, esz);
         if (rc) return rc;
     }
     p.num_taps = d->num_taps;
@@ -317,7 +341,7 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
         uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->n_rows};
         uint64_t strides[1] = {(uint64_t)d->ktot};
         uint32_t box[2] = {(uint32_t)d->kwidth, (uint32_t)d->n_tile};
-        int rc = make_tmap_bf16(&p.b_map, d->weights, 2, dims, strides, box, swz);
+        int rc = make_tmap_elem(&p.b_map, esz, d->weights, 2, dims, strides, box, swz);
         if (rc) return rc;
     }
     p.W = d->W; p.H = d->H; p.B = d->B;
@@ -325,8 +349,8 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     p.tiles_y = ceil_div(d->H, p.tile_h);
     p.n_tile = d->n_tile;
     p.N = d->N;
-    p.a_bytes = 128u * d->kwidth * 2u;
-    p.b_bytes = ((uint32_t)d->n_tile * d->kwidth * 2u + 1023u) & ~1023u;
+    p.a_bytes = 128u * d->kwidth * (uint32_t)esz;
+    p.b_bytes = ((uint32_t)d->n_tile * d->kwidth * (uint32_t)esz + 1023u) & ~1023u;
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     // two co-resident CTAs per SM when the stage is small enough, else one with a deeper ring
     const uint32_t budget = (stage_bytes * 3 <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
@@ -351,13 +375,18 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     dim3 grid((unsigned)((long long)p.tiles_x * p.tiles_y * d->B), (unsigned)ceil_div(d->N, d->n_tile), 1);
     static bool attr_set = false;      // opt in to the full 227 KB of shared memory once (not a stream operation)
     if (!attr_set) {
-        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+        DMM_CUDA(cudaFuncSetAttribute(igemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
         attr_set = true;
     }
     DMM_CHECK(smem <= (size_t)kMaxSmem, "dmm_conv_igemm: %zu bytes of shared memory requested", smem);
-    if (d->out_mode == 0) launch_k(igemm_kernel<0>, grid, kThreads, smem, stream, p);
-    else launch_k(igemm_kernel<1>, grid, kThreads, smem, stream, p);
+    if (tf32) {
+        if (d->out_mode == 0) launch_k(igemm_kernel<0, true>, grid, kThreads, smem, stream, p);
+        else launch_k(igemm_kernel<1, true>, grid, kThreads, smem, stream, p);
+    } else if (d->out_mode == 0) launch_k(igemm_kernel<0, false>, grid, kThreads, smem, stream, p);
+    else launch_k(igemm_kernel<1, false>, grid, kThreads, smem, stream, p);
     DMM_LAUNCH_CHECK("igemm_kernel");
     return 0;
 }

@@ -842,10 +842,10 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     }
     int max_taps = 1;
     for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
-    // staging slots per epilogue team (out_mode 0): the 1x1 convolutions are output-heavy and their TMA stores queue behind the
-    // prefetched operand loads of the SM's TMA unit - three slots let the epilogue run ahead of the drain (DMM_IGEMM_NSLOT)
+    // staging slots per epilogue team (out_mode 0, DMM_IGEMM_NSLOT): more than one lets the epilogue run ahead of the drain of its
+    // TMA stores
     static const int nslot_env = env_int("DMM_IGEMM_NSLOT", 0);
-    int nslot = nslot_env > 0 ? nslot_env : ((max_taps == 1 && !bnb) ? 3 : 1);
+    int nslot = nslot_env > 0 ? nslot_env : 1;       // measured (r02): 3 slots 86.2 ms / step, 1 slot 85.0 - the epilogue does not wait for the drain
     if (nslot > 3) nslot = 3;
     if (d->out_mode != 0) nslot = 1;
     const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 2 : 0)) * (int)kStageSlot
@@ -889,8 +889,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             const int b_stage_c = ceil_div(c.tps, tpk) * (int)b_tap;
             c.sb = rest / b_stage_c;
             if (c.sb > 4) c.sb = 4;
-            static const int sb1 = env_int("DMM_IGEMM_SB1", 3);      // 1x1: one weight block per stage, few stages suffice
-            if (max_taps == 1) { if (c.sb > sb1) c.sb = sb1; if (c.sb < 2) c.sb = 2; }
+            static const int sb1 = env_int("DMM_IGEMM_SB1", 6);      // 1x1: one weight block per stage
+            if (max_taps == 1) {
+                if (sb1 >= 6) { if (b_stage_c <= 16384 && rest / b_stage_c >= 6) c.sb = 6; }
+                else { if (c.sb > sb1) c.sb = sb1; if (c.sb < 2) c.sb = 2; }
+            }
             int sa = (avail - c.sb * b_stage_c) / (int)c.a_stage;
             c.sa = sa > 4 ? 4 : sa;
             c.tiles = (long long)ceil_div(d->W, fold ? c.TW - (d->fold_kw - 1) : c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;

@@ -97,12 +97,22 @@ class _BNInfo:
 
 class Engine:
     def __init__(self, params, model_cfg, B, H, W, training=True, need_backward=True, plan_only=False,
-                 bucket_bytes=32 << 20, _order_only=False):
+                 bucket_bytes=32 << 20, _order_only=False, precision="bf16"):
         """params: dict name -> CUDA tensor with the reference's state_dict keys (parameters fp32, BN buffers);
         model_cfg: mapping with the keys of helper:111-123.  plan_only=True builds the launch programs without a
-        GPU (host-logic tests); such an engine cannot run."""
+        GPU (host-logic tests); such an engine cannot run.
+        precision: "bf16" (production: bf16 storage, kind::f16 MMAs) or "tf32" - the STRICT forward mode: fp32 storage of every
+        activation and packed weight, kind::tf32 MMAs with fp32 accumulation, unfused plan (forward + loss only)."""
         self.lib = _lib.load() if plan_only else ops.require_device()
         self.plan_only = plan_only
+        if precision not in ("bf16", "tf32"):
+            raise ValueError("precision must be 'bf16' or 'tf32'")
+        self.f32 = precision == "tf32"
+        self.precision = precision
+        if self.f32 and need_backward and training:
+            raise NotImplementedError("dmmfods_b200: the strict tf32 mode covers forward + loss (need_backward=False)")
+        self.kwidth = 32 if self.f32 else ops.KWIDTH
+        self.adt = torch.float32 if self.f32 else torch.bfloat16
         self.p = params
         self.training = training
         self.need_backward = need_backward and training
@@ -218,8 +228,8 @@ class Engine:
     # small allocation helpers
     # ------------------------------------------------------------------------------------------------
     def _mat(self, B, H, W, ld):
-        self.mem_bytes += B * H * W * ld * 2
-        m = Mat(torch.empty((B * H * W, ld), dtype=torch.bfloat16, device=self._alloc_dev), B, H, W)
+        self.mem_bytes += B * H * W * ld * (4 if self.f32 else 2)
+        m = Mat(torch.empty((B * H * W, ld), dtype=self.adt, device=self._alloc_dev), B, H, W)
         self._keep.append(m)      # launch descriptors hold raw addresses only
         return m
 
@@ -262,21 +272,25 @@ class Engine:
         fold_kw (out_mode 2): `taps` / `tap_off` are the kernel ROWS; the kernel columns are folded into the GEMM's N (packed
         weight row kw*Cout + n)."""
         T = len(taps)
-        Kp = ceil_to(Cin, ops.KWIDTH)
+        Kp = ceil_to(Cin, self.kwidth)
         N = Cout * fold_kw if fold_kw else Cout
         n_tile = ops.pick_n_tile(N)
         n_rows = ceil_to(N, n_tile)
         if not self.training:
             stats = None
+        assert not (self.f32 and (fold_kw or out_mode >= 2)), "strict mode: unfolded convolutions only"
         wid = self._req_wpk(n_rows, T * Kp)
-        job = dict(w=self.p[wname], wid=wid, n_valid=N, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off, sn=sn, sc=sc, cdiv=cdiv, sc2=sc2)
+        job = dict(w=self.p[wname], wid=wid, n_valid=N, n_rows=n_rows, C=Cin, T=T, tap_off=tap_off, sn=sn, sc=sc, cdiv=cdiv, sc2=sc2,
+                   kwidth=self.kwidth)
         if fold_kw:
             job.update(ndiv=Cout, sn=1, sn2=sn)        # row kw*Cout + n <- w[n, :, kh, kw]
         self._pack_jobs.append(job)
         d = ops.make_igemm(srcs, taps, 0, T * Kp, n_rows, W, H, B, N,
                            out_ptr if out_ptr is not None else out.ptr(), 0 if out is None else out.ld, coff=coff,
                            out_mode=out_mode, stats=stats, stats_off=stats_off, out_stride=out_stride,
-                           out_phase=out_phase, out_hw=out_hw, n_tile=n_tile, fold_kw=fold_kw, tile_w=tile_w)
+                           out_phase=out_phase, out_hw=out_hw, n_tile=n_tile, fold_kw=fold_kw, tile_w=tile_w, kwidth=self.kwidth)
+        if self.f32:
+            d.dtype = 1
         P = B * H * W
         osz = 4 if out_mode in (1, 2) else 2
         kk = fold_kw if fold_kw else 1
@@ -360,7 +374,8 @@ class Engine:
         if not self.training:
             ystats = None
         d = ops.make_bn_apply(x, xc0, C_, b, y, yc0, pool=pool, ystats=ystats, ystats_off=ystats_off)
-        self._emit(lst, self.lib.dmm_bn_relu_apply, d, name, kind="bn_relu_apply", nbytes=(x.P + y.P) * C_ * 2)
+        fn = self.lib.dmm_bn_relu_apply_f32 if self.f32 else self.lib.dmm_bn_relu_apply
+        self._emit(lst, fn, d, name, kind="bn_relu_apply", nbytes=(x.P + y.P) * C_ * x.esize)
 
     def _bn_bwd(self, lst, name, bn, x, xc0, C_, g_ptr, ldg, out_ptr, ldo, out_mode, gmode=0, g_is_f32=False, bn_c0=0,
                 gbuf=None, dz_tmp=None, producer=None):
@@ -503,7 +518,7 @@ class Engine:
             z0s = self._new_stats(self.nif)
             self.named[prefix + ".conv0"] = z0
             # (a single-channel stream keeps the small im2col matrix: its 7 narrow tap loads make the weight gradient slower)
-            unfold = 7 * cin <= 64 and cin >= int(os.environ.get("DMM_STEM_UNFOLD_MIN_C", "2"))
+            unfold = 7 * cin <= 64 and cin >= int(os.environ.get("DMM_STEM_UNFOLD_MIN_C", "2")) and not self.f32
             if unfold:
                 # horizontal unfold only: xw[(b, iy, ox)][kw*cin + c] = x[c](iy, 2 ox + kw - 3) for ALL input rows; conv0 is then
                 # a 7-tap vertical convolution over the even-row / odd-row views of xw (input row 2 oy + kh - 3 = 2 (oy + dy) + p)
@@ -523,8 +538,9 @@ class Engine:
                 col = self._mat(B, H2, W2, kpad)
 
                 def run_im2col(_a, stream, x1=x1, x2=x2, c1=c1, c2=c2, col=col, lib=self.lib):
-                    return lib.dmm_im2col_7x7s2(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
-                                                B, H, W, col.ptr(), col.ld, stream)
+                    fn = lib.dmm_im2col_7x7s2_f32 if self.f32 else lib.dmm_im2col_7x7s2
+                    return fn(C.c_void_p(x1.data_ptr()), c1, C.c_void_p(x2.data_ptr()) if c2 else None, c2,
+                              B, H, W, col.ptr(), col.ld, stream)
                 self._emit(fwd, run_im2col, None, prefix + ".im2col", kind="im2col",
                            nbytes=B * H * W * cin * 4 + B * H2 * W2 * kpad * 2)
                 self._conv_fwd(fwd, prefix + ".conv0", prefix + ".conv0.weight", [col.view(0, kpad)], [(0, 0, 0)], [0],
@@ -565,7 +581,7 @@ class Engine:
                 bn2 = _BNInfo(self, lp + ".norm2", bnk)
                 z1 = self._mat(B, Hb, Wb, bnk)
                 z1s = self._new_stats(bnk)
-                if FUSE_BN_PROLOGUE:
+                if FUSE_BN_PROLOGUE and not self.f32:
                     # norm1 + relu1 run inside conv1: its A tiles are the raw block-buffer channels, activated in shared memory
                     a1 = None
                     d1 = self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [blk.buf.view(0, Ci)], conv1x1[0], conv1x1[2],
@@ -577,7 +593,7 @@ class Engine:
                     self._apply(fwd, lp + ".norm1", bn1, blk.buf, 0, Ci, blk.stats, 0, a1, 0)
                     self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [a1.view()], conv1x1[0], conv1x1[2], Ci, bnk, Ci, 1,
                                    Wb, Hb, B, z1, 0, z1s, 0)
-                if FUSE_BN_PROLOGUE_KXK:
+                if FUSE_BN_PROLOGUE_KXK and not self.f32:
                     a2 = None
                     d2 = self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [z1.view()], conv3x3[0], conv3x3[2], bnk, k,
                                         bnk * 9, 9, Wb, Hb, B, blk.buf, Ci, blk.stats, Ci)
@@ -586,7 +602,7 @@ class Engine:
                 else:
                     a2 = self._mat(B, Hb, Wb, bnk)
                     self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
-                    if k == 32 and os.environ.get("DMM_CONV2_FOLD", "1") != "0":
+                    if k == 32 and os.environ.get("DMM_CONV2_FOLD", "1") != "0" and not self.f32:
                         # kernel columns folded into N: 3 taps of N = 96 instead of 9 taps of N = 32 (2.9x fewer MMA cycles),
                         # the epilogue adds the three horizontal neighbours with warp shuffles (igemm out_mode 3)
                         self._conv_fwd(fwd, lp + ".conv2", lp + ".conv2.weight", [a2.view()], [(0, kh - 1, 0) for kh in range(3)],
@@ -818,13 +834,13 @@ class Engine:
         hd.bn_u = self._bn_fwd(bn0, us, 0, u.P, rep=4.0)
         hd.bn_x = self._bn_fwd(bn0, xst, 0, B * H * W, c0=Cu)
         hd.out, hd.ldo = a0.ptr().value, a0.ld
-        self._emit(fwd, self.lib.dmm_head_input, hd, hp + ".upsample+cat+norm0", kind="head_input",
+        self._emit(fwd, self.lib.dmm_head_input_f32 if self.f32 else self.lib.dmm_head_input, hd, hp + ".upsample+cat+norm0", kind="head_input",
                    nbytes=u.P * Cu * 2 + B * H * W * (cx * 4 + ld0 * 2))
         r0 = self._mat(B, H, W, nf2)
         r0s = self._new_stats(nf2)
         self.named["head.a0"] = a0
         self.named["head.refine0"] = r0
-        if nf2 == 64 and os.environ.get("DMM_HEAD_FOLD0", "0") != "0":
+        if nf2 == 64 and os.environ.get("DMM_HEAD_FOLD0", "0") != "0" and not self.f32:
             # kernel columns folded into N = 192 (igemm out_mode 3): 3 taps at 96 cycles per MMA instead of 9 taps of N = 64.
             # Parity-tested but OFF: only one 128-pixel sub-tile fits in TMEM at N = 192, so every tile re-streams all weights
             # and the launch is L2-bound at the same 3.9 ms as the 9-tap form (measured)
@@ -836,7 +852,7 @@ class Engine:
         a1h = self._mat(B, H, W, nf2)
         self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
         conv5 = ops.conv_taps(5, 2)
-        if 5 * self.ncls <= 16 and os.environ.get("DMM_HEAD_FOLD", "1") != "0":
+        if 5 * self.ncls <= 16 and os.environ.get("DMM_HEAD_FOLD", "1") != "0" and not self.f32:
             # kernel columns folded into N: 5 (kernel rows) instead of 25 MMAs per pixel tile, horizontal sum in the epilogue
             self._conv_fwd(fwd, hp + ".refine1", hp + ".refine1.weight", [a1h.view()], [(0, kh - 2, 0) for kh in range(5)],
                            [5 * kh for kh in range(5)], nf2, self.ncls, nf2 * 25, 25, W, H, B, None, 0, None, 0, out_mode=2,
@@ -920,15 +936,16 @@ class Engine:
         for n in self._wpk_req:
             offs.append(tot)
             tot += ceil_to(n, 512)      # 1 KiB alignment for TMA
-        self._wpk = torch.zeros(max(tot, 1), dtype=torch.bfloat16, device=dev)
-        self.mem_bytes += tot * 2
+        wsz = 4 if self.f32 else 2
+        self._wpk = torch.zeros(max(tot, 1), dtype=self.adt, device=dev)
+        self.mem_bytes += tot * wsz
         base = self._wpk.data_ptr()
         for d, wid in self._fix_w:
-            d.weights = base + 2 * offs[wid]
+            d.weights = base + wsz * offs[wid]
         pj = np.zeros(len(self._pack_jobs), dtype=_PACK_DT)
         for i, j in enumerate(self._pack_jobs):
             pj[i]["w"] = j["w"].data_ptr()
-            pj[i]["dst"] = base + 2 * offs[j["wid"]]
+            pj[i]["dst"] = base + wsz * offs[j["wid"]]
             pj[i]["n_valid"], pj[i]["n_rows"], pj[i]["C"], pj[i]["T"] = j["n_valid"], j["n_rows"], j["C"], j["T"]
             pj[i]["kwidth"] = j.get("kwidth", ops.KWIDTH)
             pj[i]["tap_off"][:j["T"]] = j["tap_off"]
@@ -1115,7 +1132,10 @@ class Engine:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.training:
             self._stats.zero_used()
-        if BALANCED_PACK:
+        if self.f32:
+            _lib.check(self.lib.dmm_pack_weights_work_f32(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
+                                                          self._pack_work.shape[0], WORK_CHUNK, stream), "dmm_pack_weights_work_f32")
+        elif BALANCED_PACK:
             _lib.check(self.lib.dmm_pack_weights_work(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
                                                       self._pack_work.shape[0], WORK_CHUNK, stream), "dmm_pack_weights_work")
         else:

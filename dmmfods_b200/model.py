@@ -221,15 +221,18 @@ class Dense_U_Net_lidar(nn.Module):
                 "num_classes": self.num_classes, "concat_before_block_num": self.concat_before_block_num,
                 "stream_1_in_channels": self.stream_1_in_channels, "stream_2_in_channels": self.stream_2_in_channels}
 
-    def engine(self, B, H, W, training=None, need_backward=True):
-        """the (cached) execution engine for one input shape; rebuilt when parameters were re-allocated."""
+    def engine(self, B, H, W, training=None, need_backward=True, precision="bf16"):
+        """the (cached) execution engine for one input shape; rebuilt when parameters were re-allocated.
+        precision="tf32": the strict forward mode (fp32 storage, kind::tf32 MMAs; forward + loss only)."""
         training = self.training if training is None else training
+        if precision == "tf32":
+            need_backward = False
         sd = self.state_dict(keep_vars=True)
         dev = next(iter(sd.values())).device
         if dev.type != "cuda":
             raise RuntimeError("dmmfods_b200: the model must live on a CUDA (sm_100) device - there is no CPU path")
         sig = tuple(v.data_ptr() for v in sd.values())
-        key = (B, H, W, bool(training), bool(need_backward and training))
+        key = (B, H, W, bool(training), bool(need_backward and training), precision)
         ent = self._engines.get(key)
         if ent is None or ent[1] != sig:
             for v in sd.values():
@@ -238,7 +241,7 @@ class Dense_U_Net_lidar(nn.Module):
             params = OrderedDict((k, v.data if isinstance(v, nn.Parameter) else v) for k, v in sd.items())
             # drop engines of stale parameter storage (their buffers would otherwise stay alive)
             self._engines = {k: e for k, e in self._engines.items() if e[1] == sig}
-            eng = Engine(params, self.model_cfg(), B, H, W, training=training, need_backward=need_backward)
+            eng = Engine(params, self.model_cfg(), B, H, W, training=training, need_backward=need_backward, precision=precision)
             eng.fwd_count = 0
             self._engines[key] = (eng, sig)
             ent = self._engines[key]

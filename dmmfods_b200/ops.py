@@ -39,27 +39,28 @@ def ceil_to(v, m):
 
 
 class Mat:
-    """bf16 pixel-major activation matrix [B*H*W, ld] living in `t` (2-D bf16 tensor)."""
+    """pixel-major activation matrix [B*H*W, ld] living in `t` (2-D tensor): bf16, or fp32 in the strict (tf32) mode."""
 
     def __init__(self, t, B, H, W):
-        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.is_contiguous()
+        assert t.dtype in (torch.bfloat16, torch.float32) and t.dim() == 2 and t.is_contiguous()
         assert t.shape[0] == B * H * W, (t.shape, B, H, W)
         self.t, self.B, self.H, self.W = t, B, H, W
         self.ld = t.shape[1]
+        self.esize = t.element_size()
 
     @property
     def P(self):
         return self.B * self.H * self.W
 
     def ptr(self, c0=0):
-        return C.c_void_p(self.t.data_ptr() + 2 * c0)
+        return C.c_void_p(self.t.data_ptr() + self.esize * c0)
 
     def view(self, c0=0, C_=None):
         """dmm_view_t of channels [c0, c0+C_)."""
         C_ = self.ld - c0 if C_ is None else C_
         assert c0 % 8 == 0 and c0 + C_ <= self.ld
         v = View()
-        v.ptr = self.t.data_ptr() + 2 * c0
+        v.ptr = self.t.data_ptr() + self.esize * c0
         v.C, v.W, v.H, v.B = C_, self.W, self.H, self.B
         v.sw, v.sh, v.sb = self.ld, self.ld * self.W, self.ld * self.W * self.H
         return v
@@ -68,7 +69,7 @@ class Mat:
         """view of the image rows 2i+py (all columns) - even / odd input rows of a stride-2 convolution."""
         C_ = self.ld - c0 if C_ is None else C_
         v = View()
-        v.ptr = self.t.data_ptr() + 2 * (py * self.W * self.ld + c0)
+        v.ptr = self.t.data_ptr() + self.esize * (py * self.W * self.ld + c0)
         v.C, v.W, v.H, v.B = C_, self.W, (self.H - py + 1) // 2, self.B
         v.sw, v.sh, v.sb = self.ld, 2 * self.ld * self.W, self.ld * self.W * self.H
         return v
@@ -77,7 +78,7 @@ class Mat:
         """view of the pixels (2i+py, 2j+px) - sub-pixel phase of a stride-2 transposed conv output."""
         C_ = self.ld - c0 if C_ is None else C_
         v = View()
-        v.ptr = self.t.data_ptr() + 2 * ((py * self.W + px) * self.ld + c0)
+        v.ptr = self.t.data_ptr() + self.esize * ((py * self.W + px) * self.ld + c0)
         v.C, v.W, v.H, v.B = C_, (self.W - px + 1) // 2, (self.H - py + 1) // 2, self.B
         v.sw, v.sh, v.sb = 2 * self.ld, 2 * self.ld * self.W, self.ld * self.W * self.H
         return v

@@ -124,6 +124,11 @@ typedef struct {
     int32_t pro_enable;
     int32_t fold_kw;         /* out_mode 2 / 3: kernel width folded into N (odd); else 0 */
     dmm_bn_t pro_bn;
+    /* Arithmetic / storage type: 0 = bf16 storage, tcgen05.mma kind::f16, fp32 accumulate (everything above).
+     * 1 = STRICT mode: fp32 storage of sources, packed weights ([n_rows][ktot] float, kwidth 32) and output, tcgen05.mma
+     * kind::tf32 with fp32 accumulate; out_mode 0 (fp32 pixel-major rows) or 1; no prologue / fused BN backward / folds. */
+    int32_t dtype;
+    int32_t pad_;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 
@@ -428,6 +433,18 @@ int dmm_step_metrics(const float* pred, const float* gt, int32_t planes, int64_t
 int dmm_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   void* stream);
+
+/* ---- STRICT arithmetic mode (fp32 storage, tf32 tensor-core convolutions: dmm_igemm_t.dtype == 1) - forward pass ----------
+ * fp32-row restatements of dmm_bn_relu_apply / dmm_head_input / dmm_im2col_7x7s2 / dmm_pack_weights_work: same descriptors,
+ * every activation pointer / pitch refers to float rows (C, ldx, ldy, ldu, ldo in elements; C % 8 == 0).  Used by
+ * Engine(precision="tf32") to measure the distance of the bf16 production path from the reference's fp32 arithmetic
+ * (Dense_U_Net_lidar_Agent.py:17,54-61 runs fp32 without AMP). */
+int dmm_bn_relu_apply_f32(const dmm_bn_apply_t* d, void* stream);
+int dmm_head_input_f32(const dmm_head_t* d, void* stream);
+int dmm_im2col_7x7s2_f32(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H, int32_t W, void* out,
+                         int32_t kpad, void* stream);
+int dmm_pack_weights_work_f32(const dmm_pack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
+                              void* stream);
 
 /* sizeof() of the structs above in declaration order (0 = dmm_view_t, 1 = dmm_igemm_t, 2 = dmm_wgrad_t,
  * 3 = dmm_bn_t, 4 = dmm_bn_apply_t, 5 = dmm_bn_bwd_t, 6 = dmm_bn_bwd_args_t, 7 = dmm_head_t,

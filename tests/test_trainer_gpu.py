@@ -8,7 +8,11 @@ with `model` = the drop-in module, `loss` = FusedBCEWithLogits and `optimizer` =
 round trip of Agent.py:96-163 (state_dict -> load_state_dict) and the batched-file reader feeding the trainer (N3).
 Both arms run the same CUDA kernels; they differ in everything around them (flat buffers vs per-tensor parameters, fused
 vs torch Adam, graph replay vs eager launches, prefetch ring vs direct copies).  The weight-gradient split-K uses fp32
-reduce-adds whose order is not fixed, so gradients agree to fp32 round-off, not bit for bit: tolerances are written below.
+reduce-adds whose order is not fixed, so gradients agree to fp32 round-off (1e-7), not bit for bit.  This small network at
+64x96 (train-mode BatchNorm over 12 ... 3 000 samples, bf16 storage) is CHAOTIC: two runs of the SAME execution form stay
+within 2e-9 in the parameters for two steps, then one flipped bf16 rounding is amplified to 4e-3 in the gradients of step 3 and
+3e-1 in step 4 (scripts/r02_diag_trainer.py, measured on a B200).  Parameter / BatchNorm-buffer equality is therefore asserted
+after TWO optimisation steps, where every difference is still round-off; the per-step inputs and step-1/2 losses over more steps.
 """
 import copy
 import os
@@ -96,13 +100,13 @@ def _compare_states(got, want, init, label):
     e_p, e_u = (num / den) ** 0.5, (unum / uden) ** 0.5
     print("\n[%s] parameters after the steps: relL2 %.3e; relL2 of the updates %.3e" % (label, e_p, e_u))
     # Adam's first updates are lr * sign-like (g / |g|): an element whose gradient is pure round-off may move the other way
-    assert e_p < 1e-4, (label, e_p)
-    assert e_u < 5e-2, (label, e_u)
+    assert e_p < 1e-6, (label, e_p)
+    assert e_u < 1e-3, (label, e_u)
 
 
 @pytest.mark.parametrize("use_graph,prefetch", [(False, False), (True, False), (True, True), (False, True)])
 def test_trainer_steps_equal_the_reference_loop_body(use_graph, prefetch):
-    K = 3
+    K = 2
     ref_model = _model().cuda()
     init = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
     ref_sums = _agent_loop(ref_model, _batches(K))
@@ -210,6 +214,7 @@ def test_batch_file_ring_feeds_the_trainer_bit_identically(tmp_path):
     cur = next(ring)
     tr.prefetch(*cur)
     step = 0
+    after2 = None
     while cur is not None:
         nxt = next(ring, None)
         tr.step(*cur, prefetch_next=nxt)
@@ -219,13 +224,15 @@ def test_batch_file_ring_feeds_the_trainer_bit_identically(tmp_path):
         assert torch.equal(tr._static_target, full[:, 4:])
         cur = nxt
         step += 1
+        if step == 2:
+            after2 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     assert step == K
 
     direct = _model().cuda()
     td = Trainer(direct, B, H, W, lr=LR, use_graph=False)
-    for j in order:
+    for j in order[:2]:
         full = files[j].cuda()
         td.step(full[:, :3].contiguous(), full[:, 3:4].contiguous(), full[:, 4:].contiguous())
     torch.cuda.synchronize()
     init = {k: v.detach().clone() for k, v in _model().state_dict().items()}
-    _compare_states(model.state_dict(), direct.state_dict(), init, "ring-fed vs direct")
+    _compare_states(after2, direct.state_dict(), init, "ring-fed vs direct, after two steps")
