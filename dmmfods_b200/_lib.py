@@ -143,7 +143,7 @@ SIGNATURES = {
     "dmm_bn_relu_apply_f32": (C.c_int, [C.POINTER(BnApply), c_void_p]),
     "dmm_head_input_f32": (C.c_int, [C.POINTER(Head), c_void_p]),
     "dmm_im2col_7x7s2_f32": (C.c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
-    "dmm_pack_weights_work_f32": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "dmm_pack_weights_work_f32": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "dmm_lidar_splat": (C.c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dmm_lidar_splat_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dmm_heatmap_boxes_batched": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -27,7 +27,9 @@ struct IgemmKParams {
     int tile_w, tile_h, tiles_x, tiles_y;
     int n_tile;   // UMMA N of this launch (multiple of 16)
     int N;        // valid output channels overall
-    int kwidth;   // 64 | 16
+    int kwidth;   // 64 | 16 (bf16), 32 (fp32 storage)
+    int split3;   // TF32: 3xTF32 error-compensated products (A = Ahi + Alo, B = Bhi + Blo; hi*hi + hi*lo + lo*hi)
+    int lo_row0;  // split3: first row of the Blo matrix inside the packed weight tensor ([2][n_rows][ktot])
     int stages;
     uint32_t a_bytes, b_bytes;   // per stage
     uint32_t tmem_cols;
@@ -51,11 +53,15 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment (SWIZZLE_128B atoms)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    // stage layout: A | (split3: Alo) | B | (split3: Blo)
+    const bool split3 = TF32 && p.split3;
+    const uint32_t stage_bytes = (split3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
+    const uint32_t off_b = (split3 ? 2u : 1u) * p.a_bytes;
     uint8_t* tail = smem + (size_t)p.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
     uint64_t* empty_bar = full_bar + 8;
-    uint64_t* tmem_full_bar = empty_bar + 8;
+    uint64_t* ready_bar = empty_bar + 8;                       // split3: Alo of the stage has been written (4 warp arrivals)
+    uint64_t* tmem_full_bar = ready_bar + 8;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* red_smem = reinterpret_cast<float*>(tail + 256);   // [4 warps][2][n_tile]
 
@@ -78,6 +84,7 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&ready_bar[s], 4);
         }
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
@@ -109,10 +116,11 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
                     const uint32_t ph = (kb / p.stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
-                    uint8_t* sb = sa + p.a_bytes;
-                    mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                    uint8_t* sb = sa + off_b;
+                    mbar_arrive_expect_tx(&full_bar[s], p.a_bytes + (split3 ? 2u : 1u) * p.b_bytes);
                     tma_load_4d(sa, &p.a_maps[src], &full_bar[s], cb * p.kwidth, cx, cy, b);
                     tma_load_2d(sb, &p.b_map, &full_bar[s], kb * p.kwidth, n0);
+                    if (split3) tma_load_2d(sb + p.b_bytes, &p.b_map, &full_bar[s], kb * p.kwidth, p.lo_row0 + n0);
                 }
             }
         }
@@ -129,17 +137,24 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
             for (int cb = 0; cb < nblk; ++cb, ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (kb / p.stages) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(split3 ? &ready_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t sb = sa + p.a_bytes;
+                    const uint32_t sb = sa + off_b;
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[src] : full_ksteps;
                     for (int k = 0; k < ksteps; ++k) {
                         const uint64_t ad = make_smem_desc(sa + k * 32, 16, sbo, layout);
                         const uint64_t bd = make_smem_desc(sb + k * 32, 16, sbo, layout);
                         if (TF32) umma_tf32(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         else umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (split3) {
+                            // the tensor core reads the upper 19 bits of an fp32 operand (truncation): A, B act as Ahi, Bhi
+                            const uint64_t ald = make_smem_desc(sa + p.a_bytes + k * 32, 16, sbo, layout);
+                            const uint64_t bld = make_smem_desc(sb + p.b_bytes + k * 32, 16, sbo, layout);
+                            umma_tf32(tmem_base, ad, bld, idesc, 1u);
+                            umma_tf32(tmem_base, ald, bd, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                     if (kb == num_kb - 1) umma_commit(tmem_full_bar);
@@ -158,6 +173,34 @@ igemm_kernel(const __grid_constant__ IgemmKParams p) {
         const long long pix = ((long long)b * p.OH + oy) * p.OW + ox;
         const bool do_stats = (p.stats != nullptr);
 
+        if (split3) {
+            // ---- 3xTF32 split team: Alo = A - trunc_tf32(A) for every landed stage (exact in fp32), written next to A ----
+            const int e = (warp - 2) * 32 + lane;          // 0..127: 16-byte chunk e & 7 of rows e >> 3, e >> 3 + 16, ...
+            int kb = 0;
+            for (int tp = 0; tp < p.num_taps; ++tp) {
+                const int nblk = p.src_nblk[p.tap_src[tp]];
+                for (int cb = 0; cb < nblk; ++cb, ++kb) {
+                    const int s = kb % p.stages;
+                    const uint32_t ph = (kb / p.stages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t off = (uint32_t)((e >> 3) + 16 * i) * 128u + (uint32_t)(e & 7) * 16u;   // same (swizzled) position in both tiles
+                        const uint4 v = lds_v4(base + off);
+                        uint4 lo;
+                        lo.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+                        lo.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+                        lo.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+                        lo.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+                        sts_v4(base + p.a_bytes + off, lo);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ready_bar[s]);
+                }
+            }
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int nchunks = p.n_tile / 16;
@@ -280,8 +323,8 @@ using namespace dmm;
 extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DMM_CHECK(d != nullptr, "dmm_conv_igemm: null descriptor");
-    DMM_CHECK(d->dtype == 0 || d->dtype == 1, "dmm_conv_igemm: dtype must be 0 (bf16) or 1 (fp32 storage, tf32 MMA)");
-    DMM_CHECK(d->dtype == 1 ? d->kwidth == 32 : (d->kwidth == 64 || d->kwidth == 16), "dmm_conv_igemm: kwidth must be 64 or 16 (32 in the fp32 mode), got %d", d->kwidth);
+    DMM_CHECK(d->dtype >= 0 && d->dtype <= 2, "dmm_conv_igemm: dtype must be 0 (bf16), 1 (fp32 storage, tf32 MMA) or 2 (fp32 storage, 3xTF32)");
+    DMM_CHECK(d->dtype != 0 ? d->kwidth == 32 : (d->kwidth == 64 || d->kwidth == 32 || d->kwidth == 16), "dmm_conv_igemm: kwidth must be 64, 32 or 16 (32 in the fp32 mode), got %d", d->kwidth);
     DMM_CHECK(d->num_src >= 1 && d->num_src <= DMM_MAX_SRC, "dmm_conv_igemm: bad num_src %d", d->num_src);
     DMM_CHECK(d->num_taps >= 1 && d->num_taps <= DMM_MAX_TAPS, "dmm_conv_igemm: bad num_taps %d", d->num_taps);
     DMM_CHECK(d->tile_w == 128 || d->tile_w == 64 || d->tile_w == 32 || d->tile_w == 16 || d->tile_w == 8,
@@ -294,20 +337,22 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
         // v2 (persistent, halo patches in shared memory) handles every kwidth-64 launch; DMM_IGEMM_V1=1 keeps v1
         static const bool force_v1 = getenv("DMM_IGEMM_V1") != nullptr && atoi(getenv("DMM_IGEMM_V1")) != 0;
         // (and the kwidth-16 launches whose single tapped source has <= 16 channels: four taps share a 64-wide K block)
-        bool packed16 = d->kwidth == 16;
+        bool packed16 = d->kwidth == 16 || (d->kwidth == 32 && d->dtype == 0);      // several taps share one 64-wide K block
         int tapped = 0;
         for (int s = 0; s < d->num_src && packed16; ++s) {
             bool used = false;
             for (int t = 0; t < d->num_taps; ++t) used = used || d->tap_src[t] == s;
-            if (used) { ++tapped; packed16 = d->src[s].C <= 16; }
+            if (used) { ++tapped; packed16 = d->src[s].C <= d->kwidth; }
         }
         packed16 = packed16 && tapped == 1;
-        if (d->dtype != 1 && (d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode >= 2)) return igemm2_launch(d, stream);
+        if (d->dtype == 0 && (d->kwidth == 64 || packed16) && (!force_v1 || d->out_mode >= 2)) return igemm2_launch(d, stream);
     }
     DMM_CHECK(d->out_mode < 2, "dmm_conv_igemm: out_mode 2 / 3 need kwidth 64");
-    const bool tf32 = d->dtype == 1;
+    const bool tf32 = d->dtype == 1 || d->dtype == 2;
+    const bool split3 = d->dtype == 2;
     const int esz = tf32 ? 4 : 2;
     const int kstep = tf32 ? 8 : 16;
+    if (split3) DMM_CHECK(d->n_rows % d->n_tile == 0, "dmm_conv_igemm: 3xTF32 needs n_rows to be a multiple of n_tile");
     if (tf32) DMM_CHECK(d->kwidth == 32 && !d->pro_enable && d->bnb_sums == nullptr && d->fold_kw == 0,
                         "dmm_conv_igemm: the fp32 / tf32 mode needs kwidth 32 and no fused prologue / BN-backward epilogue");
 
@@ -338,7 +383,7 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     DMM_CHECK(ktot == d->ktot, "dmm_conv_igemm: packed weight K (%lld) != tap table K (%lld)", (long long)d->ktot, ktot);
     DMM_CHECK(d->n_rows >= d->N, "dmm_conv_igemm: weight rows %d < N %d", d->n_rows, d->N);
     {
-        uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->n_rows};
+        uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->n_rows * (split3 ? 2u : 1u)};      // split3: [Bhi ; Blo] stacked
         uint64_t strides[1] = {(uint64_t)d->ktot};
         uint32_t box[2] = {(uint32_t)d->kwidth, (uint32_t)d->n_tile};
         int rc = make_tmap_elem(&p.b_map, esz, d->weights, 2, dims, strides, box, swz);
@@ -351,7 +396,9 @@ extern "C" int dmm_conv_igemm(const dmm_igemm_t* d, void* stream_) {
     p.N = d->N;
     p.a_bytes = 128u * d->kwidth * (uint32_t)esz;
     p.b_bytes = ((uint32_t)d->n_tile * d->kwidth * (uint32_t)esz + 1023u) & ~1023u;
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    p.split3 = split3 ? 1 : 0;
+    p.lo_row0 = d->n_rows;
+    const uint32_t stage_bytes = (split3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
     // two co-resident CTAs per SM when the stage is small enough, else one with a deeper ring
     const uint32_t budget = (stage_bytes * 3 <= 100 * 1024) ? 100 * 1024 : 200 * 1024;
     int stages = (int)(budget / stage_bytes);

@@ -23,6 +23,7 @@ namespace dmm {
 constexpr int kG2Threads = 352;          // warp 0 weight TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps, warp 10 patch TMA
 constexpr int kG2ThreadsPro = 480;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA (PRO instantiations)
 constexpr int kMaxSub = 4;
+constexpr int kMaxBStages = 16;          // weight ring slots (resident weights: one slot per (tap group, k-block) of a tile)
 constexpr int kG2MaxSmem = 232448;
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
 constexpr uint32_t kFoldPitch = 80;      // out_mode 2: fp32 staging row of 16 accumulator columns, padded to 20 words (bank spread)
@@ -50,6 +51,7 @@ struct Ig2Params {
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
     int nslot;                                      // out_mode 0: staging slots per epilogue team (1..3)
+    int w_res;                                      // weights RESIDENT: the CTA's whole weight slice is loaded once (sb = stages per tile)
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
     int Wv, Hv;
@@ -121,8 +123,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
     uint64_t* b_full = a_empty + 8;
-    uint64_t* b_empty = b_full + 8;
-    uint64_t* acc_full = b_empty + 8;
+    uint64_t* b_empty = b_full + kMaxBStages;
+    uint64_t* acc_full = b_empty + kMaxBStages;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* x_bar = acc_empty + 2;
     uint64_t* a_ready = x_bar + 2;                                       // pro: A stage transformed (4 warp arrivals)
@@ -191,6 +193,9 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             long long w_a = 0, w_b = 0;
             const long long t_begin = clock64();
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                // resident weights: every tile of this CTA uses the same weight slice (same n0) - it is loaded once, each
+                // (tap group, k-block) into its own ring slot, and never released
+                if (p.w_res && tile != blockIdx.x) break;
                 const TileCoord tc = decode_tile(p, tile);
                 for (int s = 0; s < p.num_src; ++s) {
                     const int nblk = p.src_nblk[s];
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         for (int t = t0; t < t1; t += p.tps) {
                             const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
                             c0 = clock64();
-                            mbar_wait(&b_empty[bst], bph ^ 1);
+                            if (!p.w_res) mbar_wait(&b_empty[bst], bph ^ 1);
                             w_b += clock64() - c0;
                             const int nblk_b = (nt + p.tpk - 1) / p.tpk;
                             mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nblk_b * p.b_tap);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     for (int t = t0; t < t1; t += p.tps) {
                         const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
                         c0 = clock64();
-                        mbar_wait(&b_full[bst], bph);
+                        if (!p.w_res || it == 0) mbar_wait(&b_full[bst], bph);
                         w_b += clock64() - c0;
                         tc_fence_after();
                         if (elect_one()) {
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                                 const uint32_t a_tap = a_lo + aoff;
                                 // weights of tap j: own 64-wide block, or (16-channel sources) a quarter of a shared block
                                 const uint32_t b_lo = b_lo0 + (p.tpk == 1 ? (uint32_t)j * (p.b_tap >> 4)
-                                                                          : (uint32_t)(j >> 2) * (p.b_tap >> 4) + (uint32_t)(j & 3) * 2u);
+                                                                          : (uint32_t)(j / p.tpk) * (p.b_tap >> 4) + (uint32_t)(j % p.tpk) * (8u / p.tpk));
                                 if (j + 1 < nt) aoff = p.tap_aoff[t + j + 1] >> 4;      // prefetch the next tap's offset
                                 // fully unrolled per k-step count: keeps the descriptor arithmetic in uniform registers
 #define DMM_ISSUE_TAP(KS)                                                                                                       \
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #undef DMM_ISSUE_TAP
                                 acc0 = 1;
                             }
-                            umma_commit(&b_empty[bst]);
+                            if (!p.w_res) umma_commit(&b_empty[bst]);
                             if (t + nt == t1) umma_commit(&a_empty[ast]);
                         }
                         __syncwarp();
@@ -723,15 +728,15 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct Tiling {
-    int msub, nsx, nsy, sub_w, sub_h, TW, TH, sa, sb, tps;
+    int msub, nsx, nsy, sub_w, sub_h, TW, TH, sa, sb, tps, w_res;
     uint32_t a_stage;
     long long tiles;
     double cost;
 };
 
 int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
-    DMM_CHECK(d->kwidth == 64 || d->kwidth == 16, "igemm v2: kwidth must be 64 or 16");
-    const int tpk = d->kwidth == 16 ? 4 : 1;       // kwidth 16: sources of <= 16 channels, weights packed [n][tap*16 + c]
+    DMM_CHECK(d->kwidth == 64 || d->kwidth == 32 || d->kwidth == 16, "igemm v2: kwidth must be 64, 32 or 16");
+    const int tpk = 64 / d->kwidth;                // kwidth 16 / 32: one source of <= kwidth channels, weights packed [n][tap*kwidth + c]
     DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
     DMM_CHECK(d->out_mode == 0 || d->out_mode == 3 || (d->N <= 16 && d->n_tile == 16), "igemm v2: fp32 NCHW output needs N <= 16");
     const bool fold = d->out_mode == 2 || d->out_mode == 3;
@@ -768,14 +773,14 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         maxdy[s] = d->tap_dy[t] > maxdy[s] ? d->tap_dy[t] : maxdy[s];
         ++ntap[s];
     }
-    if (tpk == 4) {
+    if (tpk > 1) {
         int tapped = 0;
         for (int s = 0; s < d->num_src; ++s) {
             if (ntap[s] == 0) continue;
             ++tapped;
-            DMM_CHECK(d->src[s].C <= 16, "igemm v2: kwidth 16 needs sources of at most 16 channels (source %d has %d)", s, d->src[s].C);
+            DMM_CHECK(d->src[s].C <= d->kwidth, "igemm v2: kwidth %d needs sources of at most %d channels (source %d has %d)", d->kwidth, d->kwidth, s, d->src[s].C);
         }
-        DMM_CHECK(tapped == 1, "igemm v2: kwidth 16 supports a single tapped source");
+        DMM_CHECK(tapped == 1, "igemm v2: kwidth 16 / 32 support a single tapped source");
     }
     int hx = 0, hy = 0;   // largest halo over the sources
     long long ktot = 0;
@@ -803,10 +808,10 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             kb += p.src_nblk[d->tap_src[t]];
         }
         ktot = (long long)kb * 64;
-        if (tpk == 4) {
-            // packed: tap t owns K columns [16 t, 16 t + 16): block t / 4 (the producer only uses taps that start a block)
-            for (int t = 0; t < d->num_taps; ++t) kb0[t] = t / 4;
-            ktot = (long long)d->num_taps * 16;
+        if (tpk > 1) {
+            // packed: tap t owns K columns [kwidth t, kwidth (t + 1)): block t / tpk (the producer only uses taps that start a block)
+            for (int t = 0; t < d->num_taps; ++t) kb0[t] = t / tpk;
+            ktot = (long long)d->num_taps * d->kwidth;
         }
         int n = 0;
         for (int s = 0; s < d->num_src; ++s) {
@@ -908,8 +913,37 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             const double per_tile = (l2 + wbytes / 32.0 > mma_cyc ? l2 + wbytes / 32.0 : mma_cyc) + 1500.0;
             const long long rounds = (c.tiles + num_sms - 1) / num_sms;
             c.cost = (double)rounds * per_tile;
+            c.w_res = 0;
             if (force_msub && m == force_msub) c.cost = -1.0;
             if (best.msub == 0 || c.cost < best.cost) best = c;
+            // RESIDENT weights: the tile loop of a CTA keeps one weight slice (tiles_n == 1, or a grid that is a multiple of
+            // tiles_n so that n0 is the same for all of its tiles); every (tap group of tpk, k-block) gets its own ring slot.
+            // The SM's TMA unit moves ~one 128-byte row per 5 cycles whatever its source (L2-hit weights included), so weight
+            // rows that are not re-streamed per tile are bandwidth handed back to the activation loads and the output stores.
+            static const int wres_on = env_int("DMM_IGEMM_WRES", 1);
+            if (wres_on && (tiles_n == 1 || num_sms / tiles_n >= 1)) {
+                int stages_r = 0;
+                for (int s = 0; s < d->num_src; ++s) stages_r += p.src_nblk[s] * ceil_div(ntap[s], tpk);
+                const long long bytes_r = (long long)stages_r * b_tap;
+                const int grid_r = tiles_n == 1 ? num_sms : (num_sms / tiles_n) * tiles_n;
+                if (stages_r <= kMaxBStages && bytes_r + 2 * (long long)c.a_stage <= avail) {
+                    Tiling r = c;
+                    r.w_res = 1;
+                    r.tps = tpk;
+                    r.sb = stages_r;
+                    int sa_r = (int)((avail - bytes_r) / (long long)c.a_stage);
+                    r.sa = sa_r > 4 ? 4 : sa_r;
+                    double waits_r = 0;
+                    for (int s = 0; s < d->num_src; ++s)
+                        if (ntap[s]) waits_r += (double)p.src_nblk[s];
+                    const double mma_r = (double)m * nmma_steps * mma_hw + 350.0 * waits_r;
+                    const double per_tile_r = (l2 > mma_r ? l2 : mma_r) + 1500.0;
+                    const long long rounds_r = (c.tiles + grid_r - 1) / grid_r;
+                    r.cost = (double)rounds_r * per_tile_r + (double)bytes_r / 32.0;
+                    if (force_msub && m == force_msub) r.cost = -2.0;
+                    if (r.cost < best.cost) best = r;
+                }
+            }
         }
     }
     DMM_CHECK(best.msub > 0, "igemm v2: no tiling fits in shared memory (n_tile %d, halo %dx%d)", d->n_tile, hx, hy);
@@ -917,6 +951,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
     p.nslot = nslot;
+    p.w_res = best.w_res;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
     p.x_step = fold ? p.TW - (d->fold_kw - 1) : p.TW;
@@ -1019,7 +1054,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
 
     const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 512 + 1024;
     DMM_CHECK(smem <= (size_t)kG2MaxSmem, "igemm v2: %zu bytes of shared memory requested", smem);
-    const unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
+    if (p.w_res && tiles_n > 1) {
+        const unsigned g = (unsigned)((num_sms / tiles_n) * tiles_n);
+        grid = p.total_tiles < (long long)g ? (unsigned)p.total_tiles : g;       // total_tiles is a multiple of tiles_n
+    }
     const int nch = ceil_div(p.n_tile, 64);
     typedef void (*KernelFn)(const Ig2Params);
     KernelFn fn = nullptr;
@@ -1065,9 +1104,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         for (unsigned i = 0; i < grid; ++i)
             for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j] / grid;
         fprintf(stderr,
-                "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d tps %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
+                "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d tps %d wres %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
                 "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f (cycles, CTA average)\n",
-                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.w_res, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
     }
     DMM_LAUNCH_CHECK("igemm2_kernel");
     return 0;

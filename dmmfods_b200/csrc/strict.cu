@@ -1,6 +1,7 @@
-// STRICT arithmetic mode of the forward pass (BASELINE north_star: "rel 1e-3 fp32/tf32"): fp32 STORAGE of every activation
-// and of the packed weights, tcgen05.mma kind::tf32 with fp32 accumulation for the convolutions (igemm.cu, dmm_igemm_t.dtype 1),
-// fp64 BatchNorm statistics.  This file holds the HBM-bound forward kernels of that mode: they restate the bf16 kernels of
+// STRICT arithmetic modes of the forward pass (BASELINE north_star: "rel 1e-3 fp32/tf32"): fp32 STORAGE of every activation
+// and of the packed weights, tcgen05.mma kind::tf32 with fp32 accumulation for the convolutions (igemm.cu, dmm_igemm_t.dtype 1;
+// dtype 2 = 3xTF32: operands split into tf32 head + exact remainder, three MMAs per product - fp32-grade products), fp64
+// BatchNorm statistics.  This file holds the HBM-bound forward kernels of that mode: they restate the bf16 kernels of
 // elementwise.cu on fp32 rows (same C-ABI descriptors, `_f32` entry points) and favour clarity over the last GB/s - the mode
 // exists to measure how far the bf16 production path is from the reference's fp32 arithmetic, not to be the fast path.
 //   dmm_bn_relu_apply_f32   y = relu(bn(x)) with optional 2x2 avg-pool / 3x3-s2 max-pool of the activated tensor + output statistics
@@ -191,8 +192,10 @@ __global__ void __launch_bounds__(kSThreads) im2col_7x7s2_f32_kernel(const float
     }
 }
 
+// split != 0 (3xTF32): the packed tensor is [2][n_rows][ktot]: w itself (the tensor core reads its upper 19 bits = trunc_tf32(w))
+// and the exactly representable remainder w - trunc_tf32(w)
 __global__ void __launch_bounds__(256) pack_weights_work_f32_kernel(const dmm_pack_job_t* __restrict__ jobs, const int2* __restrict__ work,
-                                                                    int chunk_elems) {
+                                                                    int chunk_elems, int split) {
     const int2 w = work[blockIdx.x];
     const dmm_pack_job_t& j = jobs[w.x];
     const int Kp = (j.C + j.kwidth - 1) / j.kwidth * j.kwidth;
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(256) pack_weights_work_f32_kernel(const dmm_pa
             v = __ldg(j.w + nidx + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]);
         }
         dst[i] = v;
+        if (split) dst[total + i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
 }
 
@@ -270,10 +274,10 @@ extern "C" int dmm_im2col_7x7s2_f32(const float* x1, int32_t C1, const float* x2
 }
 
 extern "C" int dmm_pack_weights_work_f32(const dmm_pack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
-                                         void* stream) {
+                                         int32_t split, void* stream) {
     DMM_CHECK(nwork >= 0 && (nwork == 0 || (jobs_device && work_device)) && chunk_elems >= 256, "dmm_pack_weights_work_f32: bad arguments");
     if (nwork == 0) return 0;
-    pack_weights_work_f32_kernel<<<(unsigned)nwork, 256, 0, (cudaStream_t)stream>>>(jobs_device, reinterpret_cast<const int2*>(work_device), chunk_elems);
+    pack_weights_work_f32_kernel<<<(unsigned)nwork, 256, 0, (cudaStream_t)stream>>>(jobs_device, reinterpret_cast<const int2*>(work_device), chunk_elems, split);
     DMM_LAUNCH_CHECK("pack_weights_work_f32_kernel");
     return 0;
 }

@@ -40,6 +40,8 @@ FUSE_BN_PROLOGUE = os.environ.get("DMM_FUSE_BN_PROLOGUE", "1") != "0"
 FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE_KXK", "0") != "0"
 
 
+# data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
+PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
 # weight pack / gradient unpack as load-balanced (job, chunk) launches (DMM_BALANCED_PACK=0: 32 blocks per job as in round 1)
 BALANCED_PACK = os.environ.get("DMM_BALANCED_PACK", "1") != "0"
 WORK_CHUNK = 8192
@@ -101,13 +103,15 @@ class Engine:
         """params: dict name -> CUDA tensor with the reference's state_dict keys (parameters fp32, BN buffers);
         model_cfg: mapping with the keys of helper:111-123.  plan_only=True builds the launch programs without a
         GPU (host-logic tests); such an engine cannot run.
-        precision: "bf16" (production: bf16 storage, kind::f16 MMAs) or "tf32" - the STRICT forward mode: fp32 storage of every
-        activation and packed weight, kind::tf32 MMAs with fp32 accumulation, unfused plan (forward + loss only)."""
+        precision: "bf16" (production: bf16 storage, kind::f16 MMAs), or a STRICT forward mode with fp32 storage of every
+        activation and packed weight, fp32 accumulation, unfused plan (forward + loss only): "tf32" = one kind::tf32 MMA per
+        product (operands truncated to 10 mantissa bits), "tf32x3" = 3xTF32 error-compensated products (fp32-grade)."""
         self.lib = _lib.load() if plan_only else ops.require_device()
         self.plan_only = plan_only
-        if precision not in ("bf16", "tf32"):
-            raise ValueError("precision must be 'bf16' or 'tf32'")
-        self.f32 = precision == "tf32"
+        if precision not in ("bf16", "tf32", "tf32x3"):
+            raise ValueError("precision must be 'bf16', 'tf32' or 'tf32x3'")
+        self.f32 = precision in ("tf32", "tf32x3")
+        self.split3 = precision == "tf32x3"
         self.precision = precision
         if self.f32 and need_backward and training:
             raise NotImplementedError("dmmfods_b200: the strict tf32 mode covers forward + loss (need_backward=False)")
@@ -253,7 +257,7 @@ class Engine:
 
     # deferred arenas: record requests, resolve pointers in _finalize()
     def _req_wpk(self, n_rows, ktot):
-        self._wpk_req.append(n_rows * ktot)
+        self._wpk_req.append(n_rows * ktot * (2 if getattr(self, "split3", False) else 1))
         return len(self._wpk_req) - 1
 
     def _req_dw(self, numel):
@@ -290,7 +294,7 @@ class Engine:
                            out_mode=out_mode, stats=stats, stats_off=stats_off, out_stride=out_stride,
                            out_phase=out_phase, out_hw=out_hw, n_tile=n_tile, fold_kw=fold_kw, tile_w=tile_w, kwidth=self.kwidth)
         if self.f32:
-            d.dtype = 1
+            d.dtype = 2 if self.split3 else 1
         P = B * H * W
         osz = 4 if out_mode in (1, 2) else 2
         kk = fold_kw if fold_kw else 1
@@ -304,6 +308,8 @@ class Engine:
         T = len(taps)
         # a narrow (<= 16 channels) single gradient source: four taps share one 64-wide K block of the packed weights
         kwidth = 16 if (Cg <= 16 and len(srcs) == 1 and T > 1) else ops.KWIDTH
+        if 16 < Cg <= 32 and len(srcs) == 1 and T > 1 and PACK32:
+            kwidth = 32          # growth-rate-wide gradient sources: two taps per 64-wide K block (half the weight bytes per tile)
         Kp = ceil_to(Cg, kwidth)
         n_tile = ops.pick_n_tile(Cin)
         n_rows = ceil_to(Cin, n_tile)
@@ -1134,7 +1140,8 @@ class Engine:
             self._stats.zero_used()
         if self.f32:
             _lib.check(self.lib.dmm_pack_weights_work_f32(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
-                                                          self._pack_work.shape[0], WORK_CHUNK, stream), "dmm_pack_weights_work_f32")
+                                                          self._pack_work.shape[0], WORK_CHUNK, 1 if self.split3 else 0, stream),
+                       "dmm_pack_weights_work_f32")
         elif BALANCED_PACK:
             _lib.check(self.lib.dmm_pack_weights_work(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
                                                       self._pack_work.shape[0], WORK_CHUNK, stream), "dmm_pack_weights_work")

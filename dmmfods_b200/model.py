@@ -225,7 +225,7 @@ class Dense_U_Net_lidar(nn.Module):
         """the (cached) execution engine for one input shape; rebuilt when parameters were re-allocated.
         precision="tf32": the strict forward mode (fp32 storage, kind::tf32 MMAs; forward + loss only)."""
         training = self.training if training is None else training
-        if precision == "tf32":
+        if precision in ("tf32", "tf32x3"):
             need_backward = False
         sd = self.state_dict(keep_vars=True)
         dev = next(iter(sd.values())).device

@@ -126,7 +126,10 @@ typedef struct {
     dmm_bn_t pro_bn;
     /* Arithmetic / storage type: 0 = bf16 storage, tcgen05.mma kind::f16, fp32 accumulate (everything above).
      * 1 = STRICT mode: fp32 storage of sources, packed weights ([n_rows][ktot] float, kwidth 32) and output, tcgen05.mma
-     * kind::tf32 with fp32 accumulate; out_mode 0 (fp32 pixel-major rows) or 1; no prologue / fused BN backward / folds. */
+     * kind::tf32 with fp32 accumulate; out_mode 0 (fp32 pixel-major rows) or 1; no prologue / fused BN backward / folds.
+     * 2 = like 1 with 3xTF32 products: the tensor core truncates fp32 operands to tf32, so A*B is evaluated as
+     * Ahi*Bhi + Ahi*Blo + Alo*Bhi with the exact remainders Alo (computed in shared memory) and Blo (second half of the packed
+     * weights, [2][n_rows][ktot]); n_rows must be a multiple of n_tile. */
     int32_t dtype;
     int32_t pad_;
 } dmm_igemm_t;
@@ -443,8 +446,9 @@ int dmm_bn_relu_apply_f32(const dmm_bn_apply_t* d, void* stream);
 int dmm_head_input_f32(const dmm_head_t* d, void* stream);
 int dmm_im2col_7x7s2_f32(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t H, int32_t W, void* out,
                          int32_t kpad, void* stream);
+/* split != 0: every job's packed tensor is [2][n_rows][ktot] floats: the weights and their tf32 remainders (3xTF32, dtype 2) */
 int dmm_pack_weights_work_f32(const dmm_pack_job_t* jobs_device, const int32_t* work_device, int32_t nwork, int32_t chunk_elems,
-                              void* stream);
+                              int32_t split, void* stream);
 
 /* sizeof() of the structs above in declaration order (0 = dmm_view_t, 1 = dmm_igemm_t, 2 = dmm_wgrad_t,
  * 3 = dmm_bn_t, 4 = dmm_bn_apply_t, 5 = dmm_bn_bwd_t, 6 = dmm_bn_bwd_args_t, 7 = dmm_head_t,
