@@ -42,7 +42,7 @@ class Igemm(C.Structure):
                 ("bnb_x", c_void_p), ("bnb_ldx", c_int64), ("bnb_gamma", c_void_p), ("bnb_beta", c_void_p),
                 ("bnb_mean", c_void_p), ("bnb_invstd", c_void_p), ("bnb_sums", c_void_p), ("bnb_sums_ld", c_int32),
                 ("bnb_sums_off", c_int32), ("pro_enable", c_int32), ("fold_kw", c_int32), ("pro_bn", Bn),
-                ("dtype", c_int32), ("pad_", c_int32)]
+                ("dtype", c_int32), ("epi_relu", c_int32), ("epi_bias", c_void_p)]
 
 
 WG_MAX_A = 8
@@ -119,6 +119,7 @@ SIGNATURES = {
                                    C.POINTER(c_int32), c_int64, c_int64, c_int32, c_void_p]),
     "dmm_pack_weights_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_unpack_wgrad_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
+    "dmm_bn_fold_batched": (C.c_int, [c_void_p, c_int32, c_void_p]),
     "dmm_pack_weights_work": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "dmm_unpack_wgrad_work": (C.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "dmm_bn_relu_apply": (C.c_int, [C.POINTER(BnApply), c_void_p]),

@@ -1695,6 +1695,7 @@ __device__ __forceinline__ void pack_job_range(const dmm_pack_job_t& j, long lon
         if (n < j.n_valid && c < j.C) {
             const long long nidx = j.ndiv > 1 ? (long long)(n / j.ndiv) * j.sn + (long long)(n % j.ndiv) * j.sn2 : (long long)n * j.sn;
             v = __ldg(j.w + nidx + (long long)(c / cdiv) * j.sc + (long long)(c % cdiv) * j.sc2 + j.tap_off[t]);
+            if (j.rscale) v *= __ldg(j.rscale + (j.ndiv > 1 ? n % j.ndiv : n));     // folded kernel columns: row kw*Cout + n -> channel n
         }
         dst[i] = __float2bfloat16_rn(v);
     }
@@ -2104,6 +2105,23 @@ extern "C" int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int
     if (njobs == 0) return 0;
     launch_k(unpack_wgrad_batched_kernel, dim3(32, (unsigned)njobs, 1), 256, 0, (cudaStream_t)stream, jobs_device);
     DMM_LAUNCH_CHECK("unpack_wgrad_batched_kernel");
+    return 0;
+}
+
+__global__ void __launch_bounds__(128) bn_fold_kernel(const dmm_bn_fold_job_t* __restrict__ jobs) {
+    const dmm_bn_fold_job_t& j = jobs[blockIdx.x];
+    for (int c = threadIdx.x; c < j.C; c += blockDim.x) {
+        const float sc = (j.gamma ? j.gamma[c] : 1.f) / sqrtf(j.running_var[c] + j.eps);
+        j.scale[c] = sc;
+        j.shift[c] = (j.beta ? j.beta[c] : 0.f) - j.running_mean[c] * sc;
+    }
+}
+
+extern "C" int dmm_bn_fold_batched(const dmm_bn_fold_job_t* jobs_device, int32_t njobs, void* stream) {
+    DMM_CHECK(njobs >= 0 && (njobs == 0 || jobs_device), "dmm_bn_fold_batched: bad arguments");
+    if (njobs == 0) return 0;
+    bn_fold_kernel<<<(unsigned)njobs, 128, 0, (cudaStream_t)stream>>>(jobs_device);
+    DMM_LAUNCH_CHECK("bn_fold_kernel");
     return 0;
 }
 

@@ -69,6 +69,8 @@ struct Ig2Params {
     int pro_c;                     // valid channels of source 0
     int pro_pw;                    // > 0: K x K prologue - patch width in pixels; out-of-image patch pixels are forced to zero
     dmm_bn_t pro_bn;
+    const float* epi_bias;         // out_mode 0: out = act(acc + epi_bias[n]) (a folded eval-mode BatchNorm's shift), or NULL
+    int epi_relu;
     int bnb;
     const float* bnb_gamma;
     const float* bnb_beta;
@@ -430,6 +432,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint32_t it = 0;
         int last_n0 = 0;
         long long w_full = 0;
+        long long ph_store_wait = 0, ph_tmem = 0, ph_bar1 = 0, ph_pack = 0, ph_bar2 = 0, ph_stats = 0;      // DMM_IGEMM_PROF phase cycles (thread r == 0)
         const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
@@ -563,6 +566,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
                         uint32_t v[4][16];
+                        const long long e0 = clock64();
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
@@ -574,11 +578,33 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                         }
+                        const long long e1 = clock64();
                         tmem_ld_wait();
+                        const long long e2 = clock64();
                         epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
+                        const long long e3 = clock64();
+                        ph_store_wait += e1 - e0; ph_tmem += e2 - e1; ph_bar1 += e3 - e2;
                         if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
                             mbar_arrive_expect_tx(&x_bar[team], kStageSlot);
                             tma_load_4d(xslot, &p.x_map, &x_bar[team], tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
+                        }
+                        if (p.epi_bias) {
+                            // folded BatchNorm shift (+ ReLU) on the fp32 accumulators; the bias vector is padded to n_rows entries
+                            const float4* bp = reinterpret_cast<const float4*>(p.epi_bias + tc.n0 + 64 * c);
+                            const float lo = p.epi_relu ? 0.f : -INFINITY;
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                if (g < ngrp) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float4 b4 = __ldg(bp + 4 * g + q);
+                                        v[g][4 * q + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 0]) + b4.x, lo));
+                                        v[g][4 * q + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 1]) + b4.y, lo));
+                                        v[g][4 * q + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 2]) + b4.z, lo));
+                                        v[g][4 * q + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 3]) + b4.w, lo));
+                                    }
+                                }
+                            }
                         }
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
@@ -599,12 +625,16 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             }
                         }
                         fence_proxy_async();
+                        const long long e4 = clock64();
                         epi_bar(team);
+                        const long long e5 = clock64();
                         if (r == 0) {
                             tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
                         if (++slot_i == (uint32_t)p.nslot) slot_i = 0;
+                        ph_pack += e4 - e3; ph_bar2 += e5 - e4;
+                        const long long e6 = clock64();
                         if (do_stats) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
@@ -650,6 +680,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             sacc[c][0] += (double)s1a; sacc[c][1] += (double)s1b;
                             sacc[c][2] += (double)s2a; sacc[c][3] += (double)s2b;
                         }
+                        ph_stats += clock64() - e6;
                     }
                 } else {
                     // fp32 NCHW logits: out[((b*N + n)*OH + oy)*OW + ox], N <= 16; the teams alternate sub-tiles
@@ -708,6 +739,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
+            p.prof[blockIdx.x * 16 + 10] = ph_store_wait; p.prof[blockIdx.x * 16 + 11] = ph_tmem; p.prof[blockIdx.x * 16 + 12] = ph_bar1;
+            p.prof[blockIdx.x * 16 + 13] = ph_pack; p.prof[blockIdx.x * 16 + 14] = ph_bar2; p.prof[blockIdx.x * 16 + 15] = ph_stats;
         }
         }   // epilogue team
     }
@@ -1037,6 +1070,12 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         p.pro_pw = (hx > 0 || hy > 0) ? p.TW + (maxdx[0] - mindx[0]) : 0;
         p.pro_bn = d->pro_bn;
     }
+    if (d->epi_bias) {
+        DMM_CHECK(d->out_mode == 0 && !bnb && (reinterpret_cast<uintptr_t>(d->epi_bias) & 15) == 0,
+                  "igemm v2: the bias epilogue needs out_mode 0, no fused BN backward and a 16-byte aligned bias vector");
+        p.epi_bias = d->epi_bias;
+        p.epi_relu = d->epi_relu;
+    }
     if (bnb) {
         dmm_view_t xv;
         xv.ptr = d->bnb_x;
@@ -1105,8 +1144,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j] / grid;
         fprintf(stderr,
                 "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d tps %d wres %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
-                "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f (cycles, CTA average)\n",
-                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.w_res, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+                "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f | team 0 phases: store-read wait %.0f tmem %.0f bar1 %.0f pack %.0f bar2 %.0f stats %.0f (cycles, CTA average)\n",
+                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.w_res, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
     }
     DMM_LAUNCH_CHECK("igemm2_kernel");
     return 0;

@@ -42,6 +42,7 @@ FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE
 
 # data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
 PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
+DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "64"))
 # weight pack / gradient unpack as load-balanced (job, chunk) launches (DMM_BALANCED_PACK=0: 32 blocks per job as in round 1)
 BALANCED_PACK = os.environ.get("DMM_BALANCED_PACK", "1") != "0"
 WORK_CHUNK = 8192
@@ -626,7 +627,10 @@ class Engine:
                     # shared scratch of the widest layer, re-pitched to this layer's channel count: dense rows for the
                     # data-gradient store and the contribution pass (a [P, Ct] pitch would leave holes in every DRAM page)
                     da1_full = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
-                    da1 = Mat(da1_full.t.view(-1)[:B * Hb * Wb * Ci].view(B * Hb * Wb, Ci), B, Hb, Wb)
+                    # ... with the pitch rounded up to 64 channels: every 128-byte row of a TMA store then starts on a 128-byte
+                    # boundary (measured r02: a 1984-byte pitch makes the 1x1 data gradient's stores ~2x slower)
+                    pitch = min(ceil_to(Ci, DA1_ALIGN), blk.Ct)
+                    da1 = Mat(da1_full.t.view(-1)[:B * Hb * Wb * pitch].view(B * Hb * Wb, pitch), B, Hb, Wb)
                     self._gather(st, lp + ".gout", blk, Ci, k, go)
                     self._conv_wgrad(st, lp + ".conv2.wgrad", lp + ".conv2.weight", (z1 if a2 is None else a2).view(),
                                      [go.view(0, k)], conv3x3[0], conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B,

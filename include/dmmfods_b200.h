@@ -131,7 +131,11 @@ typedef struct {
      * Ahi*Bhi + Ahi*Blo + Alo*Bhi with the exact remainders Alo (computed in shared memory) and Blo (second half of the packed
      * weights, [2][n_rows][ktot]); n_rows must be a multiple of n_tile. */
     int32_t dtype;
-    int32_t pad_;
+    /* Optional epilogue of out_mode 0 (inference: an eval-mode BatchNorm FOLDED into this convolution - its scale goes into
+     * the packed weight rows (dmm_pack_job_t.rscale), its shift arrives here): out = (epi_relu ? max(., 0) : .)(acc + epi_bias[n]).
+     * epi_bias: float[N], 16-byte aligned; NULL = plain store. */
+    int32_t epi_relu;
+    const float* epi_bias;
 } dmm_igemm_t;
 int dmm_conv_igemm(const dmm_igemm_t* d, void* stream);
 
@@ -209,6 +213,7 @@ typedef struct {
     int32_t cdiv;            /* 0 or 1: plain channel index */
     int32_t ndiv;            /* 0 or 1: nidx = n*sn; else nidx = (n / ndiv)*sn + (n % ndiv)*sn2 (kernel columns folded into n) */
     int64_t sn2;
+    const float* rscale;     /* optional per-row factor (float[n_valid]): packed row n = rscale[n] * w row (a folded eval-mode BatchNorm) */
 } dmm_pack_job_t;
 typedef struct {
     const float* dw;
@@ -223,6 +228,19 @@ typedef struct {
 } dmm_unpack_job_t;
 int dmm_pack_weights_batched(const dmm_pack_job_t* jobs_device, int32_t njobs, void* stream);
 int dmm_unpack_wgrad_batched(const dmm_unpack_job_t* jobs_device, int32_t njobs, void* stream);
+/* Eval-mode BatchNorm folding (inference extras): scale[c] = gamma[c] / sqrt(running_var[c] + eps),
+ * shift[c] = beta[c] - running_mean[c] * scale[c] for every job of a device-resident table, one launch. */
+typedef struct {
+    const float* gamma;
+    const float* beta;
+    const float* running_mean;
+    const float* running_var;
+    float* scale;
+    float* shift;
+    int32_t C;
+    float eps;
+} dmm_bn_fold_job_t;
+int dmm_bn_fold_batched(const dmm_bn_fold_job_t* jobs_device, int32_t njobs, void* stream);
 /* Load-balanced forms: `work_device` = int32 pairs (job index, chunk index) in device memory, one thread block per pair
  * handles elements [chunk*chunk_elems, (chunk+1)*chunk_elems) of that job (the tensors of one network span 64 ... 9.4 M
  * elements; 32 blocks per job left the largest job alone on the GPU for 0.9 ms). */
