@@ -153,6 +153,7 @@ extern "C" int dmm_sizeof(int which) {
         case 9: return (int)sizeof(dmm_pack_job_t);
         case 10: return (int)sizeof(dmm_unpack_job_t);
         case 11: return (int)sizeof(dmm_grad_gather_t);
+        case 12: return (int)sizeof(dmm_bn_fold_job_t);
         default: return -1;
     }
 }

@@ -61,6 +61,9 @@ struct Ig2Params {
     int tw_log, sw_log, sh_log;    // out_mode 2: log2 of TW, sub_w, sub_h
     long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
     float* out32;
+    __nv_bfloat16* out16;          // out_mode 0 with lsu_store: pixel-major bf16 output (already offset by the channel offset)
+    long long ldo;
+    int lsu_store;                 // out_mode 0: write the staged chunk with coalesced st.global.v4 instead of a TMA tensor store
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
     int stats_ld, stats_off;
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
+        const int sw_shift = __ffs(p.sub_w) - 1;
         uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow);
         const uint32_t slot0_u = slot_u, xslot_u = smem_u32(xslot);
         double sacc[NCH][4];
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         // round-robin slot; its previous TMA store (nslot chunks ago) must have finished reading it
                         slot_u = slot0_u + slot_i * kStageSlot;
                         srow_u = slot_u + r * 128;
-                        if (r == 0) {
+                        if (r == 0 && !p.lsu_store) {
                             if (p.nslot == 1) bulk_wait_read0();
                             else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
@@ -624,11 +628,30 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                                 sts_v4(srow_u + (((2 * g + 1) ^ (r & 7)) << 4), w1);
                             }
                         }
-                        fence_proxy_async();
+                        if (!p.lsu_store) fence_proxy_async();
                         const long long e4 = clock64();
                         epi_bar(team);
                         const long long e5 = clock64();
-                        if (r == 0) {
+                        if (p.lsu_store) {
+                            // the SM's TMA unit queues tensor stores BEHIND the prefetched operand loads (measured: ~1 200 cycles
+                            // of issue stall per chunk): write the staged tile through the load/store unit instead.  Thread e
+                            // moves 16-byte chunk e & 7 of rows (e >> 3) + 16 i: one warp instruction = four complete 128-byte rows.
+                            const int j8 = r & 7;
+                            const int col = tc.n0 + 64 * c + j8 * 8;
+                            if (col < p.N) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int row = (r >> 3) + 16 * i;
+                                    const int rx = row & (p.sub_w - 1), ry = row >> sw_shift;      // sub_w is a power of two
+                                    const int xx = tc.x0 + p.sub_x[sub] + rx, yy = tc.y0 + p.sub_y[sub] + ry;
+                                    if (xx < p.Wv && yy < p.Hv) {
+                                        const uint4 w = lds_v4(slot_u + row * 128 + ((j8 ^ (row & 7)) << 4));
+                                        const long long pix = ((long long)tc.b * p.OH + (yy * p.out_sy + p.out_py)) * p.OW + (xx * p.out_sx + p.out_px);
+                                        *reinterpret_cast<uint4*>(p.out16 + pix * p.ldo + col) = w;
+                                    }
+                                }
+                            }
+                        } else if (r == 0) {
                             tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
@@ -1057,6 +1080,10 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         ov.sb = (long long)OH * OW * d->ldo;
         int rc = view_to_tmap(&p.o_map, ov, 64, d->out_mode == 3 ? p.sub_w - 2 : p.sub_w, p.sub_h, 128);
         if (rc) return rc;
+        static const int lsu_env = env_int("DMM_IGEMM_LSU_STORE", 1);
+        p.out16 = reinterpret_cast<__nv_bfloat16*>(d->out) + d->coff;
+        p.ldo = d->ldo;
+        p.lsu_store = (d->out_mode == 0 && lsu_env && d->N % 8 == 0) ? 1 : 0;
     } else {
         p.out32 = reinterpret_cast<float*>(d->out);
     }

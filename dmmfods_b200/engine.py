@@ -43,6 +43,9 @@ FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE
 # data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
 PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
 DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "64"))
+# inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
+# the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
+FOLD_EVAL_BN = os.environ.get("DMM_FOLD_EVAL_BN", "1") != "0"
 # weight pack / gradient unpack as load-balanced (job, chunk) launches (DMM_BALANCED_PACK=0: 32 blocks per job as in round 1)
 BALANCED_PACK = os.environ.get("DMM_BALANCED_PACK", "1") != "0"
 WORK_CHUNK = 8192
@@ -217,6 +220,7 @@ class Engine:
         self._dw_req = []
         self._wpk_req = []
         self._pack_jobs = []
+        self._fold_jobs = []     # eval-mode BatchNorms folded into their producing convolution: (bn, c0, C, scale, shift)
         self._unpack_jobs = []
         self._stage_params = {}
         self._tmp = {}
@@ -272,7 +276,8 @@ class Engine:
         lst.append(Op(fn, arg, name, gbuf, kind, flops, nbytes))
 
     def _conv_fwd(self, lst, name, wname, srcs, taps, tap_off, Cin, Cout, sn, sc, W, H, B, out, coff, stats, stats_off,
-                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None, fold_kw=0, tile_w=None, cdiv=0, sc2=0):
+                  out_stride=(1, 1), out_phase=(0, 0), out_hw=None, out_mode=0, out_ptr=None, fold_kw=0, tile_w=None, cdiv=0, sc2=0,
+                  fold=None):
         """emit pack job + igemm launch for a forward convolution (or one ConvTranspose phase).
         fold_kw (out_mode 2): `taps` / `tap_off` are the kernel ROWS; the kernel columns are folded into the GEMM's N (packed
         weight row kw*Cout + n)."""
@@ -296,6 +301,11 @@ class Engine:
                            out_phase=out_phase, out_hw=out_hw, n_tile=n_tile, fold_kw=fold_kw, tile_w=tile_w, kwidth=self.kwidth)
         if self.f32:
             d.dtype = 2 if self.split3 else 1
+        if fold is not None:
+            # (scale, shift) of an eval-mode BatchNorm over this convolution's output: relu(bn(conv(x))) in ONE launch
+            assert out_mode == 0 and not fold_kw
+            job["rscale"] = fold[0]
+            d.epi_bias, d.epi_relu = fold[1].data_ptr(), 1
         P = B * H * W
         osz = 4 if out_mode in (1, 2) else 2
         kk = fold_kw if fold_kw else 1
@@ -370,6 +380,19 @@ class Engine:
         self._unpack_jobs.append(dict(wname=wname, did=did, grad=g, dt=16, dm=1, dn=ld, M=r, N=Nvalid, T=T, tap_off=[tap_off[t] for t in order],
                                       sn=sn, sc=sc, stage=id(lst)))
         self._stage_params.setdefault(id(lst), []).append(wname)
+
+    def _fold(self, bn, C_, c0=0):
+        """eval mode: (scale, shift) vectors of channels [c0, c0+C_) of `bn` (filled by dmm_bn_fold_batched at the head of every
+        forward), padded to a multiple of 256 entries so that an n-tile may read past C_."""
+        n = ceil_to(C_, 256)
+        off = self._save.take(2 * n, 64)
+        scale, shift = self._save.buf[off:off + n], self._save.buf[off + n:off + 2 * n]
+        self._fold_jobs.append((bn, c0, C_, scale, shift))
+        return scale, shift
+
+    @property
+    def fold_eval(self):
+        return (not self.training) and (not self.f32) and FOLD_EVAL_BN
 
     def _bn_fwd(self, bn, stats, stats_off, count, c0=0, rep=1.0):
         return ops.make_bn(stats, stats_off, count, bn.gamma, bn.beta, bn.rm, bn.rv, bn.save_mean, bn.save_invstd,
@@ -586,13 +609,17 @@ class Engine:
                 lp = "%s.denselayer%d" % (prefix, i + 1)
                 bn1 = _BNInfo(self, lp + ".norm1", Ci)
                 bn2 = _BNInfo(self, lp + ".norm2", bnk)
-                z1 = self._mat(B, Hb, Wb, bnk)
+                fold2 = self.fold_eval and FUSE_BN_PROLOGUE
+                a2f = self._mat(B, Hb, Wb, bnk) if fold2 else None
+                z1 = None if fold2 else self._mat(B, Hb, Wb, bnk)
                 z1s = self._new_stats(bnk)
                 if FUSE_BN_PROLOGUE and not self.f32:
                     # norm1 + relu1 run inside conv1: its A tiles are the raw block-buffer channels, activated in shared memory
+                    # (inference: norm2 + relu2 are folded into the same launch - weights scaled, shift + ReLU in the epilogue)
                     a1 = None
                     d1 = self._conv_fwd(fwd, lp + ".conv1", lp + ".conv1.weight", [blk.buf.view(0, Ci)], conv1x1[0], conv1x1[2],
-                                        Ci, bnk, Ci, 1, Wb, Hb, B, z1, 0, z1s, 0)
+                                        Ci, bnk, Ci, 1, Wb, Hb, B, a2f if fold2 else z1, 0, z1s, 0,
+                                        fold=self._fold(bn2, bnk) if fold2 else None)
                     d1.pro_enable = 1
                     d1.pro_bn = self._bn_fwd(bn1, blk.stats, 0, blk.buf.P)
                 else:
@@ -607,8 +634,11 @@ class Engine:
                     d2.pro_enable = 1
                     d2.pro_bn = self._bn_fwd(bn2, z1s, 0, z1.P)
                 else:
-                    a2 = self._mat(B, Hb, Wb, bnk)
-                    self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
+                    if fold2:
+                        a2 = a2f
+                    else:
+                        a2 = self._mat(B, Hb, Wb, bnk)
+                        self._apply(fwd, lp + ".norm2", bn2, z1, 0, bnk, z1s, 0, a2, 0)
                     if k == 32 and os.environ.get("DMM_CONV2_FOLD", "1") != "0" and not self.f32:
                         # kernel columns folded into N: 3 taps of N = 96 instead of 9 taps of N = 32 (2.9x fewer MMA cycles),
                         # the epilogue adds the three horizontal neighbours with warp shuffles (igemm out_mode 3)
@@ -764,12 +794,17 @@ class Engine:
                 a = self._mat(B, hk, wk, num_in)
                 self._apply(fwd, sp + ".norm0[up]", bn0, u, 0, Cu, us, 0, a, 0)
                 self._apply(fwd, sp + ".norm0[skip]", bn0, skip_blk.buf, 0, skip_blk.Ct, skip_blk.stats, 0, a, Cu, bn_c0=Cu)
-            r = self._mat(B, hk, wk, num_f)
             rs = self._new_stats(num_f)
-            self._conv_fwd(fwd, sp + ".conv_reduce", sp + ".conv_reduce.weight", [a.view()], conv1x1[0], conv1x1[2], num_in,
-                           num_f, num_in, 1, wk, hk, B, r, 0, rs, 0)
             a1 = self._mat(B, hk, wk, num_f)
-            self._apply(fwd, sp + ".norm1", bn1, r, 0, num_f, rs, 0, a1, 0)
+            if self.fold_eval:
+                r = a1       # inference: norm1 + relu1 folded into conv_reduce
+                self._conv_fwd(fwd, sp + ".conv_reduce", sp + ".conv_reduce.weight", [a.view()], conv1x1[0], conv1x1[2], num_in,
+                               num_f, num_in, 1, wk, hk, B, a1, 0, rs, 0, fold=self._fold(bn1, num_f))
+            else:
+                r = self._mat(B, hk, wk, num_f)
+                self._conv_fwd(fwd, sp + ".conv_reduce", sp + ".conv_reduce.weight", [a.view()], conv1x1[0], conv1x1[2], num_in,
+                               num_f, num_in, 1, wk, hk, B, r, 0, rs, 0)
+                self._apply(fwd, sp + ".norm1", bn1, r, 0, num_f, rs, 0, a1, 0)
             oh, ow = sizes.pop()
             for dim_in, dim_out in ((hk, oh), (wk, ow)):
                 if not (2 * dim_in - 1 <= dim_out <= 2 * dim_in):
@@ -856,11 +891,17 @@ class Engine:
             # and the launch is L2-bound at the same 3.9 ms as the 9-tap form (measured)
             self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], [(0, kh - 1, 0) for kh in range(3)],
                            [3 * kh for kh in range(3)], Ct, nf2, Ct * 9, 9, W, H, B, r0, 0, r0s, 0, out_mode=3, fold_kw=3, tile_w=32)
+            a1h = self._mat(B, H, W, nf2)
+            self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
+        elif self.fold_eval:
+            a1h = r0         # inference: norm1 + relu1 folded into refine0
+            self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
+                           W, H, B, r0, 0, r0s, 0, fold=self._fold(bn1, nf2))
         else:
             self._conv_fwd(fwd, hp + ".refine0", hp + ".refine0.weight", [a0.view(0, Ct)], conv3x3[0], conv3x3[2], Ct, nf2, Ct * 9, 9,
                            W, H, B, r0, 0, r0s, 0)
-        a1h = self._mat(B, H, W, nf2)
-        self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
+            a1h = self._mat(B, H, W, nf2)
+            self._apply(fwd, hp + ".norm1", bn1, r0, 0, nf2, r0s, 0, a1h, 0)
         conv5 = ops.conv_taps(5, 2)
         if 5 * self.ncls <= 16 and os.environ.get("DMM_HEAD_FOLD", "1") != "0" and not self.f32:
             # kernel columns folded into N: 5 (kernel rows) instead of 25 MMAs per pixel tile, horizontal sum in the epilogue
@@ -962,6 +1003,14 @@ class Engine:
             pj[i]["sn"], pj[i]["sc"] = j["sn"], j["sc"]
             pj[i]["sc2"], pj[i]["cdiv"] = j.get("sc2", 0), j.get("cdiv", 0)
             pj[i]["sn2"], pj[i]["ndiv"] = j.get("sn2", 0), j.get("ndiv", 0)
+            pj[i]["rscale"] = j["rscale"].data_ptr() if j.get("rscale") is not None else 0
+        fj = np.zeros(len(self._fold_jobs), dtype=_FOLD_DT)
+        for i, (bn, c0, C_, scale, shift) in enumerate(self._fold_jobs):
+            fj[i]["gamma"], fj[i]["beta"] = bn.gamma.data_ptr() + 4 * c0, bn.beta.data_ptr() + 4 * c0
+            fj[i]["rm"], fj[i]["rv"] = bn.rm.data_ptr() + 4 * c0, bn.rv.data_ptr() + 4 * c0
+            fj[i]["scale"], fj[i]["shift"] = scale.data_ptr(), shift.data_ptr()
+            fj[i]["C"], fj[i]["eps"] = C_, ops.BN_EPS
+        self._fold_tab = torch.from_numpy(fj.view(np.uint8).copy()).to(dev) if len(fj) else None
         self._pack_tab = torch.from_numpy(pj.view(np.uint8).copy()).to(dev)
         self._n_pack = len(self._pack_jobs)
         # load-balanced launch: one block per WORK_CHUNK consecutive packed elements of a job
@@ -1142,6 +1191,9 @@ class Engine:
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         if self.training:
             self._stats.zero_used()
+        if self._fold_tab is not None:
+            _lib.check(self.lib.dmm_bn_fold_batched(C.c_void_p(self._fold_tab.data_ptr()), len(self._fold_jobs), stream),
+                       "dmm_bn_fold_batched")
         if self.f32:
             _lib.check(self.lib.dmm_pack_weights_work_f32(C.c_void_p(self._pack_tab.data_ptr()), C.c_void_p(self._pack_work.data_ptr()),
                                                           self._pack_work.shape[0], WORK_CHUNK, 1 if self.split3 else 0, stream),
@@ -1205,7 +1257,10 @@ class Engine:
 
 _PACK_DT = np.dtype([("w", np.uint64), ("dst", np.uint64), ("n_valid", np.int32), ("n_rows", np.int32), ("C", np.int32),
                      ("kwidth", np.int32), ("T", np.int32), ("tap_off", np.int32, (32,)), ("sn", np.int64),
-                     ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("ndiv", np.int32), ("sn2", np.int64)], align=True)
+                     ("sc", np.int64), ("sc2", np.int64), ("cdiv", np.int32), ("ndiv", np.int32), ("sn2", np.int64),
+                     ("rscale", np.uint64)], align=True)
+_FOLD_DT = np.dtype([("gamma", np.uint64), ("beta", np.uint64), ("rm", np.uint64), ("rv", np.uint64), ("scale", np.uint64),
+                     ("shift", np.uint64), ("C", np.int32), ("eps", np.float32)], align=True)
 _UNPACK_DT = np.dtype([("dw", np.uint64), ("grad", np.uint64), ("dt", np.int64), ("dm", np.int64), ("dn", np.int64),
                        ("M", np.int32), ("N", np.int32), ("T", np.int32), ("accumulate", np.int32),
                        ("tap_off", np.int32, (32,)), ("sn", np.int64), ("sc", np.int64), ("sn2", np.int64), ("ndiv", np.int32),

@@ -470,7 +470,8 @@ int dmm_pack_weights_work_f32(const dmm_pack_job_t* jobs_device, const int32_t* 
 
 /* sizeof() of the structs above in declaration order (0 = dmm_view_t, 1 = dmm_igemm_t, 2 = dmm_wgrad_t,
  * 3 = dmm_bn_t, 4 = dmm_bn_apply_t, 5 = dmm_bn_bwd_t, 6 = dmm_bn_bwd_args_t, 7 = dmm_head_t,
- * 8 = dmm_head_bwd_t, 9 = dmm_pack_job_t, 10 = dmm_unpack_job_t, 11 = dmm_grad_gather_t) so a binding can verify its layout. */
+ * 8 = dmm_head_bwd_t, 9 = dmm_pack_job_t, 10 = dmm_unpack_job_t, 11 = dmm_grad_gather_t, 12 = dmm_bn_fold_job_t) so a binding can
+ * verify its layout. */
 int dmm_sizeof(int which);
 
 #ifdef __cplusplus

@@ -44,6 +44,7 @@ def test_struct_layouts_match_header_sizes():
     assert engine._PACK_DT.itemsize == lib.dmm_sizeof(9)
     assert engine._UNPACK_DT.itemsize == lib.dmm_sizeof(10)
     assert ctypes.sizeof(_lib.GradGather) == lib.dmm_sizeof(11)
+    assert engine._FOLD_DT.itemsize == lib.dmm_sizeof(12)
 
 
 def test_default_config_matches_reference_defaults():
