@@ -633,9 +633,9 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         epi_bar(team);
                         const long long e5 = clock64();
                         if (p.lsu_store) {
-                            // the SM's TMA unit queues tensor stores BEHIND the prefetched operand loads (measured: ~1 200 cycles
-                            // of issue stall per chunk): write the staged tile through the load/store unit instead.  Thread e
-                            // moves 16-byte chunk e & 7 of rows (e >> 3) + 16 i: one warp instruction = four complete 128-byte rows.
+                            // experiment (off by default, slower): write the staged tile through the load/store unit instead of the
+                            // TMA unit, whose stores queue behind the prefetched operand loads (~1 200 cycles of issue stall per
+                            // chunk).  Thread e moves 16-byte chunk e & 7 of rows (e >> 3) + 16 i: one warp instruction = four rows.
                             const int j8 = r & 7;
                             const int col = tc.n0 + 64 * c + j8 * 8;
                             if (col < p.N) {
@@ -1080,7 +1080,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         ov.sb = (long long)OH * OW * d->ldo;
         int rc = view_to_tmap(&p.o_map, ov, 64, d->out_mode == 3 ? p.sub_w - 2 : p.sub_w, p.sub_h, 128);
         if (rc) return rc;
-        static const int lsu_env = env_int("DMM_IGEMM_LSU_STORE", 1);
+        // measured (r02, profiles/r02_epilogue_experiments.txt): 95.5 ms / step with st.global stores vs 88.3 with TMA stores on the same box
+        static const int lsu_env = env_int("DMM_IGEMM_LSU_STORE", 0);
         p.out16 = reinterpret_cast<__nv_bfloat16*>(d->out) + d->coff;
         p.ldo = d->ldo;
         p.lsu_store = (d->out_mode == 0 && lsu_env && d->N % 8 == 0) ? 1 : 0;
