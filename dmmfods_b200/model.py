@@ -221,7 +221,7 @@ class Dense_U_Net_lidar(nn.Module):
                 "num_classes": self.num_classes, "concat_before_block_num": self.concat_before_block_num,
                 "stream_1_in_channels": self.stream_1_in_channels, "stream_2_in_channels": self.stream_2_in_channels}
 
-    def engine(self, B, H, W, training=None, need_backward=True, precision="bf16"):
+    def engine(self, B, H, W, training=None, need_backward=True, precision="bf16", bucket_bytes=32 << 20):
         """the (cached) execution engine for one input shape; rebuilt when parameters were re-allocated.
         precision="tf32": the strict forward mode (fp32 storage, kind::tf32 MMAs; forward + loss only)."""
         training = self.training if training is None else training
@@ -232,7 +232,7 @@ class Dense_U_Net_lidar(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("dmmfods_b200: the model must live on a CUDA (sm_100) device - there is no CPU path")
         sig = tuple(v.data_ptr() for v in sd.values())
-        key = (B, H, W, bool(training), bool(need_backward and training), precision)
+        key = (B, H, W, bool(training), bool(need_backward and training), precision, int(bucket_bytes))
         ent = self._engines.get(key)
         if ent is None or ent[1] != sig:
             for v in sd.values():
@@ -241,7 +241,8 @@ class Dense_U_Net_lidar(nn.Module):
             params = OrderedDict((k, v.data if isinstance(v, nn.Parameter) else v) for k, v in sd.items())
             # drop engines of stale parameter storage (their buffers would otherwise stay alive)
             self._engines = {k: e for k, e in self._engines.items() if e[1] == sig}
-            eng = Engine(params, self.model_cfg(), B, H, W, training=training, need_backward=need_backward, precision=precision)
+            eng = Engine(params, self.model_cfg(), B, H, W, training=training, need_backward=need_backward, precision=precision,
+                         bucket_bytes=bucket_bytes)
             eng.fwd_count = 0
             self._engines[key] = (eng, sig)
             ent = self._engines[key]

@@ -97,7 +97,7 @@ class Trainer:
         if dev.type != "cuda":
             raise RuntimeError("dmmfods_b200.Trainer: the model must live on a CUDA device (no CPU path)")
         # flatten the parameters in the engine's gradient order so that Adam and the all-reduce see flat ranges
-        order = Engine.gradient_order(params, model.model_cfg(), B, H, W)
+        order = Engine.gradient_order(params, model.model_cfg(), B, H, W)      # (independent of the bucket size)
         total = sum(named[n].numel() for n in order)
         self.pflat = torch.empty(total, dtype=torch.float32, device=dev)
         off = 0
@@ -107,19 +107,18 @@ class Trainer:
             view.copy_(p.data)
             p.data = view
             off += p.numel()
-        self.eng = model.engine(B, H, W)
+        self.eng = model.engine(B, H, W, bucket_bytes=bucket_bytes)
         assert self.eng.param_names == order
-        self.eng.bucket_bytes = bucket_bytes
         self.exp_avg = torch.zeros_like(self.pflat)
         self.exp_avg_sq = torch.zeros_like(self.pflat)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.steps = 0
         self.reducer = BucketReducer(self.dist, dev) if self.dist is not None else None
-        # one CUDA graph for forward + loss + backward; data parallel: the bucket all-reduces (NCCL, side stream) are captured
-        # INSIDE that graph (graph_nccl, default), or - DMM_GRAPH_NCCL=0 / capture failure - one graph for forward + loss and
-        # one per backward segment with the all-reduces issued between them
+        # one CUDA graph for forward + loss + backward; data parallel: one graph for forward + loss and one per backward segment
+        # with the bucket all-reduces (NCCL, side stream) issued between them (default), or - graph_nccl / DMM_GRAPH_NCCL=1,
+        # experimental - the all-reduces captured INSIDE one step graph
         self.use_graph = bool(use_graph)
-        self.graph_nccl = (os.environ.get("DMM_GRAPH_NCCL", "1") != "0") if graph_nccl is None else bool(graph_nccl)
+        self.graph_nccl = (os.environ.get("DMM_GRAPH_NCCL", "0") != "0") if graph_nccl is None else bool(graph_nccl)
         self.graph = None
         self.seg_graphs = None
         # preprocess(lidar_buffer, target_buffer): optional on-GPU pre-processing launched at the head of every step (inside the

@@ -18,3 +18,9 @@ ncu --set full --clock-control none --import-source on --profile-from-start off 
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:head_input_kernel -c 1 -o gpurun_out/${TAG}_head_input $B > gpurun_out/ncu_head.log 2>&1
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:grad_gather -s 3 -c 1 -o gpurun_out/${TAG}_grad_gather $B > gpurun_out/ncu_gather.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# round 2: the two batched pre-processing kernels of BASELINE config 4 (one --set full capture each)
+B4="python bench.py --workload cfg4 --steps 2 --warmup 3 --graph 0 --profile-step"
+$B4 > gpurun_out/plain_bench_cfg4.log 2>&1 &&
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:lidar_splat_tile -c 1 -o gpurun_out/${TAG}_lidar_splat_tile $B4 > gpurun_out/ncu_splat.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:heatmap_tile -c 1 -o gpurun_out/${TAG}_heatmap_tile $B4 > gpurun_out/ncu_heat.log 2>&1
+ls -la gpurun_out/${TAG}_*.ncu-rep

@@ -1,9 +1,8 @@
 #!/bin/bash
-# 2 GPUs: NCCL correctness test + scaling pair (1 GPU and 2 GPUs back to back on the same box), both graph forms
+# 2 GPUs: NCCL correctness test + scaling pair (1 GPU and 2 GPUs back to back on the same box); every command under its own timeout
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_ddp_nccl_gpu.py -m gpu -q -s > gpurun_out/r02_tests_nccl.log 2>&1; echo "rc $?" >> gpurun_out/r02_tests_nccl.log
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_scale_1gpu.log 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_scale_2gpu.log 2>&1
-DMM_GRAPH_NCCL=0 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_scale_2gpu_seg.log 2>&1
+timeout 240 python -m pytest tests/test_ddp_nccl_gpu.py -m gpu -q -s > gpurun_out/r02_tests_nccl.log 2>&1; echo "rc $?" >> gpurun_out/r02_tests_nccl.log
+timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_scale_1gpu.log 2>&1
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_scale_2gpu.log 2>&1
 tail -5 gpurun_out/r02_tests_nccl.log; tail -c 300 gpurun_out/r02_scale_2gpu.log
