@@ -51,7 +51,6 @@ struct Ig2Params {
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
     int nslot;                                      // out_mode 0: staging slots per epilogue team (1..3)
-    int st_lane;                                    // out_mode 0: TMA stores issued by two dedicated lanes of warp 0 (not by the epilogue teams)
     int w_res;                                      // weights RESIDENT: the CTA's whole weight slice is loaded once (sb = stages per tile)
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
@@ -62,9 +61,6 @@ struct Ig2Params {
     int tw_log, sw_log, sh_log;    // out_mode 2: log2 of TW, sub_w, sub_h
     long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
     float* out32;
-    __nv_bfloat16* out16;          // out_mode 0 with lsu_store: pixel-major bf16 output (already offset by the channel offset)
-    long long ldo;
-    int lsu_store;                 // out_mode 0: write the staged chunk with coalesced st.global.v4 instead of a TMA tensor store
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
     int stats_ld, stats_off;
@@ -134,10 +130,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* x_bar = acc_empty + 2;
     uint64_t* a_ready = x_bar + 2;                                       // pro: A stage transformed (4 warp arrivals)
-    uint64_t* st_full = a_ready + 8;                                     // st_lane: [team][slot] staged chunk ready (4 warp arrivals)
-    uint64_t* st_free = st_full + 6;                                     // st_lane: [team][slot] the TMA store has read the slot
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(st_free + 6);
-    float* pcoef = reinterpret_cast<float*>(tail + 1024);                // pro: [2][pro_kp] scale / shift
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 8);
+    float* pcoef = reinterpret_cast<float*>(tail + 512);                 // pro: [2][pro_kp] scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -156,10 +150,6 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             mbar_init(&acc_full[s], 1);
             mbar_init(&acc_empty[s], 8);
             mbar_init(&x_bar[s], 1);
-        }
-        for (int s = 0; s < 6; ++s) {
-            mbar_init(&st_full[s], 4);
-            mbar_init(&st_free[s], 1);
         }
         fence_mbar_init();
     }
@@ -235,38 +225,6 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 p.prof[blockIdx.x * 16 + 1] = w_a;
                 p.prof[blockIdx.x * 16 + 2] = w_b;
             }
-        } else if (OUT_MODE == 0 && p.st_lane && (lane == 1 || lane == 2)) {
-            // ================= TMA store issuers: lane 1 serves epilogue team 0, lane 2 team 1 =================
-            // The SM's TMA unit takes a tensor store only after the operand loads queued before it: the issuing thread stalls for
-            // ~1 000 cycles per chunk.  These two lanes absorb that stall, so the 128 threads of an epilogue team go straight on
-            // to the next chunk (other slot).  Each lane walks its team's chunk sequence: wait "slot staged" -> store -> commit;
-            // a slot is handed back (st_free) once the store issued nslot - 1 chunks later has been accepted and its own read is done.
-            const int team = lane - 1;
-            uint32_t chunk_ctr = 0, n_issued = 0;
-            uint32_t si = 0, ph_full = 0;
-            for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(p, tile);
-                for (int sub = 0; sub < MSUB; ++sub) {
-                    for (int c = 0; c < NCH; ++c) {
-                        if (tc.n0 + 64 * c >= p.N) break;
-                        if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
-                        mbar_wait(&st_full[team * 3 + si], ph_full);
-                        tma_store_4d(&p.o_map, stg + (size_t)(team * p.nslot + si) * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub],
-                                     tc.y0 + p.sub_y[sub], tc.b);
-                        bulk_commit();
-                        ++n_issued;
-                        // the store issued (nslot - 1) chunks ago has now been read out of shared memory: free its slot
-                        if (p.nslot == 1) { bulk_wait_read0(); mbar_arrive(&st_free[team * 3 + si]); }
-                        else if (n_issued >= (uint32_t)p.nslot) {
-                            if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-                            mbar_arrive(&st_free[team * 3 + (si + 1) % p.nslot]);
-                        }
-                        if (++si == (uint32_t)p.nslot) { si = 0; ph_full ^= 1; }
-                    }
-                }
-            }
-            bulk_wait_all();
         }
     } else if (warp == (PRO ? 14 : 10)) {
         // ================= halo-patch (A) TMA producer =================
@@ -451,7 +409,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         // out_mode 0: `nslot` staging slots per team, used round-robin: the TMA store of a chunk drains (behind whatever loads are
         // queued in the SM's TMA unit) while the next chunks are staged; FOLD3 keeps one slot per team
         uint8_t* slot = stg + team * (OUT_MODE == 0 ? p.nslot : 1) * kStageSlot;
-        uint32_t slot_i = 0, st_phase = 0;
+        uint32_t slot_i = 0;
         if (FOLD3) {
             // compact staging: 4 image rows x (32 - 2) valid pixels = 120 rows; rows 120..127 stay zero for the statistics loop
             if (r >= 120) {
@@ -463,7 +421,6 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
-        const int sw_shift = __ffs(p.sub_w) - 1;
         uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow);
         const uint32_t slot0_u = slot_u, xslot_u = smem_u32(xslot);
         double sacc[NCH][4];
@@ -616,10 +573,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         // round-robin slot; its previous TMA store (nslot chunks ago) must have finished reading it
                         slot_u = slot0_u + slot_i * kStageSlot;
                         srow_u = slot_u + r * 128;
-                        if (p.st_lane) {
-                            // the slot's st_free completes once per use; the first `nslot` uses find it free (parity trick of empty barriers)
-                            mbar_wait(&st_free[team * 3 + slot_i], st_phase ^ 1);
-                        } else if (r == 0 && !p.lsu_store) {
+                        if (r == 0) {
                             if (p.nslot == 1) bulk_wait_read0();
                             else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
@@ -627,9 +581,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         const long long e1 = clock64();
                         tmem_ld_wait();
                         const long long e2 = clock64();
-                        // every thread of the team is done with the previous chunk (st_lane with >= 2 slots: the statistics barrier of
-                        // the previous chunk already separates the readers of this slot from its next writers)
-                        if (!(p.st_lane && p.nslot >= 2)) epi_bar(team);
+                        epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
                         const long long e3 = clock64();
                         ph_store_wait += e1 - e0; ph_tmem += e2 - e1; ph_bar1 += e3 - e2;
                         if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
@@ -672,41 +624,15 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                                 sts_v4(srow_u + (((2 * g + 1) ^ (r & 7)) << 4), w1);
                             }
                         }
-                        if (!p.lsu_store) fence_proxy_async();
+                        fence_proxy_async();
                         const long long e4 = clock64();
-                        if (p.st_lane) {
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&st_full[team * 3 + slot_i]);      // 4 warp arrivals: the chunk is staged
-                            if (do_stats || p.nslot < 2) epi_bar(team);                     // the statistics loop reads all rows of the slot
-                        } else {
-                            epi_bar(team);
-                        }
+                        epi_bar(team);
                         const long long e5 = clock64();
-                        if (p.st_lane) {
-                        } else if (p.lsu_store) {
-                            // experiment (off by default, slower): write the staged tile through the load/store unit instead of the
-                            // TMA unit, whose stores queue behind the prefetched operand loads (~1 200 cycles of issue stall per
-                            // chunk).  Thread e moves 16-byte chunk e & 7 of rows (e >> 3) + 16 i: one warp instruction = four rows.
-                            const int j8 = r & 7;
-                            const int col = tc.n0 + 64 * c + j8 * 8;
-                            if (col < p.N) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int row = (r >> 3) + 16 * i;
-                                    const int rx = row & (p.sub_w - 1), ry = row >> sw_shift;      // sub_w is a power of two
-                                    const int xx = tc.x0 + p.sub_x[sub] + rx, yy = tc.y0 + p.sub_y[sub] + ry;
-                                    if (xx < p.Wv && yy < p.Hv) {
-                                        const uint4 w = lds_v4(slot_u + row * 128 + ((j8 ^ (row & 7)) << 4));
-                                        const long long pix = ((long long)tc.b * p.OH + (yy * p.out_sy + p.out_py)) * p.OW + (xx * p.out_sx + p.out_px);
-                                        *reinterpret_cast<uint4*>(p.out16 + pix * p.ldo + col) = w;
-                                    }
-                                }
-                            }
-                        } else if (r == 0) {
+                        if (r == 0) {
                             tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
-                        if (++slot_i == (uint32_t)p.nslot) { slot_i = 0; st_phase ^= 1; }
+                        if (++slot_i == (uint32_t)p.nslot) slot_i = 0;
                         ph_pack += e4 - e3; ph_bar2 += e5 - e4;
                         const long long e6 = clock64();
                         if (do_stats) {
@@ -809,7 +735,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 }
             }
         }
-        if ((OUT_MODE == 0 || FOLD3) && r == 0 && !p.st_lane) bulk_wait_all();
+        if ((OUT_MODE == 0 || FOLD3) && r == 0) bulk_wait_all();
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
@@ -957,16 +883,13 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     // staging slots per epilogue team (out_mode 0, DMM_IGEMM_NSLOT): more than one lets the epilogue run ahead of the drain of its
     // TMA stores
     static const int nslot_env = env_int("DMM_IGEMM_NSLOT", 0);
-    // dedicated store-issuing lanes (DMM_IGEMM_ST_LANE, out_mode 0 without the fused BN-backward reduce): two slots per team
-    static const int st_lane_env = env_int("DMM_IGEMM_ST_LANE", 1);
-    const int st_lane = (st_lane_env && d->out_mode == 0 && !bnb) ? 1 : 0;
-    int nslot = nslot_env > 0 ? nslot_env : (st_lane ? 2 : 1);       // measured (r02): 3 slots 86.2 ms / step, 1 slot 85.0 - the epilogue does not wait for the drain
+    int nslot = nslot_env > 0 ? nslot_env : 1;       // measured (r02): 3 slots 86.2 ms / step, 1 slot 85.0 - the epilogue does not wait for the drain
     if (nslot > 3) nslot = 3;
     if (d->out_mode != 0) nslot = 1;
     const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 2 : 0)) * (int)kStageSlot
                                           : (d->out_mode == 3 ? 2 * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0))) +
                         (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
-    const int avail = kG2MaxSmem - 1024 - 1024 - staging;
+    const int avail = kG2MaxSmem - 1024 - 512 - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
     const int mma_hw = d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4;   // cycles per MMA (measured law)
@@ -1061,7 +984,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
     p.nslot = nslot;
-    p.st_lane = st_lane;
     p.w_res = best.w_res;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
@@ -1135,11 +1057,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         ov.sb = (long long)OH * OW * d->ldo;
         int rc = view_to_tmap(&p.o_map, ov, 64, d->out_mode == 3 ? p.sub_w - 2 : p.sub_w, p.sub_h, 128);
         if (rc) return rc;
-        // measured (r02, profiles/r02_epilogue_experiments.txt): 95.5 ms / step with st.global stores vs 88.3 with TMA stores on the same box
-        static const int lsu_env = env_int("DMM_IGEMM_LSU_STORE", 0);
-        p.out16 = reinterpret_cast<__nv_bfloat16*>(d->out) + d->coff;
-        p.ldo = d->ldo;
-        p.lsu_store = (d->out_mode == 0 && lsu_env && d->N % 8 == 0) ? 1 : 0;
     } else {
         p.out32 = reinterpret_cast<float*>(d->out);
     }
@@ -1174,7 +1091,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     while ((int)cols < 2 * p.msub * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
 
-    const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 1024 + 1024;
+    const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 512 + 1024;
     DMM_CHECK(smem <= (size_t)kG2MaxSmem, "igemm v2: %zu bytes of shared memory requested", smem);
     unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (p.w_res && tiles_n > 1) {
