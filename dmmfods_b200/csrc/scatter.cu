@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(256) pool_kxk_kernel(const float* __restrict__
 //          from the LAST to the first and takes the first hit of its class - "later boxes overwrite earlier ones" without atomics.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSplatTW = 256, kSplatTH = 64;      // 64 KB of int32 per tile
-constexpr int kSplatChunk = 2048;
 
 __global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __restrict__ pts, const int32_t* __restrict__ offs, int H, int W,
                                                                int shift, int mode, float* __restrict__ img) {
@@ -189,19 +188,22 @@ __global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __re
     const int p0 = offs[b], n = offs[b + 1] - p0;
     const float* fp = pts + 3ll * p0;
     const float fs = (float)shift;
-    // the frame's points stream through shared memory in chunks of kSplatChunk (coalesced loads, every CTA of the frame reads
-    // the same L2-resident list); each thread then tests kSplatChunk / 256 points against the tile
-    __shared__ float sxy[2][kSplatChunk];
-    for (int c0 = 0; c0 < n; c0 += kSplatChunk) {
-        const int cn = min(kSplatChunk, n - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
-            sxy[0][i] = __ldg(fp + 3ll * (c0 + i) + 0);
-            sxy[1][i] = __ldg(fp + 3ll * (c0 + i) + 1);
+    // every CTA of the frame scans the same (L2-resident) point list: 8 points per thread and step, all 16 coordinate loads in
+    // flight before the first test (the scan is latency-bound: two 80 KB CTAs per SM leave only 16 warps to hide it)
+    constexpr int U = 8;
+    for (int i0 = threadIdx.x; i0 < n; i0 += U * (int)blockDim.x) {
+        float xs[U], ys[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            xs[u] = i < n ? __ldg(fp + 3ll * i + 0) : 0.f;
+            ys[u] = i < n ? __ldg(fp + 3ll * i + 1) : 0.f;
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < cn; i += blockDim.x) {
-            const float x = sxy[0][i], y = sxy[1][i];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            if (i >= n) break;
+            const float x = xs[u], y = ys[u];
             // identical arithmetic to lidar_mark_kernel (helper:503-511)
             int min_y = py_int(__fsub_rn(y, fs));
             if (min_y < 0) min_y = 0;
@@ -218,9 +220,8 @@ __global__ void __launch_bounds__(256) lidar_splat_tile_kernel(const float* __re
             int x0, x1;
             py_slice(min_x, max_x, W, x0, x1);
             x0 = max(x0, tx0); x1 = min(x1, tx0 + tw);
-            const int idx = c0 + i;
             for (int yy = y0; yy < y1; ++yy)
-                for (int xx = x0; xx < x1; ++xx) atomicMax(&tile[(yy - ty0) * kSplatTW + (xx - tx0)], idx);
+                for (int xx = x0; xx < x1; ++xx) atomicMax(&tile[(yy - ty0) * kSplatTW + (xx - tx0)], i);
         }
     }
     __syncthreads();

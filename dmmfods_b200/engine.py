@@ -42,7 +42,7 @@ FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE
 
 # data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
 PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
-DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "64"))
+DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "8"))       # 64 (128-byte aligned rows) measured = (88.3 vs 87.9 ms): dense pitch kept
 # inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
 # the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
 FOLD_EVAL_BN = os.environ.get("DMM_FOLD_EVAL_BN", "1") != "0"
@@ -657,8 +657,7 @@ class Engine:
                     # shared scratch of the widest layer, re-pitched to this layer's channel count: dense rows for the
                     # data-gradient store and the contribution pass (a [P, Ct] pitch would leave holes in every DRAM page)
                     da1_full = self._tmpmat("da1", B, Hb, Wb, blk.Ct)
-                    # ... with the pitch rounded up to 64 channels: every 128-byte row of a TMA store then starts on a 128-byte
-                    # boundary (measured r02: a 1984-byte pitch makes the 1x1 data gradient's stores ~2x slower)
+                    # (DMM_DA1_ALIGN=64 rounds the pitch up so that every 128-byte TMA-store row starts on a 128-byte boundary)
                     pitch = min(ceil_to(Ci, DA1_ALIGN), blk.Ct)
                     da1 = Mat(da1_full.t.view(-1)[:B * Hb * Wb * pitch].view(B * Hb * Wb, pitch), B, Hb, Wb)
                     self._gather(st, lp + ".gout", blk, Ci, k, go)
