@@ -18,6 +18,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+// per-phase cycle counters of the epilogue (profiles/r02_epilogue_experiments.txt): compiled in only with -DDMM_IGEMM_PHASE_PROF,
+// the twelve extra registers make every out_mode-0 instantiation spill
+#ifdef DMM_IGEMM_PHASE_PROF
+#define DMM_PH(...) __VA_ARGS__
+#else
+#define DMM_PH(...)
+#endif
+
 namespace dmm {
 
 constexpr int kG2Threads = 352;          // warp 0 weight TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps, warp 10 patch TMA
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint32_t it = 0;
         int last_n0 = 0;
         long long w_full = 0;
-        long long ph_store_wait = 0, ph_tmem = 0, ph_bar1 = 0, ph_pack = 0, ph_bar2 = 0, ph_stats = 0;      // DMM_IGEMM_PROF phase cycles (thread r == 0)
+        DMM_PH(long long ph_store_wait = 0, ph_tmem = 0, ph_bar1 = 0, ph_pack = 0, ph_bar2 = 0, ph_stats = 0;)      // phase cycles (thread r == 0)
         const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
                         uint32_t v[4][16];
-                        const long long e0 = clock64();
+                        DMM_PH(const long long e0 = clock64();)
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
@@ -578,12 +586,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                         }
-                        const long long e1 = clock64();
+                        DMM_PH(const long long e1 = clock64();)
                         tmem_ld_wait();
-                        const long long e2 = clock64();
+                        DMM_PH(const long long e2 = clock64();)
                         epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
-                        const long long e3 = clock64();
-                        ph_store_wait += e1 - e0; ph_tmem += e2 - e1; ph_bar1 += e3 - e2;
+                        DMM_PH(const long long e3 = clock64(); ph_store_wait += e1 - e0; ph_tmem += e2 - e1; ph_bar1 += e3 - e2;)
                         if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
                             mbar_arrive_expect_tx(&x_bar[team], kStageSlot);
                             tma_load_4d(xslot, &p.x_map, &x_bar[team], tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 if (g < ngrp) {
-#pragma unroll
+#pragma unroll 1
                                     for (int q = 0; q < 4; ++q) {
                                         const float4 b4 = __ldg(bp + 4 * g + q);
                                         v[g][4 * q + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 0]) + b4.x, lo));
@@ -625,16 +632,15 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             }
                         }
                         fence_proxy_async();
-                        const long long e4 = clock64();
+                        DMM_PH(const long long e4 = clock64();)
                         epi_bar(team);
-                        const long long e5 = clock64();
+                        DMM_PH(const long long e5 = clock64();)
                         if (r == 0) {
                             tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
                         if (++slot_i == (uint32_t)p.nslot) slot_i = 0;
-                        ph_pack += e4 - e3; ph_bar2 += e5 - e4;
-                        const long long e6 = clock64();
+                        DMM_PH(ph_pack += e4 - e3; ph_bar2 += e5 - e4; const long long e6 = clock64();)
                         if (do_stats) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             sacc[c][0] += (double)s1a; sacc[c][1] += (double)s1b;
                             sacc[c][2] += (double)s2a; sacc[c][3] += (double)s2b;
                         }
-                        ph_stats += clock64() - e6;
+                        DMM_PH(ph_stats += clock64() - e6;)
                     }
                 } else {
                     // fp32 NCHW logits: out[((b*N + n)*OH + oy)*OW + ox], N <= 16; the teams alternate sub-tiles
@@ -739,8 +745,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
-            p.prof[blockIdx.x * 16 + 10] = ph_store_wait; p.prof[blockIdx.x * 16 + 11] = ph_tmem; p.prof[blockIdx.x * 16 + 12] = ph_bar1;
-            p.prof[blockIdx.x * 16 + 13] = ph_pack; p.prof[blockIdx.x * 16 + 14] = ph_bar2; p.prof[blockIdx.x * 16 + 15] = ph_stats;
+            DMM_PH(p.prof[blockIdx.x * 16 + 10] = ph_store_wait; p.prof[blockIdx.x * 16 + 11] = ph_tmem; p.prof[blockIdx.x * 16 + 12] = ph_bar1;
+                   p.prof[blockIdx.x * 16 + 13] = ph_pack; p.prof[blockIdx.x * 16 + 14] = ph_bar2; p.prof[blockIdx.x * 16 + 15] = ph_stats;)
         }
         }   // epilogue team
     }
