@@ -1225,7 +1225,8 @@ __global__ void __launch_bounds__(256) nchw_stats_kernel(const float* __restrict
 // One block = one output row (b, y); thread t owns chunk t % chunks for pixels t / chunks, t / chunks + ppb, ... so the
 // inner loop has no divisions, 16-byte stores of a row are contiguous, and every up-sampled source row is read by
 // exactly two blocks.
-__global__ void __launch_bounds__(256, 4) head_input_kernel(const dmm_head_t p) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) head_input_kernel(const dmm_head_t p) {
     pdl_prologue();
     extern __shared__ float coef[];   // [2][Cpad]
     const int Ct = p.Cu + p.C1 + p.C2;
@@ -1958,16 +1959,20 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
               "dmm_head_input: unsupported channel split (Cu=%d, raw=%d, ldo=%lld)", d->Cu, d->C1 + d->C2, (long long)d->ldo);
     const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * 2 * d->W) * sizeof(float);
     DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: two rows of %d raw channels x %d pixels do not fit in shared memory", d->C1 + d->C2, d->W);
+    // MINB = 4 (64 registers, 120 bytes of spills) or 3 (85 registers, none): DMM_HEAD_MINB
+    static const int minb = env_int_ew("DMM_HEAD_MINB", 4);
+    void (*kern)(const dmm_head_t) = minb == 3 ? head_input_kernel<3> : head_input_kernel<4>;
     static bool head_attr = false;
     if (!head_attr) {
-        DMM_CUDA(cudaFuncSetAttribute(head_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        DMM_CUDA(cudaFuncSetAttribute(head_input_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        DMM_CUDA(cudaFuncSetAttribute(head_input_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         head_attr = true;
     }
     int head_bps = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&head_bps, head_input_kernel, 256, smem) != cudaSuccess || head_bps < 1) head_bps = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&head_bps, kern, 256, smem) != cudaSuccess || head_bps < 1) head_bps = minb;
     static const int head_bps_env = env_int_ew("DMM_HEAD_BPS", 0);
     const long long hrows = (long long)d->B * (d->H / 2), hcap = (long long)kNumSm * (head_bps_env > 0 ? head_bps_env : head_bps);
-    launch_k(head_input_kernel, (unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream, *d);
+    launch_k(kern, (unsigned)(hrows < hcap ? hrows : hcap), 256, smem, (cudaStream_t)stream, *d);
     DMM_LAUNCH_CHECK("head_input_kernel");
     return 0;
 }

@@ -29,7 +29,8 @@
 namespace dmm {
 
 constexpr int kG2Threads = 352;          // warp 0 weight TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps, warp 10 patch TMA
-constexpr int kG2ThreadsPro = 480;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA (PRO instantiations)
+constexpr int kG2ThreadsPro = 480;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA (PRO instantiations; 128 registers per
+                                         // thread: ptxas rounds the budget to 512 threads, so a 448-thread variant gains nothing - measured)
 constexpr int kMaxSub = 4;
 constexpr int kMaxBStages = 16;          // weight ring slots (resident weights: one slot per (tap group, k-block) of a tile)
 constexpr int kG2MaxSmem = 232448;
@@ -58,7 +59,6 @@ struct Ig2Params {
     int n_tile, N;
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
-    int nslot;                                      // out_mode 0: staging slots per epilogue team (1..3)
     int w_res;                                      // weights RESIDENT: the CTA's whole weight slice is loaded once (sb = stages per tile)
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + (OUT_MODE == 0 ? 2 * p.nslot * kStageSlot : (FOLD3 ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0)));   // bnb: one x tile per team
+    uint8_t* xstg = stg + ((OUT_MODE == 0 || FOLD3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
     uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
@@ -414,10 +414,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         const int px = r % p.sub_w, py = r / p.sub_w;
         const bool do_stats = (OUT_MODE == 0 || FOLD3) && (p.stats != nullptr);
         const int cp = r & 31, rq = r >> 5;  // statistics: column pair / row quarter of the staged chunk
-        // out_mode 0: `nslot` staging slots per team, used round-robin: the TMA store of a chunk drains (behind whatever loads are
-        // queued in the SM's TMA unit) while the next chunks are staged; FOLD3 keeps one slot per team
-        uint8_t* slot = stg + team * (OUT_MODE == 0 ? p.nslot : 1) * kStageSlot;
-        uint32_t slot_i = 0;
+        uint8_t* slot = stg + team * kStageSlot;
         if (FOLD3) {
             // compact staging: 4 image rows x (32 - 2) valid pixels = 120 rows; rows 120..127 stay zero for the statistics loop
             if (r >= 120) {
@@ -429,8 +426,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint8_t* srow = slot + r * 128;
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
-        uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow);
-        const uint32_t slot0_u = slot_u, xslot_u = smem_u32(xslot);
+        const uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow), xslot_u = smem_u32(xslot);
         double sacc[NCH][4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
@@ -578,14 +574,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
-                        // round-robin slot; its previous TMA store (nslot chunks ago) must have finished reading it
-                        slot_u = slot0_u + slot_i * kStageSlot;
-                        srow_u = slot_u + r * 128;
-                        if (r == 0) {
-                            if (p.nslot == 1) bulk_wait_read0();
-                            else if (p.nslot == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                            else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-                        }
+                        if (r == 0) bulk_wait_read0();       // the team's previous TMA store has finished reading the slot
                         DMM_PH(const long long e1 = clock64();)
                         tmem_ld_wait();
                         DMM_PH(const long long e2 = clock64();)
@@ -602,7 +591,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
                                 if (g < ngrp) {
-#pragma unroll 1
+                                    asm volatile("" ::: "memory");        // keep the 4 bias loads of one group together: 16 hoisted float4 spill
+#pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const float4 b4 = __ldg(bp + 4 * g + q);
                                         v[g][4 * q + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 0]) + b4.x, lo));
@@ -636,10 +626,9 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         epi_bar(team);
                         DMM_PH(const long long e5 = clock64();)
                         if (r == 0) {
-                            tma_store_4d(&p.o_map, slot + slot_i * kStageSlot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
+                            tma_store_4d(&p.o_map, slot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
-                        if (++slot_i == (uint32_t)p.nslot) slot_i = 0;
                         DMM_PH(ph_pack += e4 - e3; ph_bar2 += e5 - e4; const long long e6 = clock64();)
                         if (do_stats) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
@@ -886,12 +875,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     }
     int max_taps = 1;
     for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
-    // staging slots per epilogue team (out_mode 0, DMM_IGEMM_NSLOT): more than one lets the epilogue run ahead of the drain of its
-    // TMA stores
-    static const int nslot_env = env_int("DMM_IGEMM_NSLOT", 0);
-    int nslot = nslot_env > 0 ? nslot_env : 1;       // measured (r02): 3 slots 86.2 ms / step, 1 slot 85.0 - the epilogue does not wait for the drain
-    if (nslot > 3) nslot = 3;
-    if (d->out_mode != 0) nslot = 1;
+    const int nslot = 1;      // staging slots per epilogue team (2 / 3 measured slower: profiles/r02_epilogue_experiments.txt)
     const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 2 : 0)) * (int)kStageSlot
                                           : (d->out_mode == 3 ? 2 * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0))) +
                         (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
@@ -989,7 +973,6 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.msub = best.msub; p.sub_w = best.sub_w; p.sub_h = best.sub_h;
     p.TW = best.TW; p.TH = best.TH;
     p.sa = best.sa; p.sb = best.sb;
-    p.nslot = nslot;
     p.w_res = best.w_res;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
