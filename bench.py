@@ -288,6 +288,7 @@ def cpu_baseline_obj(wl, args):
 def run_cfg5(args, wl):
     """BASELINE configs[4]: DenseNet-201 mid-fusion, eval mode (running-statistics BatchNorm), heat-map throughput for batch
     1 ... 128 on one GPU through the graph-captured Evaluator (forward + per-class loss + IoU / accuracy counters)."""
+    import gc
     import torch
     from dmmfods_b200 import synthetic
     from dmmfods_b200.model import densenet201_u_lidar
@@ -339,8 +340,9 @@ def run_cfg5(args, wl):
             fam = kernel_breakdown(ev.eng, x1, x2, tg, backward=False) if B == 32 else None
             if fam is not None:
                 roof, kernels, _ = roofline_from({k: v for k, v in fam.items()}, peaks)
-        del ev, x1, x2, tg
+        del ev, x1, x2, tg, hx1, hx2, htg
         model._engines = {}
+        gc.collect()              # an engine's launch closures reference its own buffers: cycles, freed by the collector only
         torch.cuda.empty_cache()
     clocks = sampler.stop()
     line = {"metric": "inference heat-map images/sec (DenseNet-201 mid-fusion, eval mode, 640x960)", "value": best["images_per_s"],

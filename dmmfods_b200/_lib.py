@@ -79,7 +79,7 @@ class BnBwdArgs(C.Structure):
                 ("gmode", c_int32), ("B", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32),
                 ("bn", BnBwd), ("out", c_void_p), ("ldo", c_int64), ("out_mode", c_int32), ("dz_out", c_void_p),
                 ("lddz", c_int64), ("argmax", c_void_p), ("ldarg", c_int64), ("out_gw", c_int32), ("pad_", c_int32),
-                ("out_plane", c_int64)]
+                ("out_plane", c_int64), ("fin_k", c_void_p), ("fin_ctr", c_void_p)]
 
 
 class Head(C.Structure):

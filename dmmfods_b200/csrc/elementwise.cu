@@ -891,6 +891,34 @@ __global__ void __launch_bounds__(kEwThreads, kFastBps) bn_bwd_contrib_kernel(co
         for (int j = 0; j < 8; ++j) s2[j] *= cf[3][threadIdx.x * 8 + j];
     }
     block_col_reduce_atomic(s1, s2, sm, cx, ry, chunk, nchunks, p.bn.sums, p.bn.sums_ld, p.bn.sums_off);
+    if (p.fin_k != nullptr) {
+        // fused dmm_bn_bwd_finalize: the last block of this channel group (ticket counter) sees every block's atomics
+        __shared__ int last;
+        __threadfence();
+        __syncthreads();
+        const int tid = threadIdx.y * cx + threadIdx.x;
+        if (tid == 0) last = atomicAdd(p.fin_ctr + blockIdx.y, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (last) {
+            __threadfence();
+            const int c = blockIdx.y * cx * 8 + tid;
+            if (tid < cx * 8 && c < p.C) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int s = 0; s < DMM_STATS_SLOTS; ++s) {
+                    const double* r = p.bn.sums + (size_t)s * 2 * p.bn.sums_ld + p.bn.sums_off + c;
+                    a += __ldcg(r);
+                    b += __ldcg(r + p.bn.sums_ld);
+                }
+                const float invstd = p.bn.save_invstd[c];
+                const float A = (p.bn.gamma ? p.bn.gamma[c] : 1.f) * invstd;
+                if (p.bn.dgamma) p.bn.dgamma[c] = (float)b;
+                if (p.bn.dbeta) p.bn.dbeta[c] = (float)a;
+                p.fin_k[c] = A * (float)(a / p.bn.count);
+                p.fin_k[p.C + c] = A * invstd * (float)(b / p.bn.count);
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const dmm_bn_bwd_t bn, int C, float* __restrict__ k) {
@@ -1959,8 +1987,8 @@ extern "C" int dmm_head_input(const dmm_head_t* d, void* stream) {
               "dmm_head_input: unsupported channel split (Cu=%d, raw=%d, ldo=%lld)", d->Cu, d->C1 + d->C2, (long long)d->ldo);
     const size_t smem = ((size_t)2 * chunks * 8 + (size_t)(d->C1 + d->C2) * 2 * d->W) * sizeof(float);
     DMM_CHECK(smem <= 96 * 1024, "dmm_head_input: two rows of %d raw channels x %d pixels do not fit in shared memory", d->C1 + d->C2, d->W);
-    // MINB = 4 (64 registers, 120 bytes of spills) or 3 (85 registers, none): DMM_HEAD_MINB
-    static const int minb = env_int_ew("DMM_HEAD_MINB", 4);
+    // MINB = 3 (85 registers, no spills; default) or 4 (64 registers, 120 bytes of spills): DMM_HEAD_MINB
+    static const int minb = env_int_ew("DMM_HEAD_MINB", 3);      // measured r02: 1.85 -> 1.71 ms
     void (*kern)(const dmm_head_t) = minb == 3 ? head_input_kernel<3> : head_input_kernel<4>;
     static bool head_attr = false;
     if (!head_attr) {

@@ -46,6 +46,8 @@ DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "8"))       # 64 (128-byte align
 # inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
 # the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
 FOLD_EVAL_BN = os.environ.get("DMM_FOLD_EVAL_BN", "1") != "0"
+# dense-layer norm1 backward: dmm_bn_bwd_finalize fused into the contribution launch (76 launches fewer per step on DenseNet-121)
+FUSE_FINALIZE = os.environ.get("DMM_FUSE_FINALIZE", "1") != "0"
 # weight pack / gradient unpack as load-balanced (job, chunk) launches (DMM_BALANCED_PACK=0: 32 blocks per job as in round 1)
 BALANCED_PACK = os.environ.get("DMM_BALANCED_PACK", "1") != "0"
 WORK_CHUNK = 8192
@@ -220,6 +222,7 @@ class Engine:
         self._dw_req = []
         self._wpk_req = []
         self._pack_jobs = []
+        self._fin_req = []       # contribution launches with the fused finalize: ticket counters assigned in _finalize
         self._fold_jobs = []     # eval-mode BatchNorms folded into their producing convolution: (bn, c0, C, scale, shift)
         self._unpack_jobs = []
         self._stage_params = {}
@@ -458,10 +461,14 @@ class Engine:
         self._emit(lst, self.lib.dmm_bn_relu_bwd_contrib, d, name + ".contrib", kind="bn_relu_bwd_apply", nbytes=blk.buf.P * C_ * 6)
         off = self._save.take(2 * C_, 4)
         kvec = self._save.buf[off:off + 2 * C_]
-
-        def run_fin(_a, stream, b=b, C_=C_, kvec=kvec, lib=self.lib):
-            return lib.dmm_bn_bwd_finalize(C.byref(b), C_, C.c_void_p(kvec.data_ptr()), stream)
-        self._emit(lst, run_fin, None, name + ".finalize", kind="bn_finalize", nbytes=C_ * 150)
+        if FUSE_FINALIZE:
+            # the last block of the contribution launch finalises dgamma / dbeta / k itself (ticket counters, zeroed per backward)
+            d.fin_k = kvec.data_ptr()
+            self._fin_req.append(d)
+        else:
+            def run_fin(_a, stream, b=b, C_=C_, kvec=kvec, lib=self.lib):
+                return lib.dmm_bn_bwd_finalize(C.byref(b), C_, C.c_void_p(kvec.data_ptr()), stream)
+            self._emit(lst, run_fin, None, name + ".finalize", kind="bn_finalize", nbytes=C_ * 150)
         self._keep.append(b)
         blk.contribs.append(dict(mat=slab, C=C_, k=kvec, mean=bn.save_mean, gw=gw))
 
@@ -1070,6 +1077,9 @@ class Engine:
                 self.segments.append((seg_ops, job_lo, job_i - job_lo, lo, hi))
                 self._seg_work.append(_work_table(self._unpack_sizes[job_lo:job_i], dev))
                 seg_ops, seg_names, job_lo = [], [], job_i
+        self._fin_ctr = torch.zeros(max(8 * len(self._fin_req), 8), dtype=torch.int32, device=dev)
+        for i, d in enumerate(self._fin_req):
+            d.fin_ctr = self._fin_ctr.data_ptr() + 4 * 8 * i
         self.gather_launches = 0
         for op, blk, c0, C_, dst, descs in self._gathers:
             srcs = [c for c in blk.contribs if c["C"] >= c0 + C_]
@@ -1228,6 +1238,8 @@ class Engine:
         the backward program in individual CUDA graphs with the gradient all-reduce between them)."""
         self._sums.zero_used()
         self._dw.zero_()
+        if self._fin_req:
+            self._fin_ctr.zero_()
 
     def backward_segment(self, i):
         """run backward segment i (stages whose parameter gradients form gradient bucket i); returns the bucket's range

@@ -305,6 +305,11 @@ typedef struct {
     int32_t out_gw;          /* dmm_bn_relu_bwd_contrib only: > 0 = "planar" slab, channel group g = c / out_gw is its own */
     int32_t pad_;            /* contiguous [rows, out_gw] matrix at out + g * out_plane (elements); ldo is ignored          */
     int64_t out_plane;
+    /* dmm_bn_relu_bwd_contrib only, optional: fuse dmm_bn_bwd_finalize into the launch.  fin_k: float[2][C] correction vectors;
+     * fin_ctr: uint32 ticket counters (one per 256-channel group of this launch, >= 8 entries), zeroed by the caller before
+     * every launch: the LAST block to finish a channel group reads the completed sums and writes dgamma / dbeta / k. */
+    float* fin_k;
+    uint32_t* fin_ctr;
 } dmm_bn_bwd_args_t;
 int dmm_bn_relu_bwd_reduce(const dmm_bn_bwd_args_t* d, void* stream);
 int dmm_bn_relu_bwd_apply(const dmm_bn_bwd_args_t* d, void* stream);
