@@ -238,3 +238,53 @@ def test_gather_chain_beyond_gather_max(monkeypatch):
         assert all(d.src[0] == dst.ptr().value and d.plane[0] == 0 for d in descs[1:])      # accumulator first
         assert sum(d.nsrc for d in descs) - (len(descs) - 1) == len([c_ for c_ in g[1].contribs if c_["C"] >= g[2] + g[3]])
     assert eng.gather_launches > len(eng._gathers)
+
+
+def test_inference_plan_folds_batchnorms_into_their_producers():
+    """eval-mode engines: norm2 -> conv1, decoder norm1 -> conv_reduce, head norm1 -> refine0 are folded (scaled
+    packed rows + bias / ReLU epilogue); what is left are the BatchNorms over multi-consumer block buffers and the pooled ones."""
+    from dmmfods_b200.engine import Engine
+    m = Dense_U_Net_lidar(_cfg(1, 3))
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    ev = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True, training=False, need_backward=False)
+    tr = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True, training=True, need_backward=False)
+    n_layers = 2 * (6 + 12) + 24 + 16
+    assert len(ev._fold_jobs) == n_layers + 4 + 1            # dense layers + decoder stages + head
+    assert len(tr._fold_jobs) == 0
+    assert len(ev.fwd) == len(tr.fwd) - len(ev._fold_jobs) - 1          # (- the input-statistics launch of training mode)
+    folded = [op for op in ev.fwd if op.kind == "igemm_fprop" and op.arg.epi_bias]
+    assert len(folded) == len(ev._fold_jobs) and all(op.arg.epi_relu == 1 and op.arg.out_mode == 0 for op in folded)
+    conv1 = [op for op in ev.fwd if op.name.endswith(".conv1")]
+    assert all(op.arg.pro_enable == 1 and op.arg.epi_bias for op in conv1)       # norm1 as prologue, norm2 as epilogue
+    assert not any(op.name.endswith(".norm2") for op in ev.fwd)
+    left = sorted(op.name for op in ev.fwd if op.kind == "bn_relu_apply")
+    assert len(left) == 16 and all(("norm0" in n) or ("norm+pool" in n) or ("concat_module" in n) for n in left), left
+
+
+@pytest.mark.parametrize("precision,dtype", [("tf32", 1), ("tf32x3", 2)])
+def test_strict_plan(precision, dtype):
+    """the strict forward plan: fp32 buffers, every convolution an unfused / unfolded dtype-1 (tf32) or dtype-2 (3xTF32) launch."""
+    from dmmfods_b200.engine import Engine
+    m = Dense_U_Net_lidar(_cfg(1, 3))
+    params = {k: (v.data if isinstance(v, torch.nn.Parameter) else v) for k, v in m.state_dict(keep_vars=True).items()}
+    eng = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True, need_backward=False, precision=precision)
+    convs = [op for op in eng.fwd if op.kind == "igemm_fprop"]
+    assert convs and all(op.arg.dtype == dtype and op.arg.kwidth == 32 and op.arg.out_mode in (0, 1) and not op.arg.pro_enable
+                         and not op.arg.fold_kw for op in convs)
+    from dmmfods_b200.ops import Mat
+    assert eng._wpk.dtype == torch.float32 and all(m_.t.dtype == torch.float32 for m_ in eng._keep if isinstance(m_, Mat))
+    if dtype == 2:          # [values ; remainders]: twice the packed weights
+        single = Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True, need_backward=False, precision="tf32")
+        assert eng._wpk.numel() == 2 * single._wpk.numel()
+    with pytest.raises(NotImplementedError):
+        Engine(params, m.model_cfg(), 1, 64, 96, plan_only=True, need_backward=True, precision=precision)
+
+
+def test_work_table_covers_every_element_once():
+    from dmmfods_b200.engine import WORK_CHUNK, _work_table
+    sizes = [1, WORK_CHUNK, WORK_CHUNK + 1, 5 * WORK_CHUNK - 3, 0, 64]
+    t = _work_table(sizes, "cpu")
+    assert t.dtype == torch.int32 and t.shape[1] == 2
+    for j, n in enumerate(sizes):
+        chunks = sorted(int(c) for jj, c in t.tolist() if jj == j)
+        assert chunks == list(range((n + WORK_CHUNK - 1) // WORK_CHUNK))
