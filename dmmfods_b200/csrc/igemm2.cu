@@ -923,7 +923,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
                 else { if (c.sb > sb1) c.sb = sb1; if (c.sb < 2) c.sb = 2; }
             }
             int sa = (avail - c.sb * b_stage_c) / (int)c.a_stage;
-            c.sa = sa > 4 ? 4 : sa;
+            static const int sa_cap1 = env_int("DMM_IGEMM_SA_CAP1", 4);      // 1x1 launches: cap of the A ring (prefetch depth)
+            const int sa_cap = max_taps == 1 ? sa_cap1 : 4;
+            c.sa = sa > sa_cap ? sa_cap : sa;
             c.tiles = (long long)ceil_div(d->W, fold ? c.TW - (d->fold_kw - 1) : c.TW) * ceil_div(d->H, c.TH) * d->B * tiles_n;
             // crude per-tile time (cycles): L2 -> smem bytes at 32 B/cycle/SM vs MMA time + stage hand-overs
             const double l2 = (double)nkb_total * pw * ph * 128.0 / 32.0;
@@ -955,7 +957,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
                     r.tps = tpk;
                     r.sb = stages_r;
                     int sa_r = (int)((avail - bytes_r) / (long long)c.a_stage);
-                    r.sa = sa_r > 4 ? 4 : sa_r;
+                    r.sa = sa_r > sa_cap ? sa_cap : sa_r;
                     double waits_r = 0;
                     for (int s = 0; s < d->num_src; ++s)
                         if (ntap[s]) waits_r += (double)p.src_nblk[s];
