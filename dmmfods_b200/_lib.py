@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmmfods_b200.so")
+# DMM_B200_LIB: an experiment build of the SAME sources (dmmfods_b200/build.py, DMM_BUILD_TAG); never a different implementation
+LIB_PATH = os.environ.get("DMM_B200_LIB") or os.path.join(_HERE, "libdmmfods_b200.so")
 
 MAX_SRC = 4
 MAX_TAPS = 32

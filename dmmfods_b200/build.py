@@ -9,13 +9,18 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CSRC = os.path.join(HERE, "csrc")
+CSRC = os.environ.get("DMM_BUILD_CSRC") or os.path.join(HERE, "csrc")      # experiment builds may compile another checkout's sources
 BUILD = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libdmmfods_b200.so")
+# experiment builds (scripts/): DMM_BUILD_DEFINES="-DX -DY" + DMM_BUILD_TAG=name -> objects in _build_<name>/, libdmmfods_b200_<name>.so;
+# the package loads such a library only when DMM_B200_LIB points at it
+_TAG = os.environ.get("DMM_BUILD_TAG", "")
+if _TAG:
+    BUILD += "_" + _TAG
+LIB = os.path.join(HERE, "libdmmfods_b200%s.so" % ("_" + _TAG if _TAG else ""))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 SOURCES = ["common.cu", "igemm.cu", "igemm2.cu", "wgrad.cu", "elementwise.cu", "scatter.cu", "strict.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-I", INCLUDE]
+              "-Xcompiler", "-fPIC", "-I", INCLUDE] + os.environ.get("DMM_BUILD_DEFINES", "").split()
 
 
 def _nvcc():

@@ -25,6 +25,21 @@
 #else
 #define DMM_PH(...)
 #endif
+// wait-time counters of the producer / MMA / epilogue loops: two clock reads per wait are compiled in only with the phase profile
+// (a 9-tap convolution paid 20 CS2R per tile inside the MMA issue path)
+#ifdef DMM_IGEMM_PHASE_PROF
+#define DMM_WAIT_T(ctr, ...) { const long long c0_ = clock64(); __VA_ARGS__; ctr += clock64() - c0_; }
+#else
+#define DMM_WAIT_T(ctr, ...) { __VA_ARGS__; }
+#endif
+// "what-if" timing experiments (results are garbage, only the clock counts): -DDMM_IGEMM_WHATIF + env DMM_IGEMM_WHATIF=<mask>
+//   1 no A loads  2 no B loads  4 no MMAs  8 no TMA stores  16 no statistics loop  32 no proxy fence in the epilogue
+//   64 no conversion / staging writes  128 prologue team does not transform
+#ifdef DMM_IGEMM_WHATIF
+#define DMM_WI(bit) (p.whatif & (bit))
+#else
+#define DMM_WI(bit) false
+#endif
 
 namespace dmm {
 
@@ -55,19 +70,22 @@ struct Ig2Params {
     int sub_x[kMaxSub], sub_y[kMaxSub];
     int msub, sub_w, sub_h;
     int W, H, B, TW, TH, tiles_x, tiles_y, tiles_n;
+    FastDiv fd_n, fd_x, fd_y;
     long long total_tiles;
     int n_tile, N;
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
     int w_res;                                      // weights RESIDENT: the CTA's whole weight slice is loaded once (sb = stages per tile)
     int tps;                                        // taps per weight stage
-    int tpk;                                        // taps per 64-wide K block of the weights: 1, or 4 (16-channel sources)
+    int tpk;                                        // taps per 64-wide K block of the weights: 1, 2 (32-channel sources) or 4 (16-channel sources)
+    int tpk_log;                                    // log2(tpk)
     int Wv, Hv;
     int x_step, x_org;             // tile column origin = tx * x_step + x_org (out_mode 2: tiles overlap by fold_kw - 1 columns)
     int nsx;                       // sub-tiles per tile row
     int fold_kw, fold_c;           // out_mode 2: kernel width folded into N, classes (<= 4)
     int tw_log, sw_log, sh_log;    // out_mode 2: log2 of TW, sub_w, sub_h
     long long* prof;     // debug (DMM_IGEMM_PROF=1): per-CTA cycle counters
+    int whatif;
     float* out32;
     int OH, OW, out_sy, out_sx, out_py, out_px;
     double* stats;
@@ -96,6 +114,43 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// packed fp32 pairs (sm_100 add.f32x2 / fma.rn.f32x2): the statistics of two neighbouring channels per instruction
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// bf16x2 word -> (fp32 of the low half, fp32 of the high half)
+__device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t u) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(u << 16), "r"(u & 0xffff0000u));
+    return d;
+}
+__device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+// Statistics of one staged [128 pixels x 64 channels] bf16 chunk, vectorised: thread (j = r & 7, g = r >> 3) owns the 16-byte chunk
+// j (channels 8j .. 8j+7) of rows g, g + 16, ..., g + 112 (8 x ld.shared.v4, the swizzled chunk position is the same for all of them),
+// and keeps sum / sum of squares of its 8 channels as 8 packed fp32 pairs ACROSS all chunks of the CTA (acc[0..3] sums, acc[4..7] squares).
+__device__ __forceinline__ void stats_chunk_v(uint32_t sbase, uint64_t* acc) {
+    uint4 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = lds_v4(sbase + i * 2048);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t u[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t v = bf16x2_to_f2(u[k]);
+            acc[k] = f2_add(acc[k], v);
+            acc[4 + k] = f2_fma(v, v, acc[4 + k]);
+        }
+    }
+}
 __device__ __forceinline__ void epi_bar(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
 // upper 32 bits of a K-major SWIZZLE_128B shared-memory descriptor (SBO, descriptor version 1, layout type 2); the
@@ -104,17 +159,15 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) &
 struct TileCoord {
     int b, x0, y0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t) {
+__device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long tile) {
     TileCoord c;
-    const int nt = (int)(t % p.tiles_n);
-    t /= p.tiles_n;
-    const int tx = (int)(t % p.tiles_x);
-    t /= p.tiles_x;
-    const int ty = (int)(t % p.tiles_y);
-    c.b = (int)(t / p.tiles_y);
-    c.x0 = tx * p.x_step + p.x_org;
-    c.y0 = ty * p.TH;
-    c.n0 = nt * p.n_tile;
+    uint32_t nt, tx, ty;
+    uint32_t t = fast_divmod((uint32_t)tile, p.fd_n, nt);      // total_tiles < 2^31 (checked by the launcher)
+    t = fast_divmod(t, p.fd_x, tx);
+    c.b = (int)fast_divmod(t, p.fd_y, ty);
+    c.x0 = (int)tx * p.x_step + p.x_org;
+    c.y0 = (int)ty * p.TH;
+    c.n0 = (int)nt * p.n_tile;
     return c;
 }
 
@@ -212,16 +265,14 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     const int t0 = p.src_tap0[s], t1 = p.src_tap0[s + 1];
                     if (t0 == t1) continue;
                     for (int cb = 0; cb < nblk; ++cb) {
-                        long long c0;
                         for (int t = t0; t < t1; t += p.tps) {
                             const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
-                            c0 = clock64();
-                            if (!p.w_res) mbar_wait(&b_empty[bst], bph ^ 1);
-                            w_b += clock64() - c0;
-                            const int nblk_b = (nt + p.tpk - 1) / p.tpk;
-                            mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nblk_b * p.b_tap);
+                            DMM_WAIT_T(w_b, if (!p.w_res) mbar_wait(&b_empty[bst], bph ^ 1));
+                            const int nblk_b = (nt + p.tpk - 1) >> p.tpk_log;
+                            if (DMM_WI(2)) mbar_arrive(&b_full[bst]);
+                            else mbar_arrive_expect_tx(&b_full[bst], (uint32_t)nblk_b * p.b_tap);
                             uint8_t* bdst = b_ring + (size_t)bst * p.b_stage;
-                            for (int j = 0; j < nblk_b; ++j)
+                            for (int j = 0; j < nblk_b && !DMM_WI(2); ++j)
                                 tma_load_2d(bdst + (size_t)j * p.b_tap, &p.b_map, &b_full[bst], (p.tap_kb0[t + j * p.tpk] + cb) * 64, tc.n0);
                             if (++bst == p.sb) { bst = 0; bph ^= 1; }
                         }
@@ -246,9 +297,12 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     const int nblk = p.src_nblk[s];
                     for (int cb = 0; cb < nblk; ++cb) {
                         mbar_wait(&a_empty[ast], aph ^ 1);
+                        if (DMM_WI(1)) mbar_arrive(&a_full[ast]);
+                        else {
                         mbar_arrive_expect_tx(&a_full[ast], p.src_tx[s]);
                         tma_load_4d(a_ring + (size_t)ast * p.a_stage, &p.a_maps[s], &a_full[ast], cb * 64, tc.x0 + p.src_ox[s],
                                     tc.y0 + p.src_oy[s], tc.b);
+                        }
                         if (++ast == p.sa) { ast = 0; aph ^= 1; }
                     }
                 }
@@ -268,12 +322,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint32_t aph = 0, bph = 0;
         uint32_t it = 0;
         long long w_a = 0, w_b = 0, w_acc = 0;
+        DMM_PH(long long ph_taps = 0, ph_hdr = 0;)      // cycles inside the elected issue block / between a k-block's operand wait and it
         const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const uint32_t as = it & 1, accph = (it >> 1) & 1;
-            long long c0 = clock64();
-            mbar_wait(&acc_empty[as], accph ^ 1);
-            w_acc += clock64() - c0;
+            DMM_WAIT_T(w_acc, mbar_wait(&acc_empty[as], accph ^ 1));
             tc_fence_after();
             const uint32_t d0 = tmem_u + as * MSUB * p.n_tile;
             uint32_t acc0 = 0;      // 0 only for the first MMA of every accumulator of this tile
@@ -286,43 +339,48 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
 #pragma unroll
                 for (int i = 0; i < MSUB; ++i) so[i] = p.sub_aoff[s][i] >> 4;
                 for (int cb = 0; cb < nblk; ++cb) {
-                    c0 = clock64();
-                    mbar_wait(PRO ? &a_ready[ast] : &a_full[ast], aph);
-                    w_a += clock64() - c0;
+                    DMM_WAIT_T(w_a, mbar_wait(PRO ? &a_ready[ast] : &a_full[ast], aph));
+                    DMM_PH(const long long h0 = clock64();)
                     const uint32_t a_lo = ((a_ring_u + (uint32_t)ast * p.a_stage) >> 4) | (1u << 16);
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
-                    for (int t = t0; t < t1; t += p.tps) {
-                        const int nt = (t1 - t) < p.tps ? (t1 - t) : p.tps;
-                        c0 = clock64();
-                        if (!p.w_res || it == 0) mbar_wait(&b_full[bst], bph);
-                        w_b += clock64() - c0;
+                    // resident weights, after the CTA's first tile: nothing to wait for, and the (tap group, k-block) slots of one
+                    // k-block are consecutive in the ring - all taps are issued from ONE elected block (no per-tap loop overhead)
+                    const bool fused = p.w_res && it > 0;
+                    const int tstep = fused ? (t1 - t0) : p.tps;
+                    for (int t = t0; t < t1; t += tstep) {
+                        const int nt = (t1 - t) < tstep ? (t1 - t) : tstep;
+                        if (!fused) DMM_WAIT_T(w_b, if (!p.w_res || it == 0) mbar_wait(&b_full[bst], bph));
                         tc_fence_after();
                         if (elect_one()) {
+                            DMM_PH(const long long h1 = clock64(); if (t == t0) ph_hdr += h1 - h0;)
                             const uint32_t b_lo0 = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
                             uint32_t aoff = p.tap_aoff[t] >> 4;
+                            const uint32_t tpk_mask = (uint32_t)p.tpk - 1u, tap_sub = 8u >> p.tpk_log, b_tap16 = p.b_tap >> 4;
                             for (int j = 0; j < nt; ++j) {
                                 const uint32_t a_tap = a_lo + aoff;
-                                // weights of tap j: own 64-wide block, or (16-channel sources) a quarter of a shared block
-                                const uint32_t b_lo = b_lo0 + (p.tpk == 1 ? (uint32_t)j * (p.b_tap >> 4)
-                                                                          : (uint32_t)(j / p.tpk) * (p.b_tap >> 4) + (uint32_t)(j % p.tpk) * (8u / p.tpk));
+                                // weights of tap j: own 64-wide block, or (16 / 32-channel sources) a quarter / half of a shared block
+                                const uint32_t b_lo = b_lo0 + ((uint32_t)j >> p.tpk_log) * b_tap16 + ((uint32_t)j & tpk_mask) * tap_sub;
                                 if (j + 1 < nt) aoff = p.tap_aoff[t + j + 1] >> 4;      // prefetch the next tap's offset
                                 // fully unrolled per k-step count: keeps the descriptor arithmetic in uniform registers
 #define DMM_ISSUE_TAP(KS)                                                                                                       \
     _Pragma("unroll") for (int k = 0; k < KS; ++k) _Pragma("unroll") for (int sub = 0; sub < MSUB; ++sub)                      \
         umma_bf16(d0 + sub * p.n_tile, ahi | (a_tap + so[sub] + 2 * k), bhi | (b_lo + 2 * k), idesc, k == 0 ? acc0 : 1u)
-                                if (ksteps == 4) { DMM_ISSUE_TAP(4); }
+                                if (DMM_WI(4)) {}
+                                else if (ksteps == 4) { DMM_ISSUE_TAP(4); }
                                 else if (ksteps == 1) { DMM_ISSUE_TAP(1); }
                                 else if (ksteps == 2) { DMM_ISSUE_TAP(2); }
                                 else { DMM_ISSUE_TAP(3); }
 #undef DMM_ISSUE_TAP
                                 acc0 = 1;
                             }
+                            DMM_PH(ph_taps += clock64() - h1;)
                             if (!p.w_res) umma_commit(&b_empty[bst]);
                             if (t + nt == t1) umma_commit(&a_empty[ast]);
                         }
                         __syncwarp();
                         acc0 = 1;
-                        if (++bst == p.sb) { bst = 0; bph ^= 1; }
+                        bst += fused ? ((nt + p.tpk - 1) >> p.tpk_log) : 1;
+                        if (bst >= p.sb) { bst -= p.sb; bph ^= 1; }
                     }
                     if (++ast == p.sa) { ast = 0; aph ^= 1; }
                 }
@@ -336,6 +394,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             p.prof[blockIdx.x * 16 + 6] = w_b;
             p.prof[blockIdx.x * 16 + 7] = w_acc;
         }
+        DMM_PH(if (p.prof && elect_one()) { p.prof[blockIdx.x * 16 + 1] = ph_taps; p.prof[blockIdx.x * 16 + 3] = ph_hdr; })
     } else {
         // ================= epilogue: two teams of 4 warps, alternating 64-column chunks =================
         const int team = (warp - 2) >> 2;
@@ -387,7 +446,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             pc += 16;
                             while (pc >= p.pro_pw) { pc -= p.pro_pw; ++pr; }
                         }
-                    } else {
+                    } else if (!DMM_WI(128)) {
 #pragma unroll 4
                     for (int r = e >> 3; r < rows; r += 16) {
                         const uint32_t ptr = base + r * 128 + ((j ^ (r & 7)) << 4);
@@ -427,11 +486,61 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint8_t* xslot = xstg + team * kStageSlot;
         uint32_t x_phase = 0;
         const uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow), xslot_u = smem_u32(xslot);
-        double sacc[NCH][4];
+        // VSTATS (n_tile <= 128, no fused BN backward): vectorised statistics, accumulators = 8 packed fp32 pairs per 64-channel block;
+        // otherwise 4 doubles per block (column pair cp of row quarter rq), stored in the same registers
+        constexpr bool VS = NCH <= 2;
+        const bool vstats = VS && !p.bnb;
+        const uint32_t sbase = slot_u + (uint32_t)(r >> 3) * 128u + (uint32_t)(((r & 7) ^ ((r >> 3) & 7)) << 4);
+        uint64_t sraw[NCH][VS ? 8 : 4];
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sacc[c][j] = 0.0;
+            for (int j = 0; j < (VS ? 8 : 4); ++j) sraw[c][j] = 0ull;
+#define sacc_add(c, j, x) sraw[c][j] = (uint64_t)__double_as_longlong(__longlong_as_double((long long)sraw[c][j]) + (double)(x))
+#define sacc_get(c, j) __longlong_as_double((long long)sraw[c][j])
+        // flush the accumulators of this thread into the global statistics slots (channel block c starts at column n0 + 64 c)
+        auto flush_stats = [&](int n0) {
+            double* st = p.stats + (size_t)(blockIdx.x % DMM_STATS_SLOTS) * 2 * p.stats_ld + p.stats_off;
+            const int lim_l = FOLD3 ? p.fold_c : p.n_tile, lim_g = FOLD3 ? p.fold_c : p.N;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (vstats) {
+                    if constexpr (VS) {
+                        // the 4 lanes of a warp that share j (lane bits 3, 4 = row groups) are summed first: 16 atomics in 8 lanes
+                        float v[16];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { v[2 * k] = f2_lo(sraw[c][k]); v[2 * k + 1] = f2_hi(sraw[c][k]); }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+                            v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+                        }
+                        if (lane < 8) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int cl = c * 64 + 8 * lane + e, col = n0 + cl;
+                                if (cl < lim_l && col < lim_g) {
+                                    atomicAdd(st + col, (double)v[e]);
+                                    atomicAdd(st + p.stats_ld + col, (double)v[8 + e]);
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    const int col = n0 + c * 64 + 2 * cp;
+                    if (c * 64 + 2 * cp < lim_l && col < lim_g) {
+                        atomicAdd(st + col, sacc_get(c, 0));
+                        atomicAdd(st + p.stats_ld + col, p.bnb ? sacc_get(c, 2) * (double)p.bnb_invstd[col] : sacc_get(c, 2));
+                        if (col + 1 < lim_g) {
+                            atomicAdd(st + col + 1, sacc_get(c, 1));
+                            atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc_get(c, 3) * (double)p.bnb_invstd[col + 1] : sacc_get(c, 3));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < (VS ? 8 : 4); ++j) sraw[c][j] = 0ull;
+            }
+        };
         uint32_t chunk_ctr = 0;
         uint32_t it = 0;
         int last_n0 = 0;
@@ -442,9 +551,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             const TileCoord tc = decode_tile(p, tile);
             const uint32_t as = it & 1, accph = (it >> 1) & 1;
             last_n0 = tc.n0;
-            const long long c0 = clock64();
-            mbar_wait(&acc_full[as], accph);
-            w_full += clock64() - c0;
+            DMM_WAIT_T(w_full, mbar_wait(&acc_full[as], accph));
             tc_fence_after();
             if (OUT_MODE == 2) {
                 // kernel columns folded into N: stage the fp32 accumulators of the whole tile, then every output pixel sums its
@@ -550,18 +657,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         bulk_commit();
                     }
                     if (do_stats) {
-                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                        const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
-                        const int j = cp >> 2;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t u = lds_u32(base + i * 128 + ((j ^ (i & 7)) << 4));
-                            const float a = bf16_lo(u), b = bf16_hi(u);
-                            s1a += a; s1b += b;
-                            s2a = fmaf(a, a, s2a); s2b = fmaf(b, b, s2b);
-                        }
-                        sacc[0][0] += (double)s1a; sacc[0][1] += (double)s1b;
-                        sacc[0][2] += (double)s2a; sacc[0][3] += (double)s2b;
+                        if constexpr (VS) stats_chunk_v(sbase, sraw[0]);      // chunks beyond FC hold stale bytes: never flushed
                     }
                 } else if (OUT_MODE == 0) {
 #pragma unroll
@@ -569,10 +665,13 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         if (tc.n0 + 64 * c >= p.N) break;
                         if (((chunk_ctr++) & 1) != (uint32_t)team) continue;
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
-                        uint32_t v[4][16];
+                        // accumulator columns are read GL groups of 16 at a time: all four at once, or (prologue instantiations,
+                        // 128 registers per thread) two and two so that the statistics accumulators need not be spilled
+                        constexpr int GL = PRO ? 2 : 4;
+                        uint32_t v[GL][16];
                         DMM_PH(const long long e0 = clock64();)
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
+                        for (int g = 0; g < GL; ++g)
                             if (g < ngrp) tmem_ld16(trow + c * 64 + g * 16, v[g]);
                         if (r == 0) bulk_wait_read0();       // the team's previous TMA store has finished reading the slot
                         DMM_PH(const long long e1 = clock64();)
@@ -584,57 +683,69 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             mbar_arrive_expect_tx(&x_bar[team], kStageSlot);
                             tma_load_4d(xslot, &p.x_map, &x_bar[team], tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                         }
-                        if (p.epi_bias) {
-                            // folded BatchNorm shift (+ ReLU) on the fp32 accumulators; the bias vector is padded to n_rows entries
-                            const float4* bp = reinterpret_cast<const float4*>(p.epi_bias + tc.n0 + 64 * c);
-                            const float lo = p.epi_relu ? 0.f : -INFINITY;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (g < ngrp) {
-                                    asm volatile("" ::: "memory");        // keep the 4 bias loads of one group together: 16 hoisted float4 spill
+                        for (int h = 0; h < 4 / GL; ++h) {
+                            if (h > 0) {
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        const float4 b4 = __ldg(bp + 4 * g + q);
-                                        v[g][4 * q + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 0]) + b4.x, lo));
-                                        v[g][4 * q + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 1]) + b4.y, lo));
-                                        v[g][4 * q + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 2]) + b4.z, lo));
-                                        v[g][4 * q + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 3]) + b4.w, lo));
+                                for (int g = 0; g < GL; ++g)
+                                    if (h * GL + g < ngrp) tmem_ld16(trow + c * 64 + (h * GL + g) * 16, v[g]);
+                                tmem_ld_wait();
+                            }
+                            if (p.epi_bias) {
+                                // folded BatchNorm shift (+ ReLU) on the fp32 accumulators; the bias vector is padded to n_rows entries
+                                const float4* bp = reinterpret_cast<const float4*>(p.epi_bias + tc.n0 + 64 * c);
+                                const float lo = p.epi_relu ? 0.f : -INFINITY;
+#pragma unroll
+                                for (int g = 0; g < GL; ++g) {
+                                    if (h * GL + g < ngrp) {
+                                        asm volatile("" ::: "memory");        // keep the 4 bias loads of one group together: 16 hoisted float4 spill
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) {
+                                            const float4 b4 = __ldg(bp + 4 * (h * GL + g) + q);
+                                            v[g][4 * q + 0] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 0]) + b4.x, lo));
+                                            v[g][4 * q + 1] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 1]) + b4.y, lo));
+                                            v[g][4 * q + 2] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 2]) + b4.z, lo));
+                                            v[g][4 * q + 3] = __float_as_uint(fmaxf(__uint_as_float(v[g][4 * q + 3]) + b4.w, lo));
+                                        }
                                     }
                                 }
                             }
-                        }
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (g < ngrp) {
-                                uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
-                                if (valid) {
-                                    w0.x = pack_bf16x2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1]));
-                                    w0.y = pack_bf16x2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3]));
-                                    w0.z = pack_bf16x2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5]));
-                                    w0.w = pack_bf16x2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7]));
-                                    w1.x = pack_bf16x2(__uint_as_float(v[g][8]), __uint_as_float(v[g][9]));
-                                    w1.y = pack_bf16x2(__uint_as_float(v[g][10]), __uint_as_float(v[g][11]));
-                                    w1.z = pack_bf16x2(__uint_as_float(v[g][12]), __uint_as_float(v[g][13]));
-                                    w1.w = pack_bf16x2(__uint_as_float(v[g][14]), __uint_as_float(v[g][15]));
+                            for (int g = 0; g < GL; ++g) {
+                                const int gg = h * GL + g;
+                                if (gg < ngrp && !DMM_WI(64)) {
+                                    uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+                                    if (valid) {
+                                        w0.x = pack_bf16x2(__uint_as_float(v[g][0]), __uint_as_float(v[g][1]));
+                                        w0.y = pack_bf16x2(__uint_as_float(v[g][2]), __uint_as_float(v[g][3]));
+                                        w0.z = pack_bf16x2(__uint_as_float(v[g][4]), __uint_as_float(v[g][5]));
+                                        w0.w = pack_bf16x2(__uint_as_float(v[g][6]), __uint_as_float(v[g][7]));
+                                        w1.x = pack_bf16x2(__uint_as_float(v[g][8]), __uint_as_float(v[g][9]));
+                                        w1.y = pack_bf16x2(__uint_as_float(v[g][10]), __uint_as_float(v[g][11]));
+                                        w1.z = pack_bf16x2(__uint_as_float(v[g][12]), __uint_as_float(v[g][13]));
+                                        w1.w = pack_bf16x2(__uint_as_float(v[g][14]), __uint_as_float(v[g][15]));
+                                    }
+                                    sts_v4(srow_u + (((2 * gg) ^ (r & 7)) << 4), w0);
+                                    sts_v4(srow_u + (((2 * gg + 1) ^ (r & 7)) << 4), w1);
                                 }
-                                sts_v4(srow_u + (((2 * g) ^ (r & 7)) << 4), w0);
-                                sts_v4(srow_u + (((2 * g + 1) ^ (r & 7)) << 4), w1);
                             }
                         }
-                        fence_proxy_async();
+                        if (!DMM_WI(32)) fence_proxy_async();
                         DMM_PH(const long long e4 = clock64();)
                         epi_bar(team);
                         DMM_PH(const long long e5 = clock64();)
-                        if (r == 0) {
+                        if (r == 0 && !DMM_WI(8)) {
                             tma_store_4d(&p.o_map, slot, tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
                             bulk_commit();
                         }
                         DMM_PH(ph_pack += e4 - e3; ph_bar2 += e5 - e4; const long long e6 = clock64();)
-                        if (do_stats) {
+                        if (do_stats && !DMM_WI(16)) {
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
                             const int j = cp >> 2;
-                            if (!p.bnb) {
+                            if (vstats) {
+                                if constexpr (VS) stats_chunk_v(sbase, sraw[c]);
+                            } else if (!p.bnb) {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     // row = rq*32 + i: (row & 7) == (i & 7), a compile-time pattern after unrolling
@@ -672,8 +783,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                                     s2a = fmaf(a, xa - mu0, s2a); s2b = fmaf(b, xb - mu1, s2b);
                                 }
                             }
-                            sacc[c][0] += (double)s1a; sacc[c][1] += (double)s1b;
-                            sacc[c][2] += (double)s2a; sacc[c][3] += (double)s2b;
+                            if (!vstats) {
+                                sacc_add(c, 0, s1a); sacc_add(c, 1, s1b);
+                                sacc_add(c, 2, s2a); sacc_add(c, 3, s2b);
+                            }
                         }
                         DMM_PH(ph_stats += clock64() - e6;)
                     }
@@ -697,39 +810,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
-            if (do_stats && p.tiles_n > 1) {
-                double* st = p.stats + (size_t)(blockIdx.x % DMM_STATS_SLOTS) * 2 * p.stats_ld + p.stats_off;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    const int col = tc.n0 + c * 64 + 2 * cp;
-                    if (c * 64 + 2 * cp < (FOLD3 ? p.fold_c : p.n_tile) && col < (FOLD3 ? p.fold_c : p.N)) {
-                        atomicAdd(st + col, sacc[c][0]);
-                        atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                        if (col + 1 < (FOLD3 ? p.fold_c : p.N)) {
-                            atomicAdd(st + col + 1, sacc[c][1]);
-                            atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) sacc[c][j] = 0.0;
-                }
-            }
+            if (do_stats && p.tiles_n > 1) flush_stats(tc.n0);
         }
-        if (do_stats && p.tiles_n == 1 && it > 0) {
-            double* st = p.stats + (size_t)(blockIdx.x % DMM_STATS_SLOTS) * 2 * p.stats_ld + p.stats_off;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const int col = last_n0 + c * 64 + 2 * cp;
-                if (c * 64 + 2 * cp < (FOLD3 ? p.fold_c : p.n_tile) && col < (FOLD3 ? p.fold_c : p.N)) {
-                    atomicAdd(st + col, sacc[c][0]);
-                    atomicAdd(st + p.stats_ld + col, p.bnb ? sacc[c][2] * (double)p.bnb_invstd[col] : sacc[c][2]);
-                    if (col + 1 < (FOLD3 ? p.fold_c : p.N)) {
-                        atomicAdd(st + col + 1, sacc[c][1]);
-                        atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc[c][3] * (double)p.bnb_invstd[col + 1] : sacc[c][3]);
-                    }
-                }
-            }
-        }
+        if (do_stats && p.tiles_n == 1 && it > 0) flush_stats(last_n0);
+#undef sacc_add
+#undef sacc_get
         if ((OUT_MODE == 0 || FOLD3) && r == 0) bulk_wait_all();
         if (p.prof && r == 0 && team == 0) {
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
@@ -977,6 +1062,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.sa = best.sa; p.sb = best.sb;
     p.w_res = best.w_res;
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
+    p.tpk_log = tpk == 4 ? 2 : (tpk == 2 ? 1 : 0);
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
     p.x_step = fold ? p.TW - (d->fold_kw - 1) : p.TW;
     p.x_org = fold ? -(d->fold_kw / 2) : 0;
@@ -994,6 +1080,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.tiles_x = ceil_div(d->W, p.x_step);
     p.tiles_y = ceil_div(d->H, p.TH);
     p.tiles_n = tiles_n;
+    DMM_CHECK(best.tiles < (1ll << 31), "igemm v2: %lld tiles", best.tiles);
+    p.fd_n = make_fastdiv(p.tiles_n); p.fd_x = make_fastdiv(p.tiles_x); p.fd_y = make_fastdiv(p.tiles_y);
     p.total_tiles = best.tiles;
     p.W = d->W; p.H = d->H; p.B = d->B;
     p.n_tile = d->n_tile; p.N = d->N;
@@ -1120,6 +1208,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     }
     static const int prof = env_int("DMM_IGEMM_PROF", 0);
     static long long* prof_buf = nullptr;
+#ifdef DMM_IGEMM_WHATIF
+    p.whatif = env_int("DMM_IGEMM_WHATIF", 0);
+#endif
     if (prof) {
         if (!prof_buf) DMM_CUDA(cudaMalloc(&prof_buf, 160 * 16 * sizeof(long long)));
         DMM_CUDA(cudaMemsetAsync(prof_buf, 0, 160 * 16 * sizeof(long long), stream));
@@ -1135,8 +1226,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             for (int j = 0; j < 16; ++j) a[j] += (double)h[i * 16 + j] / grid;
         fprintf(stderr,
                 "[ig2] tiles %lld grid %u msub %d n_tile %d TWxTH %dx%d sa %d sb %d tps %d wres %d a_stage %u | producer total %.0f wait a_empty %.0f b_empty %.0f | "
-                "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f | epilogue total %.0f wait acc_full %.0f | team 0 phases: store-read wait %.0f tmem %.0f bar1 %.0f pack %.0f bar2 %.0f stats %.0f (cycles, CTA average)\n",
-                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.w_res, p.a_stage, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
+                "mma total %.0f wait a_full %.0f b_full %.0f acc_empty %.0f (issue blocks %.0f, k-block headers %.0f) | epilogue total %.0f wait acc_full %.0f | team 0 phases: store-read wait %.0f tmem %.0f bar1 %.0f pack %.0f bar2 %.0f stats %.0f (cycles, CTA average)\n",
+                p.total_tiles, grid, p.msub, p.n_tile, p.TW, p.TH, p.sa, p.sb, p.tps, p.w_res, p.a_stage, a[0], 0.0, a[2], a[4], a[5], a[6], a[7], a[1], a[3], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]);
     }
     DMM_LAUNCH_CHECK("igemm2_kernel");
     return 0;

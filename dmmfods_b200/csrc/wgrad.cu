@@ -56,6 +56,7 @@ struct WgradKParams {
     uint32_t sg_lbo[DMM_WG_MAX_B];
     int ya, yb, a_step, b_step;
     int kpx, tile_w, tile_h, tiles_x, tiles_y;
+    FastDiv fd_x, fd_y;
     long long total_tiles;
     int splits;
     int stages;
@@ -159,12 +160,10 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                 int s = 0;
                 uint32_t ph = 0;
                 for (int kb = 0; kb < num_k; ++kb) {
-                    long long t = tile_lo + kb;
-                    const int tx = (int)(t % p.tiles_x);
-                    t /= p.tiles_x;
-                    const int ty = (int)(t % p.tiles_y);
-                    const int b = (int)(t / p.tiles_y);
-                    const int x0 = tx * p.tile_w, y0 = ty * p.tile_h;
+                    uint32_t tx, ty;
+                    const uint32_t trow = fast_divmod((uint32_t)(tile_lo + kb), p.fd_x, tx);      // total_tiles < 2^31 (checked by the launcher)
+                    const int b = (int)fast_divmod(trow, p.fd_y, ty);
+                    const int x0 = (int)tx * p.tile_w, y0 = (int)ty * p.tile_h;
                     const long long c0 = clock64();
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     w_e += clock64() - c0;
@@ -257,9 +256,10 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                 for (int kb = 0; kb < num_k; ++kb) {
                     int mx0 = 0, my0 = 0;
                     if (p.pro_mask) {
-                        long long t = tile_lo + kb;
-                        mx0 = (int)(t % p.tiles_x) * p.tile_w;
-                        my0 = (int)((t / p.tiles_x) % p.tiles_y) * p.tile_h;
+                        uint32_t tx, ty;
+                        fast_divmod(fast_divmod((uint32_t)(tile_lo + kb), p.fd_x, tx), p.fd_y, ty);
+                        mx0 = (int)tx * p.tile_w;
+                        my0 = (int)ty * p.tile_h;
                     }
                     mbar_wait(&full_bar[s], ph);
                     uint8_t* sa = smem + (size_t)s * p.stage_bytes;
@@ -519,6 +519,8 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
     p.tiles_x = ceil_div(d->W, p.tile_w);
     p.tiles_y = ceil_div(d->H, p.tile_h);
     p.total_tiles = (long long)p.tiles_x * p.tiles_y * d->B;
+    DMM_CHECK(p.total_tiles < (1ll << 31), "dmm_conv_wgrad: %lld tiles", p.total_tiles);
+    p.fd_x = make_fastdiv(p.tiles_x); p.fd_y = make_fastdiv(p.tiles_y);
     p.stage_bytes = p.a_chunk_bytes * 2 * na + b_part;
     p.stage_bytes = (p.stage_bytes + 1023u) & ~1023u;
     int stages = (int)((200u * 1024u) / p.stage_bytes);

@@ -42,6 +42,8 @@ FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE
 
 # data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
 PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
+# the reduce pass of norm2's backward inside the growth convolutions' data gradient (igemm epilogue) or as its own launch
+CONV2_DGRAD_FUSED = os.environ.get("DMM_CONV2_DGRAD_FUSED", "1") != "0"
 DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "8"))       # 64 (128-byte aligned rows) measured = (88.3 vs 87.9 ms): dense pitch kept
 # inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
 # the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
@@ -672,7 +674,7 @@ class Engine:
                                      [go.view(0, k)], conv3x3[0], conv3x3[2], bnk, k, bnk, k, bnk * 9, 9, Wb, Hb, B,
                                      pro=bn2 if a2 is None else None)
                     dg2 = self._conv_dgrad(st, lp + ".conv2.dgrad", lp + ".conv2.weight", [go.view(0, k)], conv3x3[1], conv3x3[2],
-                                           k, bnk, 9, bnk * 9, Wb, Hb, B, da2)
+                                           k, bnk, 9, bnk * 9, Wb, Hb, B, da2, heavy=CONV2_DGRAD_FUSED)
                     self._bn_bwd(st, lp + ".norm2.bwd", bn2, z1, 0, bnk, da2.ptr(), da2.ld, dz1.ptr(), dz1.ld, 0, producer=dg2)
                     if a1 is None:
                         self._conv_wgrad(st, lp + ".conv1.wgrad", lp + ".conv1.weight", blk.buf.view(0, Ci), [dz1.view()],

@@ -350,6 +350,7 @@ def plan_conv_wgrad(x, ys, taps, M, N):
     # general: one launch per tap, A = activation shifted by +tap, B = output gradient in 128-channel groups
     nb = 1 if N <= 128 else 2
     na = max(1, min(4 // nb, (mch + 1) // 2))
+    na = max(1, min(na, int(os.environ.get("DMM_WGRAD_NA", "4"))))      # experiment knob: m-tiles per CTA
     n_slots = min(2 * na, mch)
     npad = ceil_to(N, 128)
     ya = (mch + 2 * na - 1) // (2 * na)

@@ -33,13 +33,20 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "b3_conv1_dgrad_n640": (32, 40, 60, 128, 640, 1, 0),
     "b3_conv1_dgrad_n992": (32, 40, 60, 128, 992, 1, 0),
     "b4_conv1_dgrad_n768": (32, 20, 30, 128, 768, 1, 0),
+    # growth convolution data gradient as the engine launches it: two 32-channel taps per 64-wide K block (kwidth 32) and the
+    # reduce pass of norm2's backward fused into the epilogue (out_mode 5 here)
+    "b1_conv2_dgrad_bnb": (32, 160, 240, 32, 128, 3, 5),
+    "b2_conv2_dgrad_bnb": (32, 80, 120, 32, 128, 3, 5),
+    "b3_conv2_dgrad_bnb": (32, 40, 60, 32, 128, 3, 5),
+    "b1_conv2_dgrad_k32": (32, 160, 240, 32, 128, 3, 6),        # same without the fused reduce
 }
 
 def run(name, reps=5):
     B, H, W, Cin, Cout, K, om = CASES[name]
     torch.manual_seed(0)
     pro = om == 2
-    if pro:
+    bnb, k32 = om == 5, om in (5, 6)
+    if pro or k32:
         om = 0
     ld = ops.ceil_to(Cin, 8) if not pro else (256 if Cin <= 256 else (512 if Cin <= 512 else 1024))
     a = ops.Mat((torch.randn(B * H * W, ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
@@ -50,7 +57,7 @@ def run(name, reps=5):
     else:
         taps = ops.conv_taps(K, (K - 1) // 2)[0]
     T = len(taps)
-    kwidth = 16 if (Cin <= 16 and T > 1) else 64
+    kwidth = 16 if (Cin <= 16 and T > 1) else (32 if k32 else 64)
     Kp = ops.ceil_to(Cin, kwidth)
     n_tile = ops.pick_n_tile(Cout)
     n_rows = ops.ceil_to(Cout, n_tile)
@@ -58,8 +65,18 @@ def run(name, reps=5):
     if om == 0:
         out = ops.new_mat(B, H, W, ops.ceil_to(Cout, 8))
         st = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
+        # data gradients of the network carry no statistics: IG_NOSTATS=1 (or a "dgrad" case name) drops them
+        nostats = os.environ.get("IG_NOSTATS", "0") != "0" or "dgrad" in name
+        if bnb:
+            xr = ops.Mat((torch.randn(B * H * W, out.ld, device="cuda") * 0.5).to(torch.bfloat16), B, H, W)
+            sums = torch.zeros(ops.Stats.size(out.ld), dtype=torch.float64, device="cuda")
+            g_, b2_, sm_, si_ = (torch.rand(out.ld, device="cuda") for _ in range(4))
+            bb = ops.make_bn_bwd(ops.Stats(sums, 0, out.ld), 0, B * H * W, g_, b2_, sm_, si_)
+            keep2 = (xr, sums, g_, b2_, sm_, si_, bb)
         d = ops.make_igemm([a.view(0, Cin)], taps, wp, T * Kp, n_rows, W, H, B, Cout, out.ptr(), out.ld,
-                           stats=ops.Stats(st, 0, out.ld), n_tile=n_tile, kwidth=kwidth)
+                           stats=None if nostats else ops.Stats(st, 0, out.ld), n_tile=n_tile, kwidth=kwidth)
+        if bnb:
+            ops.fuse_bn_bwd_reduce(d, xr, 0, bb)
         if pro:
             bst = torch.rand(ops.Stats.size(ld), dtype=torch.float64, device="cuda") * 1000 + 5000
             g, b_ = torch.ones(ld, device="cuda"), torch.zeros(ld, device="cuda")

@@ -15,6 +15,9 @@ CASES = {   # name: (B, H, W, Cin(M), Cout(N), K)
     "refine0": (32, 640, 960, 132, 64, 3),
     "reduce4": (32, 160, 240, 512, 128, 1),
     "reduce1": (32, 20, 30, 1024, 1024, 1),
+    "b3_conv1_k1024": (32, 40, 60, 1024, 128, 1),
+    "b4_conv1_k1024": (32, 20, 30, 1024, 128, 1),
+    "b2_conv1_k512": (32, 80, 120, 512, 128, 1),
 }
 
 def run(name, reps=5):
@@ -31,10 +34,14 @@ def run(name, reps=5):
             ops.run_wgrad(d)
     go(); torch.cuda.synchronize()
     ts = []
+    inner = int(os.environ.get("WG_INNER", "20"))       # back-to-back launches per timing: keeps the clocks up, hides launch latency
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); go(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record()
+        for _i in range(inner):
+            go()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / inner)
     ms = sorted(ts)[len(ts) // 2]
     fl = 2.0 * B * H * W * M * N * K * K
     by = B * H * W * (M + N) * 2
