@@ -43,12 +43,14 @@
 
 namespace dmm {
 
-constexpr int kG2Threads = 352;          // warp 0 weight TMA, warp 1 MMA, warps 2..9 = two epilogue teams of 4 warps, warp 10 patch TMA
-constexpr int kG2ThreadsPro = 480;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA (PRO instantiations; 128 registers per
+constexpr int kG2Threads = 384;          // warp 0 weight TMA, warp 1 MMA (even tiles), warps 2..9 = two epilogue teams of 4 warps, warp 10 patch
+                                         // TMA, warp 11 MMA (odd tiles)
+constexpr int kG2ThreadsPro = 512;       // warps 10..13 = BN-ReLU prologue team, warp 14 patch TMA, warp 15 MMA (odd tiles) (PRO instantiations; 128 registers per
                                          // thread: ptxas rounds the budget to 512 threads, so a 448-thread variant gains nothing - measured)
 constexpr int kMaxSub = 4;
 constexpr int kMaxBStages = 16;          // weight ring slots (resident weights: one slot per (tap group, k-block) of a tile)
 constexpr int kG2MaxSmem = 232448;
+constexpr int kTailBytes = 1024;         // mbarriers + TMEM address holder behind the rings / staging slots
 constexpr uint32_t kStageSlot = 16384;   // one 128-row x 128-byte staging slot
 constexpr uint32_t kFoldPitch = 80;      // out_mode 2: fp32 staging row of 16 accumulator columns, padded to 20 words (bank spread)
 
@@ -75,6 +77,10 @@ struct Ig2Params {
     int n_tile, N;
     int sa, sb;
     uint32_t a_stage, b_stage, b_tap, tmem_cols;   // b_stage = tps * b_tap
+    int mma2;                                       // two MMA issuer warps (alternate tiles) / one
+    int last_src;                                   // last source with taps
+    int a_adv, b_adv;                               // ring stages one tile consumes, modulo the ring depth ...
+    uint32_t a_flip, b_flip;                        // ... and the parity of its full wraps (the two MMA warps skip each other's tiles)
     int w_res;                                      // weights RESIDENT: the CTA's whole weight slice is loaded once (sb = stages per tile)
     int tps;                                        // taps per weight stage
     int tpk;                                        // taps per 64-wide K block of the weights: 1, 2 (32-channel sources) or 4 (16-channel sources)
@@ -98,6 +104,7 @@ struct Ig2Params {
     const float* epi_bias;         // out_mode 0: out = act(acc + epi_bias[n]) (a folded eval-mode BatchNorm's shift), or NULL
     int epi_relu;
     int bnb;
+    int bnb_np;                    // bnb: channels of the coefficient table in shared memory (tiles_n * n_tile, + 2)
     const float* bnb_gamma;
     const float* bnb_beta;
     const float* bnb_mean;
@@ -151,6 +158,40 @@ __device__ __forceinline__ void stats_chunk_v(uint32_t sbase, uint64_t* acc) {
         }
     }
 }
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(__float_as_uint(lo)), "r"(__float_as_uint(hi)));
+    return d;
+}
+// Fused BatchNorm-ReLU backward reduce over one staged chunk, same thread mapping as stats_chunk_v: g = the staged output gradient,
+// x = the raw BatchNorm input of the same pixels / channels (second staging tile); dz = g * [scale * x + shift > 0];
+// acc[0..3] += dz, acc[4..7] += dz * (x - mean) for the thread's 8 channels.  coef: 8 channels x (scale, shift, -mean) as 12 pairs.
+__device__ __forceinline__ void bnb_chunk_v(uint32_t gbase, uint32_t xbase, const uint64_t* coef, uint64_t* acc) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {          // two batches of 4 rows: 8 x ld.shared.v4 in flight
+        uint4 gw[4], xw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            gw[i] = lds_v4(gbase + (4 * h + i) * 2048);
+            xw[i] = lds_v4(xbase + (4 * h + i) * 2048);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t gu[4] = {gw[i].x, gw[i].y, gw[i].z, gw[i].w};
+            const uint32_t xu[4] = {xw[i].x, xw[i].y, xw[i].z, xw[i].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t xv = bf16x2_to_f2(xu[k]);
+                const uint64_t t = f2_fma(xv, coef[k], coef[4 + k]);
+                const float a0 = f2_lo(t) > 0.f ? __uint_as_float(gu[k] << 16) : 0.f;
+                const float a1 = f2_hi(t) > 0.f ? __uint_as_float(gu[k] & 0xffff0000u) : 0.f;
+                const uint64_t av = f2_pack(a0, a1);
+                acc[k] = f2_add(acc[k], av);
+                acc[4 + k] = f2_fma(av, f2_add(xv, coef[8 + k]), acc[4 + k]);
+            }
+        }
+    }
+}
 __device__ __forceinline__ void epi_bar(int team) { asm volatile("bar.sync %0, 128;" ::"r"(team + 1) : "memory"); }
 
 // upper 32 bits of a K-major SWIZZLE_128B shared-memory descriptor (SBO, descriptor version 1, layout type 2); the
@@ -171,18 +212,24 @@ __device__ __forceinline__ TileCoord decode_tile(const Ig2Params& p, long long t
     return c;
 }
 
-template <int NCH, int OUT_MODE, int MSUB, bool PRO>
-__global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
+// VAR: 0 plain, 1 BN-ReLU prologue on the A tiles (PRO), 2 fused BatchNorm backward reduce in the epilogue (BNB; out_mode 0 only).
+// Separate instantiations: the statistics code of BNB (x-tile cursor, coefficient registers) made the plain kernels spill.
+template <int NCH, int OUT_MODE, int MSUB, int VAR>
+__global__ void __launch_bounds__(VAR == 1 ? kG2ThreadsPro : kG2Threads, 1) igemm2_kernel(const __grid_constant__ Ig2Params p) {
+    constexpr bool PRO = VAR == 1;
     // OUT_MODE 3 / 4 (internal): 3 kernel columns folded into N = 3 * FC for FC = 32 / 64 output channels (C-ABI out_mode 3)
     constexpr bool FOLD3 = OUT_MODE == 3 || OUT_MODE == 4;
     constexpr int FC = OUT_MODE == 4 ? 64 : 32;
+    // fused BN backward reduce: out_mode 0 without the prologue (the host rejects other combinations); a compile-time false keeps
+    // its code - x-tile cursor, second statistics loop - out of the register-starved prologue instantiations
+    constexpr bool bnb_on = OUT_MODE == 0 && VAR == 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_stage;
     uint8_t* stg = b_ring + (size_t)p.sb * p.b_stage;
-    uint8_t* xstg = stg + ((OUT_MODE == 0 || FOLD3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: one x tile per team
-    uint8_t* tail = xstg + ((OUT_MODE == 0 && p.bnb) ? 2 * kStageSlot : 0);
+    uint8_t* xstg = stg + ((OUT_MODE == 0 || FOLD3) ? 2 * kStageSlot : (OUT_MODE == 2 ? MSUB * 128 * kFoldPitch : 0));   // bnb: two x tiles per team
+    uint8_t* tail = xstg + ((OUT_MODE == 0 && bnb_on) ? 4 * kStageSlot : 0);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* a_empty = a_full + 8;
     uint64_t* b_full = a_empty + 8;
@@ -190,9 +237,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
     uint64_t* acc_full = b_empty + kMaxBStages;
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* x_bar = acc_empty + 2;
-    uint64_t* a_ready = x_bar + 2;                                       // pro: A stage transformed (4 warp arrivals)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 8);
-    float* pcoef = reinterpret_cast<float*>(tail + 512);                 // pro: [2][pro_kp] scale / shift
+    uint64_t* a_ready = x_bar + 2;                                       // pro: A stage transformed (4 warp arrivals); bnb (never
+                                                                         // together with pro): a_ready[0..1] are x_bar[2..3]
+    uint64_t* turn = a_ready + 8;                                        // hand-over between the two MMA warps (see there)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(turn + 2);
+    float* pcoef = reinterpret_cast<float*>(tail + kTailBytes);                 // pro: [2][pro_kp] scale / shift
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -212,6 +261,12 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             mbar_init(&acc_empty[s], 8);
             mbar_init(&x_bar[s], 1);
         }
+        if (bnb_on) {
+            mbar_init(&x_bar[2], 1);
+            mbar_init(&x_bar[3], 1);
+        }
+        mbar_init(&turn[0], 1);
+        mbar_init(&turn[1], 1);
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -222,7 +277,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         tma_prefetch_desc(&p.b_map);
         if (p.src_tap0[1] > 0) tma_prefetch_desc(&p.a_maps[0]);
         if (OUT_MODE == 0 || FOLD3) tma_prefetch_desc(&p.o_map);
-        if (OUT_MODE == 0 && p.bnb) tma_prefetch_desc(&p.x_map);
+        if (OUT_MODE == 0 && bnb_on) tma_prefetch_desc(&p.x_map);
     }
     // everything above is independent of earlier kernels: wait for them (programmatic dependent launch) only here
     pdl_prologue();
@@ -239,6 +294,23 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             }
             pcoef[c] = sc;
             pcoef[C + c] = sh;
+        }
+    }
+    if (bnb_on) {
+        // fused BatchNorm backward reduce: (scale, shift, -mean) of all N output channels, [3][bnb_np] floats; per-chunk global
+        // loads of these cost 2 100 cycles per chunk (phase counters); channels beyond N get zeros (dz = 0)
+        const int NP = p.bnb_np;
+        for (int c = threadIdx.x; c < NP; c += blockDim.x) {
+            float sc = 0.f, sh = 0.f, nm = 0.f;
+            if (c < p.N) {
+                const float mu = __ldg(p.bnb_mean + c);
+                sc = (p.bnb_gamma ? __ldg(p.bnb_gamma + c) : 1.f) * __ldg(p.bnb_invstd + c);
+                sh = (p.bnb_beta ? __ldg(p.bnb_beta + c) : 0.f) - mu * sc;
+                nm = -mu;
+            }
+            pcoef[c] = sc;
+            pcoef[NP + c] = sh;
+            pcoef[2 * NP + c] = nm;
         }
     }
     tc_fence_before();
@@ -308,8 +380,14 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || warp == (PRO ? 15 : 11)) {
+        // ================= MMA issuers =================
+        // TWO issuing warps take the CTA's tiles alternately (warp 1 the even ones = accumulator stage 0, the other the odd ones):
+        // the ~2 500 cycles one warp spends per tile on barrier waits, descriptor set-up and commits (measured with the phase
+        // counters: more than the tensor time of a 3-tap N = 96 tile) now overlap with the other warp's MMAs.  Ring stages are
+        // consumed in tile order whoever waits for them; a commit only tracks the MMAs of the thread that issued it.
+        const uint32_t mma_id = warp == 1 ? 0u : 1u;
+        const uint32_t nmma = p.mma2 ? 2u : 1u;           // mma2 == 0: warp 1 issues every tile, the second warp idles
         // The issue block is guarded by elect.sync: nvcc then emits straight-line UTCHMMA (a `lane == 0` guard makes it
         // wrap every MMA in an ELECT/BRA.U.ANY loop, ~45 instead of <40 cycles per instruction).  The tensor core needs
         // (4096 + 32 N) / 128 cycles per M=128, K=16 instruction (operands stream from shared memory at 128 B/cycle,
@@ -318,15 +396,32 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
         const uint64_t bhi = (uint64_t)desc_hi(1024u) << 32;
+        // ONE elected thread runs the whole issue loop (waits included): no per-stage elect / reconvergence / warp sync, whose
+        // latencies added up to ~2 000 cycles per 9-tap tile next to 2 600 cycles of tensor time (phase counters)
+        if (elect_one()) {
         int ast = 0, bst = 0;
         uint32_t aph = 0, bph = 0;
-        uint32_t it = 0;
+        uint32_t it = mma_id;
+        // ring positions after the tile the OTHER warp handles (host: stages per tile modulo the ring depth, parity of the wraps)
+        auto skip_tile = [&]() {
+            ast += p.a_adv; aph ^= p.a_flip;
+            if (ast >= p.sa) { ast -= p.sa; aph ^= 1; }
+            bst += p.b_adv; bph ^= p.b_flip;
+            if (bst >= p.sb) { bst -= p.sb; bph ^= 1; }
+        };
+        if (mma_id) skip_tile();
+        if (mma_id >= nmma) it = 0x7fffffffu;             // no tiles for this warp
         long long w_a = 0, w_b = 0, w_acc = 0;
         DMM_PH(long long ph_taps = 0, ph_hdr = 0;)      // cycles inside the elected issue block / between a k-block's operand wait and it
         const long long t_begin = clock64();
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (long long tile = mma_id >= nmma ? p.total_tiles : blockIdx.x + (long long)mma_id * gridDim.x; tile < p.total_tiles;
+             tile += (long long)nmma * gridDim.x, it += nmma) {
             const uint32_t as = it & 1, accph = (it >> 1) & 1;
             DMM_WAIT_T(w_acc, mbar_wait(&acc_empty[as], accph ^ 1));
+            // A ring barrier is waited for by PARITY: a warp may only start waiting for the stages of its tile once the other warp
+            // has completed all operand waits of the tile before (otherwise "use k" and "use k - 2" of a stage are the same parity).
+            // turn[w] is arrived on by warp w after the last operand wait of each of its tiles; the two warps alternate strictly.
+            if (it > 0 && nmma == 2) mbar_wait(&turn[mma_id ^ 1], ((it - 1) >> 1) & 1);
             tc_fence_after();
             const uint32_t d0 = tmem_u + as * MSUB * p.n_tile;
             uint32_t acc0 = 0;      // 0 only for the first MMA of every accumulator of this tile
@@ -345,13 +440,14 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     const int ksteps = (cb == nblk - 1) ? p.src_lastk[s] : 4;
                     // resident weights, after the CTA's first tile: nothing to wait for, and the (tap group, k-block) slots of one
                     // k-block are consecutive in the ring - all taps are issued from ONE elected block (no per-tap loop overhead)
-                    const bool fused = p.w_res && it > 0;
+                    const bool fused = p.w_res && it >= nmma;   // it < nmma: this warp's first tile (it waits for the weight stages once)
                     const int tstep = fused ? (t1 - t0) : p.tps;
                     for (int t = t0; t < t1; t += tstep) {
                         const int nt = (t1 - t) < tstep ? (t1 - t) : tstep;
-                        if (!fused) DMM_WAIT_T(w_b, if (!p.w_res || it == 0) mbar_wait(&b_full[bst], bph));
+                        if (!fused) DMM_WAIT_T(w_b, mbar_wait(&b_full[bst], bph));
+                        if (s == p.last_src && cb == nblk - 1 && t + nt == t1) mbar_arrive(&turn[mma_id]);      // last operand wait of this tile
                         tc_fence_after();
-                        if (elect_one()) {
+                        {
                             DMM_PH(const long long h1 = clock64(); if (t == t0) ph_hdr += h1 - h0;)
                             const uint32_t b_lo0 = ((b_ring_u + (uint32_t)bst * p.b_stage) >> 4) | (1u << 16);
                             uint32_t aoff = p.tap_aoff[t] >> 4;
@@ -377,7 +473,6 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             if (!p.w_res) umma_commit(&b_empty[bst]);
                             if (t + nt == t1) umma_commit(&a_empty[ast]);
                         }
-                        __syncwarp();
                         acc0 = 1;
                         bst += fused ? ((nt + p.tpk - 1) >> p.tpk_log) : 1;
                         if (bst >= p.sb) { bst -= p.sb; bph ^= 1; }
@@ -385,16 +480,17 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     if (++ast == p.sa) { ast = 0; aph ^= 1; }
                 }
             }
-            if (elect_one()) umma_commit(&acc_full[as]);
-            __syncwarp();
+            umma_commit(&acc_full[as]);
+            if (nmma == 2) skip_tile();
         }
-        if (p.prof && lane == 0) {
+        if (p.prof && mma_id == 0) {
             p.prof[blockIdx.x * 16 + 4] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 5] = w_a;
             p.prof[blockIdx.x * 16 + 6] = w_b;
             p.prof[blockIdx.x * 16 + 7] = w_acc;
         }
-        DMM_PH(if (p.prof && elect_one()) { p.prof[blockIdx.x * 16 + 1] = ph_taps; p.prof[blockIdx.x * 16 + 3] = ph_hdr; })
+        DMM_PH(if (p.prof && mma_id == 0) { p.prof[blockIdx.x * 16 + 1] = ph_taps; p.prof[blockIdx.x * 16 + 3] = ph_hdr; })
+        }   // elected thread
     } else {
         // ================= epilogue: two teams of 4 warps, alternating 64-column chunks =================
         const int team = (warp - 2) >> 2;
@@ -483,13 +579,40 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             epi_bar(team);
         }
         uint8_t* srow = slot + r * 128;
-        uint8_t* xslot = xstg + team * kStageSlot;
-        uint32_t x_phase = 0;
+        // bnb: the x tile of a chunk is loaded ONE CHUNK AHEAD into the team's other x buffer (a load issued in the chunk itself
+        // exposed the whole DRAM latency in front of the statistics loop: 3 600 cycles per chunk, measured).  Thread r == 0 walks a
+        // second cursor over the team's chunks; xi = index of the team's current chunk: buffer xi & 1, barrier parity (xi >> 1) & 1.
+        uint8_t* xslot = xstg + team * 2 * kStageSlot;
+        uint32_t xi = 0;
         const uint32_t slot_u = smem_u32(slot), srow_u = smem_u32(srow), xslot_u = smem_u32(xslot);
+        long long xq_tile = blockIdx.x;
+        int xq_sub = 0, xq_c = -1;
+        uint32_t xq_ctr = 0, xq_n = 0;
+        TileCoord xq_tc = decode_tile(p, xq_tile < p.total_tiles ? xq_tile : 0);
+        auto x_prefetch_next = [&]() {       // advance the cursor to the team's next chunk and load its x tile (thread r == 0)
+            if (xq_tile >= p.total_tiles) return;
+            for (;;) {
+                ++xq_c;
+                if (xq_c >= NCH || xq_tc.n0 + 64 * xq_c >= p.N) { xq_c = 0; ++xq_sub; }
+                if (xq_sub >= MSUB) {
+                    xq_sub = 0;
+                    xq_tile += gridDim.x;
+                    if (xq_tile >= p.total_tiles) return;
+                    xq_tc = decode_tile(p, xq_tile);
+                }
+                if (((xq_ctr++) & 1) == (uint32_t)team) break;
+            }
+            uint64_t* bar = &x_bar[team * 2 + (xq_n & 1)];
+            mbar_arrive_expect_tx(bar, kStageSlot);
+            tma_load_4d(xslot + (xq_n & 1) * kStageSlot, &p.x_map, bar, xq_tc.n0 + 64 * xq_c, xq_tc.x0 + p.sub_x[xq_sub], xq_tc.y0 + p.sub_y[xq_sub],
+                        xq_tc.b);
+            ++xq_n;
+        };
+        if (OUT_MODE == 0 && bnb_on && r == 0) x_prefetch_next();
         // VSTATS (n_tile <= 128, no fused BN backward): vectorised statistics, accumulators = 8 packed fp32 pairs per 64-channel block;
         // otherwise 4 doubles per block (column pair cp of row quarter rq), stored in the same registers
         constexpr bool VS = NCH <= 2;
-        const bool vstats = VS && !p.bnb;
+        const bool vstats = VS;                // NCH <= 2: both statistics kinds are vectorised
         const uint32_t sbase = slot_u + (uint32_t)(r >> 3) * 128u + (uint32_t)(((r & 7) ^ ((r >> 3) & 7)) << 4);
         uint64_t sraw[NCH][VS ? 8 : 4];
 #pragma unroll
@@ -521,7 +644,7 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                                 const int cl = c * 64 + 8 * lane + e, col = n0 + cl;
                                 if (cl < lim_l && col < lim_g) {
                                     atomicAdd(st + col, (double)v[e]);
-                                    atomicAdd(st + p.stats_ld + col, (double)v[8 + e]);
+                                    atomicAdd(st + p.stats_ld + col, bnb_on ? (double)v[8 + e] * (double)p.bnb_invstd[col] : (double)v[8 + e]);
                                 }
                             }
                         }
@@ -530,10 +653,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                     const int col = n0 + c * 64 + 2 * cp;
                     if (c * 64 + 2 * cp < lim_l && col < lim_g) {
                         atomicAdd(st + col, sacc_get(c, 0));
-                        atomicAdd(st + p.stats_ld + col, p.bnb ? sacc_get(c, 2) * (double)p.bnb_invstd[col] : sacc_get(c, 2));
+                        atomicAdd(st + p.stats_ld + col, bnb_on ? sacc_get(c, 2) * (double)p.bnb_invstd[col] : sacc_get(c, 2));
                         if (col + 1 < lim_g) {
                             atomicAdd(st + col + 1, sacc_get(c, 1));
-                            atomicAdd(st + p.stats_ld + col + 1, p.bnb ? sacc_get(c, 3) * (double)p.bnb_invstd[col + 1] : sacc_get(c, 3));
+                            atomicAdd(st + p.stats_ld + col + 1, bnb_on ? sacc_get(c, 3) * (double)p.bnb_invstd[col + 1] : sacc_get(c, 3));
                         }
                     }
                 }
@@ -545,7 +668,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
         uint32_t it = 0;
         int last_n0 = 0;
         long long w_full = 0;
-        DMM_PH(long long ph_store_wait = 0, ph_tmem = 0, ph_bar1 = 0, ph_pack = 0, ph_bar2 = 0, ph_stats = 0;)      // phase cycles (thread r == 0)
+        DMM_PH(long long ph_store_wait = 0, ph_tmem = 0, ph_bar1 = 0, ph_pack = 0, ph_bar2 = 0, ph_stats = 0;)
+        DMM_PH(long long ph_xpre = 0, ph_coef = 0, ph_xwait = 0, ph_loop = 0;)      // BNB variant: x prefetch, coefficient loads, x wait, loop      // phase cycles (thread r == 0)
         const long long t_begin = clock64();
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(p, tile);
@@ -667,7 +791,8 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         const int ngrp = min(64, p.n_tile - 64 * c) >> 4;      // 16-column groups in this chunk (1..4)
                         // accumulator columns are read GL groups of 16 at a time: all four at once, or (prologue instantiations,
                         // 128 registers per thread) two and two so that the statistics accumulators need not be spilled
-                        constexpr int GL = PRO ? 2 : 4;
+                        constexpr int GL = (PRO || bnb_on) ? 2 : 4;      // (with a maximal shared-memory carve-out the L1 is too small for spills:
+                                                                         // 24 spilled registers cost the BNB variant ~2 500 cycles per chunk)
                         uint32_t v[GL][16];
                         DMM_PH(const long long e0 = clock64();)
 #pragma unroll
@@ -679,10 +804,10 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                         DMM_PH(const long long e2 = clock64();)
                         epi_bar(team);                       // ... and every thread of the team is done with the previous chunk
                         DMM_PH(const long long e3 = clock64(); ph_store_wait += e1 - e0; ph_tmem += e2 - e1; ph_bar1 += e3 - e2;)
-                        if (p.bnb && r == 0) {               // x tile of the same pixels / channels for the fused BN backward reduce
-                            mbar_arrive_expect_tx(&x_bar[team], kStageSlot);
-                            tma_load_4d(xslot, &p.x_map, &x_bar[team], tc.n0 + 64 * c, tc.x0 + p.sub_x[sub], tc.y0 + p.sub_y[sub], tc.b);
-                        }
+                        // fused BN backward reduce: the team's other x buffer is free (the barrier above), load the NEXT chunk's tile
+                        DMM_PH(const long long xp0 = clock64();)
+                        if (bnb_on && r == 0) x_prefetch_next();
+                        DMM_PH(if (bnb_on) ph_xpre += clock64() - xp0;)
 #pragma unroll
                         for (int h = 0; h < 4 / GL; ++h) {
                             if (h > 0) {
@@ -743,9 +868,31 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
                             const uint32_t base = slot_u + ((cp & 3) << 2) + rq * 32 * 128;
                             const int j = cp >> 2;
-                            if (vstats) {
+                            if (vstats && !bnb_on) {
                                 if constexpr (VS) stats_chunk_v(sbase, sraw[c]);
-                            } else if (!p.bnb) {
+                            } else if (vstats) {
+                                if constexpr (VS) {
+                                    // per-channel (scale, shift, -mean) of the thread's 8 channels; channels beyond N get zeros (dz = 0)
+                                    DMM_PH(const long long b0 = clock64();)
+                                    const int ch0 = tc.n0 + 64 * c + 8 * (r & 7);
+                                    uint64_t coef[12];
+                                    const uint32_t cb_u = smem_u32(pcoef) + (uint32_t)ch0 * 4u;
+#pragma unroll
+                                    for (int a = 0; a < 3; ++a) {
+                                        const uint4 lo = lds_v4(cb_u + (uint32_t)(a * p.bnb_np) * 4u), hi = lds_v4(cb_u + (uint32_t)(a * p.bnb_np) * 4u + 16u);
+                                        coef[4 * a + 0] = ((uint64_t)lo.y << 32) | lo.x;
+                                        coef[4 * a + 1] = ((uint64_t)lo.w << 32) | lo.z;
+                                        coef[4 * a + 2] = ((uint64_t)hi.y << 32) | hi.x;
+                                        coef[4 * a + 3] = ((uint64_t)hi.w << 32) | hi.z;
+                                    }
+                                    DMM_PH(const long long b1 = clock64();)
+                                    mbar_wait(&x_bar[team * 2 + (xi & 1)], (xi >> 1) & 1);
+                                    DMM_PH(const long long b2 = clock64();)
+                                    bnb_chunk_v(sbase, sbase - slot_u + xslot_u + (xi & 1) * kStageSlot, coef, sraw[c]);
+                                    DMM_PH(ph_coef += b1 - b0; ph_xwait += b2 - b1; ph_loop += clock64() - b2;)
+                                    ++xi;
+                                }
+                            } else if (!bnb_on) {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     // row = rq*32 + i: (row & 7) == (i & 7), a compile-time pattern after unrolling
@@ -757,20 +904,11 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
                             } else {
                                 // fused BatchNorm-ReLU backward reduce: dz = g * [bn(x) > 0]; sums of dz and dz * (x - mean)
                                 const int col = tc.n0 + 64 * c + 2 * cp;
-                                float sc0 = 0.f, sh0 = 0.f, mu0 = 0.f, sc1 = 0.f, sh1 = 0.f, mu1 = 0.f;
-                                if (col < p.N) {
-                                    mu0 = __ldg(p.bnb_mean + col);
-                                    sc0 = (p.bnb_gamma ? __ldg(p.bnb_gamma + col) : 1.f) * __ldg(p.bnb_invstd + col);
-                                    sh0 = (p.bnb_beta ? __ldg(p.bnb_beta + col) : 0.f) - mu0 * sc0;
-                                }
-                                if (col + 1 < p.N) {
-                                    mu1 = __ldg(p.bnb_mean + col + 1);
-                                    sc1 = (p.bnb_gamma ? __ldg(p.bnb_gamma + col + 1) : 1.f) * __ldg(p.bnb_invstd + col + 1);
-                                    sh1 = (p.bnb_beta ? __ldg(p.bnb_beta + col + 1) : 0.f) - mu1 * sc1;
-                                }
-                                const uint32_t xbase = xslot_u + ((cp & 3) << 2) + rq * 32 * 128;
-                                mbar_wait(&x_bar[team], x_phase);
-                                x_phase ^= 1;
+                                const float sc0 = pcoef[col], sh0 = pcoef[p.bnb_np + col], mu0 = -pcoef[2 * p.bnb_np + col];
+                                const float sc1 = pcoef[col + 1], sh1 = pcoef[p.bnb_np + col + 1], mu1 = -pcoef[2 * p.bnb_np + col + 1];
+                                const uint32_t xbase = xslot_u + (xi & 1) * kStageSlot + ((cp & 3) << 2) + rq * 32 * 128;
+                                mbar_wait(&x_bar[team * 2 + (xi & 1)], (xi >> 1) & 1);
+                                ++xi;
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) {
                                     const int o = i * 128 + ((j ^ (i & 7)) << 4);
@@ -820,7 +958,9 @@ __global__ void __launch_bounds__(PRO ? kG2ThreadsPro : kG2Threads, 1) igemm2_ke
             p.prof[blockIdx.x * 16 + 8] = clock64() - t_begin;
             p.prof[blockIdx.x * 16 + 9] = w_full;
             DMM_PH(p.prof[blockIdx.x * 16 + 10] = ph_store_wait; p.prof[blockIdx.x * 16 + 11] = ph_tmem; p.prof[blockIdx.x * 16 + 12] = ph_bar1;
-                   p.prof[blockIdx.x * 16 + 13] = ph_pack; p.prof[blockIdx.x * 16 + 14] = ph_bar2; p.prof[blockIdx.x * 16 + 15] = ph_stats;)
+                   p.prof[blockIdx.x * 16 + 13] = ph_pack; p.prof[blockIdx.x * 16 + 14] = ph_bar2; p.prof[blockIdx.x * 16 + 15] = ph_stats;
+                   if (bnb_on) { p.prof[blockIdx.x * 16 + 10] = ph_xpre; p.prof[blockIdx.x * 16 + 11] = ph_coef; p.prof[blockIdx.x * 16 + 12] = ph_xwait;
+                                 p.prof[blockIdx.x * 16 + 14] = ph_loop; })
         }
         }   // epilogue team
     }
@@ -946,6 +1086,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     const bool bnb = d->bnb_sums != nullptr;
     if (bnb) {
         DMM_CHECK(d->out_mode == 0 && d->stats == nullptr, "igemm v2: fused BN backward reduce needs out_mode 0 and no forward statistics");
+        DMM_CHECK(!d->pro_enable, "igemm v2: the fused BN backward reduce and the BN-ReLU prologue share barrier slots (never used together)");
         DMM_CHECK(d->out_sy <= 1 && d->out_sx <= 1 && d->out_py == 0 && d->out_px == 0, "igemm v2: fused BN backward reduce: no output stride");
         DMM_CHECK(d->bnb_x && d->bnb_mean && d->bnb_invstd && d->bnb_ldx % 8 == 0, "igemm v2: fused BN backward reduce: missing inputs");
     }
@@ -961,10 +1102,10 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     int max_taps = 1;
     for (int s = 0; s < d->num_src; ++s) max_taps = ntap[s] > max_taps ? ntap[s] : max_taps;
     const int nslot = 1;      // staging slots per epilogue team (2 / 3 measured slower: profiles/r02_epilogue_experiments.txt)
-    const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 2 : 0)) * (int)kStageSlot
+    const int staging = (d->out_mode == 0 ? (2 * nslot + (bnb ? 4 : 0)) * (int)kStageSlot
                                           : (d->out_mode == 3 ? 2 * (int)kStageSlot : (fold ? kMaxSub * 128 * (int)kFoldPitch : 0))) +
-                        (pro ? 2 * pro_kp * (int)sizeof(float) : 0);
-    const int avail = kG2MaxSmem - 1024 - 512 - staging;
+                        (pro ? 2 * pro_kp * (int)sizeof(float) : 0) + (bnb ? 3 * (ceil_div(d->N, d->n_tile) * d->n_tile + 8) * (int)sizeof(float) : 0);
+    const int avail = kG2MaxSmem - 1024 - kTailBytes - staging;
     const uint32_t b_tap = (uint32_t)d->n_tile * 128u;      // one tap's [n_tile x 64] weight slice
     const int tiles_n = ceil_div(d->N, d->n_tile);
     const int mma_hw = d->n_tile / 2 > 32 + d->n_tile / 4 ? d->n_tile / 2 : 32 + d->n_tile / 4;   // cycles per MMA (measured law)
@@ -1064,6 +1205,20 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     p.a_stage = best.a_stage; p.b_tap = b_tap; p.tps = best.tps; p.tpk = tpk;
     p.tpk_log = tpk == 4 ? 2 : (tpk == 2 ? 1 : 0);
     p.b_stage = (uint32_t)ceil_div(best.tps, tpk) * b_tap;
+    {
+        // ring stages one tile consumes (the MMA warp that skips a tile advances its ring positions by these)
+        int a_per = 0, b_per = 0;
+        for (int s = 0; s < d->num_src; ++s) {
+            if (ntap[s] == 0) continue;
+            p.last_src = s;
+            a_per += p.src_nblk[s];
+            b_per += p.src_nblk[s] * ceil_div(ntap[s], best.tps);
+        }
+        static const int mma2_env = env_int("DMM_IGEMM_MMA2", 1);
+        p.mma2 = mma2_env;
+        p.a_adv = a_per % best.sa; p.a_flip = (uint32_t)(a_per / best.sa) & 1u;
+        p.b_adv = best.w_res ? 0 : b_per % best.sb; p.b_flip = best.w_res ? 0u : ((uint32_t)(b_per / best.sb) & 1u);
+    }
     p.x_step = fold ? p.TW - (d->fold_kw - 1) : p.TW;
     p.x_org = fold ? -(d->fold_kw / 2) : 0;
     p.nsx = best.nsx;
@@ -1163,6 +1318,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         int rc = view_to_tmap(&p.x_map, xv, 64, p.sub_w, p.sub_h, 128);
         if (rc) return rc;
         p.bnb = 1;
+        p.bnb_np = tiles_n * d->n_tile + 8;
         p.bnb_gamma = d->bnb_gamma; p.bnb_beta = d->bnb_beta; p.bnb_mean = d->bnb_mean; p.bnb_invstd = d->bnb_invstd;
         p.stats = d->bnb_sums; p.stats_ld = d->bnb_sums_ld; p.stats_off = d->bnb_sums_off;
     }
@@ -1170,7 +1326,7 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
     while ((int)cols < 2 * p.msub * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
 
-    const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + 512 + 1024;
+    const size_t smem = (size_t)p.sa * p.a_stage + (size_t)p.sb * p.b_stage + staging + kTailBytes + 1024;
     DMM_CHECK(smem <= (size_t)kG2MaxSmem, "igemm v2: %zu bytes of shared memory requested", smem);
     unsigned grid = (unsigned)(p.total_tiles < num_sms ? p.total_tiles : num_sms);
     if (p.w_res && tiles_n > 1) {
@@ -1187,12 +1343,13 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         else if (nch == 3) fn = igemm2_kernel<3, 0, 1, PROFLAG>;                                                                           \
         else fn = igemm2_kernel<4, 0, 1, PROFLAG>;                                                                                         \
     } while (0)
-    if (d->out_mode == 3 && d->N == 192) fn = igemm2_kernel<1, 4, 1, false>;
-    else if (d->out_mode == 3) fn = p.msub == 2 ? igemm2_kernel<1, 3, 2, false> : igemm2_kernel<1, 3, 1, false>;
-    else if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, false> : igemm2_kernel<1, 2, 1, false>);
-    else if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, false> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, false> : igemm2_kernel<1, 1, 1, false>);
-    else if (pro) DMM_IG2_PICK(true);
-    else DMM_IG2_PICK(false);
+    if (d->out_mode == 3 && d->N == 192) fn = igemm2_kernel<1, 4, 1, 0>;
+    else if (d->out_mode == 3) fn = p.msub == 2 ? igemm2_kernel<1, 3, 2, 0> : igemm2_kernel<1, 3, 1, 0>;
+    else if (d->out_mode == 2) fn = p.msub == 4 ? igemm2_kernel<1, 2, 4, 0> : (p.msub == 2 ? igemm2_kernel<1, 2, 2, 0> : igemm2_kernel<1, 2, 1, 0>);
+    else if (d->out_mode == 1) fn = p.msub == 4 ? igemm2_kernel<1, 1, 4, 0> : (p.msub == 2 ? igemm2_kernel<1, 1, 2, 0> : igemm2_kernel<1, 1, 1, 0>);
+    else if (pro) DMM_IG2_PICK(1);
+    else if (bnb) DMM_IG2_PICK(2);
+    else DMM_IG2_PICK(0);
 #undef DMM_IG2_PICK
     DMM_CHECK(nch <= 2 || p.msub == 1, "igemm v2: internal msub error");
     DMM_CHECK(nch <= 1 || p.msub <= 2, "igemm v2: internal msub error");

@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                     const uint32_t trow = fast_divmod((uint32_t)(tile_lo + kb), p.fd_x, tx);      // total_tiles < 2^31 (checked by the launcher)
                     const int b = (int)fast_divmod(trow, p.fd_y, ty);
                     const int x0 = (int)tx * p.tile_w, y0 = (int)ty * p.tile_h;
+#ifdef DMM_IGEMM_PHASE_PROF
                     const long long c0 = clock64();
+#endif
                     mbar_wait(&empty_bar[s], ph ^ 1);
+#ifdef DMM_IGEMM_PHASE_PROF
                     w_e += clock64() - c0;
+#endif
                     uint8_t* sa = smem + (size_t)s * p.stage_bytes;
                     uint8_t* sb = sa + a_bytes;
                     mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
@@ -206,16 +210,23 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
             const uint64_t bhi = (uint64_t)(((p.b_sbo >> 4) & 0x3FFFu) | (1u << 14) | ((p.b_layout & 7u) << 29)) << 32;
             const uint32_t a_lbo = ((p.a_chunk_bytes >> 4) & 0x3FFFu) << 16;
             const uint32_t a_mt = (2u * p.a_chunk_bytes) >> 4, b_ks = p.b_kstep >> 4;
+            // one elected thread runs the whole issue loop, waits included (no per-stage elect / reconvergence / warp sync); the
+            // wait counter costs two clock reads per stage and is compiled in only with the phase profile
+            if (elect_one()) {
             long long w_f = 0;
             const long long t_begin = clock64();
             int s = 0;
             uint32_t ph = 0;
             for (int kb = 0; kb < num_k; ++kb) {
+#ifdef DMM_IGEMM_PHASE_PROF
                 const long long c0 = clock64();
+#endif
                 mbar_wait(p.pro ? &ready_bar[s] : &full_bar[s], ph);
+#ifdef DMM_IGEMM_PHASE_PROF
                 w_f += clock64() - c0;
+#endif
                 tc_fence_after();
-                if (elect_one()) {
+                {
                     const uint32_t sa = ((smem_u + (uint32_t)s * p.stage_bytes) >> 4);
                     const uint32_t sb = sa + (a_bytes >> 4);
                     for (int i = 0; i < p.num_sg; ++i) {
@@ -236,13 +247,13 @@ __global__ void __launch_bounds__(kWgThreadsPro, 1) wgrad_kernel(const __grid_co
                     umma_commit(&empty_bar[s]);
                     if (kb == num_k - 1) umma_commit(tmem_full_bar);
                 }
-                __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            if (p.prof && lane == 0) {
+            if (p.prof) {
                 p.prof[cta * 8 + 2] = clock64() - t_begin;
                 p.prof[cta * 8 + 3] = w_f;
             }
+            }   // elected thread
         } else {
             // ================= epilogue: TMEM -> swizzled fp32 staging -> TMA reduce-add into dw =================
             const int q = warp & 3;                       // TMEM lane quadrant = rows q*32 .. q*32+31 of the m-tile

@@ -43,7 +43,9 @@ FUSE_BN_PROLOGUE_KXK = FUSE_BN_PROLOGUE and os.environ.get("DMM_FUSE_BN_PROLOGUE
 # data gradients of the 3x3 growth convolutions (32 gradient channels): two taps share one 64-wide K block of the packed weights
 PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
 # the reduce pass of norm2's backward inside the growth convolutions' data gradient (igemm epilogue) or as its own launch
-CONV2_DGRAD_FUSED = os.environ.get("DMM_CONV2_DGRAD_FUSED", "1") != "0"
+# (measured r02: the separate launch wins, 82.2 vs 83.3 ms per step - the growth data gradient is epilogue-bound, and a chunk
+# with the fused statistics costs 3-4x a plain one)
+CONV2_DGRAD_FUSED = os.environ.get("DMM_CONV2_DGRAD_FUSED", "0") != "0"
 DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "8"))       # 64 (128-byte aligned rows) measured = (88.3 vs 87.9 ms): dense pitch kept
 # inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
 # the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
