@@ -347,6 +347,22 @@ def plan_conv_wgrad(x, ys, taps, M, N):
                 launches.append(dict(a_srcs=list(ys), b_srcs=[x], a_slots=a_slots, b_slots=[(0, 0, 0, 0, 0)], n_tile=nt,
                                      ya=1, yb=1, a_step=0, b_step=0))
             return dict(launches=launches, rows=T * npad, ld=nt, dt=npad * nt, dm=1, dn=nt, tap_order=list(range(T)))
+    if len(ys) > 1 and N <= 128 and mch <= 2 and os.environ.get("DMM_WGRAD_GROUP_TAPS", "1") != "0":
+        # several output-gradient sources (the four sub-pixel phases of a ConvTranspose) and one m-tile per tap: ONE launch per
+        # source, A = the activation at the shifts of all taps that read this source (up to 4 taps = 4 accumulators of 128 columns),
+        # B = the source once.  A launch per tap (below) streams every phase once per tap and the activation nine times:
+        # 3.6x the algorithmic DRAM traffic on Transposed_Convolution_4 (ncu), and these launches are bound by the bytes the SM
+        # takes in.  dw rows = (tap, input channel), columns = output channel.
+        mpad, npad = mch * 64, ceil_to(N, 128)
+        launches = []
+        for y in sorted({t[0] for t in taps}):
+            group = [t for t in range(T) if taps[t][0] == y]
+            per = max(1, _lib.WG_MAX_A // mch)
+            for g0 in range(0, len(group), per):
+                a_slots = [(0, taps[t][1], taps[t][2], 64 * i, t * mpad + 64 * i) for t in group[g0:g0 + per] for i in range(mch)]
+                launches.append(dict(a_srcs=[x], b_srcs=list(ys), a_slots=a_slots, b_slots=[(y, 0, 0, 0, 0)], n_tile=128, ya=1, yb=1,
+                                     a_step=0, b_step=0))
+        return dict(launches=launches, rows=T * mpad, ld=npad, dt=mpad * npad, dm=npad, dn=1, tap_order=list(range(T)))
     # general: one launch per tap, A = activation shifted by +tap, B = output gradient in 128-channel groups
     nb = 1 if N <= 128 else 2
     na = max(1, min(4 // nb, (mch + 1) // 2))
