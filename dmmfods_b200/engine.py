@@ -46,6 +46,7 @@ PACK32 = os.environ.get("DMM_DGRAD_PACK32", "1") != "0"
 # (measured r02: the separate launch wins, 82.2 vs 83.3 ms per step - the growth data gradient is epilogue-bound, and a chunk
 # with the fused statistics costs 3-4x a plain one)
 CONV2_DGRAD_FUSED = os.environ.get("DMM_CONV2_DGRAD_FUSED", "0") != "0"
+FUSE_MIN_PIXELS = int(os.environ.get("DMM_FUSE_MIN_PIXELS", "1000000"))
 DA1_ALIGN = int(os.environ.get("DMM_DA1_ALIGN", "8"))       # 64 (128-byte aligned rows) measured = (88.3 vs 87.9 ms): dense pitch kept
 # inference (eval-mode engines): fold every BatchNorm whose only producer is one convolution into that convolution - scale into
 # the packed weight rows, shift + ReLU into the igemm epilogue (Agent.py:337-352 validation / notebook inference)
@@ -341,7 +342,9 @@ class Engine:
         self._fix_w.append((d, wid))
         # "heavy": enough MMA work per output chunk that a longer epilogue stays hidden (KxK data gradients); the 1x1 data
         # gradients of the dense layers are epilogue/HBM-bound and lose more than the separate reduce pass costs
-        lst[-1].heavy = (T * ceil_to(Cg, 64) >= 512) if heavy is None else heavy
+        # ... and few-pixel launches (deep decoder stages) lose more ring depth to the two x-tile buffers per team than the separate
+        # reduce pass over P x Cin elements costs (ncu r02: three such launches, 1.57 ms for 1.6 GB)
+        lst[-1].heavy = (T * ceil_to(Cg, 64) >= 512 and P >= FUSE_MIN_PIXELS) if heavy is None else heavy
         return lst[-1]
 
     def _conv_wgrad(self, lst, name, wname, x, ys, taps, tap_off, M, N, Mvalid, Nvalid, sn, sc, W, H, B, pro=None, n_off=0, ndiv=0, sn2=0):
