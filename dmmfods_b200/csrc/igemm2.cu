@@ -987,7 +987,37 @@ struct Tiling {
     double cost;
 };
 
+static int igemm2_launch_impl(const dmm_igemm_t* d, cudaStream_t stream, bool swapped);
+
+// KxK launches tile the image in sub-tiles of 8 (x) by 16 (y) pixels (an 8-pixel core-matrix group is one patch row segment).
+// A 30 x 20 or 60 x 40 image (dense blocks 3 / 4, the deep decoder stages) wastes 60 % / 20 % of every tile column in y; with the
+// roles of x and y exchanged - views with swapped extents and strides, taps with swapped offsets, the output / x tensor maps built
+// with swapped strides - the same kernel covers it in 8 (y) by 16 (x) sub-tiles: 25 % / 17 % fewer tiles.  Nothing in the kernel
+// knows about it.
 int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
+    static const int swap_env = env_int("DMM_IGEMM_SWAP_XY", 1);
+    bool halo = false;
+    for (int t = 0; t < d->num_taps; ++t) halo = halo || d->tap_dx[t] != 0 || d->tap_dy[t] != 0;
+    if (swap_env && halo && d->out_mode == 0 && d->W > 0 && d->H > 0) {
+        const long long plain = (long long)ceil_div(d->W, 8) * 8 * ceil_div(d->H, 16) * 16;
+        const long long swp = (long long)ceil_div(d->H, 8) * 8 * ceil_div(d->W, 16) * 16;
+        if (swp * 20 < plain * 19) {
+            dmm_igemm_t t = *d;
+            t.W = d->H; t.H = d->W;
+            for (int i = 0; i < d->num_taps; ++i) { t.tap_dx[i] = d->tap_dy[i]; t.tap_dy[i] = d->tap_dx[i]; }
+            for (int s = 0; s < d->num_src; ++s) {
+                t.src[s].W = d->src[s].H; t.src[s].H = d->src[s].W;
+                t.src[s].sw = d->src[s].sh; t.src[s].sh = d->src[s].sw;
+            }
+            t.out_sx = d->out_sy; t.out_sy = d->out_sx; t.out_px = d->out_py; t.out_py = d->out_px;
+            t.OW = d->OH; t.OH = d->OW;
+            return igemm2_launch_impl(&t, stream, true);
+        }
+    }
+    return igemm2_launch_impl(d, stream, false);
+}
+
+static int igemm2_launch_impl(const dmm_igemm_t* d, cudaStream_t stream, bool swapped) {
     DMM_CHECK(d->kwidth == 64 || d->kwidth == 32 || d->kwidth == 16, "igemm v2: kwidth must be 64, 32 or 16");
     const int tpk = 64 / d->kwidth;                // kwidth 16 / 32: one source of <= kwidth channels, weights packed [n][tap*kwidth + c]
     DMM_CHECK(d->n_tile % 64 == 0 || d->n_tile >= d->N, "igemm v2: n_tile %d must be a multiple of 64 or cover N=%d", d->n_tile, d->N);
@@ -1169,8 +1199,8 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
             if (best.msub == 0 || c.cost < best.cost) best = c;
             // RESIDENT weights: the tile loop of a CTA keeps one weight slice (tiles_n == 1, or a grid that is a multiple of
             // tiles_n so that n0 is the same for all of its tiles); every (tap group of tpk, k-block) gets its own ring slot.
-            // The SM's TMA unit moves ~one 128-byte row per 5 cycles whatever its source (L2-hit weights included), so weight
-            // rows that are not re-streamed per tile are bandwidth handed back to the activation loads and the output stores.
+            // Weight rows that are not re-streamed per tile free ring stages, barrier hand-overs and MMA-warp waits (L2-hit weight
+            // tiles arrive at 58 B/cycle/SM - scripts/ubench/load_rate.cu - so it is the hand-overs, not the bytes, that cost).
             static const int wres_on = env_int("DMM_IGEMM_WRES", 1);
             if (wres_on && (tiles_n == 1 || num_sms / tiles_n >= 1)) {
                 int stages_r = 0;
@@ -1284,10 +1314,11 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         DMM_CHECK(d->ldo % 8 == 0 && d->coff % 8 == 0, "igemm v2: output pitch %lld / channel offset %d must be multiples of 8",
                   (long long)d->ldo, d->coff);
         dmm_view_t ov;
-        ov.ptr = reinterpret_cast<const uint16_t*>(d->out) + ((long long)d->out_py * OW + d->out_px) * d->ldo + d->coff;
+        // memory is [B][rows][columns][ldo]; swapped: this launch's x runs over the rows (OH = number of columns)
+        ov.ptr = reinterpret_cast<const uint16_t*>(d->out) + (swapped ? ((long long)d->out_px * OH + d->out_py) : ((long long)d->out_py * OW + d->out_px)) * d->ldo + d->coff;
         ov.C = d->out_mode == 3 ? d->N / d->fold_kw : d->N; ov.W = OWv; ov.H = OHv; ov.B = d->B;
-        ov.sw = (long long)osx * d->ldo;
-        ov.sh = (long long)osy * OW * d->ldo;
+        ov.sw = swapped ? (long long)osx * OH * d->ldo : (long long)osx * d->ldo;
+        ov.sh = swapped ? (long long)osy * d->ldo : (long long)osy * OW * d->ldo;
         ov.sb = (long long)OH * OW * d->ldo;
         int rc = view_to_tmap(&p.o_map, ov, 64, d->out_mode == 3 ? p.sub_w - 2 : p.sub_w, p.sub_h, 128);
         if (rc) return rc;
@@ -1314,7 +1345,9 @@ int igemm2_launch(const dmm_igemm_t* d, cudaStream_t stream) {
         dmm_view_t xv;
         xv.ptr = d->bnb_x;
         xv.C = d->N; xv.W = d->W; xv.H = d->H; xv.B = d->B;
-        xv.sw = d->bnb_ldx; xv.sh = (long long)d->W * d->bnb_ldx; xv.sb = (long long)d->H * d->W * d->bnb_ldx;
+        xv.sw = swapped ? (long long)d->H * d->bnb_ldx : d->bnb_ldx;
+        xv.sh = swapped ? d->bnb_ldx : (long long)d->W * d->bnb_ldx;
+        xv.sb = (long long)d->H * d->W * d->bnb_ldx;
         int rc = view_to_tmap(&p.x_map, xv, 64, p.sub_w, p.sub_h, 128);
         if (rc) return rc;
         p.bnb = 1;

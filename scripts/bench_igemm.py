@@ -39,6 +39,13 @@ CASES = {   # name: (B, H, W, Cin, Cout, K, out_mode)
     "b2_conv2_dgrad_bnb": (32, 80, 120, 32, 128, 3, 5),
     "b3_conv2_dgrad_bnb": (32, 40, 60, 32, 128, 3, 5),
     "b1_conv2_dgrad_k32": (32, 160, 240, 32, 128, 3, 6),        # same without the fused reduce
+    # deep decoder stages: few pixels, K and N in the thousands (weights streamed from L2 per tile)
+    "convT1_phase11": (32, 20, 30, 1024, 1024, 2, 0),
+    "convT2_phase11": (32, 40, 60, 512, 512, 2, 0),
+    "convT3_phase11": (32, 80, 120, 256, 256, 2, 0),
+    "reduce1": (32, 20, 30, 1024, 1024, 1, 0),
+    "reduce2": (32, 40, 60, 2048, 512, 1, 0),
+    "reduce3": (32, 80, 120, 1024, 256, 1, 0),
 }
 
 def run(name, reps=5):

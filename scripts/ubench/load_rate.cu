@@ -30,7 +30,7 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 __global__ void __launch_bounds__(64, 1) k(const __grid_constant__ P p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 8 * 32768);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 6 * 32768);
     uint64_t* empty = full + 8;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -66,7 +66,7 @@ int main() {
     const size_t bytes = (size_t)kblocks * ntiles * 32768;
     uint8_t* w; cudaMalloc(&w, bytes); cudaMemset(w, 1, bytes);
     long long* cyc; cudaMalloc(&cyc, 148 * 8);
-    const int smem = 8 * 32768 + 1024 + 256;
+    const int smem = 6 * 32768 + 1024 + 256;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     for (int nstage : {2, 4, 6}) {
         for (int mode = 0; mode < 3; ++mode) {
@@ -85,7 +85,7 @@ int main() {
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             for (int rep = 0; rep < 3; ++rep) {
                 cudaEventRecord(e0); k<<<148, 64, smem>>>(p); cudaEventRecord(e1);
-                cudaError_t e = cudaDeviceSynchronize();
+                cudaError_t e = cudaGetLastError(); if (e == cudaSuccess) e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                 float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
             }

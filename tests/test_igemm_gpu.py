@@ -62,7 +62,8 @@ def test_conv1x1_channel_offset_into_block_buffer():
     _conv_case(2, 128, 32, 12, 20, 1, seed=5, coff=96, extra=32)
 
 
-@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 32, 16, 24), (128, 32, 7, 9), (132, 64, 12, 16), (64, 64, 33, 17)])
+@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 32, 16, 24), (128, 32, 7, 9), (132, 64, 12, 16), (64, 64, 33, 17),
+                                          (128, 32, 20, 30), (32, 128, 40, 60)])      # the last two: x / y roles swapped by the launcher
 def test_conv3x3(Cin, Cout, H, W):
     _conv_case(2, Cin, Cout, H, W, 3, seed=Cin + H, cin_ld=ops.ceil_to(Cin, 8))
 
@@ -116,7 +117,8 @@ def test_conv5x5_logits_folded_kernel_columns(H, W, tile_w):
     assert err < 1e-5, "folded 5x5 fp32 logits relL2 %.3e" % err
 
 
-@pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (256, 5, 7, 10, 14), (128, 5, 7, 9, 13), (64, 4, 4, 8, 7)])
+@pytest.mark.parametrize("C,H,W,OH,OW", [(128, 6, 8, 12, 16), (256, 5, 7, 10, 14), (128, 5, 7, 9, 13), (64, 4, 4, 8, 7),
+                                         (128, 20, 30, 40, 60), (64, 20, 30, 39, 59)])   # 20 x 30: x / y roles swapped by the launcher
 def test_conv_transpose_phases(C, H, W, OH, OW):
     """nn.ConvTranspose2d(C, C, 3, stride=2, padding=1)(x, output_size=(OH, OW)) as 4 sub-pixel GEMMs."""
     torch.manual_seed(C + OH)
