@@ -490,7 +490,13 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # the loss of the very FIRST optimiser step (seeded parameters and inputs: deterministic up to kernel round-off) is the
+    # regression guard of the benched configuration; it also is one more warm-up step
+    loss_first = None
     try:
+        step_e2e()
+        torch.cuda.synchronize()
+        loss_first = [float(v) for v in loss_host]
         for _ in range(max(args.warmup, 3)):
             step_dev()
         torch.cuda.synchronize()
@@ -499,6 +505,10 @@ def main():
             raise
         sys.stderr.write("CUDA graph capture failed (%s); using plain launches\n" % e)
         trainer.use_graph, trainer.graph, graph_ok = False, None, False
+        if loss_first is None:
+            step_e2e()
+            torch.cuda.synchronize()
+            loss_first = [float(v) for v in loss_host]
         for _ in range(max(args.warmup, 3)):
             step_dev()
         torch.cuda.synchronize()
@@ -565,21 +575,26 @@ def main():
         launches = (len(eng.fwd) + len(eng.bwd) + 2 + len([s_ for s_ in eng.segments if s_[2]]) + 2) * args.steps
     else:
         launches = (trainer.launches_per_step() + (2 if cfg4 else 0)) * args.steps
-    # regression guard on the numerics of the benched configuration: per-class loss sums of the e2e step after the same number
-    # of optimiser steps, against the value stored with a green run of this configuration (profiles/bench_loss_golden.json).
-    # Reported as loss_check.ok (25 %); --strict-loss-check turns it into an assertion.  46 Adam steps of this bf16
-    # network are chaotic: two runs on ONE box gave class-0 sums of 651 003 and 682 416 (4.8 % apart), so the guard catches
-    # garbage / NaN / a broken optimiser, not round-off
+    # regression guard on the numerics of the benched configuration (profiles/bench_loss_golden.json, written from a green run):
+    #  * "first": per-class loss sums of the FIRST optimiser step - deterministic up to kernel round-off, checked to 2 %
+    #    (--strict-loss-check turns it into an assertion);
+    #  * the sums after all steps of the run are only reported next to the stored ones: a few dozen Adam steps of this bf16 network
+    #    are chaotic (two runs on ONE box: class-0 sums 651 003 and 682 416; different kernel builds: up to 35 % apart after 13 steps)
     loss_check = None
     gfile = os.path.join(ROOT, "profiles", "bench_loss_golden.json")
     key = "%s/%s/B%d/%dx%d/steps%d/warmup%d/gpus%d" % (args.workload, args.api, B, H, W, args.steps, max(args.warmup, 3), world)
     if os.path.isfile(gfile):
-        gold = json.load(open(gfile)).get(key)
-        if gold is not None:
-            rel = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(loss_per_class, gold))
-            loss_check = {"golden": gold, "max_rel_diff": rel, "ok": rel < 0.25}
+        gj = json.load(open(gfile))
+        gold, gold_first = gj.get(key), gj.get("%s/%s/B%d/%dx%d/first" % (args.workload, args.api, B, H, W))
+        loss_check = {}
+        if gold_first is not None:
+            rel = max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(loss_first, gold_first))
+            loss_check.update({"first_step_golden": gold_first, "first_step_max_rel_diff": rel, "ok": rel < 2e-2})
             if args.strict_loss_check:
-                assert rel < 0.25, "per-class loss %s deviates from the stored value %s (rel %.3e)" % (loss_per_class, gold, rel)
+                assert rel < 2e-2, "first-step per-class loss %s deviates from the stored value %s (rel %.3e)" % (loss_first, gold_first, rel)
+        if gold is not None:
+            loss_check.update({"last_step_golden": gold,
+                               "last_step_max_rel_diff": max(abs(a - b) / max(abs(b), 1e-30) for a, b in zip(loss_per_class, gold))})
     metric = {"mid": "train images/sec (mid-fusion Dense-U-Net, DenseNet-121, 640x960)",
               "cfg4": "train images/sec (mid-fusion Dense-U-Net, DenseNet-121, 1280x1920, incl. on-GPU LiDAR projection + heat-map masks)"}[args.workload]
     line = {
@@ -599,6 +614,7 @@ def main():
         "kernels": kernels,
         "model_tflops": total_flops / (ms / args.steps * 1e9),
         "loss_per_class": loss_per_class,
+        "loss_first_step": loss_first,
         "loss_check": loss_check,
         "cpu_baseline": cpu,
     }
