@@ -288,3 +288,61 @@ def test_work_table_covers_every_element_once():
     for j, n in enumerate(sizes):
         chunks = sorted(int(c) for jj, c in t.tolist() if jj == j)
         assert chunks == list(range((n + WORK_CHUNK - 1) // WORK_CHUNK))
+
+
+def _view(C_, W, H, B):
+    v = _lib.View()
+    v.ptr, v.C, v.W, v.H, v.B = 4096, C_, W, H, B
+    v.sw, v.sh, v.sb = C_, C_ * W, C_ * W * H
+    return v
+
+
+def test_convtranspose_wgrad_plan_groups_taps_per_phase():
+    """ConvTranspose2d(128, 128, 3, stride 2): ONE weight-gradient launch per output phase (1 / 2 / 2 / 4 taps as A chunks at their
+    shifts, the phase view once as B) instead of one launch per tap; every (tap, input channel) row of the scratch matrix is
+    written by exactly one A chunk."""
+    from dmmfods_b200 import ops
+    x, ys = _view(128, 240, 160, 32), [_view(128, 240, 160, 32) for _ in range(4)]
+    taps, _ = ops.convt_wgrad_taps()
+    plan = ops.plan_conv_wgrad(x, ys, taps, 128, 128)
+    assert len(plan["launches"]) == 4 and plan["tap_order"] == list(range(9))
+    assert (plan["rows"], plan["ld"], plan["dt"], plan["dm"], plan["dn"]) == (9 * 128, 128, 128 * 128, 128, 1)
+    rows = []
+    for l in plan["launches"]:
+        (ysrc, dy, dx, ch0, out0), = l["b_slots"]
+        assert (dy, dx, ch0, out0) == (0, 0, 0, 0)
+        for (s_, ady, adx, c0, o0) in l["a_slots"]:
+            t = o0 // 128
+            assert s_ == 0 and taps[t] == (ysrc, ady, adx) and o0 % 128 == c0 and c0 in (0, 64)
+            rows.append(o0)
+        d = ops.make_wgrad(W=240, H=160, B=32, dw=0, ld=plan["ld"], **l)
+        assert ((d.num_a + 1) // 2) * d.num_b * d.n_tile <= 512          # TMEM columns
+    assert sorted(rows) == [64 * i for i in range(18)]
+    # 256 channels: an accumulator per tap already fills TMEM - one launch per tap as before
+    plan = ops.plan_conv_wgrad(_view(256, 120, 80, 32), [_view(256, 120, 80, 32) for _ in range(4)], taps, 256, 256)
+    assert len(plan["launches"]) == 9
+
+
+def test_wgrad_plan_uses_one_m_tile_per_cta_for_small_layers(monkeypatch):
+    from dmmfods_b200 import ops
+    monkeypatch.delenv("DMM_WGRAD_NA", raising=False)
+    taps = ops.conv_taps(1, 0)[0]
+    small = ops.plan_conv_wgrad(_view(1024, 30, 20, 32), [_view(128, 30, 20, 32)], taps, 1024, 128)["launches"][0]
+    big = ops.plan_conv_wgrad(_view(256, 240, 160, 32), [_view(128, 240, 160, 32)], taps, 256, 128)["launches"][0]
+    assert len(small["a_slots"]) == 2 and small["ya"] == 8 and small["a_step"] == 128          # 19 200 pixels: 128 channels per CTA
+    assert len(big["a_slots"]) == 4 and big["ya"] == 1                                          # 1.2 M pixels: all 256 channels in one CTA
+
+
+def test_family_wgrad_swaps_image_axes_when_that_pads_less():
+    """3x3 weight gradient with 32 output-gradient channels (family launch, 8 x 16 pixel tiles): on a 30 x 20 image the views and
+    shifts are handed to the kernel with x and y exchanged (24 x 32 instead of 32 x 32 padded pixels); 240 x 160 stays as it is."""
+    from dmmfods_b200 import ops
+    taps = ops.conv_taps(3, 1)[0]
+    for (W, H, swapped) in ((30, 20, True), (240, 160, False), (60, 40, True)):
+        x, y = _view(128, W, H, 2), _view(32, W, H, 2)
+        l = ops.plan_conv_wgrad(x, [y], taps, 128, 32)["launches"][0]
+        d = ops.make_wgrad(W=W, H=H, B=2, dw=0, ld=9 * 32, **l)
+        assert d.tile_w == 8 and (d.W, d.H) == ((H, W) if swapped else (W, H))
+        assert (d.b_src[0].W, d.b_src[0].sw) == ((H, 32 * W) if swapped else (W, 32))
+        for i, (s_, dy, dx, c0, o0) in enumerate(l["b_slots"]):
+            assert (d.b[i].dy, d.b[i].dx) == ((dx, dy) if swapped else (dy, dx))
