@@ -123,8 +123,11 @@ def pick_tile_w(W, H, pixels):
 
 
 def pick_n_tile(N):
-    if N <= 256:
+    cap = int(os.environ.get("DMM_NTILE_MAX", "256"))      # experiment knob
+    if N <= cap:
         return ceil_to(N, 16)
+    if cap < 256:
+        return cap
     return 256 if N % 256 == 0 or N > 512 else 128
 
 
