@@ -559,6 +559,9 @@ extern "C" int dmm_conv_wgrad(const dmm_wgrad_t* d, void* stream_) {
         if (split_div > 1) splits = splits / split_div > 0 ? splits / split_div : 1;
         const long long min_k = 8;                        // amortise prologue + reduce epilogue
         if (splits > p.total_tiles / min_k) splits = p.total_tiles / min_k;
+        // experiment knob: few-pixel launches on fewer SMs (longer K loops, SMs left to the other stream's kernels)
+        static const int small_ctas = wg_env_int("DMM_WGRAD_SMALL_CTAS", 0), small_tiles = wg_env_int("DMM_WGRAD_SMALL_TILES", 1200);
+        if (small_ctas > 0 && p.total_tiles <= small_tiles && splits * items > small_ctas) splits = small_ctas / items > 0 ? small_ctas / items : 1;
     }
     if (splits > p.total_tiles) splits = p.total_tiles;
     if (splits < 1) splits = 1;
