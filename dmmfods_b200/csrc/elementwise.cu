@@ -2235,6 +2235,27 @@ __global__ void __launch_bounds__(256) unfold_w7s2_kernel(const float* __restric
         }
         __syncthreads();
         __nv_bfloat16* orow = out + (long long)row * OW * ld;
+        if (CT > 0 && chunks <= 3) {
+            // one thread per output pixel, its (at most three) 16-byte chunks unrolled: column -> (kernel column, channel) is
+            // then a compile-time split (the generic loop below spent ~100 instructions per chunk on it: ncu r02, 77 % issue-bound)
+            const int ncol = K * CT, koff = 3 - (K >> 1);
+            for (int ox = threadIdx.x; ox < OW; ox += blockDim.x) {
+                const float* u = urow + stride * ox + koff;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    if (ch < chunks) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int col = ch * 8 + j, kw = col / (CT > 0 ? CT : 1), c = col - kw * (CT > 0 ? CT : 1);
+                            const int kk = flip ? K - 1 - kw : kw;
+                            f[j] = col < ncol ? u[c * pitch + kk] : 0.f;
+                        }
+                        *reinterpret_cast<uint4*>(orow + ((long long)ox * chunks + ch) * 8) = pack8(f);
+                    }
+                }
+            }
+        } else
         for (int i = threadIdx.x; i < OW * chunks; i += blockDim.x) {
             const int ox = i / chunks, ch = i - ox * chunks;
             float f[8];
